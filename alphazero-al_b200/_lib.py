@@ -1,0 +1,78 @@
+"""Loader for libazb200.so (the CUDA kernels + C ABI declared in include/azb200.h).
+
+There is NO CPU fallback: if the library is missing it is built with nvcc, and if that fails - or no CUDA
+device is present when an engine is created - the caller gets an exception."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libazb200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+
+class AzSearchConfig(C.Structure):
+    """az_search_config (include/azb200.h) == SearchConfig (src/cpp/MCTSNode.h:47-61)."""
+    _fields_ = [(n, C.c_float) for n in (
+        "c_init", "c_base", "dirichlet_alpha", "noise_epsilon", "fpu_reduction", "mlh_slope", "mlh_cap",
+        "score_utility_factor", "score_scale", "value_decay")] + [("use_symmetry", C.c_int32), ("vl_count", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    """Compile every CUDA source for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC] + (["-B"] if force else [])
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libazb200.so failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    L = C.CDLL(LIB_PATH)
+    L.az_version.restype = C.c_char_p
+    L.az_global_last_error.restype = C.c_char_p
+    L.az_mcts_last_error.restype = C.c_char_p
+    L.az_mcts_last_error.argtypes = [_vp]
+    L.az_mcts_create.restype = _vp
+    L.az_mcts_create.argtypes = [_i, _i, _i]
+    L.az_mcts_destroy.restype = None
+    L.az_mcts_destroy.argtypes = [_vp]
+    L.az_search_config_defaults.restype = None
+    sig = {
+        "az_mcts_num_envs": [_vp],
+        "az_mcts_set_config": [_vp, _vp], "az_mcts_get_config": [_vp, _vp],
+        "az_mcts_set_seed": [_vp, _i64], "az_mcts_reset_env": [_vp, _i], "az_mcts_prune_roots": [_vp, _vp],
+        "az_mcts_search_batch": [_vp] + [_vp] * 9,
+        "az_mcts_backprop_batch": [_vp] + [_vp] * 6,
+        "az_mcts_remove_all_vl": [_vp, _i],
+        "az_mcts_search_batch_vl": [_vp, _i] + [_vp] * 10,
+        "az_mcts_backprop_batch_vl": [_vp, _i] + [_vp] * 7,
+        "az_mcts_search": [_vp, _i, _vp, _vp, _i],
+        "az_mcts_get_counts": [_vp, _vp], "az_mcts_get_root_stats": [_vp, _vp],
+        "az_mcts_prune_roots_dev": [_vp, _vp, _vp],
+        "az_mcts_search_dev": [_vp, _i] + [_vp] * 12,
+        "az_mcts_backprop_dev": [_vp, _i] + [_vp] * 8,
+        "az_mcts_search_eval_dev": [_vp, _i, _vp, _vp, _i, _vp],
+        "az_mcts_get_counts_dev": [_vp, _vp, _vp], "az_mcts_get_root_stats_dev": [_vp, _vp, _vp],
+        "az_mcts_enable_stats": [_vp, _i], "az_mcts_get_stats": [_vp, _vp],
+        "az_eval_synthetic_dev": [_i, _i, _i] + [_vp] * 12,
+        "az_game_action_size": [_i], "az_game_board_size": [_i], "az_game_board_rows": [_i], "az_game_board_cols": [_i],
+        "az_game_num_symmetries": [_i],
+    }
+    for name, argt in sig.items():
+        f = getattr(L, name)
+        f.restype = _i
+        f.argtypes = argt
+    _lib = L
+    return L

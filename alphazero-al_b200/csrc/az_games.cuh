@@ -1,0 +1,217 @@
+// Bitboard game logic shared by the CUDA kernels and the host-side Env mirror.
+//
+// Semantics follow the reference's game classes (citations are relative to /root/reference/):
+//   Connect4  src/cpp/Connect4.h:31-295   - 2 x u64, 7 bits per column (6 rows + sentinel)
+//   Othello   src/cpp/Othello.h:28-388    - 2 x u64, bit i = (row i/8, col i%8), action 64 = pass
+// but the state is re-designed for registers: no byte board, no height array (column heights are popcounts
+// of the occupancy), 16 bytes of bitboards + three small ints.  The byte board the Python API exposes is
+// materialised only at the boundary (export_cell / import helpers).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AZ_HD __host__ __device__ __forceinline__
+#else
+#define AZ_HD inline
+#endif
+
+namespace az {
+
+AZ_HD int popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+AZ_HD int ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+
+enum { GAME_C4 = 0, GAME_OTH = 1 };
+
+// Register-resident state common to both games.
+struct State {
+    uint64_t bb[2];   // bb[0] = player +1, bb[1] = player -1
+    int turn;         // side to move (+1 / -1)
+    int passes;       // Othello consecutive passes
+    int last;         // index (0/1) of the player who moved last, -1 = nobody
+};
+
+// ------------------------------------------------------------------------------------------------
+// Connect4
+// ------------------------------------------------------------------------------------------------
+struct C4 {
+    static constexpr int GAME = GAME_C4;
+    static constexpr int ROWS = 6, COLS = 7;
+    static constexpr int A = 7;          // ACTION_SIZE
+    static constexpr int S = 42;         // BOARD_SIZE
+    static constexpr int NUM_SYM = 2;
+    static constexpr int MAX_EDGES = 7;
+    static constexpr int MAX_DEPTH = 44; // 42 plies + slack
+    static constexpr bool AUX_PLUS_ONE = true, AUX_NEGATE = false;   // Connect4.h:34-35
+
+    AZ_HD static void reset(State &s) { s.bb[0] = s.bb[1] = 0; s.turn = 1; s.passes = 0; s.last = -1; }   // :62-72
+    AZ_HD static int col_height(uint64_t occ, int c) { return popc64((occ >> (c * 7)) & 0x3FULL); }
+    AZ_HD static int n_pieces(const State &s) { return popc64(s.bb[0] | s.bb[1]); }
+    // import_board / sync_from_board (:87-129): the last mover is inferred from piece-count parity.
+    AZ_HD static void finish_import(State &s, int turn) {
+        int n = n_pieces(s);
+        s.last = n > 0 ? ((n & 1) ? 0 : 1) : -1;
+        s.turn = turn; s.passes = 0;
+    }
+    AZ_HD static void step(State &s, int col) {                       // :159-172 (no legality check)
+        uint64_t occ = s.bb[0] | s.bb[1];
+        int p = s.turn == 1 ? 0 : 1;
+        s.bb[p] |= 1ULL << (col * 7 + col_height(occ, col));
+        s.last = p; s.turn = -s.turn;
+    }
+    AZ_HD static int winner(const State &s) {                         // :182-203 (last mover only)
+        if (s.last < 0) return 0;
+        uint64_t b = s.bb[s.last], t;
+        int res = s.last == 0 ? 1 : -1;
+        t = b & (b >> 1); if (t & (t >> 2))  return res;
+        t = b & (b >> 7); if (t & (t >> 14)) return res;
+        t = b & (b >> 6); if (t & (t >> 12)) return res;
+        t = b & (b >> 8); if (t & (t >> 16)) return res;
+        return 0;
+    }
+    AZ_HD static bool full(const State &s) { return n_pieces(s) == 42; }   // :221-224
+    AZ_HD static bool done(const State &s) { return winner(s) != 0 || full(s); }   // env_connect4.h:43-44
+    // legal moves as a bit mask over actions (bit c = column c not full), ascending = edge order (:209-218)
+    AZ_HD static uint64_t legal(const State &s) {
+        uint64_t occ = s.bb[0] | s.bb[1], top = occ >> 5;               // bit 7c+5 = top row of column c
+        uint64_t m = 0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) m |= ((~top >> (c * 7)) & 1ULL) << c;
+        return m;
+    }
+    AZ_HD static uint64_t flip_bb(uint64_t b) {                        // :249-268
+        uint64_t d = 0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) d |= ((b >> (c * 7)) & 0x7FULL) << ((6 - c) * 7);
+        return d;
+    }
+    AZ_HD static void symmetry(State &s, int sym) { if (sym) { s.bb[0] = flip_bb(s.bb[0]); s.bb[1] = flip_bb(s.bb[1]); } }
+    // map an action of the ORIGINAL frame to its index in the symmetrised frame (self-inverse, :288-294)
+    AZ_HD static int sym_action(int sym, int a) { return sym ? 6 - a : a; }
+    // value of row-major cell j of the byte board (sync_to_board, :135-150)
+    AZ_HD static int cell(const State &s, int j) {
+        int r = j / 7, c = j - r * 7, bit = c * 7 + (5 - r);
+        return (int)((s.bb[0] >> bit) & 1ULL) - (int)((s.bb[1] >> bit) & 1ULL);
+    }
+    AZ_HD static int cell_bit(int j) { int r = j / 7, c = j - r * 7; return c * 7 + (5 - r); }
+    AZ_HD static float terminal_aux_dummy() { return 0.0f; }           // :226-229
+};
+
+// ------------------------------------------------------------------------------------------------
+// Othello
+// ------------------------------------------------------------------------------------------------
+struct Oth {
+    static constexpr int GAME = GAME_OTH;
+    static constexpr int ROWS = 8, COLS = 8;
+    static constexpr int A = 65;
+    static constexpr int S = 64;
+    static constexpr int NUM_SYM = 8;
+    static constexpr int PASS = 64;
+    static constexpr int MAX_EDGES = 48;  // known maximum mobility is 33; three 16-lane passes cover 48
+    static constexpr int MAX_DEPTH = 128; // <= 60 placements + interleaved single passes
+    static constexpr bool AUX_PLUS_ONE = false, AUX_NEGATE = true;     // Othello.h:31-32
+    static constexpr uint64_t NOT_A = 0xFEFEFEFEFEFEFEFEULL, NOT_H = 0x7F7F7F7F7F7F7F7FULL;
+
+    AZ_HD static void reset(State &s) {                                // :62-75
+        s.bb[0] = (1ULL << 28) | (1ULL << 35); s.bb[1] = (1ULL << 27) | (1ULL << 36);
+        s.turn = 1; s.passes = 0; s.last = -1;
+    }
+    AZ_HD static int n_pieces(const State &s) { return popc64(s.bb[0]) + popc64(s.bb[1]); }
+    AZ_HD static void finish_import(State &s, int turn) { s.turn = turn; s.passes = 0; s.last = -1; }   // :92-111
+    template <int D> AZ_HD static uint64_t shift(uint64_t b) {         // :133-147
+        if (D == 0) return b >> 8;
+        if (D == 1) return (b >> 7) & NOT_A;
+        if (D == 2) return (b << 1) & NOT_A;
+        if (D == 3) return (b << 9) & NOT_A;
+        if (D == 4) return b << 8;
+        if (D == 5) return (b << 7) & NOT_H;
+        if (D == 6) return (b >> 1) & NOT_H;
+        return (b >> 9) & NOT_H;
+    }
+    template <int D> AZ_HD static uint64_t valid_dir(uint64_t own, uint64_t opp, uint64_t empty) {
+        uint64_t c = shift<D>(own) & opp;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) c |= shift<D>(c) & opp;
+        return shift<D>(c) & empty;
+    }
+    AZ_HD static uint64_t valid_positions(const State &s) {             // :155-171
+        int p = s.turn == 1 ? 0 : 1;
+        uint64_t own = s.bb[p], opp = s.bb[1 - p], empty = ~(own | opp);
+        return valid_dir<0>(own, opp, empty) | valid_dir<1>(own, opp, empty) | valid_dir<2>(own, opp, empty) |
+               valid_dir<3>(own, opp, empty) | valid_dir<4>(own, opp, empty) | valid_dir<5>(own, opp, empty) |
+               valid_dir<6>(own, opp, empty) | valid_dir<7>(own, opp, empty);
+    }
+    template <int D> AZ_HD static uint64_t flips_dir(uint64_t placed, uint64_t own, uint64_t opp) {
+        uint64_t cand = 0, sq = shift<D>(placed);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {          // a run of opponent discs is at most 6 long
+            uint64_t hit = sq & opp;
+            cand |= hit;
+            sq = hit ? shift<D>(sq) : sq;
+        }
+        return (sq & own) ? cand : 0;
+    }
+    AZ_HD static uint64_t flips(const State &s, int pos) {              // :177-198
+        int p = s.turn == 1 ? 0 : 1;
+        uint64_t own = s.bb[p], opp = s.bb[1 - p], pl = 1ULL << pos;
+        return flips_dir<0>(pl, own, opp) | flips_dir<1>(pl, own, opp) | flips_dir<2>(pl, own, opp) |
+               flips_dir<3>(pl, own, opp) | flips_dir<4>(pl, own, opp) | flips_dir<5>(pl, own, opp) |
+               flips_dir<6>(pl, own, opp) | flips_dir<7>(pl, own, opp);
+    }
+    AZ_HD static void step(State &s, int a) {                           // :206-235
+        if (a == PASS) { s.passes++; s.turn = -s.turn; return; }
+        int p = s.turn == 1 ? 0 : 1;
+        uint64_t f = flips(s, a);
+        s.bb[p] |= (1ULL << a) | f;
+        s.bb[1 - p] &= ~f;
+        s.passes = 0; s.last = p; s.turn = -s.turn;
+    }
+    AZ_HD static bool over(const State &s) { return n_pieces(s) == 64 || s.passes >= 2; }   // :241-244
+    AZ_HD static int winner(const State &s) {                           // :250-258
+        if (!over(s)) return 0;
+        int a = popc64(s.bb[0]), b = popc64(s.bb[1]);
+        return a > b ? 1 : (b > a ? -1 : 0);
+    }
+    AZ_HD static bool full(const State &s) { return over(s); }          // :299-302
+    AZ_HD static bool done(const State &s) { return over(s); }          // env_othello.h:43-44
+    // legal placements as a mask; pass is reported separately (get_valid_moves, :282-296)
+    AZ_HD static uint64_t legal(const State &s) { return over(s) ? 0ULL : valid_positions(s); }
+    AZ_HD static void xform(int sym, int r, int c, int &nr, int &nc) {  // :312-326
+        switch (sym) {
+        case 1: nr = c;     nc = 7 - r; break;
+        case 2: nr = 7 - r; nc = 7 - c; break;
+        case 3: nr = 7 - c; nc = r;     break;
+        case 4: nr = r;     nc = 7 - c; break;
+        case 5: nr = 7 - r; nc = c;     break;
+        case 6: nr = c;     nc = r;     break;
+        case 7: nr = 7 - c; nc = 7 - r; break;
+        default: nr = r;    nc = c;     break;
+        }
+    }
+    AZ_HD static int xform_idx(int sym, int i) { int nr, nc; xform(sym, i >> 3, i & 7, nr, nc); return nr * 8 + nc; }
+    AZ_HD static uint64_t xform_bb(uint64_t b, int sym) {               // :329-341
+        if (sym == 0) return b;
+        uint64_t r = 0;
+        for (; b; b &= b - 1) r |= 1ULL << xform_idx(sym, ctz64(b));
+        return r;
+    }
+    AZ_HD static void symmetry(State &s, int sym) { if (sym) { s.bb[0] = xform_bb(s.bb[0], sym); s.bb[1] = xform_bb(s.bb[1], sym); } }
+    AZ_HD static int inverse_sym(int sym) { return (sym == 1) ? 3 : (sym == 3 ? 1 : sym); }   // :356-361
+    // inverse_symmetry_policy (:373-387): restored[T_inv(i)] = given[i]  <=>  restored[a] = given[T_sym(a)]
+    AZ_HD static int sym_action(int sym, int a) { return (a == PASS || sym == 0) ? a : xform_idx(sym, a); }
+    AZ_HD static int cell(const State &s, int j) { return (int)((s.bb[0] >> j) & 1ULL) - (int)((s.bb[1] >> j) & 1ULL); }
+    AZ_HD static int cell_bit(int j) { return j; }
+};
+
+}  // namespace az

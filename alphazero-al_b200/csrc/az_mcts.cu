@@ -1,0 +1,1242 @@
+// Batched PUCT MCTS for sm_100a: N independent search trees resident in HBM, advanced in lockstep.
+//
+// What it computes follows the reference engine (citations relative to /root/reference/):
+//   src/cpp/MCTS.h:46-675 (single tree), src/cpp/BatchedMCTS.h:26-442 (batch manager), src/cpp/MCTSNode.h.
+// How it computes it is re-designed for the GPU:
+//
+//   * One LANE GROUP per tree (8 lanes for Connect4, 16 for Othello; 4 / 2 trees per warp).  Lane e owns edge e
+//     of the node being scanned, so FPU + PUCT for all children is one coalesced sweep and the arg-max is a
+//     shuffle reduction with lowest-index tie-break (the reference's strict `>` scan, MCTS.h:227).
+//   * A node has no record of its own.  Its statistics (N, in-flight, W_d/W_p1/W_p2, M_sum), its flags and the
+//     pointer to its edge block live in the 32-byte SLOT of the edge that leads to it, inside its parent's
+//     block; the root's live in the per-tree TreeRec.  Descending one level is therefore ONE dependent
+//     32-byte-per-lane load (the reference chases node -> edge -> child: 3 dependent cache lines, MCTS.h:140-234),
+//     and back-propagation updates each statistic exactly once (no mirrored copies).
+//   * The K virtual-loss descents of one tree stay sequential inside its lane group, and the K back-props are
+//     applied in order k = 0..K-1 (MCTS.h:443-545, BatchedMCTS.h:309-330): that is what makes visit counts
+//     bit-exact.  Parallelism comes from the thousands of trees, not from inside a tree; there are no atomics.
+//   * fp32 PUCT arithmetic is written in the reference's operation order and this file is compiled with
+//     -fmad=false (no FMA contraction).  log() of the integer parent visit count and
+//     atan() of the integer disc difference come from host-libm look-up tables so they match glibc bit for bit.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <time.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/azb200.h"
+#include "az_games.cuh"
+#include "az_rng.cuh"
+
+namespace az {
+
+// ------------------------------------------------------------------------------------------------
+// HBM layout
+// ------------------------------------------------------------------------------------------------
+struct __align__(32) Slot {   // one edge + the statistics of the child it leads to (Edge + MCTSNode, MCTSNode.h:69-140)
+    float prior;              // Edge.prior
+    int n;                    // child n_visits
+    uint32_t meta;            // [0,16) child n_inflight | [16,24) Edge.action | [24,32) flags
+    uint32_t child;           // NONE = child not expanded, else (block offset in slots << 6) | num_edges
+    float wd, wp1, wp2, msum; // child W_d, W_p1w, W_p2w, M_sum
+};
+static_assert(sizeof(Slot) == 32, "Slot must be one 32-byte sector");
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t F_ALLOC = 1u << 24;    // child node exists (Edge.child != -1)
+constexpr uint32_t F_TERM = 1u << 25;     // child is_terminal
+constexpr uint32_t F_WIN_P1 = 1u << 26;   // cached terminal result: neither bit = draw
+constexpr uint32_t F_WIN_P2 = 1u << 27;
+constexpr uint32_t F_TURN_P1 = 1u << 28;  // child node.turn == +1
+constexpr uint32_t INFL_MASK = 0xFFFFu;
+
+struct __align__(64) TreeRec {   // per tree: the root's own statistics + allocator state
+    Slot root;                   // root.prior unused
+    uint32_t bump;               // slots used in this tree's arena
+    uint32_t noise_ctr;          // Dirichlet draw counter
+    uint32_t pad[6];
+};
+static_assert(sizeof(TreeRec) == 64, "TreeRec is one 64-byte record");
+
+struct __align__(16) LeafRec {   // what backprop needs to know about a pending leaf (MCTS.h:56-64)
+    uint64_t bb0, bb1;
+    int32_t turn;
+    int16_t passes;
+    int8_t last;
+    uint8_t flags;               // LF_*
+    uint32_t path_len;
+    uint32_t pad;
+};
+constexpr uint8_t LF_VALID = 1, LF_VLPENDING = 2;
+
+struct Dev {   // kernel-visible view of an engine
+    Slot *pool; uint32_t cap;            // cap = arena capacity (slots per tree)
+    TreeRec *trees;
+    float *noise; int noise_stride;      // root Dirichlet noise, [n_envs][noise_stride]
+    LeafRec *leaf_vl; uint32_t *path_vl; int kcap;   // [n_envs][kcap], [n_envs][kcap][MAX_DEPTH]
+    LeafRec *leaf_nv; uint32_t *path_nv; int32_t *pending_sym;   // non-VL search_batch state
+    const float *log_lut; int log_lut_n;
+    const float *atan_lut;               // 129 entries: disc difference -64..64
+    unsigned long long *stats;           // nullptr = counters off
+    int *err;                            // sticky device error flag (arena overflow)
+    int n_envs;
+    uint64_t seed, epoch;
+};
+
+template <class G> struct Lanes;
+template <> struct Lanes<C4> { static constexpr int W = 8, NCH = 1; };
+template <> struct Lanes<Oth> { static constexpr int W = 16, NCH = 3; };
+
+constexpr int CTA = 128;
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+template <int W> __device__ __forceinline__ unsigned group_mask() {
+    return (W == 32) ? 0xFFFFFFFFu : (((1u << W) - 1u) << ((threadIdx.x & 31) & ~(W - 1)));
+}
+__device__ __forceinline__ Slot ld_slot(const Slot *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    Slot s;
+    s.prior = __uint_as_float(a.x); s.n = (int)a.y; s.meta = a.z; s.child = a.w;
+    s.wd = __uint_as_float(b.x); s.wp1 = __uint_as_float(b.y); s.wp2 = __uint_as_float(b.z); s.msum = __uint_as_float(b.w);
+    return s;
+}
+__device__ __forceinline__ void st_slot(Slot *p, const Slot &s) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(__float_as_uint(s.prior), (uint32_t)s.n, s.meta, s.child);
+    q[1] = make_uint4(__float_as_uint(s.wd), __float_as_uint(s.wp1), __float_as_uint(s.wp2), __float_as_uint(s.msum));
+}
+__device__ __forceinline__ uint64_t or_reduce64(unsigned gm, uint64_t v) {
+    uint32_t lo = __reduce_or_sync(gm, (uint32_t)v), hi = __reduce_or_sync(gm, (uint32_t)(v >> 32));
+    return ((uint64_t)hi << 32) | lo;
+}
+// WDLValue::q on the running means (MCTSNode.h:23-25,118-128): 0 when unvisited (uniform thirds cancel)
+__device__ __forceinline__ float mean_q(int n, float wp1, float wp2, bool turn_p1) {
+    if (n == 0) return 0.0f;
+    float inv = 1.0f / (float)n;
+    float p1 = wp1 * inv, p2 = wp2 * inv;
+    return turn_p1 ? (p1 - p2) : (p2 - p1);
+}
+__device__ __forceinline__ float mean_m(int n, float msum) { return n == 0 ? 0.0f : msum / (float)n; }   // :131-133
+
+// import_board (+ set_turn) from the int8 board of the Python API (BatchedMCTS.h:133-137, Connect4.h:100-129,
+// Othello.h:92-111).  Cooperative: each lane reads a strip, bitboards are OR-reduced over the group.
+template <class G, int W> __device__ __forceinline__ State import_board(const int8_t *b, int turn, int lane, unsigned gm) {
+    uint64_t p0 = 0, p1 = 0;
+    if (G::GAME == GAME_C4) {
+        if (lane < 7) {            // gravity scan of column `lane`, bottom row first, stop at the first empty cell
+            for (int r = 5; r >= 0; --r) {
+                int v = b[r * 7 + lane];
+                if (v == 0) break;
+                uint64_t bit = 1ULL << (lane * 7 + (5 - r));
+                if (v == 1) p0 |= bit; else p1 |= bit;
+            }
+        }
+    } else {
+        for (int j = lane; j < 64; j += W) {
+            int v = b[j];
+            if (v == 1) p0 |= 1ULL << j; else if (v == -1) p1 |= 1ULL << j;
+        }
+    }
+    State s;
+    s.bb[0] = or_reduce64(gm, p0); s.bb[1] = or_reduce64(gm, p1);
+    G::finish_import(s, turn);
+    return s;
+}
+
+template <class G> __device__ __forceinline__ float aux_utility(float child_M, float parent_M, float child_Q, const az_search_config &cfg) {
+    if (G::GAME == GAME_C4) {      // Connect4.h:231-239
+        if (cfg.mlh_slope <= 0.0f) return 0.0f;
+        float m_diff = child_M - parent_M;
+        float v = cfg.mlh_slope * m_diff, lo = -cfg.mlh_cap, hi = cfg.mlh_cap;
+        float u = v < lo ? lo : (hi < v ? hi : v);   // std::clamp
+        return u * child_Q;
+    }
+    if (cfg.score_utility_factor <= 0.0f) return 0.0f;   // Othello.h:268-274
+    return cfg.score_utility_factor * child_M;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dirichlet noise: gamma(alpha,1) by Marsaglia-Tsang on the counter-based stream.  (MCTS.h:113-132, 347-363.)
+// RNG-dependent => distributional parity only.
+// ------------------------------------------------------------------------------------------------
+__device__ double noise_u01(const Dev &d, int env, uint32_t &ctr) {
+    uint64_t h = az_rand(d.seed, 0, STREAM_NOISE, (uint64_t)env, ctr++);
+    return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+__device__ float gamma_draw(const Dev &d, int env, uint32_t &ctr, float alpha) {
+    double a = alpha, boost = 1.0;
+    if (a < 1.0) { boost = pow(noise_u01(d, env, ctr), 1.0 / a); a += 1.0; }
+    double dd = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
+    for (int it = 0; it < 64; ++it) {
+        double u1 = noise_u01(d, env, ctr), u2 = noise_u01(d, env, ctr);
+        double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2), v = 1.0 + c * x;
+        if (v <= 0) continue;
+        v = v * v * v;
+        double u = noise_u01(d, env, ctr);
+        if (log(u) < 0.5 * x * x + dd - dd * v + dd * log(v)) return (float)(dd * v * boost);
+    }
+    return (float)(dd * boost);
+}
+__device__ void draw_root_noise(const Dev &d, int env, uint32_t &ctr, float alpha, int ne, float *row) {
+    float sum = 0.0f;
+    for (int i = 0; i < ne; ++i) { float g = gamma_draw(d, env, ctr, alpha); row[i] = g; sum += g; }
+    float inv = 1.0f / (sum + 1e-8f);
+    for (int i = 0; i < ne; ++i) row[i] = row[i] * inv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SELECT: simulate / simulate_vl (MCTS.h:242-322, 443-545) + leaf export (BatchedMCTS.h:119-171, 227-286)
+// ------------------------------------------------------------------------------------------------
+struct LeafOut {
+    int8_t *boards; float *td, *tp1, *tp2; uint8_t *is_term; int32_t *turns; int32_t *sym; uint8_t *mask; float *planes;
+};
+
+template <class G, bool VL>
+__global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int K, int write_sym, const int8_t *__restrict__ boards,
+                                                const int32_t *__restrict__ turns, LeafOut out) {
+    constexpr int W = Lanes<G>::W, NCH = Lanes<G>::NCH;
+    const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
+    if (gid >= d.n_envs) return;            // whole groups exit together (n_envs is padded to groups by the grid)
+    const int lane = threadIdx.x & (W - 1);
+    const unsigned gm = group_mask<W>();
+    const int env = gid;
+    Slot *arena = d.pool + (size_t)env * d.cap;
+    TreeRec *tr = d.trees + env;
+    const float *noise = d.noise + (size_t)env * d.noise_stride;
+    const int vl = VL ? cfg.vl_count : 0;
+
+    const State start = import_board<G, W>(boards + (size_t)env * G::S, turns[env], lane, gm);
+    unsigned long long st_depth = 0, st_edges = 0;
+
+    for (int k = 0; k < K; ++k) {
+        State st = start;
+        // current node = root (TreeRec.root); every lane holds the same copy
+        Slot cur = ld_slot(&tr->root);
+        bool is_root = true, root_vl = false;
+        uint32_t plen = 0;
+        uint32_t *path = VL ? d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH : d.path_nv + (size_t)env * G::MAX_DEPTH;
+        int winner = 0; bool full = false;
+        uint32_t last_slot = 0;          // arena offset of the slot that leads to `cur` (valid when plen > 0)
+
+        while (cur.child != NONE) {      // while (node.is_expanded)
+            if (cur.meta & F_TERM) break;
+            const int ne = (int)(cur.child & 63u);
+            if (ne == 0 || plen >= (uint32_t)G::MAX_DEPTH) break;
+            const uint32_t off = cur.child >> 6;
+            Slot s[NCH]; bool has[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                int e = c * W + lane;
+                has[c] = e < ne;
+                if (has[c]) s[c] = ld_slot(arena + off + e);
+                else { s[c].prior = 0.f; s[c].n = 0; s[c].meta = 0; s[c].child = NONE; s[c].wd = s[c].wp1 = s[c].wp2 = s[c].msum = 0.f; }
+            }
+            st_edges += (unsigned long long)ne;
+            // ---- compute_fpu (MCTS.h:140-156): seen_policy summed sequentially in edge order ----
+            const int cur_infl = (int)(cur.meta & INFL_MASK);
+            const bool cur_p1 = (cur.meta & F_TURN_P1) != 0;
+            const float parent_q = mean_q(cur.n, cur.wp1, cur.wp2, cur_p1);
+            float seen_policy = 0.0f;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float pv = (has[c] && s[c].n > 0) ? s[c].prior : 0.0f;   // + 0.0f is exact
+                const int lim = min(W, ne - c * W);
+                if (G::GAME == GAME_C4) {
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) seen_policy += __shfl_sync(gm, pv, j, W);
+                } else {
+                    for (int j = 0; j < lim; ++j) seen_policy += __shfl_sync(gm, pv, j, W);
+                }
+            }
+            const float fscale = (1.0f + parent_q) / 2.0f;
+            const float eff_fpu = cfg.fpu_reduction * fscale;
+            float fpu = parent_q - eff_fpu * sqrtf(seen_policy);
+            fpu = (-1.0f < fpu) ? fpu : -1.0f;
+            // ---- select_edge (MCTS.h:163-234) ----
+            const int pn_i = cur.n + cur_infl;
+            const float parent_n = (float)pn_i;
+            const float parent_M = mean_m(cur.n, cur.msum);
+            const float lg = (pn_i >= 0 && pn_i < d.log_lut_n) ? d.log_lut[pn_i] : logf((parent_n + cfg.c_base + 1.0f) / cfg.c_base);
+            const float c_puct = cfg.c_init + lg;
+            const float sqrt_pn = sqrtf(parent_n);
+            const float ne_eps = cfg.noise_epsilon;
+            float best_s = -INFINITY; int best_e = -1;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (!has[c]) continue;
+                const int e = c * W + lane;
+                float eff_prior = s[c].prior;
+                if (is_root && ne_eps > 0.0f) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * noise[e];
+                const int cn = s[c].n, cinf = (int)(s[c].meta & INFL_MASK);
+                float q_value, child_Q = 0.0f, child_M = 0.0f; int visits = 0;
+                const bool seen = cn > 0;
+                if (seen) {
+                    visits = cn + cinf;
+                    child_Q = mean_q(cn, s[c].wp1, s[c].wp2, (s[c].meta & F_TURN_P1) != 0);
+                    child_M = mean_m(cn, s[c].msum);
+                    if (G::AUX_NEGATE) child_M = -child_M;
+                    q_value = -child_Q;
+                } else if (cinf > 0) { q_value = fpu; visits = cinf; }
+                else q_value = fpu;
+                const float u_score = c_puct * eff_prior * sqrt_pn / (1.0f + (float)visits);
+                const float m_utility = seen ? aux_utility<G>(child_M, parent_M, child_Q, cfg) : 0.0f;
+                const float score = q_value + u_score + m_utility;
+                if (score > best_s) { best_s = score; best_e = e; }
+            }
+            // arg-max over the group; ties -> lowest edge index
+#pragma unroll
+            for (int o = W / 2; o > 0; o >>= 1) {
+                float os = __shfl_xor_sync(gm, best_s, o, W);
+                int oe = __shfl_xor_sync(gm, best_e, o, W);
+                bool take = oe >= 0 && (best_e < 0 || os > best_s || (os == best_s && oe < best_e));
+                if (take) { best_s = os; best_e = oe; }
+            }
+            if (best_e < 0) break;
+            if (VL && !root_vl) {          // root virtual loss, applied on first loop entry (MCTS.h:471-475)
+                root_vl = true;
+                if (lane == 0) tr->root.meta += (uint32_t)vl;
+            }
+            // broadcast the chosen child to the whole group
+            const int bl = best_e & (W - 1), bc = best_e / W;
+            Slot ch = s[0];
+#pragma unroll
+            for (int c = 1; c < NCH; ++c) if (bc == c) ch = s[c];
+            ch.n = __shfl_sync(gm, ch.n, bl, W);
+            ch.meta = __shfl_sync(gm, ch.meta, bl, W);
+            ch.child = __shfl_sync(gm, ch.child, bl, W);
+            ch.wp1 = __shfl_sync(gm, ch.wp1, bl, W);
+            ch.wp2 = __shfl_sync(gm, ch.wp2, bl, W);
+            ch.msum = __shfl_sync(gm, ch.msum, bl, W);
+            G::step(st, (int)((ch.meta >> 16) & 0xFFu));
+            uint32_t nmeta = ch.meta;
+            if (!(nmeta & F_ALLOC)) {      // lazy child allocation (MCTS.h:481-488): remember the child's side to move
+                nmeta |= F_ALLOC;
+                nmeta = st.turn == 1 ? (nmeta | F_TURN_P1) : (nmeta & ~F_TURN_P1);
+            }
+            nmeta += (uint32_t)vl;         // child virtual loss (MCTS.h:492)
+            winner = G::winner(st);
+            full = G::full(st);
+            const bool term_now = winner != 0 || full;
+            if (term_now) nmeta = (nmeta & ~(F_WIN_P1 | F_WIN_P2)) | F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+            last_slot = off + (uint32_t)best_e;
+            if (lane == 0) {
+                if (nmeta != ch.meta) arena[last_slot].meta = nmeta;
+                path[plen] = last_slot;
+            }
+            ++plen;
+            cur = ch; cur.meta = nmeta; is_root = false;
+            if (term_now) break;
+        }
+        st_depth += plen;
+        // ---- leaf classification (MCTS.h:512-544) ----
+        bool leaf_term = (cur.meta & F_TERM) != 0;
+        if (!leaf_term) {
+            if (winner == 0 && !full) { winner = G::winner(st); full = G::full(st); }
+            if (winner != 0 || full) {
+                leaf_term = true;
+                cur.meta = (cur.meta & ~(F_WIN_P1 | F_WIN_P2)) | F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+                if (lane == 0) { if (plen == 0) tr->root.meta = cur.meta; else arena[last_slot].meta = cur.meta; }
+            }
+        }
+        float wd = 0.f, w1 = 0.f, w2 = 0.f;
+        if (leaf_term) { if (cur.meta & F_WIN_P1) w1 = 1.f; else if (cur.meta & F_WIN_P2) w2 = 1.f; else wd = 1.f; }
+        // ---- remember the leaf for backprop ----
+        if (lane == 0) {
+            LeafRec L;
+            L.bb0 = st.bb[0]; L.bb1 = st.bb[1]; L.turn = st.turn; L.passes = (int16_t)st.passes; L.last = (int8_t)st.last;
+            L.flags = (uint8_t)(LF_VALID | ((VL && plen > 0) ? LF_VLPENDING : 0));
+            L.path_len = plen; L.pad = 0;
+            LeafRec *dst = VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env;
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<uint4 *>(&L);
+            *(reinterpret_cast<uint4 *>(dst) + 1) = *(reinterpret_cast<uint4 *>(&L) + 1);
+        }
+        // ---- leaf export: random symmetry for non-terminal leaves (BatchedMCTS.h:148-158 / 261-271) ----
+        const size_t flat = (size_t)env * K + k;
+        int sym = 0;
+        State ex = st;
+        if (!leaf_term && cfg.use_symmetry) {
+            uint64_t h = az_rand(d.seed, d.epoch, STREAM_SYM, (uint64_t)env, (uint64_t)k);
+            sym = G::GAME == GAME_C4 ? (int)(h & 1) : ((0x7620 >> (4 * (int)(h & 3))) & 0xF);   // Othello {0,2,6,7}
+            G::symmetry(ex, sym);
+        }
+        uint64_t legal = leaf_term ? 0ULL : G::legal(ex);
+        bool pass_only = false;
+        if (G::GAME == GAME_OTH) pass_only = !leaf_term && legal == 0ULL && !Oth::over(ex);
+        for (int j = lane; j < G::S; j += W) out.boards[flat * G::S + j] = (int8_t)G::cell(ex, j);
+        for (int a = lane; a < G::A; a += W) {
+            uint8_t m = (uint8_t)((legal >> (a & 63)) & 1ULL);
+            if (G::GAME == GAME_OTH && a == Oth::PASS) m = pass_only ? 1 : 0;
+            out.mask[flat * G::A + a] = m;
+        }
+        if (out.planes) {
+            float *pl = out.planes + flat * 3 * G::S;
+            const int own = st.turn == 1 ? 0 : 1;
+            const float tf = (float)st.turn;
+            for (int j = lane; j < G::S; j += W) {
+                int bit = G::cell_bit(j);
+                pl[j] = (float)((ex.bb[own] >> bit) & 1ULL);
+                pl[G::S + j] = (float)((ex.bb[1 - own] >> bit) & 1ULL);
+                pl[2 * G::S + j] = tf;
+            }
+        }
+        if (lane == 0) {
+            out.td[flat] = wd; out.tp1[flat] = w1; out.tp2[flat] = w2;
+            out.is_term[flat] = leaf_term ? 1 : 0;
+            out.turns[flat] = st.turn;
+            if (VL) { if (out.sym) out.sym[flat] = sym; }
+            else { if (write_sym) d.pending_sym[env] = sym; if (out.sym) out.sym[flat] = sym; }
+        }
+        __syncwarp(gm);   // order this descent's in-flight updates before the next descent of the same tree
+    }
+    if (d.stats && lane == 0) {
+        atomicAdd(d.stats + 0, (unsigned long long)K);
+        atomicAdd(d.stats + 1, st_depth);
+        atomicAdd(d.stats + 2, st_edges);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BACKPROP: remove_all_vl + expand_leaf + propagate (MCTS.h:329-402, 561-609; BatchedMCTS.h:176-199, 296-332)
+// ------------------------------------------------------------------------------------------------
+template <class G, int W>
+__device__ __forceinline__ void remove_vl_group(const Dev &d, const az_search_config &cfg, int env, int K, int lane, unsigned gm,
+                                                Slot *arena, Slot &root) {
+    const int vl = cfg.vl_count;
+    for (int k = 0; k < K; ++k) {
+        LeafRec *L = d.leaf_vl + (size_t)env * d.kcap + k;
+        const uint8_t fl = L->flags;
+        if (!(fl & LF_VLPENDING)) continue;
+        const uint32_t plen = L->path_len;
+        const uint32_t *path = d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH;
+        { int infl = (int)(root.meta & INFL_MASK) - vl; root.meta = (root.meta & ~INFL_MASK) | (uint32_t)max(infl, 0); }
+        for (uint32_t j = lane; j < plen; j += W) {
+            uint32_t *m = &arena[path[j]].meta;
+            uint32_t v = *m;
+            int infl = (int)(v & INFL_MASK) - vl;
+            *m = (v & ~INFL_MASK) | (uint32_t)max(infl, 0);
+        }
+        __syncwarp(gm);
+        if (lane == 0) L->flags = (uint8_t)(fl & ~LF_VLPENDING);
+    }
+}
+
+template <class G, bool VL>
+__global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, int K, int removeK, const float *__restrict__ policy,
+                                                  const float *__restrict__ dv, const float *__restrict__ p1v, const float *__restrict__ p2v,
+                                                  const float *__restrict__ mlv, const uint8_t *__restrict__ is_term,
+                                                  const int32_t *__restrict__ sym_ids) {
+    constexpr int W = Lanes<G>::W;
+    const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
+    if (gid >= d.n_envs) return;
+    const int lane = threadIdx.x & (W - 1);
+    const unsigned gm = group_mask<W>();
+    const int env = gid;
+    Slot *arena = d.pool + (size_t)env * d.cap;
+    TreeRec *tr = d.trees + env;
+    Slot root = ld_slot(&tr->root);     // kept in registers (identical in every lane), written back once
+    uint32_t bump = tr->bump, noise_ctr = tr->noise_ctr;
+    unsigned long long st_created = 0, st_expanded = 0;
+
+    if (VL) remove_vl_group<G, W>(d, cfg, env, removeK, lane, gm, arena, root);
+    __syncwarp(gm);
+
+    for (int k = 0; k < K; ++k) {
+        const LeafRec *Lp = VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env;
+        LeafRec L;
+        *reinterpret_cast<uint4 *>(&L) = *reinterpret_cast<const uint4 *>(Lp);
+        *(reinterpret_cast<uint4 *>(&L) + 1) = *(reinterpret_cast<const uint4 *>(Lp) + 1);
+        if (!(L.flags & LF_VALID)) continue;             // current_leaf_idx == -1 (MCTS.h:409,599)
+        const size_t flat = (size_t)env * K + k;
+        const bool term = is_term[flat] != 0;
+        const uint32_t plen = L.path_len;
+        const uint32_t *path = VL ? d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH : d.path_nv + (size_t)env * G::MAX_DEPTH;
+        State st; st.bb[0] = L.bb0; st.bb[1] = L.bb1; st.turn = L.turn; st.passes = L.passes; st.last = L.last;
+        Slot *leaf_slot = plen > 0 ? arena + path[plen - 1] : nullptr;
+        const uint32_t leaf_child = plen > 0 ? leaf_slot->child : root.child;
+
+        // ---- expand_leaf (MCTS.h:329-375); VL: skipped when an earlier k already expanded it (MCTS.h:601-607) ----
+        if (!term && (!VL || leaf_child == NONE)) {
+            const int sym = sym_ids ? sym_ids[flat] : 0;   // search() passes nullptr: no inverse symmetry (BatchedMCTS.h:404)
+            uint64_t legal = G::legal(st);
+            int ne; bool pass_only = false;
+            if (G::GAME == GAME_OTH) {
+                pass_only = legal == 0ULL && !Oth::over(st);
+                ne = pass_only ? 1 : popc64(legal);
+            } else ne = popc64(legal);
+            const float *prow = policy + flat * G::A;
+            // policy of the ORIGINAL frame: restored[a] = given[sym_action(a)]  (inverse_symmetry_policy)
+            float psum = 0.0f;
+            float pmine[(G::A + W - 1) / W];
+#pragma unroll
+            for (int j = 0; j < (G::A + W - 1) / W; ++j) {
+                int a = j * W + lane;
+                pmine[j] = (a < G::A) ? prow[G::sym_action(sym, a)] : 0.0f;
+            }
+            if (G::GAME == GAME_C4) {
+                const float pv = ((legal >> lane) & 1ULL) ? pmine[0] : 0.0f;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) psum += __shfl_sync(gm, pv, j, W);
+            } else if (pass_only) {
+                psum += __shfl_sync(gm, pmine[4], 0, W);          // action 64 lives in lane 0, register 4
+            } else {
+                for (uint64_t v = legal; v; v &= v - 1) {         // ascending action order
+                    int a = ctz64(v), j = a / W;
+                    float x = j == 0 ? pmine[0] : (j == 1 ? pmine[1] : (j == 2 ? pmine[2] : pmine[3]));
+                    psum += __shfl_sync(gm, x, a & (W - 1), W);
+                }
+            }
+            const float denom = psum + 1e-8f;
+            if (bump + (uint32_t)ne > d.cap) {
+                if (lane == 0) atomicExch(d.err, 1);              // host sizes the arenas so this never fires
+            } else {
+                const uint32_t off = bump;
+                Slot ns; ns.n = 0; ns.child = NONE; ns.wd = ns.wp1 = ns.wp2 = ns.msum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < (G::A + W - 1) / W; ++j) {
+                    int a = j * W + lane;
+                    if (a >= G::A) continue;
+                    bool ok; int eidx;
+                    if (G::GAME == GAME_OTH && a == Oth::PASS) { ok = pass_only; eidx = 0; }
+                    else { ok = (legal >> (a & 63)) & 1ULL; eidx = popc64(legal & ((1ULL << (a & 63)) - 1ULL)); }
+                    if (!ok) continue;
+                    ns.prior = pmine[j] / denom;
+                    ns.meta = (uint32_t)a << 16;
+                    st_slot(arena + off + eidx, ns);
+                }
+                bump += (uint32_t)ne;
+                const uint32_t cw = (off << 6) | (uint32_t)ne;
+                if (plen > 0) { if (lane == 0) leaf_slot->child = cw; }
+                else {
+                    root.child = cw;
+                    // root expansion draws Dirichlet noise when alpha > 0 (MCTS.h:347-363, leaf.parent == -1)
+                    float *nrow = d.noise + (size_t)env * d.noise_stride;
+                    if (cfg.dirichlet_alpha > 0.0f) {
+                        if (lane == 0) draw_root_noise(d, env, noise_ctr, cfg.dirichlet_alpha, ne, nrow);
+                        noise_ctr = __shfl_sync(gm, noise_ctr, 0, W);
+                    } else {
+                        for (int e = lane; e < ne; e += W) nrow[e] = 0.0f;
+                    }
+                }
+                st_created += (unsigned long long)ne; st_expanded += 1;
+            }
+        }
+        // ---- propagate (MCTS.h:381-402): leaf -> root, absolute WDL, per-level aux transform and decay ----
+        float wd = dv[flat], w1 = p1v[flat], w2 = p2v[flat];
+        float ml;
+        if (term) {                                              // Game::terminal_aux (MCTS.h:412,608)
+            if (G::GAME == GAME_C4) ml = 0.0f;
+            else ml = d.atan_lut[(popc64(st.bb[0]) - popc64(st.bb[1])) * st.turn + 64];
+        } else ml = mlv[flat];
+        const float gamma = cfg.value_decay;
+        const bool decay = gamma < 1.0f;
+        const float u3 = 1.0f / 3.0f;
+        for (uint32_t base = 0; base < plen; base += W) {
+            const uint32_t t = base + lane;                      // t-th node counted from the leaf
+            const bool mine = t < plen;
+            Slot *sp = nullptr; int n = 0; float4 w = make_float4(0, 0, 0, 0);
+            if (mine) {
+                sp = arena + path[plen - 1 - t];
+                n = sp->n;
+                w = *reinterpret_cast<const float4 *>(&sp->wd);
+            }
+            float mwd = 0, mw1 = 0, mw2 = 0, mml = 0;
+            const uint32_t lim = min((uint32_t)W, plen - base);
+            for (uint32_t i = 0; i < lim; ++i) {                 // the value sequence is inherently sequential
+                if (i == (uint32_t)lane) { mwd = wd; mw1 = w1; mw2 = w2; mml = ml; }
+                if (G::AUX_PLUS_ONE) ml += 1.0f;
+                if (G::AUX_NEGATE) ml = -ml;
+                if (decay) { wd = gamma * wd + (1 - gamma) * u3; w1 = gamma * w1 + (1 - gamma) * u3; w2 = gamma * w2 + (1 - gamma) * u3; }
+            }
+            if (mine) {
+                sp->n = n + 1;
+                w.x += mwd; w.y += mw1; w.z += mw2; w.w += mml;
+                *reinterpret_cast<float4 *>(&sp->wd) = w;
+            }
+        }
+        root.n += 1; root.wd += wd; root.wp1 += w1; root.wp2 += w2; root.msum += ml;
+        __syncwarp(gm);   // the next k of this tree must see these updates (duplicate leaves, shared ancestors)
+    }
+    if (lane == 0) { st_slot(&tr->root, root); tr->bump = bump; tr->noise_ctr = noise_ctr; }
+    if (d.stats && lane == 0) { atomicAdd(d.stats + 3, st_created); atomicAdd(d.stats + 4, st_expanded); }
+}
+
+// remove_all_vl without backprop (BatchedMCTS.h:209-216)
+template <class G>
+__global__ void __launch_bounds__(CTA) k_remove_vl(Dev d, az_search_config cfg, int K) {
+    constexpr int W = Lanes<G>::W;
+    const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
+    if (gid >= d.n_envs) return;
+    const int lane = threadIdx.x & (W - 1);
+    const unsigned gm = group_mask<W>();
+    TreeRec *tr = d.trees + gid;
+    Slot root = ld_slot(&tr->root);
+    const uint32_t before = root.meta;
+    remove_vl_group<G, W>(d, cfg, gid, K, lane, gm, d.pool + (size_t)gid * d.cap, root);
+    if (lane == 0 && root.meta != before) tr->root.meta = root.meta;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prune_root / apply_root_noise / reset (MCTS.h:77-132), one thread per tree
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reset_tree(TreeRec *tr, float *nrow, int noise_stride) {
+    Slot r; r.prior = 0.f; r.n = 0; r.meta = F_TURN_P1; r.child = NONE; r.wd = r.wp1 = r.wp2 = r.msum = 0.f;   // fresh root: turn = +1
+    st_slot(&tr->root, r);
+    tr->bump = 0;
+    for (int e = 0; e < noise_stride; ++e) nrow[e] = 0.0f;
+}
+template <class G>
+__global__ void k_prune(Dev d, az_search_config cfg, const int32_t *__restrict__ actions) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= d.n_envs) return;
+    TreeRec *tr = d.trees + env;
+    Slot *arena = d.pool + (size_t)env * d.cap;
+    float *nrow = d.noise + (size_t)env * d.noise_stride;
+    const Slot root = ld_slot(&tr->root);
+    const int action = actions[env];
+    if (root.child != NONE) {
+        const int ne = (int)(root.child & 63u); const uint32_t off = root.child >> 6;
+        for (int e = 0; e < ne; ++e) {
+            Slot s = ld_slot(arena + off + e);
+            if ((int)((s.meta >> 16) & 0xFFu) == action && (s.meta & F_ALLOC)) {
+                s.prior = 0.f;
+                st_slot(&tr->root, s);                      // promoted child becomes the root (parent = -1)
+                const int cne = s.child == NONE ? 0 : (int)(s.child & 63u);
+                if (cfg.dirichlet_alpha > 0.0f && cne > 0) {  // apply_root_noise (MCTS.h:113-132)
+                    uint32_t ctr = tr->noise_ctr;
+                    draw_root_noise(d, env, ctr, cfg.dirichlet_alpha, cne, nrow);
+                    tr->noise_ctr = ctr;
+                } else {
+                    for (int i = 0; i < d.noise_stride; ++i) nrow[i] = 0.0f;   // the promoted node's edges never had noise
+                }
+                return;
+            }
+        }
+    }
+    reset_tree(tr, nrow, d.noise_stride);
+}
+__global__ void k_reset(Dev d, int env /* -1 = all */) {
+    const int i = env >= 0 ? env : (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= d.n_envs || (env >= 0 && (blockIdx.x | threadIdx.x) != 0)) return;
+    reset_tree(d.trees + i, d.noise + (size_t)i * d.noise_stride, d.noise_stride);
+}
+__global__ void k_init_leaf(Dev d) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < (size_t)d.n_envs) { d.leaf_nv[i].flags = 0; d.leaf_nv[i].path_len = 0; d.pending_sym[i] = 0; }
+}
+__global__ void k_init_leaf_vl(LeafRec *leaf, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) { leaf[i].flags = 0; leaf[i].path_len = 0; }
+}
+__global__ void k_max_bump(Dev d, unsigned int *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int v = i < d.n_envs ? d.trees[i].bump : 0u;
+    v = __reduce_max_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, v);
+}
+__global__ void k_grow(const Slot *__restrict__ src, Slot *__restrict__ dst, const TreeRec *__restrict__ trees, uint32_t old_cap,
+                       uint32_t new_cap) {   // one CTA per tree copies the used prefix of its arena
+    const int env = blockIdx.x;
+    const uint32_t used = trees[env].bump;
+    const uint4 *s = reinterpret_cast<const uint4 *>(src + (size_t)env * old_cap);
+    uint4 *t = reinterpret_cast<uint4 *>(dst + (size_t)env * new_cap);
+    for (uint32_t i = threadIdx.x; i < used * 2; i += blockDim.x) t[i] = s[i];
+}
+
+// get_counts / get_root_stats (MCTS.h:617-673)
+template <class G>
+__global__ void k_counts(Dev d, int32_t *__restrict__ out) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= d.n_envs) return;
+    int32_t *o = out + (size_t)env * G::A;
+    for (int a = 0; a < G::A; ++a) o[a] = 0;
+    const Slot root = ld_slot(&d.trees[env].root);
+    if (root.child == NONE) return;
+    const Slot *blk = d.pool + (size_t)env * d.cap + (root.child >> 6);
+    const int ne = (int)(root.child & 63u);
+    for (int e = 0; e < ne; ++e) {
+        const Slot s = ld_slot(blk + e);
+        if (s.meta & F_ALLOC) o[(s.meta >> 16) & 0xFFu] = s.n;
+    }
+}
+template <class G>
+__global__ void k_root_stats(Dev d, float *__restrict__ out) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= d.n_envs) return;
+    constexpr int SZ = 6 + 8 * G::A;
+    float *o = out + (size_t)env * SZ;
+    const Slot root = ld_slot(&d.trees[env].root);
+    const float third = 1.f / 3;
+    if (root.n == 0) { o[3] = o[4] = o[5] = third; }
+    else { float inv = 1.0f / (float)root.n; o[3] = root.wd * inv; o[4] = root.wp1 * inv; o[5] = root.wp2 * inv; }
+    o[0] = (float)root.n;
+    o[1] = mean_q(root.n, root.wp1, root.wp2, (root.meta & F_TURN_P1) != 0);
+    o[2] = mean_m(root.n, root.msum);
+    for (int j = 6; j < SZ; ++j) o[j] = 0.0f;
+    if (root.child == NONE) return;
+    const Slot *blk = d.pool + (size_t)env * d.cap + (root.child >> 6);
+    const float *nrow = d.noise + (size_t)env * d.noise_stride;
+    const int ne = (int)(root.child & 63u);
+    for (int e = 0; e < ne; ++e) {
+        const Slot s = ld_slot(blk + e);
+        float *sl = o + 6 + ((s.meta >> 16) & 0xFFu) * 8;
+        sl[2] = s.prior; sl[3] = nrow[e];
+        if (s.meta & F_ALLOC) {
+            float cm = mean_m(s.n, s.msum);
+            if (G::AUX_NEGATE) cm = -cm;
+            sl[0] = (float)s.n;
+            sl[1] = mean_q(s.n, s.wp1, s.wp2, (s.meta & F_TURN_P1) != 0);
+            sl[4] = cm;
+            if (s.n == 0) { sl[5] = sl[6] = sl[7] = third; }
+            else { float inv = 1.0f / (float)s.n; sl[5] = s.wd * inv; sl[6] = s.wp1 * inv; sl[7] = s.wp2 * inv; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Built-in evaluators for search(): IEvaluator default and RolloutEvaluator (IEvaluator.h:56-64,
+// RolloutEvaluator.h:23-48).  One thread per tree; integer RNG draws match oracle/az_oracle.c.
+// ------------------------------------------------------------------------------------------------
+template <class G>
+__global__ void k_eval_builtin(Dev d, int kind, int playout, const uint8_t *__restrict__ is_term, const float *__restrict__ td,
+                               const float *__restrict__ tp1, const float *__restrict__ tp2, float *__restrict__ policy,
+                               float *__restrict__ dv, float *__restrict__ p1v, float *__restrict__ p2v, float *__restrict__ mlv) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= d.n_envs) return;
+    float *prow = policy + (size_t)env * G::A;
+    mlv[env] = 0.0f;
+    if (is_term[env]) {
+        for (int a = 0; a < G::A; ++a) prow[a] = 0.0f;
+        dv[env] = td[env]; p1v[env] = tp1[env]; p2v[env] = tp2[env];
+        return;
+    }
+    for (int a = 0; a < G::A; ++a) prow[a] = 1.0f;
+    if (kind == AZ_EVAL_UNIFORM) { dv[env] = p1v[env] = p2v[env] = 1.f / 3; return; }
+    const LeafRec L = d.leaf_nv[env];
+    State s; s.bb[0] = L.bb0; s.bb[1] = L.bb1; s.turn = L.turn; s.passes = L.passes; s.last = L.last;
+    int w = 0;
+    for (uint64_t step = 0; step < 256; ++step) {
+        w = G::winner(s);
+        if (w != 0 || G::full(s)) break;
+        uint64_t legal = G::legal(s);
+        int cnt = popc64(legal), a;
+        uint64_t r = az_rand(d.seed, d.epoch, STREAM_ROLLOUT, (uint64_t)env, ((uint64_t)playout << 8) | step);
+        if (G::GAME == GAME_OTH && cnt == 0) a = Oth::PASS;
+        else {
+            int idx = (int)(r % (uint64_t)cnt);
+            uint64_t v = legal;
+            for (int i = 0; i < idx; ++i) v &= v - 1;
+            a = ctz64(v);
+        }
+        G::step(s, a);
+    }
+    dv[env] = w == 0 ? 1.0f : 0.0f; p1v[env] = w == 1 ? 1.0f : 0.0f; p2v[env] = w == -1 ? 1.0f : 0.0f;
+}
+
+}  // namespace az
+
+// ================================================================================================
+// Host side: engine object + C ABI
+// ================================================================================================
+using namespace az;
+
+static thread_local std::string g_global_err;
+
+struct az_mcts {
+    int game = 0, n = 0, device = 0;
+    int A = 0, S = 0, W = 0, max_depth = 0, max_edges = 0;
+    az_search_config cfg;
+    Dev d{};
+    cudaStream_t stream = nullptr;
+    // pools
+    uint32_t cap = 0;
+    uint64_t bump_bound = 0;          // conservative upper bound of max(TreeRec.bump)
+    unsigned int *d_scratch_u32 = nullptr;
+    // LUT state
+    float lut_c_base = -1.0f, lut_scale = -1.0f;
+    int lut_n = 0;
+    float *d_log_lut = nullptr, *d_atan_lut = nullptr;
+    // VL bookkeeping
+    int kcap = 0;
+    int prepared_K = 0;               // vl_paths_.size() (MCTS.h:421-429)
+    // host-API staging (device side)
+    int io_rows = 0;                  // rows the io buffers can hold
+    int8_t *io_boards_in = nullptr; int32_t *io_turns_in = nullptr;
+    int8_t *io_boards = nullptr; float *io_td = nullptr, *io_tp1 = nullptr, *io_tp2 = nullptr; uint8_t *io_term = nullptr;
+    int32_t *io_turns = nullptr, *io_sym = nullptr; uint8_t *io_mask = nullptr;
+    float *io_policy = nullptr, *io_d = nullptr, *io_p1 = nullptr, *io_p2 = nullptr, *io_ml = nullptr; uint8_t *io_term_in = nullptr; int32_t *io_sym_in = nullptr;
+    int32_t *io_actions = nullptr; int32_t *io_counts = nullptr; float *io_stats = nullptr;
+    // pinned host staging for the host API
+    uint8_t *h_pin = nullptr; size_t h_pin_bytes = 0;
+    unsigned long long *d_stats = nullptr; int *d_err = nullptr;
+    uint64_t launches = 0;
+    bool stats_on = false;
+    std::string err;
+};
+
+#define AZ_FAIL(h, code, ...)                                   \
+    do {                                                        \
+        char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__);    \
+        (h)->err = _b; return (code);                           \
+    } while (0)
+#define CU(h, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) AZ_FAIL(h, AZ_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+static inline int grid_groups(int n, int W) { return (int)(((size_t)n * W + CTA - 1) / CTA); }
+static inline int grid_threads(int n, int bs = 128) { return (n + bs - 1) / bs; }
+
+template <class T> static int dev_alloc(az_mcts *h, T **p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    CU(h, cudaMalloc((void **)p, count * sizeof(T)));
+    return AZ_OK;
+}
+
+static int ensure_luts(az_mcts *h) {
+    const az_search_config &c = h->cfg;
+    if (!h->d_log_lut || h->lut_c_base != c.c_base || !h->d_atan_lut || h->lut_scale != c.score_scale)
+        CU(h, cudaDeviceSynchronize());      // kernels in flight on caller streams may still read the old tables
+    if (!h->d_log_lut || h->lut_c_base != c.c_base) {
+        if (h->lut_n == 0) {
+            const char *e = getenv("AZB200_LOG_LUT");
+            h->lut_n = e ? std::max(1024, atoi(e)) : (1 << 18);
+        }
+        std::vector<float> lut((size_t)h->lut_n);
+        for (int i = 0; i < h->lut_n; ++i) lut[(size_t)i] = logf(((float)i + c.c_base + 1.0f) / c.c_base);   // MCTS.h:213-214, host libm
+        if (!h->d_log_lut) { int r = dev_alloc(h, &h->d_log_lut, (size_t)h->lut_n); if (r) return r; }
+        CU(h, cudaMemcpyAsync(h->d_log_lut, lut.data(), sizeof(float) * (size_t)h->lut_n, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->lut_c_base = c.c_base;
+    }
+    if (!h->d_atan_lut || h->lut_scale != c.score_scale) {
+        float lut[129];
+        for (int k = -64; k <= 64; ++k) lut[k + 64] = atanf((float)k / c.score_scale) * (2.0f / 3.14159265f);   // Othello.h:260-266
+        if (!h->d_atan_lut) { int r = dev_alloc(h, &h->d_atan_lut, 129); if (r) return r; }
+        CU(h, cudaMemcpyAsync(h->d_atan_lut, lut, sizeof(lut), cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->lut_scale = c.score_scale;
+    }
+    h->d.log_lut = h->d_log_lut; h->d.log_lut_n = h->lut_n; h->d.atan_lut = h->d_atan_lut;
+    return AZ_OK;
+}
+
+static int ensure_kcap(az_mcts *h, int K) {
+    if (K <= h->kcap) return AZ_OK;
+    int nk = std::max(K, std::max(4, h->kcap * 2));
+    LeafRec *nl = nullptr; uint32_t *np = nullptr;
+    CU(h, cudaMalloc((void **)&nl, sizeof(LeafRec) * (size_t)h->n * nk));
+    CU(h, cudaMalloc((void **)&np, sizeof(uint32_t) * (size_t)h->n * nk * h->max_depth));
+    size_t cnt = (size_t)h->n * nk;
+    k_init_leaf_vl<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(nl, cnt);
+    // pending VL paths do not survive a regrow of K (the reference's resize keeps them, but callers never
+    // change K between a search and its backprop)
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->d.leaf_vl) cudaFree(h->d.leaf_vl);
+    if (h->d.path_vl) cudaFree(h->d.path_vl);
+    h->d.leaf_vl = nl; h->d.path_vl = np; h->kcap = nk; h->d.kcap = nk;
+    return AZ_OK;
+}
+
+static int ensure_io(az_mcts *h, int rows) {
+    if (rows <= h->io_rows) return AZ_OK;
+    int r = std::max(rows, h->io_rows * 2);
+    int rc = 0;
+    rc |= dev_alloc(h, &h->io_boards, (size_t)r * h->S); rc |= dev_alloc(h, &h->io_td, (size_t)r); rc |= dev_alloc(h, &h->io_tp1, (size_t)r);
+    rc |= dev_alloc(h, &h->io_tp2, (size_t)r); rc |= dev_alloc(h, &h->io_term, (size_t)r); rc |= dev_alloc(h, &h->io_turns, (size_t)r);
+    rc |= dev_alloc(h, &h->io_sym, (size_t)r); rc |= dev_alloc(h, &h->io_mask, (size_t)r * h->A);
+    rc |= dev_alloc(h, &h->io_policy, (size_t)r * h->A); rc |= dev_alloc(h, &h->io_d, (size_t)r); rc |= dev_alloc(h, &h->io_p1, (size_t)r);
+    rc |= dev_alloc(h, &h->io_p2, (size_t)r); rc |= dev_alloc(h, &h->io_ml, (size_t)r); rc |= dev_alloc(h, &h->io_term_in, (size_t)r);
+    rc |= dev_alloc(h, &h->io_sym_in, (size_t)r);
+    if (rc) return AZ_ERR_CUDA;
+    if (h->h_pin) { cudaFreeHost(h->h_pin); h->h_pin = nullptr; }
+    h->h_pin_bytes = (size_t)r * (size_t)(h->S + h->A * 5 + 64) + 4096;
+    CU(h, cudaMallocHost((void **)&h->h_pin, h->h_pin_bytes));
+    h->io_rows = r;
+    return AZ_OK;
+}
+
+// Make sure no tree can overflow its arena during a back-prop of `sims` simulations per tree.
+static int ensure_arena(az_mcts *h, int sims, cudaStream_t st) {
+    const uint64_t need = (uint64_t)sims * (uint64_t)(h->game == GAME_C4 ? 7 : 34);
+    if (h->bump_bound + need <= h->cap) { h->bump_bound += need; return AZ_OK; }
+    // refresh the bound from the device
+    CU(h, cudaMemsetAsync(h->d_scratch_u32, 0, sizeof(unsigned int), st));
+    k_max_bump<<<grid_threads(h->n, 256), 256, 0, st>>>(h->d, h->d_scratch_u32);
+    unsigned int mx = 0;
+    CU(h, cudaMemcpyAsync(&mx, h->d_scratch_u32, sizeof(mx), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    h->bump_bound = mx;
+    if (h->bump_bound + need > h->cap) {
+        uint64_t ncap = h->cap;
+        while (h->bump_bound + need > ncap) ncap *= 2;
+        if (ncap >= (1ull << 26)) AZ_FAIL(h, AZ_ERR_NOMEM, "tree arena would exceed 2^26 slots per tree");
+        Slot *np = nullptr;
+        cudaError_t e = cudaMalloc((void **)&np, sizeof(Slot) * (size_t)h->n * ncap);
+        if (e != cudaSuccess) AZ_FAIL(h, AZ_ERR_NOMEM, "cannot grow tree arenas to %llu slots/tree: %s", (unsigned long long)ncap, cudaGetErrorString(e));
+        k_grow<<<h->n, 256, 0, st>>>(h->d.pool, np, h->d.trees, h->cap, (uint32_t)ncap);
+        CU(h, cudaStreamSynchronize(st));
+        cudaFree(h->d.pool);
+        h->d.pool = np; h->cap = (uint32_t)ncap; h->d.cap = h->cap;
+    }
+    h->bump_bound += need;
+    return AZ_OK;
+}
+
+static int check_cfg(az_mcts *h, int K) {
+    if (h->cfg.vl_count < 0 || (int64_t)h->cfg.vl_count * std::max(K, 1) > 65535)
+        AZ_FAIL(h, AZ_ERR_INVALID, "vl_count * K must be in [0, 65535] (got vl_count=%d, K=%d)", h->cfg.vl_count, K);
+    return ensure_luts(h);
+}
+
+template <class G> static void launch_select(az_mcts *h, bool vl, int K, int write_sym, const int8_t *b, const int32_t *t, LeafOut o, cudaStream_t s) {
+    const int g = grid_groups(h->n, Lanes<G>::W);
+    if (vl) k_select<G, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, write_sym, b, t, o);
+    else k_select<G, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, write_sym, b, t, o);
+    h->launches++;
+}
+template <class G> static void launch_backprop(az_mcts *h, bool vl, int K, int removeK, const float *pol, const float *d, const float *p1, const float *p2,
+                                               const float *ml, const uint8_t *it, const int32_t *sym, cudaStream_t s) {
+    const int g = grid_groups(h->n, Lanes<G>::W);
+    if (vl) k_backprop<G, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, removeK, pol, d, p1, p2, ml, it, sym);
+    else k_backprop<G, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, 0, pol, d, p1, p2, ml, it, sym);
+    h->launches++;
+}
+
+static int do_search(az_mcts *h, int K, int write_sym, const int8_t *d_boards, const int32_t *d_turns, LeafOut o, cudaStream_t s) {
+    int rc = check_cfg(h, K); if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    const bool vl = K > 0;
+    if (vl) { rc = ensure_kcap(h, K); if (rc) return rc; h->prepared_K = K; }
+    h->d.epoch++;
+    h->d.stats = h->stats_on ? h->d_stats : nullptr;
+    if (h->game == GAME_C4) launch_select<C4>(h, vl, K, write_sym, d_boards, d_turns, o, s);
+    else launch_select<Oth>(h, vl, K, write_sym, d_boards, d_turns, o, s);
+    CU(h, cudaGetLastError());
+    return AZ_OK;
+}
+static int do_backprop(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
+                       const uint8_t *it, const int32_t *sym, cudaStream_t s) {
+    int rc = check_cfg(h, K); if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    const bool vl = K > 0;
+    if (vl && K > h->prepared_K) AZ_FAIL(h, AZ_ERR_INVALID, "backprop_batch_vl: K (%d) exceeds the K of the last search_batch_vl (%d)", K, h->prepared_K);
+    rc = ensure_arena(h, vl ? K : 1, s); if (rc) return rc;
+    h->d.stats = h->stats_on ? h->d_stats : nullptr;
+    const int removeK = vl ? std::min(K, h->prepared_K) : 0;
+    const int32_t *symp = vl ? sym : h->d.pending_sym;     // non-VL: the id remembered by search_batch (BatchedMCTS.h:194)
+    if (h->game == GAME_C4) launch_backprop<C4>(h, vl, K, removeK, pol, d, p1, p2, ml, it, symp, s);
+    else launch_backprop<Oth>(h, vl, K, removeK, pol, d, p1, p2, ml, it, symp, s);
+    CU(h, cudaGetLastError());
+    return AZ_OK;
+}
+static int check_device_error(az_mcts *h) {
+    int e = 0;
+    CU(h, cudaMemcpyAsync(&e, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (e) AZ_FAIL(h, AZ_ERR_NOMEM, "device tree arena overflow (internal sizing error)");
+    return AZ_OK;
+}
+
+extern "C" {
+
+const char *az_version(void) { return "azb200 0.1 (sm_100a)"; }
+const char *az_global_last_error(void) { return g_global_err.c_str(); }
+int az_game_action_size(int g) { return g == GAME_C4 ? C4::A : (g == GAME_OTH ? Oth::A : -1); }
+int az_game_board_size(int g) { return g == GAME_C4 ? C4::S : (g == GAME_OTH ? Oth::S : -1); }
+int az_game_board_rows(int g) { return g == GAME_C4 ? 6 : (g == GAME_OTH ? 8 : -1); }
+int az_game_board_cols(int g) { return g == GAME_C4 ? 7 : (g == GAME_OTH ? 8 : -1); }
+int az_game_num_symmetries(int g) { return g == GAME_C4 ? 2 : (g == GAME_OTH ? 8 : -1); }
+void az_search_config_defaults(az_search_config *c) {
+    c->c_init = 1.25f; c->c_base = 19652.0f; c->dirichlet_alpha = 0.3f; c->noise_epsilon = 0.25f; c->fpu_reduction = 0.4f;
+    c->mlh_slope = 0.0f; c->mlh_cap = 0.2f; c->score_utility_factor = 0.0f; c->score_scale = 8.0f; c->value_decay = 1.0f;
+    c->use_symmetry = 1; c->vl_count = 1;
+}
+
+az_mcts *az_mcts_create(int game, int n_envs, int device) {
+    if (game != GAME_C4 && game != GAME_OTH) { g_global_err = "unknown game id"; return nullptr; }
+    if (n_envs <= 0) { g_global_err = "n_envs must be positive"; return nullptr; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_global_err = std::string("no CUDA device available (the MCTS engine has no CPU fallback): ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { g_global_err = "invalid CUDA device ordinal"; return nullptr; }
+    az_mcts *h = new az_mcts();
+    h->game = game; h->n = n_envs; h->device = device;
+    h->A = az_game_action_size(game); h->S = az_game_board_size(game);
+    h->W = game == GAME_C4 ? Lanes<C4>::W : Lanes<Oth>::W;
+    h->max_depth = game == GAME_C4 ? C4::MAX_DEPTH : Oth::MAX_DEPTH;
+    h->max_edges = game == GAME_C4 ? 8 : 48;
+    az_search_config_defaults(&h->cfg);
+    auto fail = [&](const char *what) -> az_mcts * {
+        g_global_err = std::string(what) + ": " + h->err;
+        az_mcts_destroy(h);
+        return nullptr;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail("create"); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "stream create failed"; return fail("create"); }
+    const char *ce = getenv("AZB200_ARENA_SLOTS");
+    h->cap = ce ? (uint32_t)std::max(256, atoi(ce)) : (game == GAME_C4 ? 2048u : 4096u);
+    h->d.n_envs = n_envs; h->d.cap = h->cap; h->d.noise_stride = h->max_edges;
+    h->d.seed = 0x243F6A8885A308D3ULL; h->d.epoch = 0;
+    int rc = 0;
+    rc |= dev_alloc(h, &h->d.pool, (size_t)n_envs * h->cap);
+    rc |= dev_alloc(h, &h->d.trees, (size_t)n_envs);
+    rc |= dev_alloc(h, &h->d.noise, (size_t)n_envs * h->d.noise_stride);
+    rc |= dev_alloc(h, &h->d.leaf_nv, (size_t)n_envs);
+    rc |= dev_alloc(h, &h->d.path_nv, (size_t)n_envs * h->max_depth);
+    rc |= dev_alloc(h, &h->d.pending_sym, (size_t)n_envs);
+    rc |= dev_alloc(h, &h->d_stats, 8); rc |= dev_alloc(h, &h->d_err, 1); rc |= dev_alloc(h, &h->d_scratch_u32, 4);
+    rc |= dev_alloc(h, &h->io_boards_in, (size_t)n_envs * h->S); rc |= dev_alloc(h, &h->io_turns_in, (size_t)n_envs);
+    rc |= dev_alloc(h, &h->io_actions, (size_t)n_envs); rc |= dev_alloc(h, &h->io_counts, (size_t)n_envs * h->A);
+    rc |= dev_alloc(h, &h->io_stats, (size_t)n_envs * (6 + 8 * h->A));
+    if (rc) return fail("device allocation");
+    h->d.err = h->d_err;
+    cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream);
+    cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
+    k_reset<<<grid_threads(n_envs), 128, 0, h->stream>>>(h->d, -1);
+    k_init_leaf<<<grid_threads(n_envs), 128, 0, h->stream>>>(h->d);
+    if (ensure_io(h, n_envs) != AZ_OK) return fail("io allocation");
+    if (ensure_luts(h) != AZ_OK) return fail("LUT upload");
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = cudaGetErrorString(cudaGetLastError()); return fail("init kernels"); }
+    return h;
+}
+
+void az_mcts_destroy(az_mcts *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void *ptrs[] = {h->d.pool, h->d.trees, h->d.noise, h->d.leaf_vl, h->d.path_vl, h->d.leaf_nv, h->d.path_nv, h->d.pending_sym, h->d_log_lut,
+                    h->d_atan_lut, h->d_stats, h->d_err, h->d_scratch_u32, h->io_boards_in, h->io_turns_in, h->io_boards, h->io_td, h->io_tp1,
+                    h->io_tp2, h->io_term, h->io_turns, h->io_sym, h->io_mask, h->io_policy, h->io_d, h->io_p1, h->io_p2, h->io_ml,
+                    h->io_term_in, h->io_sym_in, h->io_actions, h->io_counts, h->io_stats};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+const char *az_mcts_last_error(const az_mcts *h) { return h ? h->err.c_str() : g_global_err.c_str(); }
+int az_mcts_num_envs(const az_mcts *h) { return h->n; }
+int az_mcts_set_config(az_mcts *h, const az_search_config *c) { h->cfg = *c; return AZ_OK; }
+int az_mcts_get_config(const az_mcts *h, az_search_config *c) { *c = h->cfg; return AZ_OK; }
+int az_mcts_set_seed(az_mcts *h, int64_t seed) {
+    if (seed < 0) {   // re-randomise (BatchedMCTS.h:73-76)
+        uint64_t t = (uint64_t)clock() ^ ((uint64_t)(uintptr_t)h << 16);
+        h->d.seed = splitmix64(t ^ splitmix64(h->d.seed));
+    } else h->d.seed = (uint64_t)seed;
+    h->d.epoch = 0;
+    return AZ_OK;
+}
+int az_mcts_reset_env(az_mcts *h, int i) {
+    if (i < 0 || i >= h->n) return AZ_OK;   // silently ignored (BatchedMCTS.h:93-99)
+    CU(h, cudaSetDevice(h->device));
+    k_reset<<<1, 32, 0, h->stream>>>(h->d, i);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return AZ_OK;
+}
+int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream) {
+    int rc = check_cfg(h, 1); if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->game == GAME_C4) k_prune<C4><<<grid_threads(h->n), 128, 0, s>>>(h->d, h->cfg, d_actions);
+    else k_prune<Oth><<<grid_threads(h->n), 128, 0, s>>>(h->d, h->cfg, d_actions);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return AZ_OK;
+}
+int az_mcts_prune_roots(az_mcts *h, const int32_t *actions) {
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpyAsync(h->io_actions, actions, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    int rc = az_mcts_prune_roots_dev(h, h->io_actions, h->stream); if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return AZ_OK;
+}
+
+static int host_search(az_mcts *h, int K, const int8_t *boards, const int32_t *turns, int8_t *ob, float *td, float *tp1, float *tp2,
+                       uint8_t *it, int32_t *ot, int32_t *sym, uint8_t *vm) {
+    CU(h, cudaSetDevice(h->device));
+    const int rowsK = K > 0 ? K : 1;
+    const size_t rows = (size_t)h->n * rowsK;
+    int rc = ensure_io(h, (int)rows); if (rc) return rc;
+    cudaStream_t s = h->stream;
+    CU(h, cudaMemcpyAsync(h->io_boards_in, boards, (size_t)h->n * h->S, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->io_turns_in, turns, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, s));
+    LeafOut o{h->io_boards, h->io_td, h->io_tp1, h->io_tp2, h->io_term, h->io_turns, h->io_sym, h->io_mask, nullptr};
+    rc = do_search(h, K, 1, h->io_boards_in, h->io_turns_in, o, s); if (rc) return rc;
+    CU(h, cudaMemcpyAsync(ob, h->io_boards, rows * h->S, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(td, h->io_td, rows * 4, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(tp1, h->io_tp1, rows * 4, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(tp2, h->io_tp2, rows * 4, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(it, h->io_term, rows, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(ot, h->io_turns, rows * 4, cudaMemcpyDeviceToHost, s));
+    if (sym) CU(h, cudaMemcpyAsync(sym, h->io_sym, rows * 4, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(vm, h->io_mask, rows * h->A, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+static int host_backprop(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
+                         const uint8_t *it, const int32_t *sym) {
+    CU(h, cudaSetDevice(h->device));
+    const int rowsK = K > 0 ? K : 1;
+    const size_t rows = (size_t)h->n * rowsK;
+    int rc = ensure_io(h, (int)rows); if (rc) return rc;
+    cudaStream_t s = h->stream;
+    CU(h, cudaMemcpyAsync(h->io_policy, pol, rows * h->A * 4, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->io_d, d, rows * 4, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->io_p1, p1, rows * 4, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->io_p2, p2, rows * 4, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->io_ml, ml, rows * 4, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->io_term_in, it, rows, cudaMemcpyHostToDevice, s));
+    if (sym) CU(h, cudaMemcpyAsync(h->io_sym_in, sym, rows * 4, cudaMemcpyHostToDevice, s));
+    rc = do_backprop(h, K, h->io_policy, h->io_d, h->io_p1, h->io_p2, h->io_ml, h->io_term_in, h->io_sym_in, s); if (rc) return rc;
+    return check_device_error(h);
+}
+
+int az_mcts_search_batch(az_mcts *h, const int8_t *b, const int32_t *t, int8_t *ob, float *td, float *tp1, float *tp2, uint8_t *it,
+                         int32_t *ot, uint8_t *vm) {
+    return host_search(h, 0, b, t, ob, td, tp1, tp2, it, ot, nullptr, vm);
+}
+int az_mcts_backprop_batch(az_mcts *h, const float *pol, const float *d, const float *p1, const float *p2, const float *ml, const uint8_t *it) {
+    return host_backprop(h, 0, pol, d, p1, p2, ml, it, nullptr);
+}
+int az_mcts_search_batch_vl(az_mcts *h, int K, const int8_t *b, const int32_t *t, int8_t *ob, float *td, float *tp1, float *tp2,
+                            uint8_t *it, int32_t *ot, int32_t *sym, uint8_t *vm) {
+    if (K < 1) AZ_FAIL(h, AZ_ERR_INVALID, "search_batch_vl: K must be >= 1");
+    return host_search(h, K, b, t, ob, td, tp1, tp2, it, ot, sym, vm);
+}
+int az_mcts_backprop_batch_vl(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
+                              const uint8_t *it, const int32_t *sym) {
+    if (K < 1) AZ_FAIL(h, AZ_ERR_INVALID, "backprop_batch_vl: K must be >= 1");
+    return host_backprop(h, K, pol, d, p1, p2, ml, it, sym);
+}
+int az_mcts_remove_all_vl(az_mcts *h, int K) {
+    int rc = check_cfg(h, 1); if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    const int safeK = std::min(K, h->prepared_K);
+    if (safeK <= 0) return AZ_OK;
+    const int g = grid_groups(h->n, h->W);
+    if (h->game == GAME_C4) k_remove_vl<C4><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK);
+    else k_remove_vl<Oth><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    return AZ_OK;
+}
+
+int az_mcts_search_dev(az_mcts *h, int K, const int8_t *b, const int32_t *t, int8_t *ob, float *td, float *tp1, float *tp2, uint8_t *it,
+                       int32_t *ot, int32_t *sym, uint8_t *vm, float *planes, void *stream) {
+    if (K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "search_dev: K must be >= 0");
+    LeafOut o{ob, td, tp1, tp2, it, ot, sym, vm, planes};
+    return do_search(h, K, 1, b, t, o, (cudaStream_t)stream);
+}
+int az_mcts_backprop_dev(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
+                         const uint8_t *it, const int32_t *sym, void *stream) {
+    if (K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "backprop_dev: K must be >= 0");
+    return do_backprop(h, K, pol, d, p1, p2, ml, it, sym, (cudaStream_t)stream);
+}
+
+int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const int8_t *d_boards, const int32_t *d_turns, int n_playout, void *stream) {
+    if (evaluator != AZ_EVAL_UNIFORM && evaluator != AZ_EVAL_ROLLOUT) AZ_FAIL(h, AZ_ERR_INVALID, "unknown evaluator kind %d", evaluator);
+    int rc = check_cfg(h, 1); if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    rc = ensure_io(h, h->n); if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    h->d.epoch++;                          // one epoch per search() call, like orc_search
+    const uint64_t epoch = h->d.epoch;
+    LeafOut o{h->io_boards, h->io_td, h->io_tp1, h->io_tp2, h->io_term, h->io_turns, nullptr, h->io_mask, nullptr};
+    az_search_config saved = h->cfg;
+    h->cfg.use_symmetry = 0;               // search() never symmetrises leaves (BatchedMCTS.h:357)
+    h->d.stats = h->stats_on ? h->d_stats : nullptr;
+    for (int p = 0; p < n_playout; ++p) {
+        rc = ensure_arena(h, 1, s); if (rc) { h->cfg = saved; return rc; }
+        h->d.epoch = epoch;
+        if (h->game == GAME_C4) {
+            launch_select<C4>(h, false, 1, 0, d_boards, d_turns, o, s);
+            k_eval_builtin<C4><<<grid_threads(h->n), 128, 0, s>>>(h->d, evaluator, p, h->io_term, h->io_td, h->io_tp1, h->io_tp2, h->io_policy,
+                                                                 h->io_d, h->io_p1, h->io_p2, h->io_ml);
+            // backprop without the inverse symmetry: pending_sym must not be consulted -> pass sym 0 via cfg
+            k_backprop<C4, false><<<grid_groups(h->n, Lanes<C4>::W), CTA, 0, s>>>(h->d, h->cfg, 1, 0, h->io_policy, h->io_d, h->io_p1, h->io_p2, h->io_ml,
+                                                                                  h->io_term, nullptr);
+        } else {
+            launch_select<Oth>(h, false, 1, 0, d_boards, d_turns, o, s);
+            k_eval_builtin<Oth><<<grid_threads(h->n), 128, 0, s>>>(h->d, evaluator, p, h->io_term, h->io_td, h->io_tp1, h->io_tp2, h->io_policy,
+                                                                  h->io_d, h->io_p1, h->io_p2, h->io_ml);
+            k_backprop<Oth, false><<<grid_groups(h->n, Lanes<Oth>::W), CTA, 0, s>>>(h->d, h->cfg, 1, 0, h->io_policy, h->io_d, h->io_p1, h->io_p2, h->io_ml,
+                                                                                   h->io_term, nullptr);
+        }
+        h->launches += 2;
+    }
+    h->cfg = saved;
+    CU(h, cudaGetLastError());
+    return AZ_OK;
+}
+int az_mcts_search(az_mcts *h, int evaluator, const int8_t *boards, const int32_t *turns, int n_playout) {
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpyAsync(h->io_boards_in, boards, (size_t)h->n * h->S, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->io_turns_in, turns, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    int rc = az_mcts_search_eval_dev(h, evaluator, h->io_boards_in, h->io_turns_in, n_playout, h->stream); if (rc) return rc;
+    return check_device_error(h);
+}
+
+int az_mcts_get_counts_dev(az_mcts *h, int32_t *d_out, void *stream) {
+    CU(h, cudaSetDevice(h->device));
+    if (h->game == GAME_C4) k_counts<C4><<<grid_threads(h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
+    else k_counts<Oth><<<grid_threads(h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return AZ_OK;
+}
+int az_mcts_get_counts(az_mcts *h, int32_t *out) {
+    int rc = az_mcts_get_counts_dev(h, h->io_counts, h->stream); if (rc) return rc;
+    CU(h, cudaMemcpyAsync(out, h->io_counts, sizeof(int32_t) * (size_t)h->n * h->A, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return AZ_OK;
+}
+int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream) {
+    CU(h, cudaSetDevice(h->device));
+    if (h->game == GAME_C4) k_root_stats<C4><<<grid_threads(h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
+    else k_root_stats<Oth><<<grid_threads(h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return AZ_OK;
+}
+int az_mcts_get_root_stats(az_mcts *h, float *out) {
+    int rc = az_mcts_get_root_stats_dev(h, h->io_stats, h->stream); if (rc) return rc;
+    CU(h, cudaMemcpyAsync(out, h->io_stats, sizeof(float) * (size_t)h->n * (6 + 8 * h->A), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return AZ_OK;
+}
+int az_mcts_enable_stats(az_mcts *h, int on) {
+    CU(h, cudaSetDevice(h->device));
+    h->stats_on = on != 0;
+    CU(h, cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return AZ_OK;
+}
+int az_mcts_get_stats(az_mcts *h, uint64_t *out8) {
+    CU(h, cudaSetDevice(h->device));
+    unsigned long long v[8];
+    CU(h, cudaDeviceSynchronize());
+    CU(h, cudaMemcpy(v, h->d_stats, sizeof(v), cudaMemcpyDeviceToHost));
+    CU(h, cudaMemsetAsync(h->d_scratch_u32, 0, sizeof(unsigned int), h->stream));
+    k_max_bump<<<grid_threads(h->n, 256), 256, 0, h->stream>>>(h->d, h->d_scratch_u32);
+    unsigned int mx = 0;
+    CU(h, cudaMemcpyAsync(&mx, h->d_scratch_u32, sizeof(mx), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 5; ++i) out8[i] = v[i];
+    out8[5] = mx; out8[6] = h->cap; out8[7] = h->launches;
+    return AZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+/*
+ * azb200.h - C ABI of the B200-native self-play hot path (batched PUCT MCTS + bitboard envs).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / pybind types.  Every entry point names
+ * the reference interface it replaces (paths relative to /root/reference/).  The reference exposes this path
+ * through two pybind11 modules (src/cpp/mcts_bindings.cpp, src/cpp/env_bindings.cpp); INTEGRATION.md shows the
+ * ctypes / pybind stub a maintainer adds on the reference side to bind these symbols instead.
+ *
+ * Conventions
+ *   - every function returns AZ_OK (0) or a negative error; az_*_last_error() gives the message.  No C++
+ *     exception crosses the ABI.  A handle is not re-entrant (one caller thread at a time, like the reference).
+ *   - "host" entry points take HOST pointers (numpy buffers) and copy H2D/D2H inside the call; their `_dev`
+ *     twins take CUDA DEVICE pointers plus a cudaStream_t (passed as void*) and never synchronise, so PyTorch
+ *     tensors can be handed over by data_ptr() with no copies.  All tree state always lives in HBM; there is no
+ *     CPU fallback - creating a handle without a CUDA device fails.
+ *   - flat leaf index is env*K + k, exactly as in src/cpp/BatchedMCTS.h:221,251.
+ */
+#ifndef AZB200_H
+#define AZB200_H
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZ_OK 0
+#define AZ_ERR_INVALID (-1)
+#define AZ_ERR_CUDA (-2)
+#define AZ_ERR_NOMEM (-3)
+
+#define AZ_GAME_CONNECT4 0
+#define AZ_GAME_OTHELLO 1
+
+#define AZ_EVAL_UNIFORM 0 /* IEvaluator default: uniform policy + uniform WDL (src/cpp/IEvaluator.h:56-64) */
+#define AZ_EVAL_ROLLOUT 1 /* RolloutEvaluator (src/cpp/RolloutEvaluator.h:16-49) */
+
+/* SearchConfig - src/cpp/MCTSNode.h:47-61 (same fields, same defaults; bool widened to int32). */
+typedef struct az_search_config {
+    float c_init;               /* 1.25   */
+    float c_base;               /* 19652  */
+    float dirichlet_alpha;      /* 0.3 (<=0 disables root noise) */
+    float noise_epsilon;        /* 0.25   */
+    float fpu_reduction;        /* 0.4    */
+    float mlh_slope;            /* 0 (Connect4 moves-left utility) */
+    float mlh_cap;              /* 0.2    */
+    float score_utility_factor; /* 0 (Othello score utility) */
+    float score_scale;          /* 8      */
+    float value_decay;          /* 1      */
+    int32_t use_symmetry;       /* 1      */
+    int32_t vl_count;           /* 1      */
+} az_search_config;
+
+typedef struct az_mcts az_mcts; /* BatchedMCTS<Game> - src/cpp/BatchedMCTS.h:26-442 */
+
+const char *az_version(void);
+const char *az_global_last_error(void); /* error of the last failed az_*_create on this thread */
+
+/* static traits - mcts_bindings.cpp:359-369 (action_size / board_size / board_shape class properties) */
+int az_game_action_size(int game);
+int az_game_board_size(int game);
+int az_game_board_rows(int game);
+int az_game_board_cols(int game);
+int az_game_num_symmetries(int game);
+void az_search_config_defaults(az_search_config *cfg);
+
+/* BatchedMCTS(n_envs) - mcts_bindings.cpp:52, BatchedMCTS.h:52-58.  device = CUDA ordinal. */
+az_mcts *az_mcts_create(int game, int n_envs, int device);
+void az_mcts_destroy(az_mcts *h);
+const char *az_mcts_last_error(const az_mcts *h);
+int az_mcts_num_envs(const az_mcts *h);                          /* get_num_envs, mcts_bindings.cpp:68 */
+int az_mcts_set_config(az_mcts *h, const az_search_config *cfg); /* .config setter, mcts_bindings.cpp:55-58 */
+int az_mcts_get_config(const az_mcts *h, az_search_config *cfg);
+int az_mcts_set_seed(az_mcts *h, int64_t seed);                  /* set_seed, BatchedMCTS.h:68-84 (seed<0: re-randomise) */
+int az_mcts_reset_env(az_mcts *h, int env_idx);                  /* reset_env, BatchedMCTS.h:93-99 (out of range ignored) */
+int az_mcts_prune_roots(az_mcts *h, const int32_t *actions);     /* prune_roots, BatchedMCTS.h:105-112; actions[n_envs] */
+
+/* search_batch - BatchedMCTS.h:119-171 / mcts_bindings.cpp:89-134.  One simulation per tree.
+ * in : boards int8[n,S], turns int32[n]
+ * out: leaf boards int8[n,S], term_d/p1w/p2w f32[n], is_term u8[n], leaf turns i32[n], valid_mask u8[n,A] */
+int az_mcts_search_batch(az_mcts *h, const int8_t *boards, const int32_t *turns, int8_t *out_boards, float *out_term_d,
+                         float *out_term_p1w, float *out_term_p2w, uint8_t *out_is_term, int32_t *out_turns,
+                         uint8_t *out_valid_mask);
+/* backprop_batch - BatchedMCTS.h:176-199 / mcts_bindings.cpp:139-179 */
+int az_mcts_backprop_batch(az_mcts *h, const float *policy, const float *d_vals, const float *p1w_vals,
+                           const float *p2w_vals, const float *moves_left, const uint8_t *is_term);
+/* remove_all_vl - BatchedMCTS.h:209-216 (idempotent clean-up) */
+int az_mcts_remove_all_vl(az_mcts *h, int K);
+/* search_batch_vl - BatchedMCTS.h:227-286 / mcts_bindings.cpp:197-252.  K virtual-loss simulations per tree,
+ * sequential inside a tree; outputs have n*K rows plus sym_ids i32[n*K]. */
+int az_mcts_search_batch_vl(az_mcts *h, int K, const int8_t *boards, const int32_t *turns, int8_t *out_boards,
+                            float *out_term_d, float *out_term_p1w, float *out_term_p2w, uint8_t *out_is_term,
+                            int32_t *out_turns, int32_t *out_sym_ids, uint8_t *out_valid_mask);
+/* backprop_batch_vl - BatchedMCTS.h:296-332 / mcts_bindings.cpp:257-306 */
+int az_mcts_backprop_batch_vl(az_mcts *h, int K, const float *policy, const float *d_vals, const float *p1w_vals,
+                              const float *p2w_vals, const float *moves_left, const uint8_t *is_term,
+                              const int32_t *sym_ids);
+/* search(evaluator, boards, turns, n_playout) - BatchedMCTS.h:339-407 / mcts_bindings.cpp:313-337: the whole
+ * playout loop with a built-in evaluator (AZ_EVAL_*), entirely on the device. */
+int az_mcts_search(az_mcts *h, int evaluator, const int8_t *boards, const int32_t *turns, int n_playout);
+/* get_all_counts - BatchedMCTS.h:413-427: int32[n*A] */
+int az_mcts_get_counts(az_mcts *h, int32_t *out);
+/* get_all_root_stats - BatchedMCTS.h:435-441, layout MCTS.h:634-636: f32[n, 6+8A] */
+int az_mcts_get_root_stats(az_mcts *h, float *out);
+
+/* ---- device-pointer twins (no copies, no synchronisation; stream = cudaStream_t) ---- */
+int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream);
+/* K == 0 selects the non-VL search_batch (1 leaf per tree).  d_planes (optional, may be NULL) receives the
+ * leaves encoded as the CNN input f32[n*K,3,R,C] (plane0 = side to move, plane1 = opponent, plane2 = turn;
+ * src/MCTS_cpp.py:15-20) so the network consumes them with no host round trip.  d_out_sym_ids may be NULL when
+ * K == 0 (the id is kept inside the handle like pending_sym_ids_, BatchedMCTS.h:45). */
+int az_mcts_search_dev(az_mcts *h, int K, const int8_t *d_boards, const int32_t *d_turns, int8_t *d_out_boards,
+                       float *d_out_term_d, float *d_out_term_p1w, float *d_out_term_p2w, uint8_t *d_out_is_term,
+                       int32_t *d_out_turns, int32_t *d_out_sym_ids, uint8_t *d_out_valid_mask, float *d_planes,
+                       void *stream);
+int az_mcts_backprop_dev(az_mcts *h, int K, const float *d_policy, const float *d_d, const float *d_p1w,
+                         const float *d_p2w, const float *d_moves_left, const uint8_t *d_is_term,
+                         const int32_t *d_sym_ids, void *stream);
+int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const int8_t *d_boards, const int32_t *d_turns, int n_playout,
+                            void *stream);
+int az_mcts_get_counts_dev(az_mcts *h, int32_t *d_out, void *stream);
+int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream);
+
+/* engine counters for the roofline model: out[0..7] = simulations, edges traversed (sum of depths), edges
+ * scanned, edges created, expansions, max arena use (slots), arena capacity (slots/tree), kernel launches */
+int az_mcts_enable_stats(az_mcts *h, int on);
+int az_mcts_get_stats(az_mcts *h, uint64_t *out8);
+
+/* Synthetic deterministic evaluators on device pointers (twins of alphazero-al_b200/evaluators.py): turn the
+ * leaf tuple of az_mcts_search_dev into the backprop tuple.  mode: 0 hash, 1 flip-equivariant hash (Connect4),
+ * 2 constant. */
+int az_eval_synthetic_dev(int game, int mode, int n_leaves, const int8_t *d_leaf_boards, const int32_t *d_leaf_turns,
+                          const uint8_t *d_is_term, const float *d_term_d, const float *d_term_p1w,
+                          const float *d_term_p2w, float *d_policy, float *d_d, float *d_p1w, float *d_p2w,
+                          float *d_moves_left, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#endif /* AZB200_H */

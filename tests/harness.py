@@ -69,3 +69,63 @@ def random_positions(game, n, max_plies, seed):
                 boards[i], turns[i] = e.board, e.turn
                 break
     return boards, turns
+
+
+def compare_engines(ea, eb, game, n, n_playout, K, cfg, mode="hash", boards=None, turns=None, moves=1,
+                    compare_leaves=True, seed=None):
+    """Drive two engines (same mcts_cpp surface) through identical playouts + tree reuse and require identical
+    leaves (optional), visit counts and root statistics, bit for bit.  Returns the last visit counts."""
+    import importlib
+    import oracle
+    ev_mod = importlib.import_module("alphazero-al_b200.evaluators")
+    A = oracle.ACTION_SIZE[game]
+    set_config(ea, **cfg)
+    set_config(eb, **cfg)
+    if seed is not None:
+        ea.set_seed(seed)
+        eb.set_seed(seed)
+    ev = ev_mod.HashEvaluator(game, mode)
+    if boards is None:
+        boards, turns = random_positions(game, n, 0, 0)
+    envs = [oracle.OracleEnv(game) for _ in range(n)]
+    for i, e in enumerate(envs):
+        e.import_board(boards[i], turns[i])
+    c1 = None
+    for mv in range(moves):
+        b = np.stack([e.board for e in envs])
+        t = np.array([e.turn for e in envs], np.int32)
+        r1, r2 = [], []
+        playout(ea, ev, b, t, n_playout, K, r1)
+        playout(eb, ev, b, t, n_playout, K, r2)
+        if compare_leaves:
+            assert len(r1) == len(r2)
+            for it, (x, y) in enumerate(zip(r1, r2)):
+                for j, (u, v) in enumerate(zip(x, y)):
+                    if not np.array_equal(u, v):
+                        bad = np.where((u != v).reshape(len(u), -1).any(axis=1))[0]
+                        raise AssertionError(f"move {mv} iteration {it} output {j} differs in rows {bad[:8]} "
+                                             f"(of {len(bad)}): a={u[bad[0]]!r} b={v[bad[0]]!r}")
+        c1, c2 = counts(ea, n, A), counts(eb, n, A)
+        if not np.array_equal(c1, c2):
+            bad = np.where((c1 != c2).any(axis=1))[0]
+            raise AssertionError(f"move {mv}: visit counts differ in {len(bad)} trees, first {bad[0]}: {c1[bad[0]]} vs {c2[bad[0]]}")
+        s1, s2 = ea.get_all_root_stats(), eb.get_all_root_stats()
+        if s1.tobytes() != s2.tobytes():
+            bad = np.where((s1.view(np.uint32) != s2.view(np.uint32)).any(axis=1))[0]
+            cols = np.where(s1.view(np.uint32)[bad[0]] != s2.view(np.uint32)[bad[0]])[0]
+            raise AssertionError(f"move {mv}: root stats differ in {len(bad)} trees; tree {bad[0]} cols {cols[:10]}: "
+                                 f"{s1[bad[0]][cols[:10]]} vs {s2[bad[0]][cols[:10]]}")
+        # play the most visited action (ties -> lowest); finished / unsearchable games restart from scratch
+        acts = np.zeros(n, np.int32)
+        for i, e in enumerate(envs):
+            if e.done() or c1[i].sum() == 0:
+                e.reset()
+                ea.reset_env(i)
+                eb.reset_env(i)
+                acts[i] = -1
+            else:
+                acts[i] = int(np.argmax(c1[i]))
+                e.step(acts[i])
+        ea.prune_roots(acts)
+        eb.prune_roots(acts)
+    return c1

