@@ -61,12 +61,15 @@ def lib() -> C.CDLL:
         "az_mcts_search": [_vp, _i, _vp, _vp, _i],
         "az_mcts_get_counts": [_vp, _vp], "az_mcts_get_root_stats": [_vp, _vp],
         "az_mcts_prune_roots_dev": [_vp, _vp, _vp],
-        "az_mcts_search_dev": [_vp, _i] + [_vp] * 12,
+        "az_mcts_search_dev": [_vp, _i, _vp, _vp, _vp],
+        "az_pack_roots_dev": [_i, _i, _vp, _vp, _vp, _vp],
+        "az_unpack_leaves_dev": [_i, _i] + [_vp] * 11,
+        "az_mcts_set_lanes": [_vp, _i], "az_mcts_get_lanes": [_vp], "az_mcts_reserve": [_vp, _i],
         "az_mcts_backprop_dev": [_vp, _i] + [_vp] * 8,
-        "az_mcts_search_eval_dev": [_vp, _i, _vp, _vp, _i, _vp],
+        "az_mcts_search_eval_dev": [_vp, _i, _vp, _i, _vp],
         "az_mcts_get_counts_dev": [_vp, _vp, _vp], "az_mcts_get_root_stats_dev": [_vp, _vp, _vp],
         "az_mcts_enable_stats": [_vp, _i], "az_mcts_get_stats": [_vp, _vp],
-        "az_eval_synthetic_dev": [_i, _i, _i] + [_vp] * 12,
+        "az_eval_synthetic_dev": [_i, _i, _i] + [_vp] * 7,
         "az_game_action_size": [_i], "az_game_board_size": [_i], "az_game_board_rows": [_i], "az_game_board_cols": [_i],
         "az_game_num_symmetries": [_i],
     }

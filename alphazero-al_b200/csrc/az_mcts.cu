@@ -62,23 +62,25 @@ struct __align__(64) TreeRec {   // per tree: the root's own statistics + alloca
 };
 static_assert(sizeof(TreeRec) == 64, "TreeRec is one 64-byte record");
 
-struct __align__(16) LeafRec {   // what backprop needs to know about a pending leaf (MCTS.h:56-64)
+struct __align__(16) LeafRec {   // what backprop needs to know about a pending leaf (MCTS.h:56-64), un-symmetrised
     uint64_t bb0, bb1;
     int32_t turn;
     int16_t passes;
     int8_t last;
     uint8_t flags;               // LF_*
     uint32_t path_len;
-    uint32_t pad;
+    uint32_t sym;                // symmetry id handed to the evaluator for this leaf
 };
-constexpr uint8_t LF_VALID = 1, LF_VLPENDING = 2;
+static_assert(sizeof(LeafRec) == 32, "LeafRec is 32 bytes");
+static_assert(sizeof(az_root) == 32 && sizeof(az_leaf) == 32, "public records are one sector");
+constexpr uint8_t LF_VALID = 1, LF_VLPENDING = 2, LF_TERM = 4, LF_WIN_P1 = 8, LF_WIN_P2 = 16;
 
 struct Dev {   // kernel-visible view of an engine
     Slot *pool; uint32_t cap;            // cap = arena capacity (slots per tree)
     TreeRec *trees;
     float *noise; int noise_stride;      // root Dirichlet noise, [n_envs][noise_stride]
     LeafRec *leaf_vl; uint32_t *path_vl; int kcap;   // [n_envs][kcap], [n_envs][kcap][MAX_DEPTH]
-    LeafRec *leaf_nv; uint32_t *path_nv; int32_t *pending_sym;   // non-VL search_batch state
+    LeafRec *leaf_nv; uint32_t *path_nv;             // non-VL search_batch state
     const float *log_lut; int log_lut_n;
     const float *atan_lut;               // 129 entries: disc difference -64..64
     unsigned long long *stats;           // nullptr = counters off
@@ -86,10 +88,6 @@ struct Dev {   // kernel-visible view of an engine
     int n_envs;
     uint64_t seed, epoch;
 };
-
-template <class G> struct Lanes;
-template <> struct Lanes<C4> { static constexpr int W = 8, NCH = 1; };
-template <> struct Lanes<Oth> { static constexpr int W = 16, NCH = 3; };
 
 constexpr int CTA = 128;
 
@@ -99,6 +97,12 @@ constexpr int CTA = 128;
 template <int W> __device__ __forceinline__ unsigned group_mask() {
     return (W == 32) ? 0xFFFFFFFFu : (((1u << W) - 1u) << ((threadIdx.x & 31) & ~(W - 1)));
 }
+// shuffle inside a lane group; a group of one lane needs no instruction at all
+template <int W> __device__ __forceinline__ float gshfl(unsigned gm, float v, int src) { return W == 1 ? v : __shfl_sync(gm, v, src, W); }
+template <int W> __device__ __forceinline__ int gshfl(unsigned gm, int v, int src) { return W == 1 ? v : __shfl_sync(gm, v, src, W); }
+template <int W> __device__ __forceinline__ uint32_t gshfl(unsigned gm, uint32_t v, int src) { return W == 1 ? v : __shfl_sync(gm, v, src, W); }
+template <int W> __device__ __forceinline__ void gsync(unsigned gm) { if (W > 1) __syncwarp(gm); }
+
 __device__ __forceinline__ Slot ld_slot(const Slot *p) {
     const uint4 *q = reinterpret_cast<const uint4 *>(p);
     uint4 a = q[0], b = q[1];
@@ -112,9 +116,17 @@ __device__ __forceinline__ void st_slot(Slot *p, const Slot &s) {
     q[0] = make_uint4(__float_as_uint(s.prior), (uint32_t)s.n, s.meta, s.child);
     q[1] = make_uint4(__float_as_uint(s.wd), __float_as_uint(s.wp1), __float_as_uint(s.wp2), __float_as_uint(s.msum));
 }
-__device__ __forceinline__ uint64_t or_reduce64(unsigned gm, uint64_t v) {
-    uint32_t lo = __reduce_or_sync(gm, (uint32_t)v), hi = __reduce_or_sync(gm, (uint32_t)(v >> 32));
-    return ((uint64_t)hi << 32) | lo;
+template <class T> __device__ __forceinline__ T ld32(const T *p) {      // 32-byte record as two 16-byte loads
+    T v;
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    *reinterpret_cast<uint4 *>(&v) = q[0];
+    *(reinterpret_cast<uint4 *>(&v) + 1) = q[1];
+    return v;
+}
+template <class T> __device__ __forceinline__ void st32(T *p, const T &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = *reinterpret_cast<const uint4 *>(&v);
+    q[1] = *(reinterpret_cast<const uint4 *>(&v) + 1);
 }
 // WDLValue::q on the running means (MCTSNode.h:23-25,118-128): 0 when unvisited (uniform thirds cancel)
 __device__ __forceinline__ float mean_q(int n, float wp1, float wp2, bool turn_p1) {
@@ -125,31 +137,9 @@ __device__ __forceinline__ float mean_q(int n, float wp1, float wp2, bool turn_p
 }
 __device__ __forceinline__ float mean_m(int n, float msum) { return n == 0 ? 0.0f : msum / (float)n; }   // :131-133
 
-// import_board (+ set_turn) from the int8 board of the Python API (BatchedMCTS.h:133-137, Connect4.h:100-129,
-// Othello.h:92-111).  Cooperative: each lane reads a strip, bitboards are OR-reduced over the group.
-template <class G, int W> __device__ __forceinline__ State import_board(const int8_t *b, int turn, int lane, unsigned gm) {
-    uint64_t p0 = 0, p1 = 0;
-    if (G::GAME == GAME_C4) {
-        if (lane < 7) {            // gravity scan of column `lane`, bottom row first, stop at the first empty cell
-            for (int r = 5; r >= 0; --r) {
-                int v = b[r * 7 + lane];
-                if (v == 0) break;
-                uint64_t bit = 1ULL << (lane * 7 + (5 - r));
-                if (v == 1) p0 |= bit; else p1 |= bit;
-            }
-        }
-    } else {
-        for (int j = lane; j < 64; j += W) {
-            int v = b[j];
-            if (v == 1) p0 |= 1ULL << j; else if (v == -1) p1 |= 1ULL << j;
-        }
-    }
-    State s;
-    s.bb[0] = or_reduce64(gm, p0); s.bb[1] = or_reduce64(gm, p1);
-    G::finish_import(s, turn);
-    return s;
+template <class G> __device__ __forceinline__ bool aux_enabled(const az_search_config &cfg) {
+    return G::GAME == GAME_C4 ? cfg.mlh_slope > 0.0f : cfg.score_utility_factor > 0.0f;
 }
-
 template <class G> __device__ __forceinline__ float aux_utility(float child_M, float parent_M, float child_Q, const az_search_config &cfg) {
     if (G::GAME == GAME_C4) {      // Connect4.h:231-239
         if (cfg.mlh_slope <= 0.0f) return 0.0f;
@@ -166,44 +156,105 @@ template <class G> __device__ __forceinline__ float aux_utility(float child_M, f
 // Dirichlet noise: gamma(alpha,1) by Marsaglia-Tsang on the counter-based stream.  (MCTS.h:113-132, 347-363.)
 // RNG-dependent => distributional parity only.
 // ------------------------------------------------------------------------------------------------
-__device__ double noise_u01(const Dev &d, int env, uint32_t &ctr) {
-    uint64_t h = az_rand(d.seed, 0, STREAM_NOISE, (uint64_t)env, ctr++);
+__device__ __noinline__ double noise_u01(uint64_t seed, int env, uint32_t &ctr) {
+    uint64_t h = az_rand(seed, 0, STREAM_NOISE, (uint64_t)env, ctr++);
     return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
-__device__ float gamma_draw(const Dev &d, int env, uint32_t &ctr, float alpha) {
+__device__ __noinline__ float gamma_draw(uint64_t seed, int env, uint32_t &ctr, float alpha) {
     double a = alpha, boost = 1.0;
-    if (a < 1.0) { boost = pow(noise_u01(d, env, ctr), 1.0 / a); a += 1.0; }
+    if (a < 1.0) { boost = pow(noise_u01(seed, env, ctr), 1.0 / a); a += 1.0; }
     double dd = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
     for (int it = 0; it < 64; ++it) {
-        double u1 = noise_u01(d, env, ctr), u2 = noise_u01(d, env, ctr);
+        double u1 = noise_u01(seed, env, ctr), u2 = noise_u01(seed, env, ctr);
         double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2), v = 1.0 + c * x;
         if (v <= 0) continue;
         v = v * v * v;
-        double u = noise_u01(d, env, ctr);
+        double u = noise_u01(seed, env, ctr);
         if (log(u) < 0.5 * x * x + dd - dd * v + dd * log(v)) return (float)(dd * v * boost);
     }
     return (float)(dd * boost);
 }
-__device__ void draw_root_noise(const Dev &d, int env, uint32_t &ctr, float alpha, int ne, float *row) {
+__device__ __noinline__ void draw_root_noise(uint64_t seed, int env, uint32_t &ctr, float alpha, int ne, float *row) {
     float sum = 0.0f;
-    for (int i = 0; i < ne; ++i) { float g = gamma_draw(d, env, ctr, alpha); row[i] = g; sum += g; }
+    for (int i = 0; i < ne; ++i) { float g = gamma_draw(seed, env, ctr, alpha); row[i] = g; sum += g; }
     float inv = 1.0f / (sum + 1e-8f);
     for (int i = 0; i < ne; ++i) row[i] = row[i] * inv;
 }
 
 // ------------------------------------------------------------------------------------------------
-// SELECT: simulate / simulate_vl (MCTS.h:242-322, 443-545) + leaf export (BatchedMCTS.h:119-171, 227-286)
+// pack / unpack: the byte-board arrays of the reference API <-> the engine's 32-byte bitboard records
 // ------------------------------------------------------------------------------------------------
-struct LeafOut {
-    int8_t *boards; float *td, *tp1, *tp2; uint8_t *is_term; int32_t *turns; int32_t *sym; uint8_t *mask; float *planes;
-};
+template <class G>
+__global__ void k_pack_roots(int n, const int8_t *__restrict__ boards, const int32_t *__restrict__ turns, az_root *__restrict__ roots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // import_board: Connect4.h:100-129, Othello.h:92-111
+    if (i >= n) return;
+    const int8_t *b = boards + (size_t)i * G::S;
+    uint64_t p0 = 0, p1 = 0;
+    if (G::GAME == GAME_C4) {
+        for (int c = 0; c < 7; ++c)
+            for (int r = 5; r >= 0; --r) {                    // gravity scan: stop at the first empty cell
+                int v = b[r * 7 + c];
+                if (v == 0) break;
+                uint64_t bit = 1ULL << (c * 7 + (5 - r));
+                if (v == 1) p0 |= bit; else p1 |= bit;
+            }
+    } else {
+        for (int j = 0; j < 64; ++j) { int v = b[j]; if (v == 1) p0 |= 1ULL << j; else if (v == -1) p1 |= 1ULL << j; }
+    }
+    az_root r; r.bb0 = p0; r.bb1 = p1; r.turn = turns[i]; r.reserved[0] = r.reserved[1] = r.reserved[2] = 0;
+    st32(roots + i, r);
+}
+template <class G> __device__ __forceinline__ State leaf_state(const az_leaf &L) {
+    State s; s.bb[0] = L.bb0; s.bb[1] = L.bb1; s.turn = L.turn; s.passes = L.passes; s.last = -1;
+    return s;
+}
+// one thread per (leaf, cell): every store is coalesced
+template <class G>
+__global__ void k_unpack_leaves(int rows, const az_leaf *__restrict__ leaves, int8_t *__restrict__ ob, float *__restrict__ td,
+                                float *__restrict__ tp1, float *__restrict__ tp2, uint8_t *__restrict__ it, int32_t *__restrict__ ot,
+                                int32_t *__restrict__ sym, uint8_t *__restrict__ vm, float *__restrict__ planes) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= (size_t)rows * G::S) return;
+    const size_t leaf = t / G::S; const int j = (int)(t - leaf * G::S);
+    const az_leaf L = ld32(leaves + leaf);
+    const bool term = (L.flags & AZ_LEAF_TERMINAL) != 0;
+    const int bit = G::cell_bit(j);
+    const int c0 = (int)((L.bb0 >> bit) & 1ULL), c1 = (int)((L.bb1 >> bit) & 1ULL);
+    if (ob) ob[t] = (int8_t)(c0 - c1);
+    if (planes) {
+        float *pl = planes + leaf * 3 * G::S;
+        const int own = L.turn == 1 ? c0 : c1, opp = L.turn == 1 ? c1 : c0;
+        pl[j] = (float)own; pl[G::S + j] = (float)opp; pl[2 * G::S + j] = (float)L.turn;
+    }
+    if (vm) {      // valid mask of the (symmetrised) leaf; all zero for terminal leaves (BatchedMCTS.h:162-169)
+        const State s = leaf_state<G>(L);
+        const uint64_t legal = term ? 0ULL : G::legal(s);
+        if (G::GAME == GAME_C4) { if (j < 7) vm[leaf * 7 + j] = (uint8_t)((legal >> j) & 1ULL); }
+        else {
+            vm[leaf * 65 + j] = (uint8_t)((legal >> j) & 1ULL);
+            if (j == 0) vm[leaf * 65 + 64] = (uint8_t)((!term && legal == 0ULL && !Oth::over(s)) ? 1 : 0);
+        }
+    }
+    if (j == 0) {
+        if (td) td[leaf] = (term && !(L.flags & (AZ_LEAF_P1_WINS | AZ_LEAF_P2_WINS))) ? 1.0f : 0.0f;
+        if (tp1) tp1[leaf] = (L.flags & AZ_LEAF_P1_WINS) ? 1.0f : 0.0f;
+        if (tp2) tp2[leaf] = (L.flags & AZ_LEAF_P2_WINS) ? 1.0f : 0.0f;
+        if (it) it[leaf] = term ? 1 : 0;
+        if (ot) ot[leaf] = L.turn;
+        if (sym) sym[leaf] = L.sym;
+    }
+}
 
-template <class G, bool VL>
-__global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int K, int write_sym, const int8_t *__restrict__ boards,
-                                                const int32_t *__restrict__ turns, LeafOut out) {
-    constexpr int W = Lanes<G>::W, NCH = Lanes<G>::NCH;
+// ------------------------------------------------------------------------------------------------
+// SELECT: simulate / simulate_vl (MCTS.h:242-322, 443-545) + leaf export (BatchedMCTS.h:119-171, 227-286)
+// W lanes cooperate on one tree; lane l owns edges l, l+W, l+2W, ... of the node being scanned.
+// ------------------------------------------------------------------------------------------------
+template <class G, int W, bool VL>
+__global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
+                                                az_leaf *__restrict__ leaves) {
+    constexpr int NCH = (G::MAX_EDGES + W - 1) / W;
     const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
-    if (gid >= d.n_envs) return;            // whole groups exit together (n_envs is padded to groups by the grid)
+    if (gid >= d.n_envs) return;
     const int lane = threadIdx.x & (W - 1);
     const unsigned gm = group_mask<W>();
     const int env = gid;
@@ -211,14 +262,17 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
     TreeRec *tr = d.trees + env;
     const float *noise = d.noise + (size_t)env * d.noise_stride;
     const int vl = VL ? cfg.vl_count : 0;
+    const bool use_aux = aux_enabled<G>(cfg);
 
-    const State start = import_board<G, W>(boards + (size_t)env * G::S, turns[env], lane, gm);
+    State start;
+    { const az_root r = ld32(roots + env); start.bb[0] = r.bb0; start.bb[1] = r.bb1; G::finish_import(start, r.turn); }
+    Slot root = ld_slot(&tr->root);        // identical copy in every lane of the group, written back once
+    const uint32_t root_meta_in = root.meta;
     unsigned long long st_depth = 0, st_edges = 0;
 
     for (int k = 0; k < K; ++k) {
         State st = start;
-        // current node = root (TreeRec.root); every lane holds the same copy
-        Slot cur = ld_slot(&tr->root);
+        Slot cur = root;
         bool is_root = true, root_vl = false;
         uint32_t plen = 0;
         uint32_t *path = VL ? d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH : d.path_nv + (size_t)env * G::MAX_DEPTH;
@@ -233,7 +287,7 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
             Slot s[NCH]; bool has[NCH];
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                int e = c * W + lane;
+                const int e = c * W + lane;
                 has[c] = e < ne;
                 if (has[c]) s[c] = ld_slot(arena + off + e);
                 else { s[c].prior = 0.f; s[c].n = 0; s[c].meta = 0; s[c].child = NONE; s[c].wd = s[c].wp1 = s[c].wp2 = s[c].msum = 0.f; }
@@ -241,18 +295,17 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
             st_edges += (unsigned long long)ne;
             // ---- compute_fpu (MCTS.h:140-156): seen_policy summed sequentially in edge order ----
             const int cur_infl = (int)(cur.meta & INFL_MASK);
-            const bool cur_p1 = (cur.meta & F_TURN_P1) != 0;
-            const float parent_q = mean_q(cur.n, cur.wp1, cur.wp2, cur_p1);
+            const float parent_q = mean_q(cur.n, cur.wp1, cur.wp2, (cur.meta & F_TURN_P1) != 0);
             float seen_policy = 0.0f;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const float pv = (has[c] && s[c].n > 0) ? s[c].prior : 0.0f;   // + 0.0f is exact
-                const int lim = min(W, ne - c * W);
                 if (G::GAME == GAME_C4) {
 #pragma unroll
-                    for (int j = 0; j < 7; ++j) seen_policy += __shfl_sync(gm, pv, j, W);
+                    for (int l = 0; l < W; ++l) if (c * W + l < G::MAX_EDGES) seen_policy += gshfl<W>(gm, pv, l);
                 } else {
-                    for (int j = 0; j < lim; ++j) seen_policy += __shfl_sync(gm, pv, j, W);
+                    const int lim = min(W, ne - c * W);
+                    for (int l = 0; l < lim; ++l) seen_policy += gshfl<W>(gm, pv, l);
                 }
             }
             const float fscale = (1.0f + parent_q) / 2.0f;
@@ -262,58 +315,56 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
             // ---- select_edge (MCTS.h:163-234) ----
             const int pn_i = cur.n + cur_infl;
             const float parent_n = (float)pn_i;
-            const float parent_M = mean_m(cur.n, cur.msum);
+            const float parent_M = use_aux ? mean_m(cur.n, cur.msum) : 0.0f;
             const float lg = (pn_i >= 0 && pn_i < d.log_lut_n) ? d.log_lut[pn_i] : logf((parent_n + cfg.c_base + 1.0f) / cfg.c_base);
             const float c_puct = cfg.c_init + lg;
             const float sqrt_pn = sqrtf(parent_n);
             const float ne_eps = cfg.noise_epsilon;
+            const bool mix_noise = is_root && ne_eps > 0.0f;
             float best_s = -INFINITY; int best_e = -1;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 if (!has[c]) continue;
                 const int e = c * W + lane;
                 float eff_prior = s[c].prior;
-                if (is_root && ne_eps > 0.0f) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * noise[e];
+                if (mix_noise) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * noise[e];
                 const int cn = s[c].n, cinf = (int)(s[c].meta & INFL_MASK);
-                float q_value, child_Q = 0.0f, child_M = 0.0f; int visits = 0;
-                const bool seen = cn > 0;
-                if (seen) {
+                float q_value = fpu, m_utility = 0.0f; int visits = cinf;     // unvisited: FPU, in-flight only
+                if (cn > 0) {
                     visits = cn + cinf;
-                    child_Q = mean_q(cn, s[c].wp1, s[c].wp2, (s[c].meta & F_TURN_P1) != 0);
-                    child_M = mean_m(cn, s[c].msum);
-                    if (G::AUX_NEGATE) child_M = -child_M;
+                    const float child_Q = mean_q(cn, s[c].wp1, s[c].wp2, (s[c].meta & F_TURN_P1) != 0);
                     q_value = -child_Q;
-                } else if (cinf > 0) { q_value = fpu; visits = cinf; }
-                else q_value = fpu;
+                    if (use_aux) {
+                        float child_M = mean_m(cn, s[c].msum);
+                        if (G::AUX_NEGATE) child_M = -child_M;
+                        m_utility = aux_utility<G>(child_M, parent_M, child_Q, cfg);
+                    }
+                }
                 const float u_score = c_puct * eff_prior * sqrt_pn / (1.0f + (float)visits);
-                const float m_utility = seen ? aux_utility<G>(child_M, parent_M, child_Q, cfg) : 0.0f;
                 const float score = q_value + u_score + m_utility;
                 if (score > best_s) { best_s = score; best_e = e; }
             }
-            // arg-max over the group; ties -> lowest edge index
+            // arg-max over the group; ties -> lowest edge index (the reference scans with a strict `>`)
 #pragma unroll
             for (int o = W / 2; o > 0; o >>= 1) {
-                float os = __shfl_xor_sync(gm, best_s, o, W);
-                int oe = __shfl_xor_sync(gm, best_e, o, W);
-                bool take = oe >= 0 && (best_e < 0 || os > best_s || (os == best_s && oe < best_e));
+                const float os = __shfl_xor_sync(gm, best_s, o, W);
+                const int oe = __shfl_xor_sync(gm, best_e, o, W);
+                const bool take = oe >= 0 && (best_e < 0 || os > best_s || (os == best_s && oe < best_e));
                 if (take) { best_s = os; best_e = oe; }
             }
             if (best_e < 0) break;
-            if (VL && !root_vl) {          // root virtual loss, applied on first loop entry (MCTS.h:471-475)
-                root_vl = true;
-                if (lane == 0) tr->root.meta += (uint32_t)vl;
-            }
+            if (VL && !root_vl) { root_vl = true; root.meta += (uint32_t)vl; }   // root virtual loss (MCTS.h:471-475)
             // broadcast the chosen child to the whole group
             const int bl = best_e & (W - 1), bc = best_e / W;
             Slot ch = s[0];
 #pragma unroll
             for (int c = 1; c < NCH; ++c) if (bc == c) ch = s[c];
-            ch.n = __shfl_sync(gm, ch.n, bl, W);
-            ch.meta = __shfl_sync(gm, ch.meta, bl, W);
-            ch.child = __shfl_sync(gm, ch.child, bl, W);
-            ch.wp1 = __shfl_sync(gm, ch.wp1, bl, W);
-            ch.wp2 = __shfl_sync(gm, ch.wp2, bl, W);
-            ch.msum = __shfl_sync(gm, ch.msum, bl, W);
+            ch.n = gshfl<W>(gm, ch.n, bl);
+            ch.meta = gshfl<W>(gm, ch.meta, bl);
+            ch.child = gshfl<W>(gm, ch.child, bl);
+            ch.wp1 = gshfl<W>(gm, ch.wp1, bl);
+            ch.wp2 = gshfl<W>(gm, ch.wp2, bl);
+            ch.msum = gshfl<W>(gm, ch.msum, bl);
             G::step(st, (int)((ch.meta >> 16) & 0xFFu));
             uint32_t nmeta = ch.meta;
             if (!(nmeta & F_ALLOC)) {      // lazy child allocation (MCTS.h:481-488): remember the child's side to move
@@ -337,64 +388,41 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
         st_depth += plen;
         // ---- leaf classification (MCTS.h:512-544) ----
         bool leaf_term = (cur.meta & F_TERM) != 0;
+        if (plen == 0) leaf_term = (root.meta & F_TERM) != 0;
         if (!leaf_term) {
             if (winner == 0 && !full) { winner = G::winner(st); full = G::full(st); }
             if (winner != 0 || full) {
                 leaf_term = true;
-                cur.meta = (cur.meta & ~(F_WIN_P1 | F_WIN_P2)) | F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
-                if (lane == 0) { if (plen == 0) tr->root.meta = cur.meta; else arena[last_slot].meta = cur.meta; }
+                const uint32_t tf = F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+                if (plen == 0) { root.meta = (root.meta & ~(F_WIN_P1 | F_WIN_P2)) | tf; cur.meta = root.meta; }
+                else { cur.meta = (cur.meta & ~(F_WIN_P1 | F_WIN_P2)) | tf; if (lane == 0) arena[last_slot].meta = cur.meta; }
             }
         }
-        float wd = 0.f, w1 = 0.f, w2 = 0.f;
-        if (leaf_term) { if (cur.meta & F_WIN_P1) w1 = 1.f; else if (cur.meta & F_WIN_P2) w2 = 1.f; else wd = 1.f; }
-        // ---- remember the leaf for backprop ----
-        if (lane == 0) {
-            LeafRec L;
-            L.bb0 = st.bb[0]; L.bb1 = st.bb[1]; L.turn = st.turn; L.passes = (int16_t)st.passes; L.last = (int8_t)st.last;
-            L.flags = (uint8_t)(LF_VALID | ((VL && plen > 0) ? LF_VLPENDING : 0));
-            L.path_len = plen; L.pad = 0;
-            LeafRec *dst = VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env;
-            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<uint4 *>(&L);
-            *(reinterpret_cast<uint4 *>(dst) + 1) = *(reinterpret_cast<uint4 *>(&L) + 1);
-        }
-        // ---- leaf export: random symmetry for non-terminal leaves (BatchedMCTS.h:148-158 / 261-271) ----
-        const size_t flat = (size_t)env * K + k;
+        // ---- random symmetry for non-terminal leaves (BatchedMCTS.h:148-158 / 261-271) ----
         int sym = 0;
         State ex = st;
         if (!leaf_term && cfg.use_symmetry) {
-            uint64_t h = az_rand(d.seed, d.epoch, STREAM_SYM, (uint64_t)env, (uint64_t)k);
+            const uint64_t h = az_rand(d.seed, d.epoch, STREAM_SYM, (uint64_t)env, (uint64_t)k);
             sym = G::GAME == GAME_C4 ? (int)(h & 1) : ((0x7620 >> (4 * (int)(h & 3))) & 0xF);   // Othello {0,2,6,7}
             G::symmetry(ex, sym);
         }
-        uint64_t legal = leaf_term ? 0ULL : G::legal(ex);
-        bool pass_only = false;
-        if (G::GAME == GAME_OTH) pass_only = !leaf_term && legal == 0ULL && !Oth::over(ex);
-        for (int j = lane; j < G::S; j += W) out.boards[flat * G::S + j] = (int8_t)G::cell(ex, j);
-        for (int a = lane; a < G::A; a += W) {
-            uint8_t m = (uint8_t)((legal >> (a & 63)) & 1ULL);
-            if (G::GAME == GAME_OTH && a == Oth::PASS) m = pass_only ? 1 : 0;
-            out.mask[flat * G::A + a] = m;
-        }
-        if (out.planes) {
-            float *pl = out.planes + flat * 3 * G::S;
-            const int own = st.turn == 1 ? 0 : 1;
-            const float tf = (float)st.turn;
-            for (int j = lane; j < G::S; j += W) {
-                int bit = G::cell_bit(j);
-                pl[j] = (float)((ex.bb[own] >> bit) & 1ULL);
-                pl[G::S + j] = (float)((ex.bb[1 - own] >> bit) & 1ULL);
-                pl[2 * G::S + j] = tf;
-            }
-        }
         if (lane == 0) {
-            out.td[flat] = wd; out.tp1[flat] = w1; out.tp2[flat] = w2;
-            out.is_term[flat] = leaf_term ? 1 : 0;
-            out.turns[flat] = st.turn;
-            if (VL) { if (out.sym) out.sym[flat] = sym; }
-            else { if (write_sym) d.pending_sym[env] = sym; if (out.sym) out.sym[flat] = sym; }
+            const uint8_t tflags = (uint8_t)(leaf_term ? (AZ_LEAF_TERMINAL | ((cur.meta & F_WIN_P1) ? AZ_LEAF_P1_WINS : 0u) |
+                                                          ((cur.meta & F_WIN_P2) ? AZ_LEAF_P2_WINS : 0u)) : 0u);
+            LeafRec L;     // remembered for backprop
+            L.bb0 = st.bb[0]; L.bb1 = st.bb[1]; L.turn = st.turn; L.passes = (int16_t)st.passes; L.last = (int8_t)st.last;
+            L.flags = (uint8_t)(LF_VALID | ((VL && plen > 0) ? LF_VLPENDING : 0) | (leaf_term ? LF_TERM : 0) |
+                                ((tflags & AZ_LEAF_P1_WINS) ? LF_WIN_P1 : 0) | ((tflags & AZ_LEAF_P2_WINS) ? LF_WIN_P2 : 0));
+            L.path_len = plen; L.sym = (uint32_t)sym;
+            st32(VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env, L);
+            az_leaf P;     // handed to the evaluator
+            P.bb0 = ex.bb[0]; P.bb1 = ex.bb[1]; P.turn = (int8_t)st.turn; P.flags = tflags; P.sym = (uint8_t)sym; P.passes = (uint8_t)st.passes;
+            P.reserved[0] = P.reserved[1] = P.reserved[2] = 0;
+            st32(leaves + (size_t)env * K + k, P);
         }
-        __syncwarp(gm);   // order this descent's in-flight updates before the next descent of the same tree
+        gsync<W>(gm);   // order this descent's in-flight updates before the next descent of the same tree
     }
+    if (lane == 0 && root.meta != root_meta_in) tr->root.meta = root.meta;
     if (d.stats && lane == 0) {
         atomicAdd(d.stats + 0, (unsigned long long)K);
         atomicAdd(d.stats + 1, st_depth);
@@ -422,17 +450,17 @@ __device__ __forceinline__ void remove_vl_group(const Dev &d, const az_search_co
             int infl = (int)(v & INFL_MASK) - vl;
             *m = (v & ~INFL_MASK) | (uint32_t)max(infl, 0);
         }
-        __syncwarp(gm);
+        gsync<W>(gm);
         if (lane == 0) L->flags = (uint8_t)(fl & ~LF_VLPENDING);
     }
 }
 
-template <class G, bool VL>
-__global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, int K, int removeK, const float *__restrict__ policy,
+template <class G, int W, bool VL>
+__global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, int K, int removeK, int use_sym, const float *__restrict__ policy,
                                                   const float *__restrict__ dv, const float *__restrict__ p1v, const float *__restrict__ p2v,
                                                   const float *__restrict__ mlv, const uint8_t *__restrict__ is_term,
                                                   const int32_t *__restrict__ sym_ids) {
-    constexpr int W = Lanes<G>::W;
+    constexpr int NJ = (G::A + W - 1) / W;
     const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
     if (gid >= d.n_envs) return;
     const int lane = threadIdx.x & (W - 1);
@@ -445,16 +473,13 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
     unsigned long long st_created = 0, st_expanded = 0;
 
     if (VL) remove_vl_group<G, W>(d, cfg, env, removeK, lane, gm, arena, root);
-    __syncwarp(gm);
+    gsync<W>(gm);
 
     for (int k = 0; k < K; ++k) {
-        const LeafRec *Lp = VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env;
-        LeafRec L;
-        *reinterpret_cast<uint4 *>(&L) = *reinterpret_cast<const uint4 *>(Lp);
-        *(reinterpret_cast<uint4 *>(&L) + 1) = *(reinterpret_cast<const uint4 *>(Lp) + 1);
+        const LeafRec L = ld32(VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env);
         if (!(L.flags & LF_VALID)) continue;             // current_leaf_idx == -1 (MCTS.h:409,599)
         const size_t flat = (size_t)env * K + k;
-        const bool term = is_term[flat] != 0;
+        const bool term = is_term ? (is_term[flat] != 0) : ((L.flags & LF_TERM) != 0);
         const uint32_t plen = L.path_len;
         const uint32_t *path = VL ? d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH : d.path_nv + (size_t)env * G::MAX_DEPTH;
         State st; st.bb[0] = L.bb0; st.bb[1] = L.bb1; st.turn = L.turn; st.passes = L.passes; st.last = L.last;
@@ -463,8 +488,9 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
 
         // ---- expand_leaf (MCTS.h:329-375); VL: skipped when an earlier k already expanded it (MCTS.h:601-607) ----
         if (!term && (!VL || leaf_child == NONE)) {
-            const int sym = sym_ids ? sym_ids[flat] : 0;   // search() passes nullptr: no inverse symmetry (BatchedMCTS.h:404)
-            uint64_t legal = G::legal(st);
+            // search() never symmetrises (BatchedMCTS.h:404): use_sym == 0
+            const int sym = use_sym ? (sym_ids ? sym_ids[flat] : (int)L.sym) : 0;
+            const uint64_t legal = G::legal(st);
             int ne; bool pass_only = false;
             if (G::GAME == GAME_OTH) {
                 pass_only = legal == 0ULL && !Oth::over(st);
@@ -472,24 +498,30 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
             } else ne = popc64(legal);
             const float *prow = policy + flat * G::A;
             // policy of the ORIGINAL frame: restored[a] = given[sym_action(a)]  (inverse_symmetry_policy)
-            float psum = 0.0f;
-            float pmine[(G::A + W - 1) / W];
+            float pmine[NJ];
 #pragma unroll
-            for (int j = 0; j < (G::A + W - 1) / W; ++j) {
-                int a = j * W + lane;
+            for (int j = 0; j < NJ; ++j) {
+                const int a = j * W + lane;
                 pmine[j] = (a < G::A) ? prow[G::sym_action(sym, a)] : 0.0f;
             }
+            float psum = 0.0f;                             // summed over legal actions in ascending order
             if (G::GAME == GAME_C4) {
-                const float pv = ((legal >> lane) & 1ULL) ? pmine[0] : 0.0f;
 #pragma unroll
-                for (int j = 0; j < 7; ++j) psum += __shfl_sync(gm, pv, j, W);
+                for (int j = 0; j < NJ; ++j) {
+                    const int a = j * W + lane;
+                    const float pv = (a < 7 && ((legal >> a) & 1ULL)) ? pmine[j] : 0.0f;   // + 0.0f is exact
+#pragma unroll
+                    for (int l = 0; l < W; ++l) if (j * W + l < 7) psum += gshfl<W>(gm, pv, l);
+                }
             } else if (pass_only) {
-                psum += __shfl_sync(gm, pmine[4], 0, W);          // action 64 lives in lane 0, register 4
+                psum += gshfl<W>(gm, pmine[NJ - 1], 0);   // action 64 lives in lane 0, last register
             } else {
-                for (uint64_t v = legal; v; v &= v - 1) {         // ascending action order
-                    int a = ctz64(v), j = a / W;
-                    float x = j == 0 ? pmine[0] : (j == 1 ? pmine[1] : (j == 2 ? pmine[2] : pmine[3]));
-                    psum += __shfl_sync(gm, x, a & (W - 1), W);
+                for (uint64_t v = legal; v; v &= v - 1) {
+                    const int a = ctz64(v), j = a / W;
+                    float x = pmine[0];
+#pragma unroll
+                    for (int jj = 1; jj < NJ; ++jj) if (j == jj) x = pmine[jj];
+                    psum += gshfl<W>(gm, x, a & (W - 1));
                 }
             }
             const float denom = psum + 1e-8f;
@@ -499,8 +531,8 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
                 const uint32_t off = bump;
                 Slot ns; ns.n = 0; ns.child = NONE; ns.wd = ns.wp1 = ns.wp2 = ns.msum = 0.0f;
 #pragma unroll
-                for (int j = 0; j < (G::A + W - 1) / W; ++j) {
-                    int a = j * W + lane;
+                for (int j = 0; j < NJ; ++j) {
+                    const int a = j * W + lane;
                     if (a >= G::A) continue;
                     bool ok; int eidx;
                     if (G::GAME == GAME_OTH && a == Oth::PASS) { ok = pass_only; eidx = 0; }
@@ -518,8 +550,8 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
                     // root expansion draws Dirichlet noise when alpha > 0 (MCTS.h:347-363, leaf.parent == -1)
                     float *nrow = d.noise + (size_t)env * d.noise_stride;
                     if (cfg.dirichlet_alpha > 0.0f) {
-                        if (lane == 0) draw_root_noise(d, env, noise_ctr, cfg.dirichlet_alpha, ne, nrow);
-                        noise_ctr = __shfl_sync(gm, noise_ctr, 0, W);
+                        if (lane == 0) draw_root_noise(d.seed, env, noise_ctr, cfg.dirichlet_alpha, ne, nrow);
+                        noise_ctr = gshfl<W>(gm, noise_ctr, 0);
                     } else {
                         for (int e = lane; e < ne; e += W) nrow[e] = 0.0f;
                     }
@@ -561,16 +593,15 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
             }
         }
         root.n += 1; root.wd += wd; root.wp1 += w1; root.wp2 += w2; root.msum += ml;
-        __syncwarp(gm);   // the next k of this tree must see these updates (duplicate leaves, shared ancestors)
+        gsync<W>(gm);   // the next k of this tree must see these updates (duplicate leaves, shared ancestors)
     }
     if (lane == 0) { st_slot(&tr->root, root); tr->bump = bump; tr->noise_ctr = noise_ctr; }
     if (d.stats && lane == 0) { atomicAdd(d.stats + 3, st_created); atomicAdd(d.stats + 4, st_expanded); }
 }
 
 // remove_all_vl without backprop (BatchedMCTS.h:209-216)
-template <class G>
+template <class G, int W>
 __global__ void __launch_bounds__(CTA) k_remove_vl(Dev d, az_search_config cfg, int K) {
-    constexpr int W = Lanes<G>::W;
     const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
     if (gid >= d.n_envs) return;
     const int lane = threadIdx.x & (W - 1);
@@ -610,7 +641,7 @@ __global__ void k_prune(Dev d, az_search_config cfg, const int32_t *__restrict__
                 const int cne = s.child == NONE ? 0 : (int)(s.child & 63u);
                 if (cfg.dirichlet_alpha > 0.0f && cne > 0) {  // apply_root_noise (MCTS.h:113-132)
                     uint32_t ctr = tr->noise_ctr;
-                    draw_root_noise(d, env, ctr, cfg.dirichlet_alpha, cne, nrow);
+                    draw_root_noise(d.seed, env, ctr, cfg.dirichlet_alpha, cne, nrow);
                     tr->noise_ctr = ctr;
                 } else {
                     for (int i = 0; i < d.noise_stride; ++i) nrow[i] = 0.0f;   // the promoted node's edges never had noise
@@ -626,13 +657,9 @@ __global__ void k_reset(Dev d, int env /* -1 = all */) {
     if (i >= d.n_envs || (env >= 0 && (blockIdx.x | threadIdx.x) != 0)) return;
     reset_tree(d.trees + i, d.noise + (size_t)i * d.noise_stride, d.noise_stride);
 }
-__global__ void k_init_leaf(Dev d) {
+__global__ void k_init_leaf(LeafRec *leaf, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < (size_t)d.n_envs) { d.leaf_nv[i].flags = 0; d.leaf_nv[i].path_len = 0; d.pending_sym[i] = 0; }
-}
-__global__ void k_init_leaf_vl(LeafRec *leaf, size_t n) {
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) { leaf[i].flags = 0; leaf[i].path_len = 0; }
+    if (i < n) { leaf[i].flags = 0; leaf[i].path_len = 0; leaf[i].sym = 0; }
 }
 __global__ void k_max_bump(Dev d, unsigned int *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -704,21 +731,21 @@ __global__ void k_root_stats(Dev d, float *__restrict__ out) {
 // RolloutEvaluator.h:23-48).  One thread per tree; integer RNG draws match oracle/az_oracle.c.
 // ------------------------------------------------------------------------------------------------
 template <class G>
-__global__ void k_eval_builtin(Dev d, int kind, int playout, const uint8_t *__restrict__ is_term, const float *__restrict__ td,
-                               const float *__restrict__ tp1, const float *__restrict__ tp2, float *__restrict__ policy,
-                               float *__restrict__ dv, float *__restrict__ p1v, float *__restrict__ p2v, float *__restrict__ mlv) {
+__global__ void k_eval_builtin(Dev d, int kind, int playout, float *__restrict__ policy, float *__restrict__ dv, float *__restrict__ p1v,
+                               float *__restrict__ p2v, float *__restrict__ mlv) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= d.n_envs) return;
     float *prow = policy + (size_t)env * G::A;
+    const LeafRec L = ld32(d.leaf_nv + env);
     mlv[env] = 0.0f;
-    if (is_term[env]) {
+    if (L.flags & LF_TERM) {
         for (int a = 0; a < G::A; ++a) prow[a] = 0.0f;
-        dv[env] = td[env]; p1v[env] = tp1[env]; p2v[env] = tp2[env];
+        const bool w1 = (L.flags & LF_WIN_P1) != 0, w2 = (L.flags & LF_WIN_P2) != 0;
+        dv[env] = (!w1 && !w2) ? 1.0f : 0.0f; p1v[env] = w1 ? 1.0f : 0.0f; p2v[env] = w2 ? 1.0f : 0.0f;
         return;
     }
     for (int a = 0; a < G::A; ++a) prow[a] = 1.0f;
     if (kind == AZ_EVAL_UNIFORM) { dv[env] = p1v[env] = p2v[env] = 1.f / 3; return; }
-    const LeafRec L = d.leaf_nv[env];
     State s; s.bb[0] = L.bb0; s.bb[1] = L.bb1; s.turn = L.turn; s.passes = L.passes; s.last = L.last;
     int w = 0;
     for (uint64_t step = 0; step < 256; ++step) {
@@ -751,6 +778,7 @@ static thread_local std::string g_global_err;
 struct az_mcts {
     int game = 0, n = 0, device = 0;
     int A = 0, S = 0, W = 0, max_depth = 0, max_edges = 0;
+    bool lanes_fixed = false;
     az_search_config cfg;
     Dev d{};
     cudaStream_t stream = nullptr;
@@ -767,13 +795,11 @@ struct az_mcts {
     int prepared_K = 0;               // vl_paths_.size() (MCTS.h:421-429)
     // host-API staging (device side)
     int io_rows = 0;                  // rows the io buffers can hold
-    int8_t *io_boards_in = nullptr; int32_t *io_turns_in = nullptr;
-    int8_t *io_boards = nullptr; float *io_td = nullptr, *io_tp1 = nullptr, *io_tp2 = nullptr; uint8_t *io_term = nullptr;
-    int32_t *io_turns = nullptr, *io_sym = nullptr; uint8_t *io_mask = nullptr;
-    float *io_policy = nullptr, *io_d = nullptr, *io_p1 = nullptr, *io_p2 = nullptr, *io_ml = nullptr; uint8_t *io_term_in = nullptr; int32_t *io_sym_in = nullptr;
+    int8_t *io_boards_in = nullptr; int32_t *io_turns_in = nullptr; az_root *io_roots = nullptr; az_leaf *io_leaves = nullptr;
+    uint8_t *io_out = nullptr;        // packed leaf arrays: boards | td | tp1 | tp2 | turns | sym | is_term | mask
+    uint8_t *io_in = nullptr;         // packed eval arrays: policy | d | p1 | p2 | ml | sym | is_term
     int32_t *io_actions = nullptr; int32_t *io_counts = nullptr; float *io_stats = nullptr;
-    // pinned host staging for the host API
-    uint8_t *h_pin = nullptr; size_t h_pin_bytes = 0;
+    uint8_t *h_out = nullptr, *h_in = nullptr;   // pinned mirrors of io_out / io_in
     unsigned long long *d_stats = nullptr; int *d_err = nullptr;
     uint64_t launches = 0;
     bool stats_on = false;
@@ -792,7 +818,27 @@ struct az_mcts {
     } while (0)
 
 static inline int grid_groups(int n, int W) { return (int)(((size_t)n * W + CTA - 1) / CTA); }
-static inline int grid_threads(int n, int bs = 128) { return (n + bs - 1) / bs; }
+static inline int grid_threads(size_t n, int bs = 128) { return (int)((n + bs - 1) / bs); }
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// packed staging layout shared by the device buffers and their pinned mirrors
+struct OutLayout { size_t boards, td, tp1, tp2, turns, sym, term, mask, total; };
+struct InLayout { size_t policy, d, p1, p2, ml, sym, term, total; };
+static OutLayout out_layout(size_t rows, int S, int A) {
+    OutLayout L; size_t o = 0;
+    L.boards = o; o = align256(o + rows * S);
+    L.td = o; o = align256(o + rows * 4); L.tp1 = o; o = align256(o + rows * 4); L.tp2 = o; o = align256(o + rows * 4);
+    L.turns = o; o = align256(o + rows * 4); L.sym = o; o = align256(o + rows * 4);
+    L.term = o; o = align256(o + rows); L.mask = o; o = align256(o + rows * A);
+    L.total = o; return L;
+}
+static InLayout in_layout(size_t rows, int A) {
+    InLayout L; size_t o = 0;
+    L.policy = o; o = align256(o + rows * A * 4);
+    L.d = o; o = align256(o + rows * 4); L.p1 = o; o = align256(o + rows * 4); L.p2 = o; o = align256(o + rows * 4);
+    L.ml = o; o = align256(o + rows * 4); L.sym = o; o = align256(o + rows * 4); L.term = o; o = align256(o + rows);
+    L.total = o; return L;
+}
 
 template <class T> static int dev_alloc(az_mcts *h, T **p, size_t count) {
     if (*p) { cudaFree(*p); *p = nullptr; }
@@ -833,10 +879,11 @@ static int ensure_kcap(az_mcts *h, int K) {
     if (K <= h->kcap) return AZ_OK;
     int nk = std::max(K, std::max(4, h->kcap * 2));
     LeafRec *nl = nullptr; uint32_t *np = nullptr;
+    CU(h, cudaDeviceSynchronize());
     CU(h, cudaMalloc((void **)&nl, sizeof(LeafRec) * (size_t)h->n * nk));
     CU(h, cudaMalloc((void **)&np, sizeof(uint32_t) * (size_t)h->n * nk * h->max_depth));
     size_t cnt = (size_t)h->n * nk;
-    k_init_leaf_vl<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(nl, cnt);
+    k_init_leaf<<<grid_threads(cnt, 256), 256, 0, h->stream>>>(nl, cnt);
     // pending VL paths do not survive a regrow of K (the reference's resize keeps them, but callers never
     // change K between a search and its backprop)
     CU(h, cudaStreamSynchronize(h->stream));
@@ -849,18 +896,32 @@ static int ensure_kcap(az_mcts *h, int K) {
 static int ensure_io(az_mcts *h, int rows) {
     if (rows <= h->io_rows) return AZ_OK;
     int r = std::max(rows, h->io_rows * 2);
+    CU(h, cudaDeviceSynchronize());
+    const OutLayout ol = out_layout((size_t)r, h->S, h->A);
+    const InLayout il = in_layout((size_t)r, h->A);
     int rc = 0;
-    rc |= dev_alloc(h, &h->io_boards, (size_t)r * h->S); rc |= dev_alloc(h, &h->io_td, (size_t)r); rc |= dev_alloc(h, &h->io_tp1, (size_t)r);
-    rc |= dev_alloc(h, &h->io_tp2, (size_t)r); rc |= dev_alloc(h, &h->io_term, (size_t)r); rc |= dev_alloc(h, &h->io_turns, (size_t)r);
-    rc |= dev_alloc(h, &h->io_sym, (size_t)r); rc |= dev_alloc(h, &h->io_mask, (size_t)r * h->A);
-    rc |= dev_alloc(h, &h->io_policy, (size_t)r * h->A); rc |= dev_alloc(h, &h->io_d, (size_t)r); rc |= dev_alloc(h, &h->io_p1, (size_t)r);
-    rc |= dev_alloc(h, &h->io_p2, (size_t)r); rc |= dev_alloc(h, &h->io_ml, (size_t)r); rc |= dev_alloc(h, &h->io_term_in, (size_t)r);
-    rc |= dev_alloc(h, &h->io_sym_in, (size_t)r);
+    rc |= dev_alloc(h, &h->io_leaves, (size_t)r);
+    rc |= dev_alloc(h, &h->io_out, ol.total);
+    rc |= dev_alloc(h, &h->io_in, il.total);
     if (rc) return AZ_ERR_CUDA;
-    if (h->h_pin) { cudaFreeHost(h->h_pin); h->h_pin = nullptr; }
-    h->h_pin_bytes = (size_t)r * (size_t)(h->S + h->A * 5 + 64) + 4096;
-    CU(h, cudaMallocHost((void **)&h->h_pin, h->h_pin_bytes));
+    if (h->h_out) { cudaFreeHost(h->h_out); h->h_out = nullptr; }
+    if (h->h_in) { cudaFreeHost(h->h_in); h->h_in = nullptr; }
+    CU(h, cudaMallocHost((void **)&h->h_out, ol.total));
+    CU(h, cudaMallocHost((void **)&h->h_in, il.total));
     h->io_rows = r;
+    return AZ_OK;
+}
+
+static int grow_arena(az_mcts *h, uint64_t ncap, cudaStream_t st) {
+    if (ncap >= (1ull << 26)) AZ_FAIL(h, AZ_ERR_NOMEM, "tree arena would exceed 2^26 slots per tree");
+    Slot *np = nullptr;
+    cudaError_t e = cudaMalloc((void **)&np, sizeof(Slot) * (size_t)h->n * ncap);
+    if (e != cudaSuccess) AZ_FAIL(h, AZ_ERR_NOMEM, "cannot grow tree arenas to %llu slots/tree: %s", (unsigned long long)ncap, cudaGetErrorString(e));
+    CU(h, cudaDeviceSynchronize());
+    k_grow<<<h->n, 256, 0, st>>>(h->d.pool, np, h->d.trees, h->cap, (uint32_t)ncap);
+    CU(h, cudaStreamSynchronize(st));
+    cudaFree(h->d.pool);
+    h->d.pool = np; h->cap = (uint32_t)ncap; h->d.cap = h->cap;
     return AZ_OK;
 }
 
@@ -870,7 +931,7 @@ static int ensure_arena(az_mcts *h, int sims, cudaStream_t st) {
     if (h->bump_bound + need <= h->cap) { h->bump_bound += need; return AZ_OK; }
     // refresh the bound from the device
     CU(h, cudaMemsetAsync(h->d_scratch_u32, 0, sizeof(unsigned int), st));
-    k_max_bump<<<grid_threads(h->n, 256), 256, 0, st>>>(h->d, h->d_scratch_u32);
+    k_max_bump<<<grid_threads((size_t)h->n, 256), 256, 0, st>>>(h->d, h->d_scratch_u32);
     unsigned int mx = 0;
     CU(h, cudaMemcpyAsync(&mx, h->d_scratch_u32, sizeof(mx), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
@@ -878,14 +939,7 @@ static int ensure_arena(az_mcts *h, int sims, cudaStream_t st) {
     if (h->bump_bound + need > h->cap) {
         uint64_t ncap = h->cap;
         while (h->bump_bound + need > ncap) ncap *= 2;
-        if (ncap >= (1ull << 26)) AZ_FAIL(h, AZ_ERR_NOMEM, "tree arena would exceed 2^26 slots per tree");
-        Slot *np = nullptr;
-        cudaError_t e = cudaMalloc((void **)&np, sizeof(Slot) * (size_t)h->n * ncap);
-        if (e != cudaSuccess) AZ_FAIL(h, AZ_ERR_NOMEM, "cannot grow tree arenas to %llu slots/tree: %s", (unsigned long long)ncap, cudaGetErrorString(e));
-        k_grow<<<h->n, 256, 0, st>>>(h->d.pool, np, h->d.trees, h->cap, (uint32_t)ncap);
-        CU(h, cudaStreamSynchronize(st));
-        cudaFree(h->d.pool);
-        h->d.pool = np; h->cap = (uint32_t)ncap; h->d.cap = h->cap;
+        int rc = grow_arena(h, ncap, st); if (rc) return rc;
     }
     h->bump_bound += need;
     return AZ_OK;
@@ -897,29 +951,50 @@ static int check_cfg(az_mcts *h, int K) {
     return ensure_luts(h);
 }
 
-template <class G> static void launch_select(az_mcts *h, bool vl, int K, int write_sym, const int8_t *b, const int32_t *t, LeafOut o, cudaStream_t s) {
-    const int g = grid_groups(h->n, Lanes<G>::W);
-    if (vl) k_select<G, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, write_sym, b, t, o);
-    else k_select<G, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, write_sym, b, t, o);
+static int auto_lanes(int game, int n) {
+    if (game == GAME_OTH) return 16;
+    const char *e = getenv("AZB200_LANES");
+    if (e) { int w = atoi(e); if (w == 1 || w == 2 || w == 4 || w == 8) return w; }
+    if (n < 12288) return 8;
+    if (n < 24576) return 4;
+    if (n < 98304) return 2;
+    return 1;
+}
+
+// ---- kernel dispatch over (game, lanes, VL) ----
+#define AZ_DISPATCH_W(h, KERNEL, VLFLAG, GRID, STREAM, ...)                                                          \
+    do {                                                                                                             \
+        if ((h)->game == GAME_OTH) KERNEL<Oth, 16, VLFLAG><<<GRID, CTA, 0, STREAM>>>(__VA_ARGS__);                   \
+        else switch ((h)->W) {                                                                                       \
+            case 1: KERNEL<C4, 1, VLFLAG><<<GRID, CTA, 0, STREAM>>>(__VA_ARGS__); break;                             \
+            case 2: KERNEL<C4, 2, VLFLAG><<<GRID, CTA, 0, STREAM>>>(__VA_ARGS__); break;                             \
+            case 4: KERNEL<C4, 4, VLFLAG><<<GRID, CTA, 0, STREAM>>>(__VA_ARGS__); break;                             \
+            default: KERNEL<C4, 8, VLFLAG><<<GRID, CTA, 0, STREAM>>>(__VA_ARGS__); break;                            \
+        }                                                                                                            \
+    } while (0)
+
+static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s) {
+    const int g = grid_groups(h->n, h->W);
+    if (vl) AZ_DISPATCH_W(h, k_select, true, g, s, h->d, h->cfg, K, roots, leaves);
+    else AZ_DISPATCH_W(h, k_select, false, g, s, h->d, h->cfg, 1, roots, leaves);
     h->launches++;
 }
-template <class G> static void launch_backprop(az_mcts *h, bool vl, int K, int removeK, const float *pol, const float *d, const float *p1, const float *p2,
-                                               const float *ml, const uint8_t *it, const int32_t *sym, cudaStream_t s) {
-    const int g = grid_groups(h->n, Lanes<G>::W);
-    if (vl) k_backprop<G, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, removeK, pol, d, p1, p2, ml, it, sym);
-    else k_backprop<G, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, 0, pol, d, p1, p2, ml, it, sym);
+static void launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym, const float *pol, const float *d, const float *p1,
+                            const float *p2, const float *ml, const uint8_t *it, const int32_t *sym, cudaStream_t s) {
+    const int g = grid_groups(h->n, h->W);
+    if (vl) AZ_DISPATCH_W(h, k_backprop, true, g, s, h->d, h->cfg, K, removeK, use_sym, pol, d, p1, p2, ml, it, sym);
+    else AZ_DISPATCH_W(h, k_backprop, false, g, s, h->d, h->cfg, 1, 0, use_sym, pol, d, p1, p2, ml, it, sym);
     h->launches++;
 }
 
-static int do_search(az_mcts *h, int K, int write_sym, const int8_t *d_boards, const int32_t *d_turns, LeafOut o, cudaStream_t s) {
+static int do_search(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, cudaStream_t s) {
     int rc = check_cfg(h, K); if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
     const bool vl = K > 0;
     if (vl) { rc = ensure_kcap(h, K); if (rc) return rc; h->prepared_K = K; }
     h->d.epoch++;
     h->d.stats = h->stats_on ? h->d_stats : nullptr;
-    if (h->game == GAME_C4) launch_select<C4>(h, vl, K, write_sym, d_boards, d_turns, o, s);
-    else launch_select<Oth>(h, vl, K, write_sym, d_boards, d_turns, o, s);
+    launch_select(h, vl, K, d_roots, d_leaves, s);
     CU(h, cudaGetLastError());
     return AZ_OK;
 }
@@ -932,9 +1007,8 @@ static int do_backprop(az_mcts *h, int K, const float *pol, const float *d, cons
     rc = ensure_arena(h, vl ? K : 1, s); if (rc) return rc;
     h->d.stats = h->stats_on ? h->d_stats : nullptr;
     const int removeK = vl ? std::min(K, h->prepared_K) : 0;
-    const int32_t *symp = vl ? sym : h->d.pending_sym;     // non-VL: the id remembered by search_batch (BatchedMCTS.h:194)
-    if (h->game == GAME_C4) launch_backprop<C4>(h, vl, K, removeK, pol, d, p1, p2, ml, it, symp, s);
-    else launch_backprop<Oth>(h, vl, K, removeK, pol, d, p1, p2, ml, it, symp, s);
+    // non-VL: the symmetry id is the one search_batch remembered (pending_sym_ids_, BatchedMCTS.h:45,194)
+    launch_backprop(h, vl, K, removeK, 1, pol, d, p1, p2, ml, it, vl ? sym : nullptr, s);
     CU(h, cudaGetLastError());
     return AZ_OK;
 }
@@ -946,9 +1020,17 @@ static int check_device_error(az_mcts *h) {
     return AZ_OK;
 }
 
+template <class G> static void launch_pack(int n, const int8_t *b, const int32_t *t, az_root *r, cudaStream_t s) {
+    k_pack_roots<G><<<grid_threads((size_t)n), 128, 0, s>>>(n, b, t, r);
+}
+template <class G> static void launch_unpack(int rows, const az_leaf *l, int8_t *ob, float *td, float *tp1, float *tp2, uint8_t *it, int32_t *ot,
+                                             int32_t *sym, uint8_t *vm, float *planes, cudaStream_t s) {
+    k_unpack_leaves<G><<<grid_threads((size_t)rows * G::S, 256), 256, 0, s>>>(rows, l, ob, td, tp1, tp2, it, ot, sym, vm, planes);
+}
+
 extern "C" {
 
-const char *az_version(void) { return "azb200 0.1 (sm_100a)"; }
+const char *az_version(void) { return "azb200 0.2 (sm_100a)"; }
 const char *az_global_last_error(void) { return g_global_err.c_str(); }
 int az_game_action_size(int g) { return g == GAME_C4 ? C4::A : (g == GAME_OTH ? Oth::A : -1); }
 int az_game_board_size(int g) { return g == GAME_C4 ? C4::S : (g == GAME_OTH ? Oth::S : -1); }
@@ -959,6 +1041,22 @@ void az_search_config_defaults(az_search_config *c) {
     c->c_init = 1.25f; c->c_base = 19652.0f; c->dirichlet_alpha = 0.3f; c->noise_epsilon = 0.25f; c->fpu_reduction = 0.4f;
     c->mlh_slope = 0.0f; c->mlh_cap = 0.2f; c->score_utility_factor = 0.0f; c->score_scale = 8.0f; c->value_decay = 1.0f;
     c->use_symmetry = 1; c->vl_count = 1;
+}
+
+int az_pack_roots_dev(int game, int n, const int8_t *b, const int32_t *t, az_root *r, void *stream) {
+    if (n <= 0) return AZ_OK;
+    if (game == GAME_C4) launch_pack<C4>(n, b, t, r, (cudaStream_t)stream);
+    else if (game == GAME_OTH) launch_pack<Oth>(n, b, t, r, (cudaStream_t)stream);
+    else return AZ_ERR_INVALID;
+    return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_ERR_CUDA;
+}
+int az_unpack_leaves_dev(int game, int rows, const az_leaf *l, int8_t *ob, float *td, float *tp1, float *tp2, uint8_t *it, int32_t *ot,
+                         int32_t *sym, uint8_t *vm, float *planes, void *stream) {
+    if (rows <= 0) return AZ_OK;
+    if (game == GAME_C4) launch_unpack<C4>(rows, l, ob, td, tp1, tp2, it, ot, sym, vm, planes, (cudaStream_t)stream);
+    else if (game == GAME_OTH) launch_unpack<Oth>(rows, l, ob, td, tp1, tp2, it, ot, sym, vm, planes, (cudaStream_t)stream);
+    else return AZ_ERR_INVALID;
+    return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_ERR_CUDA;
 }
 
 az_mcts *az_mcts_create(int game, int n_envs, int device) {
@@ -974,7 +1072,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     az_mcts *h = new az_mcts();
     h->game = game; h->n = n_envs; h->device = device;
     h->A = az_game_action_size(game); h->S = az_game_board_size(game);
-    h->W = game == GAME_C4 ? Lanes<C4>::W : Lanes<Oth>::W;
+    h->W = auto_lanes(game, n_envs);
     h->max_depth = game == GAME_C4 ? C4::MAX_DEPTH : Oth::MAX_DEPTH;
     h->max_edges = game == GAME_C4 ? 8 : 48;
     az_search_config_defaults(&h->cfg);
@@ -995,17 +1093,17 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     rc |= dev_alloc(h, &h->d.noise, (size_t)n_envs * h->d.noise_stride);
     rc |= dev_alloc(h, &h->d.leaf_nv, (size_t)n_envs);
     rc |= dev_alloc(h, &h->d.path_nv, (size_t)n_envs * h->max_depth);
-    rc |= dev_alloc(h, &h->d.pending_sym, (size_t)n_envs);
     rc |= dev_alloc(h, &h->d_stats, 8); rc |= dev_alloc(h, &h->d_err, 1); rc |= dev_alloc(h, &h->d_scratch_u32, 4);
     rc |= dev_alloc(h, &h->io_boards_in, (size_t)n_envs * h->S); rc |= dev_alloc(h, &h->io_turns_in, (size_t)n_envs);
+    rc |= dev_alloc(h, &h->io_roots, (size_t)n_envs);
     rc |= dev_alloc(h, &h->io_actions, (size_t)n_envs); rc |= dev_alloc(h, &h->io_counts, (size_t)n_envs * h->A);
     rc |= dev_alloc(h, &h->io_stats, (size_t)n_envs * (6 + 8 * h->A));
     if (rc) return fail("device allocation");
     h->d.err = h->d_err;
     cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream);
     cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
-    k_reset<<<grid_threads(n_envs), 128, 0, h->stream>>>(h->d, -1);
-    k_init_leaf<<<grid_threads(n_envs), 128, 0, h->stream>>>(h->d);
+    k_reset<<<grid_threads((size_t)n_envs), 128, 0, h->stream>>>(h->d, -1);
+    k_init_leaf<<<grid_threads((size_t)n_envs), 128, 0, h->stream>>>(h->d.leaf_nv, (size_t)n_envs);
     if (ensure_io(h, n_envs) != AZ_OK) return fail("io allocation");
     if (ensure_luts(h) != AZ_OK) return fail("LUT upload");
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = cudaGetErrorString(cudaGetLastError()); return fail("init kernels"); }
@@ -1015,13 +1113,13 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
 void az_mcts_destroy(az_mcts *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->d.pool, h->d.trees, h->d.noise, h->d.leaf_vl, h->d.path_vl, h->d.leaf_nv, h->d.path_nv, h->d.pending_sym, h->d_log_lut,
-                    h->d_atan_lut, h->d_stats, h->d_err, h->d_scratch_u32, h->io_boards_in, h->io_turns_in, h->io_boards, h->io_td, h->io_tp1,
-                    h->io_tp2, h->io_term, h->io_turns, h->io_sym, h->io_mask, h->io_policy, h->io_d, h->io_p1, h->io_p2, h->io_ml,
-                    h->io_term_in, h->io_sym_in, h->io_actions, h->io_counts, h->io_stats};
+    cudaDeviceSynchronize();
+    void *ptrs[] = {h->d.pool, h->d.trees, h->d.noise, h->d.leaf_vl, h->d.path_vl, h->d.leaf_nv, h->d.path_nv, h->d_log_lut,
+                    h->d_atan_lut, h->d_stats, h->d_err, h->d_scratch_u32, h->io_boards_in, h->io_turns_in, h->io_roots, h->io_leaves,
+                    h->io_out, h->io_in, h->io_actions, h->io_counts, h->io_stats};
     for (void *p : ptrs) if (p) cudaFree(p);
-    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_in) cudaFreeHost(h->h_in);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1029,6 +1127,22 @@ const char *az_mcts_last_error(const az_mcts *h) { return h ? h->err.c_str() : g
 int az_mcts_num_envs(const az_mcts *h) { return h->n; }
 int az_mcts_set_config(az_mcts *h, const az_search_config *c) { h->cfg = *c; return AZ_OK; }
 int az_mcts_get_config(const az_mcts *h, az_search_config *c) { *c = h->cfg; return AZ_OK; }
+int az_mcts_set_lanes(az_mcts *h, int lanes) {
+    if (lanes == 0) { h->W = auto_lanes(h->game, h->n); return AZ_OK; }
+    if (h->game == GAME_OTH) { if (lanes != 16) AZ_FAIL(h, AZ_ERR_INVALID, "Othello trees use 16 lanes"); return AZ_OK; }
+    if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8) AZ_FAIL(h, AZ_ERR_INVALID, "Connect4 lanes must be 1, 2, 4 or 8");
+    h->W = lanes;
+    return AZ_OK;
+}
+int az_mcts_get_lanes(const az_mcts *h) { return h->W; }
+int az_mcts_reserve(az_mcts *h, int slots_per_tree) {
+    CU(h, cudaSetDevice(h->device));
+    if (slots_per_tree <= 0) AZ_FAIL(h, AZ_ERR_INVALID, "slots_per_tree must be positive");
+    uint64_t ncap = h->cap;
+    while (ncap < (uint64_t)slots_per_tree) ncap *= 2;
+    if (ncap > h->cap) return grow_arena(h, ncap, h->stream);
+    return AZ_OK;
+}
 int az_mcts_set_seed(az_mcts *h, int64_t seed) {
     if (seed < 0) {   // re-randomise (BatchedMCTS.h:73-76)
         uint64_t t = (uint64_t)clock() ^ ((uint64_t)(uintptr_t)h << 16);
@@ -1049,8 +1163,8 @@ int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream) 
     int rc = check_cfg(h, 1); if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
-    if (h->game == GAME_C4) k_prune<C4><<<grid_threads(h->n), 128, 0, s>>>(h->d, h->cfg, d_actions);
-    else k_prune<Oth><<<grid_threads(h->n), 128, 0, s>>>(h->d, h->cfg, d_actions);
+    if (h->game == GAME_C4) k_prune<C4><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, h->cfg, d_actions);
+    else k_prune<Oth><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, h->cfg, d_actions);
     h->launches++;
     CU(h, cudaGetLastError());
     return AZ_OK;
@@ -1063,6 +1177,7 @@ int az_mcts_prune_roots(az_mcts *h, const int32_t *actions) {
     return AZ_OK;
 }
 
+// host entry points: pack -> search -> unpack into one packed staging buffer -> ONE D2H copy into pinned memory
 static int host_search(az_mcts *h, int K, const int8_t *boards, const int32_t *turns, int8_t *ob, float *td, float *tp1, float *tp2,
                        uint8_t *it, int32_t *ot, int32_t *sym, uint8_t *vm) {
     CU(h, cudaSetDevice(h->device));
@@ -1072,17 +1187,20 @@ static int host_search(az_mcts *h, int K, const int8_t *boards, const int32_t *t
     cudaStream_t s = h->stream;
     CU(h, cudaMemcpyAsync(h->io_boards_in, boards, (size_t)h->n * h->S, cudaMemcpyHostToDevice, s));
     CU(h, cudaMemcpyAsync(h->io_turns_in, turns, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, s));
-    LeafOut o{h->io_boards, h->io_td, h->io_tp1, h->io_tp2, h->io_term, h->io_turns, h->io_sym, h->io_mask, nullptr};
-    rc = do_search(h, K, 1, h->io_boards_in, h->io_turns_in, o, s); if (rc) return rc;
-    CU(h, cudaMemcpyAsync(ob, h->io_boards, rows * h->S, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaMemcpyAsync(td, h->io_td, rows * 4, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaMemcpyAsync(tp1, h->io_tp1, rows * 4, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaMemcpyAsync(tp2, h->io_tp2, rows * 4, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaMemcpyAsync(it, h->io_term, rows, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaMemcpyAsync(ot, h->io_turns, rows * 4, cudaMemcpyDeviceToHost, s));
-    if (sym) CU(h, cudaMemcpyAsync(sym, h->io_sym, rows * 4, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaMemcpyAsync(vm, h->io_mask, rows * h->A, cudaMemcpyDeviceToHost, s));
+    rc = az_pack_roots_dev(h->game, h->n, h->io_boards_in, h->io_turns_in, h->io_roots, s); if (rc) AZ_FAIL(h, rc, "pack_roots launch failed");
+    rc = do_search(h, K, h->io_roots, h->io_leaves, s); if (rc) return rc;
+    const OutLayout L = out_layout(rows, h->S, h->A);
+    uint8_t *o = h->io_out;
+    rc = az_unpack_leaves_dev(h->game, (int)rows, h->io_leaves, (int8_t *)(o + L.boards), (float *)(o + L.td), (float *)(o + L.tp1),
+                              (float *)(o + L.tp2), o + L.term, (int32_t *)(o + L.turns), (int32_t *)(o + L.sym), o + L.mask, nullptr, s);
+    if (rc) AZ_FAIL(h, rc, "unpack_leaves launch failed");
+    h->launches += 2;
+    CU(h, cudaMemcpyAsync(h->h_out, o, L.total, cudaMemcpyDeviceToHost, s));
     CU(h, cudaStreamSynchronize(s));
+    const uint8_t *p = h->h_out;
+    memcpy(ob, p + L.boards, rows * h->S); memcpy(td, p + L.td, rows * 4); memcpy(tp1, p + L.tp1, rows * 4); memcpy(tp2, p + L.tp2, rows * 4);
+    memcpy(it, p + L.term, rows); memcpy(ot, p + L.turns, rows * 4); memcpy(vm, p + L.mask, rows * h->A);
+    if (sym) memcpy(sym, p + L.sym, rows * 4);
     return AZ_OK;
 }
 static int host_backprop(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
@@ -1092,14 +1210,16 @@ static int host_backprop(az_mcts *h, int K, const float *pol, const float *d, co
     const size_t rows = (size_t)h->n * rowsK;
     int rc = ensure_io(h, (int)rows); if (rc) return rc;
     cudaStream_t s = h->stream;
-    CU(h, cudaMemcpyAsync(h->io_policy, pol, rows * h->A * 4, cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->io_d, d, rows * 4, cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->io_p1, p1, rows * 4, cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->io_p2, p2, rows * 4, cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->io_ml, ml, rows * 4, cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->io_term_in, it, rows, cudaMemcpyHostToDevice, s));
-    if (sym) CU(h, cudaMemcpyAsync(h->io_sym_in, sym, rows * 4, cudaMemcpyHostToDevice, s));
-    rc = do_backprop(h, K, h->io_policy, h->io_d, h->io_p1, h->io_p2, h->io_ml, h->io_term_in, h->io_sym_in, s); if (rc) return rc;
+    const InLayout L = in_layout(rows, h->A);
+    uint8_t *p = h->h_in;
+    memcpy(p + L.policy, pol, rows * h->A * 4); memcpy(p + L.d, d, rows * 4); memcpy(p + L.p1, p1, rows * 4); memcpy(p + L.p2, p2, rows * 4);
+    memcpy(p + L.ml, ml, rows * 4); memcpy(p + L.term, it, rows);
+    if (sym) memcpy(p + L.sym, sym, rows * 4);
+    CU(h, cudaMemcpyAsync(h->io_in, p, L.total, cudaMemcpyHostToDevice, s));
+    uint8_t *q = h->io_in;
+    rc = do_backprop(h, K, (const float *)(q + L.policy), (const float *)(q + L.d), (const float *)(q + L.p1), (const float *)(q + L.p2),
+                     (const float *)(q + L.ml), q + L.term, sym ? (const int32_t *)(q + L.sym) : nullptr, s);
+    if (rc) return rc;
     return check_device_error(h);
 }
 
@@ -1126,19 +1246,22 @@ int az_mcts_remove_all_vl(az_mcts *h, int K) {
     const int safeK = std::min(K, h->prepared_K);
     if (safeK <= 0) return AZ_OK;
     const int g = grid_groups(h->n, h->W);
-    if (h->game == GAME_C4) k_remove_vl<C4><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK);
-    else k_remove_vl<Oth><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK);
+    if (h->game == GAME_OTH) k_remove_vl<Oth, 16><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK);
+    else switch (h->W) {
+        case 1: k_remove_vl<C4, 1><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK); break;
+        case 2: k_remove_vl<C4, 2><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK); break;
+        case 4: k_remove_vl<C4, 4><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK); break;
+        default: k_remove_vl<C4, 8><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK); break;
+    }
     h->launches++;
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(h->stream));
     return AZ_OK;
 }
 
-int az_mcts_search_dev(az_mcts *h, int K, const int8_t *b, const int32_t *t, int8_t *ob, float *td, float *tp1, float *tp2, uint8_t *it,
-                       int32_t *ot, int32_t *sym, uint8_t *vm, float *planes, void *stream) {
+int az_mcts_search_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, void *stream) {
     if (K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "search_dev: K must be >= 0");
-    LeafOut o{ob, td, tp1, tp2, it, ot, sym, vm, planes};
-    return do_search(h, K, 1, b, t, o, (cudaStream_t)stream);
+    return do_search(h, K, d_roots, d_leaves, (cudaStream_t)stream);
 }
 int az_mcts_backprop_dev(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
                          const uint8_t *it, const int32_t *sym, void *stream) {
@@ -1146,36 +1269,26 @@ int az_mcts_backprop_dev(az_mcts *h, int K, const float *pol, const float *d, co
     return do_backprop(h, K, pol, d, p1, p2, ml, it, sym, (cudaStream_t)stream);
 }
 
-int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const int8_t *d_boards, const int32_t *d_turns, int n_playout, void *stream) {
+int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const az_root *d_roots, int n_playout, void *stream) {
     if (evaluator != AZ_EVAL_UNIFORM && evaluator != AZ_EVAL_ROLLOUT) AZ_FAIL(h, AZ_ERR_INVALID, "unknown evaluator kind %d", evaluator);
     int rc = check_cfg(h, 1); if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
     rc = ensure_io(h, h->n); if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     h->d.epoch++;                          // one epoch per search() call, like orc_search
-    const uint64_t epoch = h->d.epoch;
-    LeafOut o{h->io_boards, h->io_td, h->io_tp1, h->io_tp2, h->io_term, h->io_turns, nullptr, h->io_mask, nullptr};
+    const InLayout L = in_layout((size_t)h->n, h->A);
+    uint8_t *q = h->io_in;
+    float *pol = (float *)(q + L.policy), *dv = (float *)(q + L.d), *p1 = (float *)(q + L.p1), *p2 = (float *)(q + L.p2), *ml = (float *)(q + L.ml);
     az_search_config saved = h->cfg;
     h->cfg.use_symmetry = 0;               // search() never symmetrises leaves (BatchedMCTS.h:357)
     h->d.stats = h->stats_on ? h->d_stats : nullptr;
     for (int p = 0; p < n_playout; ++p) {
         rc = ensure_arena(h, 1, s); if (rc) { h->cfg = saved; return rc; }
-        h->d.epoch = epoch;
-        if (h->game == GAME_C4) {
-            launch_select<C4>(h, false, 1, 0, d_boards, d_turns, o, s);
-            k_eval_builtin<C4><<<grid_threads(h->n), 128, 0, s>>>(h->d, evaluator, p, h->io_term, h->io_td, h->io_tp1, h->io_tp2, h->io_policy,
-                                                                 h->io_d, h->io_p1, h->io_p2, h->io_ml);
-            // backprop without the inverse symmetry: pending_sym must not be consulted -> pass sym 0 via cfg
-            k_backprop<C4, false><<<grid_groups(h->n, Lanes<C4>::W), CTA, 0, s>>>(h->d, h->cfg, 1, 0, h->io_policy, h->io_d, h->io_p1, h->io_p2, h->io_ml,
-                                                                                  h->io_term, nullptr);
-        } else {
-            launch_select<Oth>(h, false, 1, 0, d_boards, d_turns, o, s);
-            k_eval_builtin<Oth><<<grid_threads(h->n), 128, 0, s>>>(h->d, evaluator, p, h->io_term, h->io_td, h->io_tp1, h->io_tp2, h->io_policy,
-                                                                  h->io_d, h->io_p1, h->io_p2, h->io_ml);
-            k_backprop<Oth, false><<<grid_groups(h->n, Lanes<Oth>::W), CTA, 0, s>>>(h->d, h->cfg, 1, 0, h->io_policy, h->io_d, h->io_p1, h->io_p2, h->io_ml,
-                                                                                   h->io_term, nullptr);
-        }
-        h->launches += 2;
+        launch_select(h, false, 1, d_roots, h->io_leaves, s);
+        if (h->game == GAME_C4) k_eval_builtin<C4><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, evaluator, p, pol, dv, p1, p2, ml);
+        else k_eval_builtin<Oth><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, evaluator, p, pol, dv, p1, p2, ml);
+        launch_backprop(h, false, 1, 0, 0, pol, dv, p1, p2, ml, nullptr, nullptr, s);
+        h->launches += 1;
     }
     h->cfg = saved;
     CU(h, cudaGetLastError());
@@ -1185,14 +1298,15 @@ int az_mcts_search(az_mcts *h, int evaluator, const int8_t *boards, const int32_
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaMemcpyAsync(h->io_boards_in, boards, (size_t)h->n * h->S, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->io_turns_in, turns, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
-    int rc = az_mcts_search_eval_dev(h, evaluator, h->io_boards_in, h->io_turns_in, n_playout, h->stream); if (rc) return rc;
+    int rc = az_pack_roots_dev(h->game, h->n, h->io_boards_in, h->io_turns_in, h->io_roots, h->stream); if (rc) AZ_FAIL(h, rc, "pack_roots launch failed");
+    rc = az_mcts_search_eval_dev(h, evaluator, h->io_roots, n_playout, h->stream); if (rc) return rc;
     return check_device_error(h);
 }
 
 int az_mcts_get_counts_dev(az_mcts *h, int32_t *d_out, void *stream) {
     CU(h, cudaSetDevice(h->device));
-    if (h->game == GAME_C4) k_counts<C4><<<grid_threads(h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
-    else k_counts<Oth><<<grid_threads(h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
+    if (h->game == GAME_C4) k_counts<C4><<<grid_threads((size_t)h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
+    else k_counts<Oth><<<grid_threads((size_t)h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
     h->launches++;
     CU(h, cudaGetLastError());
     return AZ_OK;
@@ -1205,8 +1319,8 @@ int az_mcts_get_counts(az_mcts *h, int32_t *out) {
 }
 int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream) {
     CU(h, cudaSetDevice(h->device));
-    if (h->game == GAME_C4) k_root_stats<C4><<<grid_threads(h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
-    else k_root_stats<Oth><<<grid_threads(h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
+    if (h->game == GAME_C4) k_root_stats<C4><<<grid_threads((size_t)h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
+    else k_root_stats<Oth><<<grid_threads((size_t)h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
     h->launches++;
     CU(h, cudaGetLastError());
     return AZ_OK;
@@ -1220,8 +1334,8 @@ int az_mcts_get_root_stats(az_mcts *h, float *out) {
 int az_mcts_enable_stats(az_mcts *h, int on) {
     CU(h, cudaSetDevice(h->device));
     h->stats_on = on != 0;
-    CU(h, cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaDeviceSynchronize());
+    CU(h, cudaMemset(h->d_stats, 0, 8 * sizeof(unsigned long long)));
     return AZ_OK;
 }
 int az_mcts_get_stats(az_mcts *h, uint64_t *out8) {
@@ -1230,7 +1344,7 @@ int az_mcts_get_stats(az_mcts *h, uint64_t *out8) {
     CU(h, cudaDeviceSynchronize());
     CU(h, cudaMemcpy(v, h->d_stats, sizeof(v), cudaMemcpyDeviceToHost));
     CU(h, cudaMemsetAsync(h->d_scratch_u32, 0, sizeof(unsigned int), h->stream));
-    k_max_bump<<<grid_threads(h->n, 256), 256, 0, h->stream>>>(h->d, h->d_scratch_u32);
+    k_max_bump<<<grid_threads((size_t)h->n, 256), 256, 0, h->stream>>>(h->d, h->d_scratch_u32);
     unsigned int mx = 0;
     CU(h, cudaMemcpyAsync(&mx, h->d_scratch_u32, sizeof(mx), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));

@@ -1,0 +1,123 @@
+"""Device-resident playout loop: the reference wrapper's per-move loop (src/MCTS_cpp.py:89-359 - one non-VL
+warm-up simulation, then ceil((n-1)/K) virtual-loss iterations with cur_K = min(K, remaining)) with every buffer
+in HBM and no host synchronisation.  select -> evaluator -> backprop are three stream-ordered launches per
+iteration; the evaluator is either the synthetic CUDA evaluator (csrc/az_eval.cu) or any callable working on the
+torch tensors in ``LeafBuffers`` (e.g. a CNN consuming ``planes``).
+
+PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+SYN_MODES = {"hash": 0, "equivariant": 1, "constant": 2}
+
+
+class LeafBuffers:
+    """Device buffers of one playout loop: az_root[n] in, az_leaf[rows] out of select, evaluation tuple into backprop.
+    `unpacked=True` additionally allocates the reference-format arrays (int8 boards, masks, ...) and `planes=True`
+    the CNN input tensor, both filled on demand by `unpack()`."""
+
+    def __init__(self, n: int, rows: int, A: int, board_shape, device, unpacked: bool = False, planes: bool = False):
+        dv = dict(device=device)
+        self.n, self.rows, self.A, self.board_shape = n, rows, A, tuple(board_shape)
+        self.gid = 0 if tuple(board_shape) == (6, 7) else 1
+        self.roots = torch.zeros((n, 32), dtype=torch.uint8, **dv)
+        self.leaves = torch.zeros((rows, 32), dtype=torch.uint8, **dv)
+        self.policy = torch.empty((rows, A), dtype=torch.float32, **dv)
+        self.d, self.p1w, self.p2w, self.ml = (torch.empty(rows, dtype=torch.float32, **dv) for _ in range(4))
+        self.boards = self.td = self.tp1 = self.tp2 = self.is_term = self.turns = self.sym = self.mask = self.planes = None
+        if unpacked:
+            self.boards = torch.empty((rows, *board_shape), dtype=torch.int8, **dv)
+            self.td, self.tp1, self.tp2 = (torch.empty(rows, dtype=torch.float32, **dv) for _ in range(3))
+            self.is_term = torch.empty(rows, dtype=torch.uint8, **dv)
+            self.turns = torch.empty(rows, dtype=torch.int32, **dv)
+            self.sym = torch.empty(rows, dtype=torch.int32, **dv)
+            self.mask = torch.empty((rows, A), dtype=torch.uint8, **dv)
+        if planes:
+            self.planes = torch.empty((rows, 3, *board_shape), dtype=torch.float32, **dv)
+
+    def pack_roots(self, boards: torch.Tensor, turns: torch.Tensor, stream: int):
+        """int8[n,R,C] boards + int32[n] turns (CUDA tensors) -> az_root[n]."""
+        rc = _lib.lib().az_pack_roots_dev(self.gid, self.n, boards.data_ptr(), turns.data_ptr(), self.roots.data_ptr(),
+                                          stream or None)
+        if rc != 0:
+            raise RuntimeError("az_pack_roots_dev failed (%d)" % rc)
+
+    def unpack(self, rows: int, stream: int):
+        """az_leaf[rows] -> whichever reference-format arrays / CNN planes were allocated."""
+        p = lambda t: t.data_ptr() if t is not None else None
+        rc = _lib.lib().az_unpack_leaves_dev(self.gid, rows, self.leaves.data_ptr(), p(self.boards), p(self.td), p(self.tp1),
+                                             p(self.tp2), p(self.is_term), p(self.turns), p(self.sym), p(self.mask),
+                                             p(self.planes), stream or None)
+        if rc != 0:
+            raise RuntimeError("az_unpack_leaves_dev failed (%d)" % rc)
+
+
+class SyntheticEvaluator:
+    """Device twin of evaluators.HashEvaluator (one kernel launch on the az_leaf records, no host round trip)."""
+
+    def __init__(self, game: str, mode: str = "hash"):
+        self.gid = {"Connect4": 0, "Othello": 1}[game]
+        self.mode = SYN_MODES[mode]
+        self.launches = 0
+
+    def __call__(self, buf: LeafBuffers, rows: int, stream: int):
+        rc = _lib.lib().az_eval_synthetic_dev(
+            self.gid, self.mode, rows, buf.leaves.data_ptr(), buf.policy.data_ptr(), buf.d.data_ptr(),
+            buf.p1w.data_ptr(), buf.p2w.data_ptr(), buf.ml.data_ptr(), stream or None)
+        if rc != 0:
+            raise RuntimeError("az_eval_synthetic_dev failed (%d)" % rc)
+        self.launches += 1
+
+
+def playout_device(engine, buf: LeafBuffers, n_playout: int, K: int, evaluator, stream: int | None = None,
+                   on_select=None):
+    """Run `n_playout` simulations per tree entirely on the device from the roots in `buf.roots` (see
+    LeafBuffers.pack_roots).  `on_select(rows, fn)` (optional) wraps each select launch (bench.py times the dominant
+    kernel with CUDA events through it).  Returns the number of kernels launched."""
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    n = engine.get_num_envs()
+    launches = 0
+
+    def select(k):
+        rows = n * max(k, 1)
+        assert rows <= buf.rows
+        if on_select is not None:
+            on_select(rows, lambda: engine.search_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), stream))
+        else:
+            engine.search_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), stream)
+        return rows
+
+    def backprop(k):
+        # is_term / sym ids: the engine uses what it remembered from the matching search
+        engine.backprop_dev(k, buf.policy.data_ptr(), buf.d.data_ptr(), buf.p1w.data_ptr(), buf.p2w.data_ptr(),
+                            buf.ml.data_ptr(), 0, 0, stream)
+
+    remaining = n_playout
+    if K <= 1:
+        for _ in range(n_playout):
+            rows = select(0)
+            evaluator(buf, rows, stream)
+            backprop(0)
+            launches += 3
+        return launches
+    if remaining > 0:                      # warm-up: make sure every root is expanded (src/MCTS_cpp.py:217-248)
+        rows = select(0)
+        evaluator(buf, rows, stream)
+        backprop(0)
+        remaining -= 1
+        launches += 3
+    while remaining > 0:
+        cur = min(K, remaining)
+        remaining -= cur
+        rows = select(cur)
+        evaluator(buf, rows, stream)
+        backprop(cur)
+        launches += 3
+    return launches

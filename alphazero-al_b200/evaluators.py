@@ -25,11 +25,19 @@ def splitmix64(x: np.ndarray) -> np.ndarray:
         return x ^ (x >> np.uint64(31))
 
 
+def _bit_positions(shape):
+    """Engine bit index of row-major cell j (csrc/az_games.cuh cell_bit): Connect4 col*7+(5-row), Othello j."""
+    R, Cc = shape
+    if (R, Cc) == (6, 7):
+        return np.array([c * 7 + (5 - r) for r in range(6) for c in range(7)], dtype=np.uint64)
+    return np.arange(R * Cc, dtype=np.uint64)
+
+
 def _bitboards(boards: np.ndarray):
-    """(own1, own2) uint64 per board: bit j set when row-major cell j holds +1 / -1."""
+    """(own1, own2) uint64 per board in the engine's bitboard layout (stones of +1 / -1)."""
     B = boards.shape[0]
     flat = boards.reshape(B, -1)
-    w = (np.uint64(1) << np.arange(flat.shape[1], dtype=np.uint64))[None, :]
+    w = (np.uint64(1) << _bit_positions(boards.shape[1:]))[None, :]
     own1 = ((flat == 1).astype(np.uint64) * w).sum(axis=1, dtype=np.uint64)
     own2 = ((flat == -1).astype(np.uint64) * w).sum(axis=1, dtype=np.uint64)
     return own1, own2

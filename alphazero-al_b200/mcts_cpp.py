@@ -252,32 +252,39 @@ class _BatchedMCTS:
         return out
 
     # -- B200-only: device-pointer twins (no copies, no synchronisation) ---------------------------
-    def search_dev(self, K, boards_ptr, turns_ptr, out_boards, out_td, out_tp1, out_tp2, out_is_term, out_turns,
-                   out_sym, out_mask, planes=0, stream=0):
+    # roots_ptr -> az_root[n], leaves_ptr -> az_leaf[n*max(K,1)] (32-byte records, include/azb200.h)
+    def search_dev(self, K, roots_ptr, leaves_ptr, stream=0):
         self._push_cfg()
-        self._ck(self._L.az_mcts_search_dev(self._h, int(K), boards_ptr, turns_ptr, out_boards, out_td, out_tp1, out_tp2,
-                                            out_is_term, out_turns, out_sym or None, out_mask, planes or None,
-                                            stream or None))
+        self._ck(self._L.az_mcts_search_dev(self._h, int(K), roots_ptr, leaves_ptr, stream or None))
 
-    def backprop_dev(self, K, policy, d, p1w, p2w, ml, is_term, sym=0, stream=0):
+    def backprop_dev(self, K, policy, d, p1w, p2w, ml, is_term=0, sym=0, stream=0):
         self._push_cfg()
-        self._ck(self._L.az_mcts_backprop_dev(self._h, int(K), policy, d, p1w, p2w, ml, is_term, sym or None,
+        self._ck(self._L.az_mcts_backprop_dev(self._h, int(K), policy, d, p1w, p2w, ml, is_term or None, sym or None,
                                               stream or None))
 
     def prune_roots_dev(self, actions_ptr, stream=0):
         self._push_cfg()
         self._ck(self._L.az_mcts_prune_roots_dev(self._h, actions_ptr, stream or None))
 
-    def search_eval_dev(self, evaluator_kind, boards_ptr, turns_ptr, n_playout, stream=0):
+    def search_eval_dev(self, evaluator_kind, roots_ptr, n_playout, stream=0):
         self._push_cfg()
-        self._ck(self._L.az_mcts_search_eval_dev(self._h, int(evaluator_kind), boards_ptr, turns_ptr, int(n_playout),
-                                                 stream or None))
+        self._ck(self._L.az_mcts_search_eval_dev(self._h, int(evaluator_kind), roots_ptr, int(n_playout), stream or None))
 
     def get_counts_dev(self, out_ptr, stream=0):
         self._ck(self._L.az_mcts_get_counts_dev(self._h, out_ptr, stream or None))
 
     def get_root_stats_dev(self, out_ptr, stream=0):
         self._ck(self._L.az_mcts_get_root_stats_dev(self._h, out_ptr, stream or None))
+
+    def set_lanes(self, lanes):
+        """Lanes cooperating on one tree (Connect4: 1/2/4/8, 0 = auto from n_envs)."""
+        self._ck(self._L.az_mcts_set_lanes(self._h, int(lanes)))
+
+    def get_lanes(self):
+        return self._L.az_mcts_get_lanes(self._h)
+
+    def reserve(self, slots_per_tree):
+        self._ck(self._L.az_mcts_reserve(self._h, int(slots_per_tree)))
 
     def enable_stats(self, on=True):
         self._ck(self._L.az_mcts_enable_stats(self._h, 1 if on else 0))

@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the self-play hot path: batched PUCT MCTS simulations/s, Connect4, n=200, vl_batch=4.
+
+    python bench.py [--gpus N --steps K --warmup W]              # this repo (CUDA engine)
+    python bench.py --impl reference [...]                        # the reference C++/OpenMP engine on host cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one full move search for every game of the batch: fresh trees on G mid-game Connect4 roots per GPU
+(config-2 style random rollouts, ply = g mod 20), then n=200 simulations per tree exactly as the reference wrapper
+schedules them (src/MCTS_cpp.py:217-357: 1 non-VL warm-up simulation + 50 virtual-loss iterations of K=4/3), with the
+server-default search parameters (server.py:44-72) and a deterministic constant evaluator standing in for the
+random-init CNN (the CNN is outside the path: SURVEY.md 8d).  Simulations/s = G*n/step time, whole job over all GPUs.
+
+  value : device-resident loop (inputs in HBM, CUDA-event timed, max over ranks)
+  e2e   : the same search through the reference-facing host-buffer API (mcts_cpp.search_batch[_vl] /
+          backprop_batch[_vl] with numpy arrays; H2D/D2H inside the timed region)
+  roofline     : k_select (dominant kernel) algorithmic bytes / its CUDA-event time vs measured HBM peak
+  cpu_baseline : the reference engine (oracle/_ref/timing) on this box's host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SERVER_DEFAULTS = dict(c_init=1.4, c_base=1000.0, fpu_reduction=0.2, dirichlet_alpha=0.3, noise_epsilon=0.25,
+                       mlh_slope=0.1, mlh_cap=0.2, use_symmetry=True, value_decay=1.0)
+METRIC = "mcts_simulations_per_sec"
+UNIT = "sims/s"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------------------------------
+def c4_random_roots(n: int, seed: int, max_ply: int = 20):
+    """n non-terminal Connect4 positions after (g mod max_ply) uniformly random legal plies (numpy, lockstep)."""
+    rng = np.random.default_rng(seed)
+    boards = np.zeros((n, 6, 7), np.int8)
+    turns = np.ones(n, np.int32)
+    heights = np.zeros((n, 7), np.int64)
+    target = np.arange(n) % max_ply
+
+    def four(m):
+        h = m[:, :, 0:4] & m[:, :, 1:5] & m[:, :, 2:6] & m[:, :, 3:7]
+        v = m[:, 0:3, :] & m[:, 1:4, :] & m[:, 2:5, :] & m[:, 3:6, :]
+        d1 = m[:, 0:3, 0:4] & m[:, 1:4, 1:5] & m[:, 2:5, 2:6] & m[:, 3:6, 3:7]
+        d2 = m[:, 3:6, 0:4] & m[:, 2:5, 1:5] & m[:, 1:4, 2:6] & m[:, 0:3, 3:7]
+        return h.any(axis=(1, 2)) | v.any(axis=(1, 2)) | d1.any(axis=(1, 2)) | d2.any(axis=(1, 2))
+
+    for ply in range(max_ply):
+        act = np.where(target > ply)[0]
+        if act.size == 0:
+            break
+        legal = heights[act] < 6
+        col = np.argmax(np.where(legal, rng.random((act.size, 7)), -1.0), axis=1)
+        row = 5 - heights[act, col]
+        trial = boards[act].copy()
+        trial[np.arange(act.size), row, col] = turns[act]
+        ok = ~four(trial == turns[act][:, None, None])
+        good = act[ok]
+        boards[good] = trial[ok]
+        heights[good, col[ok]] += 1
+        turns[good] = -turns[good]
+        target[act[~ok]] = ply          # a winning move is not played: the game stays at this ply
+    return boards, turns
+
+
+def host_step(engine, boards, turns, n_playout, K, A, reset_actions):
+    """One step through the reference-facing host API with numpy buffers (what src/MCTS_cpp.py does)."""
+    engine.prune_roots(reset_actions)               # action -1 matches no edge -> every tree is reset (MCTS.h:107)
+    def evaluate(lt, it, td, tp1, tp2):
+        t = it.astype(bool)
+        p1 = lt == 1
+        probs = np.ones((it.shape[0], A), np.float32)
+        probs[t] = 0
+        d = np.where(t, td, np.float32(0.25)).astype(np.float32)
+        p1w = np.where(t, tp1, np.where(p1, np.float32(0.5), np.float32(0.25))).astype(np.float32)
+        p2w = np.where(t, tp2, np.where(p1, np.float32(0.25), np.float32(0.5))).astype(np.float32)
+        ml = np.where(t, np.float32(0), np.float32(10)).astype(np.float32)
+        return probs, d, p1w, p2w, ml
+    lb, td, tp1, tp2, it, lt, vm = engine.search_batch(boards, turns)
+    engine.backprop_batch(*evaluate(lt, it, td, tp1, tp2), it)
+    remaining = n_playout - 1
+    while remaining > 0:
+        cur = min(K, remaining)
+        remaining -= cur
+        lb, td, tp1, tp2, it, lt, sym, vm = engine.search_batch_vl(cur, boards, turns)
+        engine.backprop_batch_vl(cur, *evaluate(lt, it, td, tp1, tp2), it, sym)
+
+
+def step_io_bytes(n, n_playout, K, S, A):
+    """(h2d, d2h) bytes per step moved by the host API."""
+    h2d = d2h = 0
+    ks = [1]
+    rem = n_playout - 1
+    while rem > 0:
+        c = min(K, rem); rem -= c; ks.append(c)
+    for i, k in enumerate(ks):
+        rows = n * k
+        h2d += n * S + n * 4                                   # boards + turns in
+        d2h += rows * (S + 12 + 1 + 4 + A) + (rows * 4 if i else 0)   # leaves (+ sym ids for VL)
+        h2d += rows * (A * 4 + 16 + 1) + (rows * 4 if i else 0)       # policy, wdl, ml, is_term (+ sym ids)
+    h2d += n * 4                                               # prune/reset actions
+    return h2d, d2h
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for j, nm in enumerate(names) if any(len(r) > 2 + j and r[2 + j] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference engine on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(n, n_playout, K, steps, warmup, seed=0):
+    """Times the reference's own CPU implementation (oracle/_ref/timing, -O3, OpenMP over all host threads; falls back
+    to the single-thread C restatement when the build did not travel) on the same workload."""
+    import oracle
+    boards, turns = c4_random_roots(n, seed)
+    A = 7
+    if oracle.ref_available("timing"):
+        mcts_cpp, _ = oracle.load_ref("timing")
+        eng = mcts_cpp.BatchedMCTS_Connect4(n)
+        kind, cores = "reference", os.cpu_count()
+    else:
+        eng = oracle.OracleMCTS("Connect4", n)
+        kind, cores = "port", 1
+    cfg = eng.config
+    for k, v in SERVER_DEFAULTS.items():
+        setattr(cfg, k, v)
+    eng.set_seed(0)
+    reset = np.full(n, -1, np.int32)
+    for _ in range(warmup):
+        host_step(eng, boards, turns, n_playout, K, A, reset)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        host_step(eng, boards, turns, n_playout, K, A, reset)
+    dt = time.perf_counter() - t0
+    return dict(value=n * n_playout * steps / dt, ms_per_step=1e3 * dt / steps, kind=kind, cores=cores)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games-per-gpu", type=int, default=8192)
+    ap.add_argument("--n-playout", type=int, default=200)
+    ap.add_argument("--vl-batch", type=int, default=4)
+    ap.add_argument("--cpu-baseline-games", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (Connect4: 1/2/4/8, 0 = auto)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    G, n_playout, K = args.games_per_gpu, args.n_playout, args.vl_batch
+    workload = f"connect4_mcts_n{n_playout}_k{K}_fresh_midgame_roots_{G}_games_per_gpu_constant_evaluator"
+    config = {"workload": workload, "game": "Connect4", "games_per_gpu": G, "n_playout": n_playout, "vl_batch": K,
+              "search_params": "server defaults (c_init 1.4, c_base 1000, fpu 0.2, alpha 0.3, eps 0.25, mlh 0.1/0.2, symmetry on)",
+              "evaluator": "constant (uniform prior, fixed WDL/aux; stands in for the random-init CNN)",
+              "parallelism": f"{world} x independent game shards, no data-path collective"}
+    
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_reference(G, n_playout, K, args.steps, max(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                 "sample": f"{G} games x {n_playout} sims x {args.steps} steps (full per-GPU workload)"},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU path (use --impl reference for the host baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mcts_cpp = importlib.import_module("alphazero-al_b200.mcts_cpp")
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+
+    A, S = 7, 42
+    boards_np, turns_np = c4_random_roots(G, seed=1000 + rank)
+    boards = torch.from_numpy(boards_np).to(dev)
+    turns = torch.from_numpy(turns_np).to(dev)
+    reset_np = np.full(G, -1, np.int32)
+    reset_actions = torch.from_numpy(reset_np).to(dev)
+    eng = mcts_cpp.BatchedMCTS_Connect4(G, device=local_rank)
+    for k, v in SERVER_DEFAULTS.items():
+        setattr(eng.config, k, v)
+    eng.set_seed(rank)
+    if args.lanes:
+        eng.set_lanes(args.lanes)
+    buf = ds.LeafBuffers(G, G * K, A, (6, 7), dev)
+    ev = ds.SyntheticEvaluator("Connect4", "constant")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def dev_step(on_select=None):
+        eng.prune_roots_dev(reset_actions.data_ptr(), stream)
+        buf.pack_roots(boards, turns, stream)
+        return 2 + ds.playout_device(eng, buf, n_playout, K, ev, stream, on_select)
+
+    # ---- untimed pass with counters on: tree statistics for the roofline model ----
+    eng.enable_stats(True)
+    dev_step()
+    torch.cuda.synchronize()
+    st = eng.get_stats()
+    eng.enable_stats(False)
+    sims = max(st["sims"], 1)
+    d_bar, E_bar, b_bar, x_bar = st["depth"] / sims, st["edges_scanned"] / sims, st["edges_created"] / sims, st["expansions"] / sims
+    bytes_select_sim = 36 * d_bar + 40 * E_bar + 8 * (d_bar + 1) + 68 * x_bar + (S + A + 21)
+    bytes_total_sim = 36 * d_bar + 40 * E_bar + 60 * (d_bar + 1) + 16 * b_bar + S + 5 * A + 118     # SURVEY.md 8(d) B_sim
+
+    for _ in range(args.warmup):
+        dev_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sel_events = []
+
+    def on_select(rows, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        sel_events.append((rows, e0, e1))
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.get_stats()["launches"]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    launches = 0
+    for _ in range(args.steps):
+        launches += dev_step(on_select)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clk = clocks.stop() if rank == 0 else None
+    ms = t_start.elapsed_time(t_end)
+    sel_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in sel_events)
+    sel_rows = sum(r for r, _, _ in sel_events)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    total_sims = world * G * n_playout * args.steps
+    value = total_sims / (ms * 1e-3)
+
+    # ---- e2e through the host-buffer API ----
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            host_step(eng, boards_np, turns_np, n_playout, K, A, reset_np)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            host_step(eng, boards_np, turns_np, n_playout, K, A, reset_np)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        h2d, d2h = step_io_bytes(G, n_playout, K, S, A)
+        e2e = {"value": total_sims / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * dt / args.steps,
+               "api": "mcts_cpp.search_batch[_vl]/backprop_batch[_vl] with numpy buffers (C ABI host entry points)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = (sel_rows * bytes_select_sim) / (sel_ms * 1e-3) / 1e9 if sel_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": f"az::k_select<C4,{eng.get_lanes()},VL>", "lanes_per_tree": eng.get_lanes(), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "bytes_per_sim_select": bytes_select_sim, "bytes_per_sim_whole_path": bytes_total_sim,
+                "tree_stats": {"depth": d_bar, "edges_scanned": E_bar, "edges_created": b_bar, "expansions": x_bar},
+                "select_share_of_step": sel_ms / ms if world == 1 else None,
+                "whole_path_frac": value / world * bytes_total_sim / 1e9 / peak}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--games-per-gpu",
+                                  str(args.cpu_baseline_games), "--n-playout", str(n_playout), "--vl-batch", str(K),
+                                  "--steps", "3", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+            r = json.loads(out.stdout.strip().splitlines()[-1])
+            cpu = r["cpu_baseline"]
+            cpu["sample"] = f"{args.cpu_baseline_games} games x {n_playout} sims x 3 steps (same workload, fewer games)"
+        except Exception as e:   # pragma: no cover
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(config, l2="working set (tree arenas touched per step) > 126 MB L2, no flush"),
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

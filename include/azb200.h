@@ -105,36 +105,61 @@ int az_mcts_get_counts(az_mcts *h, int32_t *out);
 /* get_all_root_stats - BatchedMCTS.h:435-441, layout MCTS.h:634-636: f32[n, 6+8A] */
 int az_mcts_get_root_stats(az_mcts *h, float *out);
 
-/* ---- device-pointer twins (no copies, no synchronisation; stream = cudaStream_t) ---- */
+/* ---- device-pointer twins (no copies, no synchronisation; stream = cudaStream_t) ----
+ * On the device the engine speaks bitboards, not byte boards: roots go in as az_root, leaves come out as az_leaf
+ * (both 32 bytes, one sector).  az_pack_roots_dev / az_unpack_leaves_dev convert from / to the arrays of the
+ * reference API with fully coalesced kernels; the host entry points above are exactly pack -> search -> unpack. */
+typedef struct az_root {     /* a position to search from (import_board + set_turn, BatchedMCTS.h:133-137) */
+    uint64_t bb0, bb1;       /* stones of player +1 / -1.  Connect4: bit = col*7 + (5-row); Othello: bit = row*8+col */
+    int32_t turn;            /* side to move, +1 / -1 */
+    int32_t reserved[3];
+} az_root;
+#define AZ_LEAF_TERMINAL 1u
+#define AZ_LEAF_P1_WINS 2u
+#define AZ_LEAF_P2_WINS 4u
+typedef struct az_leaf {     /* a leaf to evaluate (SimResult + sym id, MCTS.h:22-28, BatchedMCTS.h:141-158) */
+    uint64_t bb0, bb1;       /* leaf position AFTER the random symmetry (what the network sees) */
+    int8_t turn;             /* side to move at the leaf */
+    uint8_t flags;           /* AZ_LEAF_* : terminal flag and cached result (neither win bit = draw) */
+    uint8_t sym;             /* symmetry id that was applied (0 for terminal leaves) */
+    uint8_t passes;          /* Othello consecutive passes (needed to rebuild the legal mask) */
+    int32_t reserved[3];
+} az_leaf;
+
+int az_pack_roots_dev(int game, int n, const int8_t *d_boards, const int32_t *d_turns, az_root *d_roots, void *stream);
+/* Any output pointer may be NULL.  d_planes = CNN input f32[rows,3,R,C] (plane0 = side to move, plane1 = opponent,
+ * plane2 = turn; src/MCTS_cpp.py:15-20) so the network consumes leaves with no host round trip. */
+int az_unpack_leaves_dev(int game, int rows, const az_leaf *d_leaves, int8_t *d_boards, float *d_term_d, float *d_term_p1w,
+                         float *d_term_p2w, uint8_t *d_is_term, int32_t *d_turns, int32_t *d_sym_ids, uint8_t *d_valid_mask,
+                         float *d_planes, void *stream);
+
 int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream);
-/* K == 0 selects the non-VL search_batch (1 leaf per tree).  d_planes (optional, may be NULL) receives the
- * leaves encoded as the CNN input f32[n*K,3,R,C] (plane0 = side to move, plane1 = opponent, plane2 = turn;
- * src/MCTS_cpp.py:15-20) so the network consumes them with no host round trip.  d_out_sym_ids may be NULL when
- * K == 0 (the id is kept inside the handle like pending_sym_ids_, BatchedMCTS.h:45). */
-int az_mcts_search_dev(az_mcts *h, int K, const int8_t *d_boards, const int32_t *d_turns, int8_t *d_out_boards,
-                       float *d_out_term_d, float *d_out_term_p1w, float *d_out_term_p2w, uint8_t *d_out_is_term,
-                       int32_t *d_out_turns, int32_t *d_out_sym_ids, uint8_t *d_out_valid_mask, float *d_planes,
-                       void *stream);
+/* K == 0 selects the non-VL search_batch (1 leaf per tree, d_leaves[n]); K >= 1 the virtual-loss search (d_leaves[n*K]). */
+int az_mcts_search_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, void *stream);
+/* d_is_term / d_sym_ids may be NULL: the engine then uses the flags / ids it remembered from the matching search. */
 int az_mcts_backprop_dev(az_mcts *h, int K, const float *d_policy, const float *d_d, const float *d_p1w,
                          const float *d_p2w, const float *d_moves_left, const uint8_t *d_is_term,
                          const int32_t *d_sym_ids, void *stream);
-int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const int8_t *d_boards, const int32_t *d_turns, int n_playout,
-                            void *stream);
+int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const az_root *d_roots, int n_playout, void *stream);
 int az_mcts_get_counts_dev(az_mcts *h, int32_t *d_out, void *stream);
 int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream);
+
+/* Lanes cooperating on one tree: Connect4 1/2/4/8 (0 = choose from n_envs), Othello 16.  More trees per warp means
+ * fewer replicated instructions; fewer means more warps to hide latency when n_envs is small. */
+int az_mcts_set_lanes(az_mcts *h, int lanes);
+int az_mcts_get_lanes(const az_mcts *h);
+/* Pre-size every tree arena (slots of 32 bytes per tree) so no reallocation happens later (e.g. under graph capture). */
+int az_mcts_reserve(az_mcts *h, int slots_per_tree);
 
 /* engine counters for the roofline model: out[0..7] = simulations, edges traversed (sum of depths), edges
  * scanned, edges created, expansions, max arena use (slots), arena capacity (slots/tree), kernel launches */
 int az_mcts_enable_stats(az_mcts *h, int on);
 int az_mcts_get_stats(az_mcts *h, uint64_t *out8);
 
-/* Synthetic deterministic evaluators on device pointers (twins of alphazero-al_b200/evaluators.py): turn the
- * leaf tuple of az_mcts_search_dev into the backprop tuple.  mode: 0 hash, 1 flip-equivariant hash (Connect4),
- * 2 constant. */
-int az_eval_synthetic_dev(int game, int mode, int n_leaves, const int8_t *d_leaf_boards, const int32_t *d_leaf_turns,
-                          const uint8_t *d_is_term, const float *d_term_d, const float *d_term_p1w,
-                          const float *d_term_p2w, float *d_policy, float *d_d, float *d_p1w, float *d_p2w,
-                          float *d_moves_left, void *stream);
+/* Synthetic deterministic evaluators on device pointers (twins of alphazero-al_b200/evaluators.py): turn the leaves
+ * of az_mcts_search_dev into the backprop tuple.  mode: 0 hash, 1 flip-equivariant hash (Connect4), 2 constant. */
+int az_eval_synthetic_dev(int game, int mode, int n_leaves, const az_leaf *d_leaves, float *d_policy, float *d_d,
+                          float *d_p1w, float *d_p2w, float *d_moves_left, void *stream);
 
 #ifdef __cplusplus
 }

@@ -161,3 +161,49 @@ def test_api_errors_and_shapes():
         m.IEvaluator_Connect4()
     e.search(m.RolloutEvaluator_Connect4(), b, t, 10)
     assert sum(e.get_all_counts()) == 4 * 10 - 4 + 0 or True
+
+
+# ---- lanes-per-tree variants and the device-resident loop ----
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8])
+def test_c4_every_lane_width_is_bit_exact(lanes):
+    e = _cuda("Connect4", 80)
+    e.set_lanes(lanes)
+    assert e.get_lanes() == lanes
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True, value_decay=0.98)
+    boards, turns = random_positions("Connect4", 80, 30, 21)
+    compare_engines(e, _orc("Connect4", 80), "Connect4", 80, 90, 4, cfg, boards=boards, turns=turns, moves=6, seed=5)
+
+
+@pytest.mark.parametrize("game,mode,K", [("Connect4", "hash", 4), ("Connect4", "equivariant", 8), ("Othello", "hash", 4)])
+def test_device_resident_loop_equals_host_buffer_loop(game, mode, K):
+    """search_dev -> az_eval_synthetic_dev -> backprop_dev (no host round trip, flags/sym ids remembered inside the
+    engine) must give the same trees as the reference-style host loop with the numpy twin of the evaluator."""
+    import torch
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    ev_mod = importlib.import_module("alphazero-al_b200.evaluators")
+    n, npl = 96, 70
+    A = oracle.ACTION_SIZE[game]
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True) if game == "Connect4" else dict(OTH_CFG, use_symmetry=True)
+    boards, turns = random_positions(game, n, 16, 31)
+    a, b = _cuda(game, n), _cuda(game, n)
+    for e in (a, b):
+        set_config(e, **cfg)
+        e.set_seed(17)
+    playout(a, ev_mod.HashEvaluator(game, mode), boards, turns, npl, K)
+    dev = torch.device("cuda", 0)
+    buf = ds.LeafBuffers(n, n * K, A, oracle.BOARD_SHAPE[game], dev, unpacked=True, planes=True)
+    stream = torch.cuda.current_stream().cuda_stream
+    buf.pack_roots(torch.from_numpy(boards).to(dev), torch.from_numpy(turns).to(dev), stream)
+    ds.playout_device(b, buf, npl, K, ds.SyntheticEvaluator(game, mode), stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(counts(a, n, A), counts(b, n, A))
+    assert a.get_all_root_stats().tobytes() == b.get_all_root_stats().tobytes()
+    # unpack of the last leaves: planes must equal the wrapper's 3-plane conversion (src/MCTS_cpp.py:15-20)
+    rows = n * min(K, (npl - 1) % K or K)
+    buf.unpack(rows, stream)
+    torch.cuda.synchronize()
+    lb = buf.boards[:rows].cpu().numpy()
+    lt = buf.turns[:rows].cpu().numpy()
+    ref_planes = np.stack([(lb == lt[:, None, None]), (lb == -lt[:, None, None]),
+                           np.ones_like(lb, dtype=bool) * 0 + lt[:, None, None]], axis=1).astype(np.float32)
+    assert np.array_equal(buf.planes[:rows].cpu().numpy(), ref_planes)
