@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
         "az_mcts_get_counts_dev": [_vp, _vp, _vp], "az_mcts_get_root_stats_dev": [_vp, _vp, _vp],
         "az_mcts_enable_stats": [_vp, _i], "az_mcts_get_stats": [_vp, _vp],
         "az_eval_synthetic_dev": [_i, _i, _i] + [_vp] * 7,
+        "az_eval_finalize_dev": [_i] + [_vp] * 8,
         "az_game_action_size": [_i], "az_game_board_size": [_i], "az_game_board_rows": [_i], "az_game_board_cols": [_i],
         "az_game_num_symmetries": [_i],
     }

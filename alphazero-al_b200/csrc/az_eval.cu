@@ -75,7 +75,31 @@ __global__ void k_eval_synth(int mode, int n, const az_leaf *__restrict__ leaves
     mlv[i] = aux;
 }
 
+// CNN.predict outputs -> backprop tuple: relative WDL [draw, win(to move), loss(to move)] to absolute [draw, p1w, p2w]
+// (src/MCTS_cpp.py:23-30) with terminal leaves overridden by their cached result (src/MCTS_cpp.py:276-297).
+__global__ void k_eval_finalize(int n, const az_leaf *__restrict__ leaves, const float *__restrict__ wdl_rel, const float *__restrict__ aux,
+                                float *__restrict__ dv, float *__restrict__ p1v, float *__restrict__ p2v, float *__restrict__ mlv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t flags = leaves[i].flags;
+    const int turn = leaves[i].turn;
+    if (flags & AZ_LEAF_TERMINAL) {
+        const bool w1 = (flags & AZ_LEAF_P1_WINS) != 0, w2 = (flags & AZ_LEAF_P2_WINS) != 0;
+        dv[i] = (!w1 && !w2) ? 1.0f : 0.0f; p1v[i] = w1 ? 1.0f : 0.0f; p2v[i] = w2 ? 1.0f : 0.0f; mlv[i] = 0.0f;
+        return;
+    }
+    const float d = wdl_rel[3 * i], w = wdl_rel[3 * i + 1], l = wdl_rel[3 * i + 2];
+    dv[i] = d; p1v[i] = turn == 1 ? w : l; p2v[i] = turn == 1 ? l : w; mlv[i] = aux[i];
+}
+
 }  // namespace az
+
+extern "C" int az_eval_finalize_dev(int n, const az_leaf *leaves, const float *wdl_rel, const float *aux, float *d, float *p1, float *p2,
+                                    float *ml, void *stream) {
+    if (n <= 0) return AZ_OK;
+    az::k_eval_finalize<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, leaves, wdl_rel, aux, d, p1, p2, ml);
+    return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_ERR_CUDA;
+}
 
 extern "C" int az_eval_synthetic_dev(int game, int mode, int n, const az_leaf *leaves, float *pol, float *d, float *p1, float *p2, float *ml,
                                      void *stream) {

@@ -89,6 +89,7 @@ class _BatchedMCTS:
         self._n = int(n_envs)
         if device is None:
             device = _current_device()
+        self._device = int(device)
         self._h = L.az_mcts_create(GAME_IDS[self._game], self._n, int(device))
         if not self._h:
             raise RuntimeError("BatchedMCTS_%s: %s" % (self._game, L.az_global_last_error().decode()))
@@ -245,6 +246,12 @@ class _BatchedMCTS:
         out = np.empty(self._n * self._A, np.int32)
         self._ck(self._L.az_mcts_get_counts(self._h, _ptr(out)))
         return out.tolist()          # std::vector<int> -> list (mcts_bindings.cpp:342)
+
+    def get_all_counts_array(self):
+        """B200-only convenience: the same counts as an int32 ndarray [n_envs, A] (no Python list)."""
+        out = np.empty((self._n, self._A), np.int32)
+        self._ck(self._L.az_mcts_get_counts(self._h, _ptr(out)))
+        return out
 
     def get_all_root_stats(self):
         out = np.empty((self._n, 6 + 8 * self._A), np.float32)

@@ -186,12 +186,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--games-per-gpu", type=int, default=8192)
+    ap.add_argument("--games-per-gpu", type=int, default=65536)
     ap.add_argument("--n-playout", type=int, default=200)
     ap.add_argument("--vl-batch", type=int, default=4)
-    ap.add_argument("--cpu-baseline-games", type=int, default=2048)
+    ap.add_argument("--cpu-baseline-games", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-split", action="store_true")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (Connect4: 1/2/4/8, 0 = auto)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -289,7 +290,6 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clk = clocks.stop() if rank == 0 else None
     ms = t_start.elapsed_time(t_end)
     sel_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in sel_events)
     sel_rows = sum(r for r, _, _ in sel_events)
@@ -300,27 +300,63 @@ def main():
     total_sims = world * G * n_playout * args.steps
     value = total_sims / (ms * 1e-3)
 
-    # ---- e2e through the host-buffer API ----
-    e2e = None
+    # ---- e2e: the public wrapper API with HOST buffers (numpy boards in, visit counts out) ----
+    # BatchedMCTS.batch_playout / get_visits_count are the calls src/player.py makes (src/player.py:333-343); every step
+    # copies that step's boards/turns/actions host->device and reads the visit counts back.
+    e2e = e2e_split = None
     if not args.no_e2e:
+        bm = importlib.import_module("alphazero-al_b200.batched_mcts")
+        wrap = bm.BatchedMCTS(G, SERVER_DEFAULTS["c_init"], SERVER_DEFAULTS["c_base"], SERVER_DEFAULTS["dirichlet_alpha"], n_playout,
+                              game_name="Connect4", noise_epsilon=SERVER_DEFAULTS["noise_epsilon"],
+                              fpu_reduction=SERVER_DEFAULTS["fpu_reduction"], use_symmetry=True, mlh_slope=SERVER_DEFAULTS["mlh_slope"],
+                              mlh_cap=SERVER_DEFAULTS["mlh_cap"], device=local_rank)
+        wrap.seed(rank)
+        if args.lanes:
+            wrap.mcts.set_lanes(args.lanes)
+
+        def wrap_step():
+            wrap.prune_roots(reset_np)
+            wrap.batch_playout(ev, boards_np, turns_np, vl_batch=K)
+            return wrap.get_visits_count()
+
         for _ in range(2):
-            host_step(eng, boards_np, turns_np, n_playout, K, A, reset_np)
+            c = wrap_step()
+        assert int(c.sum()) == G * (n_playout - 1), "every fresh root must hold n-1 child visits"
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            host_step(eng, boards_np, turns_np, n_playout, K, A, reset_np)
+            wrap_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
             tt = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        h2d, d2h = step_io_bytes(G, n_playout, K, S, A)
-        e2e = {"value": total_sims / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e = {"value": total_sims / dt, "unit": UNIT, "h2d_bytes_per_step": G * (S + 4 + 4), "d2h_bytes_per_step": G * A * 4,
                "ms_per_step": 1e3 * dt / args.steps,
-               "api": "mcts_cpp.search_batch[_vl]/backprop_batch[_vl] with numpy buffers (C ABI host entry points)"}
+               "api": "BatchedMCTS.prune_roots + batch_playout(numpy boards, numpy turns) + get_visits_count() (wrapper mirror of "
+                      "src/MCTS_cpp.py; evaluator runs on the device)"}
+        del wrap
+        # secondary: the split host-buffer plugin API (search_batch[_vl] / backprop_batch[_vl] with numpy leaves every iteration)
+        if world == 1 and not args.no_split:
+            Gs = min(G, 8192)
+            engs = mcts_cpp.BatchedMCTS_Connect4(Gs, device=local_rank)
+            for k, v in SERVER_DEFAULTS.items():
+                setattr(engs.config, k, v)
+            bs_np, ts_np, rs_np = boards_np[:Gs], turns_np[:Gs], reset_np[:Gs]
+            host_step(engs, bs_np, ts_np, n_playout, K, A, rs_np)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                host_step(engs, bs_np, ts_np, n_playout, K, A, rs_np)
+            dts = (time.perf_counter() - t0) / 2
+            h2d, d2h = step_io_bytes(Gs, n_playout, K, S, A)
+            e2e_split = {"value": Gs * n_playout / dts, "unit": UNIT, "games": Gs, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                         "ms_per_step": 1e3 * dts,
+                         "api": "mcts_cpp.search_batch[_vl]/backprop_batch[_vl] with numpy leaf buffers + numpy evaluator on the host"}
+            del engs
+    clk = clocks.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -354,7 +390,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(config, l2="working set (tree arenas touched per step) > 126 MB L2, no flush"),
-            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": clk, "e2e": e2e, "e2e_split_api": e2e_split, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -161,6 +161,12 @@ int az_mcts_get_stats(az_mcts *h, uint64_t *out8);
 int az_eval_synthetic_dev(int game, int mode, int n_leaves, const az_leaf *d_leaves, float *d_policy, float *d_d,
                           float *d_p1w, float *d_p2w, float *d_moves_left, void *stream);
 
+/* Network outputs -> backprop tuple on device: d_wdl_rel f32[n,3] = [draw, win(to move), loss(to move)] (CNN.predict,
+ * src/environments/Connect4/Network.py:267-288) becomes absolute d/p1w/p2w by the leaf's side to move
+ * (src/MCTS_cpp.py:23-30); terminal leaves get their cached result and moves_left 0 (src/MCTS_cpp.py:276-282). */
+int az_eval_finalize_dev(int n_leaves, const az_leaf *d_leaves, const float *d_wdl_rel, const float *d_aux, float *d_d,
+                         float *d_p1w, float *d_p2w, float *d_moves_left, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
