@@ -803,6 +803,10 @@ struct az_mcts {
     unsigned long long *d_stats = nullptr; int *d_err = nullptr;
     uint64_t launches = 0;
     bool stats_on = false;
+    // stream hand-over between the host entry points (internal stream) and the *_dev entry points (caller streams)
+    cudaEvent_t ev = nullptr;
+    cudaStream_t user_stream = nullptr; bool user_pending = false;   // device-API work possibly still in flight
+    bool internal_pending = false;                                   // un-synchronised work on the internal stream
     std::string err;
 };
 
@@ -1020,6 +1024,28 @@ static int check_device_error(az_mcts *h) {
     return AZ_OK;
 }
 
+// Host entry points run on the internal stream: first wait for whatever the caller queued through the *_dev API.
+static int enter_host(az_mcts *h) {
+    CU(h, cudaSetDevice(h->device));
+    if (h->user_pending) {
+        CU(h, cudaEventRecord(h->ev, h->user_stream));
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev, 0));
+        h->user_pending = false;
+    }
+    return AZ_OK;
+}
+// *_dev entry points run on the caller's stream: first wait for un-synchronised work of the internal stream.
+static int enter_dev(az_mcts *h, cudaStream_t s) {
+    CU(h, cudaSetDevice(h->device));
+    if (h->internal_pending && s != h->stream) {
+        CU(h, cudaEventRecord(h->ev, h->stream));
+        CU(h, cudaStreamWaitEvent(s, h->ev, 0));
+        h->internal_pending = false;
+    }
+    if (s != h->stream) { h->user_stream = s; h->user_pending = true; }
+    return AZ_OK;
+}
+
 template <class G> static void launch_pack(int n, const int8_t *b, const int32_t *t, az_root *r, cudaStream_t s) {
     k_pack_roots<G><<<grid_threads((size_t)n), 128, 0, s>>>(n, b, t, r);
 }
@@ -1083,6 +1109,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     };
     if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail("create"); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "stream create failed"; return fail("create"); }
+    if (cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming) != cudaSuccess) { h->err = "event create failed"; return fail("create"); }
     const char *ce = getenv("AZB200_ARENA_SLOTS");
     h->cap = ce ? (uint32_t)std::max(256, atoi(ce)) : (game == GAME_C4 ? 2048u : 4096u);
     h->d.n_envs = n_envs; h->d.cap = h->cap; h->d.noise_stride = h->max_edges;
@@ -1120,6 +1147,7 @@ void az_mcts_destroy(az_mcts *h) {
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->ev) cudaEventDestroy(h->ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1153,16 +1181,17 @@ int az_mcts_set_seed(az_mcts *h, int64_t seed) {
 }
 int az_mcts_reset_env(az_mcts *h, int i) {
     if (i < 0 || i >= h->n) return AZ_OK;   // silently ignored (BatchedMCTS.h:93-99)
-    CU(h, cudaSetDevice(h->device));
+    { int rc = enter_host(h); if (rc) return rc; }
     k_reset<<<1, 32, 0, h->stream>>>(h->d, i);
+    h->internal_pending = true;
     h->launches++;
     CU(h, cudaGetLastError());
     return AZ_OK;
 }
 int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream) {
     int rc = check_cfg(h, 1); if (rc) return rc;
-    CU(h, cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
+    rc = enter_dev(h, s); if (rc) return rc;
     if (h->game == GAME_C4) k_prune<C4><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, h->cfg, d_actions);
     else k_prune<Oth><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, h->cfg, d_actions);
     h->launches++;
@@ -1170,7 +1199,7 @@ int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream) 
     return AZ_OK;
 }
 int az_mcts_prune_roots(az_mcts *h, const int32_t *actions) {
-    CU(h, cudaSetDevice(h->device));
+    { int rc = enter_host(h); if (rc) return rc; }
     CU(h, cudaMemcpyAsync(h->io_actions, actions, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
     int rc = az_mcts_prune_roots_dev(h, h->io_actions, h->stream); if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
@@ -1180,7 +1209,7 @@ int az_mcts_prune_roots(az_mcts *h, const int32_t *actions) {
 // host entry points: pack -> search -> unpack into one packed staging buffer -> ONE D2H copy into pinned memory
 static int host_search(az_mcts *h, int K, const int8_t *boards, const int32_t *turns, int8_t *ob, float *td, float *tp1, float *tp2,
                        uint8_t *it, int32_t *ot, int32_t *sym, uint8_t *vm) {
-    CU(h, cudaSetDevice(h->device));
+    { int rc0 = enter_host(h); if (rc0) return rc0; }
     const int rowsK = K > 0 ? K : 1;
     const size_t rows = (size_t)h->n * rowsK;
     int rc = ensure_io(h, (int)rows); if (rc) return rc;
@@ -1205,7 +1234,7 @@ static int host_search(az_mcts *h, int K, const int8_t *boards, const int32_t *t
 }
 static int host_backprop(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
                          const uint8_t *it, const int32_t *sym) {
-    CU(h, cudaSetDevice(h->device));
+    { int rc0 = enter_host(h); if (rc0) return rc0; }
     const int rowsK = K > 0 ? K : 1;
     const size_t rows = (size_t)h->n * rowsK;
     int rc = ensure_io(h, (int)rows); if (rc) return rc;
@@ -1242,7 +1271,7 @@ int az_mcts_backprop_batch_vl(az_mcts *h, int K, const float *pol, const float *
 }
 int az_mcts_remove_all_vl(az_mcts *h, int K) {
     int rc = check_cfg(h, 1); if (rc) return rc;
-    CU(h, cudaSetDevice(h->device));
+    rc = enter_host(h); if (rc) return rc;
     const int safeK = std::min(K, h->prepared_K);
     if (safeK <= 0) return AZ_OK;
     const int g = grid_groups(h->n, h->W);
@@ -1261,20 +1290,22 @@ int az_mcts_remove_all_vl(az_mcts *h, int K) {
 
 int az_mcts_search_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, void *stream) {
     if (K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "search_dev: K must be >= 0");
+    { int rc = enter_dev(h, (cudaStream_t)stream); if (rc) return rc; }
     return do_search(h, K, d_roots, d_leaves, (cudaStream_t)stream);
 }
 int az_mcts_backprop_dev(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
                          const uint8_t *it, const int32_t *sym, void *stream) {
     if (K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "backprop_dev: K must be >= 0");
+    { int rc = enter_dev(h, (cudaStream_t)stream); if (rc) return rc; }
     return do_backprop(h, K, pol, d, p1, p2, ml, it, sym, (cudaStream_t)stream);
 }
 
 int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const az_root *d_roots, int n_playout, void *stream) {
     if (evaluator != AZ_EVAL_UNIFORM && evaluator != AZ_EVAL_ROLLOUT) AZ_FAIL(h, AZ_ERR_INVALID, "unknown evaluator kind %d", evaluator);
     int rc = check_cfg(h, 1); if (rc) return rc;
-    CU(h, cudaSetDevice(h->device));
-    rc = ensure_io(h, h->n); if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
+    rc = enter_dev(h, s); if (rc) return rc;
+    rc = ensure_io(h, h->n); if (rc) return rc;
     h->d.epoch++;                          // one epoch per search() call, like orc_search
     const InLayout L = in_layout((size_t)h->n, h->A);
     uint8_t *q = h->io_in;
@@ -1295,7 +1326,7 @@ int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const az_root *d_roots, i
     return AZ_OK;
 }
 int az_mcts_search(az_mcts *h, int evaluator, const int8_t *boards, const int32_t *turns, int n_playout) {
-    CU(h, cudaSetDevice(h->device));
+    { int rc0 = enter_host(h); if (rc0) return rc0; }
     CU(h, cudaMemcpyAsync(h->io_boards_in, boards, (size_t)h->n * h->S, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->io_turns_in, turns, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
     int rc = az_pack_roots_dev(h->game, h->n, h->io_boards_in, h->io_turns_in, h->io_roots, h->stream); if (rc) AZ_FAIL(h, rc, "pack_roots launch failed");
@@ -1304,7 +1335,7 @@ int az_mcts_search(az_mcts *h, int evaluator, const int8_t *boards, const int32_
 }
 
 int az_mcts_get_counts_dev(az_mcts *h, int32_t *d_out, void *stream) {
-    CU(h, cudaSetDevice(h->device));
+    { int rc = enter_dev(h, (cudaStream_t)stream); if (rc) return rc; }
     if (h->game == GAME_C4) k_counts<C4><<<grid_threads((size_t)h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
     else k_counts<Oth><<<grid_threads((size_t)h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
     h->launches++;
@@ -1312,13 +1343,14 @@ int az_mcts_get_counts_dev(az_mcts *h, int32_t *d_out, void *stream) {
     return AZ_OK;
 }
 int az_mcts_get_counts(az_mcts *h, int32_t *out) {
-    int rc = az_mcts_get_counts_dev(h, h->io_counts, h->stream); if (rc) return rc;
+    int rc = enter_host(h); if (rc) return rc;
+    rc = az_mcts_get_counts_dev(h, h->io_counts, h->stream); if (rc) return rc;
     CU(h, cudaMemcpyAsync(out, h->io_counts, sizeof(int32_t) * (size_t)h->n * h->A, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return AZ_OK;
 }
 int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream) {
-    CU(h, cudaSetDevice(h->device));
+    { int rc = enter_dev(h, (cudaStream_t)stream); if (rc) return rc; }
     if (h->game == GAME_C4) k_root_stats<C4><<<grid_threads((size_t)h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
     else k_root_stats<Oth><<<grid_threads((size_t)h->n), 128, 0, (cudaStream_t)stream>>>(h->d, d_out);
     h->launches++;
@@ -1326,7 +1358,8 @@ int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream) {
     return AZ_OK;
 }
 int az_mcts_get_root_stats(az_mcts *h, float *out) {
-    int rc = az_mcts_get_root_stats_dev(h, h->io_stats, h->stream); if (rc) return rc;
+    int rc = enter_host(h); if (rc) return rc;
+    rc = az_mcts_get_root_stats_dev(h, h->io_stats, h->stream); if (rc) return rc;
     CU(h, cudaMemcpyAsync(out, h->io_stats, sizeof(float) * (size_t)h->n * (6 + 8 * h->A), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return AZ_OK;
