@@ -961,7 +961,7 @@ static int auto_lanes(int game, int n) {
     if (e) { int w = atoi(e); if (w == 1 || w == 2 || w == 4 || w == 8) return w; }
     if (n < 12288) return 8;
     if (n < 24576) return 4;
-    if (n < 98304) return 2;
+    if (n < 49152) return 2;
     return 1;
 }
 

@@ -207,3 +207,26 @@ def test_device_resident_loop_equals_host_buffer_loop(game, mode, K):
     ref_planes = np.stack([(lb == lt[:, None, None]), (lb == -lt[:, None, None]),
                            np.ones_like(lb, dtype=bool) * 0 + lt[:, None, None]], axis=1).astype(np.float32)
     assert np.array_equal(buf.planes[:rows].cpu().numpy(), ref_planes)
+
+
+def test_host_and_device_entry_points_are_stream_ordered():
+    """Host entry points (internal stream) must observe work queued through the *_dev API on the caller's stream and
+    vice versa, without an explicit synchronize from the caller."""
+    import torch
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    n, A = 4096, 7
+    boards, turns = random_positions("Connect4", 64, 10, 3)
+    boards, turns = np.tile(boards, (n // 64, 1, 1)), np.tile(turns, n // 64)
+    e = _cuda("Connect4", n)
+    set_config(e, **SERVER_DEFAULTS)
+    dev = torch.device("cuda", 0)
+    buf = ds.LeafBuffers(n, n * 4, A, (6, 7), dev)
+    for _ in range(3):
+        for i in range(0, n, 997):
+            e.reset_env(i)                                   # async on the internal stream
+        e.prune_roots(np.full(n, -1, np.int32))              # host API: reset everything
+        s = torch.cuda.current_stream().cuda_stream
+        buf.pack_roots(torch.from_numpy(boards).to(dev), torch.from_numpy(turns).to(dev), s)
+        ds.playout_device(e, buf, 100, 4, ds.SyntheticEvaluator("Connect4", "constant"), s)
+        c = e.get_all_counts_array()                         # host API right after device-API work, no sync in between
+        assert (c.sum(axis=1) == 99).all()
