@@ -20,6 +20,12 @@ class AzSearchConfig(C.Structure):
         "score_utility_factor", "score_scale", "value_decay")] + [("use_symmetry", C.c_int32), ("vl_count", C.c_int32)]
 
 
+class AzRoot(C.Structure):
+    """az_root (include/azb200.h): one position as bitboards, 32 bytes."""
+    _fields_ = [("bb0", C.c_uint64), ("bb1", C.c_uint64), ("turn", C.c_int32), ("passes", C.c_int32), ("last", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 def build(force: bool = False) -> str:
     """Compile every CUDA source for sm_100a (nvcc cross-compiles without a GPU)."""
     cmd = ["make", "-C", CSRC] + (["-B"] if force else [])
@@ -74,6 +80,19 @@ def lib() -> C.CDLL:
         "az_game_action_size": [_i], "az_game_board_size": [_i], "az_game_board_rows": [_i], "az_game_board_cols": [_i],
         "az_game_num_symmetries": [_i],
     }
+    _u64 = C.c_uint64
+    sig.update({
+        "az_env_n_pieces": [_i, _vp], "az_env_winner": [_i, _vp], "az_env_full": [_i, _vp], "az_env_done": [_i, _vp],
+        "az_env_valid_moves": [_i, _vp, _vp], "az_env_inverse_symmetry_action": [_i, _i, _i],
+        "az_envs_reset_dev": [_i, _i, _vp, _vp], "az_envs_step_dev": [_i, _i, _vp, _vp, _vp, _vp, _vp],
+        "az_envs_observe_dev": [_i, _i] + [_vp] * 7,
+        "az_envs_rollout_dev": [_i, _i, _u64, _u64, _vp, _vp, _i, _i] + [_vp] * 7,
+    })
+    for name, argt in (("az_env_reset", [_i, _vp]), ("az_env_import", [_i, _vp, _vp]), ("az_env_export", [_i, _vp, _vp]),
+                       ("az_env_step", [_i, _vp, _i]), ("az_env_apply_symmetry", [_i, _vp, _i])):
+        f = getattr(L, name)
+        f.restype = None
+        f.argtypes = argt
     for name, argt in sig.items():
         f = getattr(L, name)
         f.restype = _i

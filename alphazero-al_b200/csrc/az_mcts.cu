@@ -201,7 +201,8 @@ __global__ void k_pack_roots(int n, const int8_t *__restrict__ boards, const int
     } else {
         for (int j = 0; j < 64; ++j) { int v = b[j]; if (v == 1) p0 |= 1ULL << j; else if (v == -1) p1 |= 1ULL << j; }
     }
-    az_root r; r.bb0 = p0; r.bb1 = p1; r.turn = turns[i]; r.reserved[0] = r.reserved[1] = r.reserved[2] = 0;
+    State st; st.bb[0] = p0; st.bb[1] = p1; G::finish_import(st, turns[i]);
+    az_root r; r.bb0 = p0; r.bb1 = p1; r.turn = st.turn; r.passes = st.passes; r.last = st.last; r.reserved = 0;
     st32(roots + i, r);
 }
 template <class G> __device__ __forceinline__ State leaf_state(const az_leaf &L) {

@@ -112,7 +112,9 @@ int az_mcts_get_root_stats(az_mcts *h, float *out);
 typedef struct az_root {     /* a position to search from (import_board + set_turn, BatchedMCTS.h:133-137) */
     uint64_t bb0, bb1;       /* stones of player +1 / -1.  Connect4: bit = col*7 + (5-row); Othello: bit = row*8+col */
     int32_t turn;            /* side to move, +1 / -1 */
-    int32_t reserved[3];
+    int32_t passes;          /* Othello consecutive passes   } used by the env kernels only: the search re-derives them */
+    int32_t last;            /* index of the last mover, -1  } like import_board does (Connect4.h:124-128, Othello.h:108-110) */
+    int32_t reserved;
 } az_root;
 #define AZ_LEAF_TERMINAL 1u
 #define AZ_LEAF_P1_WINS 2u

@@ -242,6 +242,15 @@ def env_rollout(game: str, seed: int, gidx: int, record: bool = True):
     return dict(plies=n, digest=digest.value)
 
 
+def env_rollout_digests(game: str, seed: int, first: int, n: int):
+    """(digests uint64[n], plies int32[n]) of config-2 games [first, first+n) on the C restatement."""
+    L = lib()
+    dig = np.empty(n, np.uint64)
+    pl = np.empty(n, np.int32)
+    L.orc_env_rollout_digests(GAMES[game], C.c_uint64(seed), C.c_uint64(first), C.c_int(n), _p(dig), _p(pl))
+    return dig, pl
+
+
 def ref_available(kind: str = "parity") -> bool:
     d = os.path.join(_HERE, "_ref", kind)
     return os.path.isdir(d) and any(f.startswith("mcts_cpp") for f in os.listdir(d))
@@ -266,6 +275,10 @@ def load_ref(kind: str = "parity"):
         spec = importlib.util.spec_from_file_location(name, os.path.join(d, cand[0]))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
+        sys.modules.setdefault(name, mod)            # lets pickle find the reference's Env classes
+        for sub in ("connect4", "othello", "gomoku"):
+            if hasattr(mod, sub):
+                sys.modules.setdefault(f"{name}.{sub}", getattr(mod, sub))
         mods.append(mod)
     _ref_cache[kind] = tuple(mods)
     return _ref_cache[kind]

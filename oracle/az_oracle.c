@@ -911,3 +911,12 @@ int orc_env_rollout(int g, uint64_t seed, uint64_t gidx, int max_plies, int8_t *
     }
     return ply;
 }
+/* digests of games [first, first+n) - the checksum-of-checksums checker for the 1M-game device run */
+void orc_env_rollout_digests(int g, uint64_t seed, uint64_t first, int n, uint64_t *digests, int32_t *plies) {
+    for (int i = 0; i < n; ++i) {
+        uint64_t d = 0;
+        int p = orc_env_rollout(g, seed, first + (uint64_t)i, g == ORC_C4 ? 42 : 128, NULL, NULL, NULL, NULL, NULL, NULL, &d);
+        digests[i] = d;
+        if (plies) plies[i] = p;
+    }
+}
