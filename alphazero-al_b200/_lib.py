@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
         "az_mcts_search_dev": [_vp, _i, _vp, _vp, _vp],
         "az_pack_roots_dev": [_i, _i, _vp, _vp, _vp, _vp],
         "az_unpack_leaves_dev": [_i, _i] + [_vp] * 11,
+        "az_mcts_set_env_base": [_vp, C.c_uint64], "az_selfplay_layout_for": [_i, _vp],
+        "az_selfplay_ply_dev": [_vp, _vp, _vp, _vp], "az_selfplay_flush_dev": [_vp, _vp],
         "az_mcts_set_lanes": [_vp, _i], "az_mcts_get_lanes": [_vp], "az_mcts_reserve": [_vp, _i],
         "az_mcts_backprop_dev": [_vp, _i] + [_vp] * 8,
         "az_mcts_search_eval_dev": [_vp, _i, _vp, _i, _vp],

@@ -53,6 +53,7 @@ struct C4 {
     static constexpr int NUM_SYM = 2;
     static constexpr int MAX_EDGES = 7;
     static constexpr int MAX_DEPTH = 44; // 42 plies + slack
+    static constexpr int MAX_PLIES = 42; // longest possible game
     static constexpr bool AUX_PLUS_ONE = true, AUX_NEGATE = false;   // Connect4.h:34-35
 
     AZ_HD static void reset(State &s) { s.bb[0] = s.bb[1] = 0; s.turn = 1; s.passes = 0; s.last = -1; }   // :62-72
@@ -120,6 +121,7 @@ struct Oth {
     static constexpr int PASS = 64;
     static constexpr int MAX_EDGES = 48;  // known maximum mobility is 33; three 16-lane passes cover 48
     static constexpr int MAX_DEPTH = 128; // <= 60 placements + interleaved single passes
+    static constexpr int MAX_PLIES = 128;
     static constexpr bool AUX_PLUS_ONE = false, AUX_NEGATE = true;     // Othello.h:31-32
     static constexpr uint64_t NOT_A = 0xFEFEFEFEFEFEFEFEULL, NOT_H = 0x7F7F7F7F7F7F7F7FULL;
 

@@ -87,6 +87,7 @@ struct Dev {   // kernel-visible view of an engine
     int *err;                            // sticky device error flag (arena overflow)
     int n_envs;
     uint64_t seed, epoch;
+    uint64_t env_base;                   // global index of env 0 (RNG keys are sharding-invariant)
 };
 
 constexpr int CTA = 128;
@@ -156,11 +157,11 @@ template <class G> __device__ __forceinline__ float aux_utility(float child_M, f
 // Dirichlet noise: gamma(alpha,1) by Marsaglia-Tsang on the counter-based stream.  (MCTS.h:113-132, 347-363.)
 // RNG-dependent => distributional parity only.
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ double noise_u01(uint64_t seed, int env, uint32_t &ctr) {
-    uint64_t h = az_rand(seed, 0, STREAM_NOISE, (uint64_t)env, ctr++);
+__device__ __noinline__ double noise_u01(uint64_t seed, uint64_t env, uint32_t &ctr) {
+    uint64_t h = az_rand(seed, 0, STREAM_NOISE, env, ctr++);
     return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
-__device__ __noinline__ float gamma_draw(uint64_t seed, int env, uint32_t &ctr, float alpha) {
+__device__ __noinline__ float gamma_draw(uint64_t seed, uint64_t env, uint32_t &ctr, float alpha) {
     double a = alpha, boost = 1.0;
     if (a < 1.0) { boost = pow(noise_u01(seed, env, ctr), 1.0 / a); a += 1.0; }
     double dd = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
@@ -174,7 +175,7 @@ __device__ __noinline__ float gamma_draw(uint64_t seed, int env, uint32_t &ctr, 
     }
     return (float)(dd * boost);
 }
-__device__ __noinline__ void draw_root_noise(uint64_t seed, int env, uint32_t &ctr, float alpha, int ne, float *row) {
+__device__ __noinline__ void draw_root_noise(uint64_t seed, uint64_t env, uint32_t &ctr, float alpha, int ne, float *row) {
     float sum = 0.0f;
     for (int i = 0; i < ne; ++i) { float g = gamma_draw(seed, env, ctr, alpha); row[i] = g; sum += g; }
     float inv = 1.0f / (sum + 1e-8f);
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
         int sym = 0;
         State ex = st;
         if (!leaf_term && cfg.use_symmetry) {
-            const uint64_t h = az_rand(d.seed, d.epoch, STREAM_SYM, (uint64_t)env, (uint64_t)k);
+            const uint64_t h = az_rand(d.seed, d.epoch, STREAM_SYM, d.env_base + (uint64_t)env, (uint64_t)k);
             sym = G::GAME == GAME_C4 ? (int)(h & 1) : ((0x7620 >> (4 * (int)(h & 3))) & 0xF);   // Othello {0,2,6,7}
             G::symmetry(ex, sym);
         }
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
                     // root expansion draws Dirichlet noise when alpha > 0 (MCTS.h:347-363, leaf.parent == -1)
                     float *nrow = d.noise + (size_t)env * d.noise_stride;
                     if (cfg.dirichlet_alpha > 0.0f) {
-                        if (lane == 0) draw_root_noise(d.seed, env, noise_ctr, cfg.dirichlet_alpha, ne, nrow);
+                        if (lane == 0) draw_root_noise(d.seed, d.env_base + (uint64_t)env, noise_ctr, cfg.dirichlet_alpha, ne, nrow);
                         noise_ctr = gshfl<W>(gm, noise_ctr, 0);
                     } else {
                         for (int e = lane; e < ne; e += W) nrow[e] = 0.0f;
@@ -642,7 +643,7 @@ __global__ void k_prune(Dev d, az_search_config cfg, const int32_t *__restrict__
                 const int cne = s.child == NONE ? 0 : (int)(s.child & 63u);
                 if (cfg.dirichlet_alpha > 0.0f && cne > 0) {  // apply_root_noise (MCTS.h:113-132)
                     uint32_t ctr = tr->noise_ctr;
-                    draw_root_noise(d.seed, env, ctr, cfg.dirichlet_alpha, cne, nrow);
+                    draw_root_noise(d.seed, d.env_base + (uint64_t)env, ctr, cfg.dirichlet_alpha, cne, nrow);
                     tr->noise_ctr = ctr;
                 } else {
                     for (int i = 0; i < d.noise_stride; ++i) nrow[i] = 0.0f;   // the promoted node's edges never had noise
@@ -754,7 +755,7 @@ __global__ void k_eval_builtin(Dev d, int kind, int playout, float *__restrict__
         if (w != 0 || G::full(s)) break;
         uint64_t legal = G::legal(s);
         int cnt = popc64(legal), a;
-        uint64_t r = az_rand(d.seed, d.epoch, STREAM_ROLLOUT, (uint64_t)env, ((uint64_t)playout << 8) | step);
+        uint64_t r = az_rand(d.seed, d.epoch, STREAM_ROLLOUT, d.env_base + (uint64_t)env, ((uint64_t)playout << 8) | step);
         if (G::GAME == GAME_OTH && cnt == 0) a = Oth::PASS;
         else {
             int idx = (int)(r % (uint64_t)cnt);
@@ -1164,6 +1165,7 @@ int az_mcts_set_lanes(az_mcts *h, int lanes) {
     return AZ_OK;
 }
 int az_mcts_get_lanes(const az_mcts *h) { return h->W; }
+int az_mcts_set_env_base(az_mcts *h, uint64_t base) { h->d.env_base = base; return AZ_OK; }
 int az_mcts_reserve(az_mcts *h, int slots_per_tree) {
     CU(h, cudaSetDevice(h->device));
     if (slots_per_tree <= 0) AZ_FAIL(h, AZ_ERR_INVALID, "slots_per_tree must be positive");

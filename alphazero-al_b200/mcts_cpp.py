@@ -290,6 +290,10 @@ class _BatchedMCTS:
     def get_lanes(self):
         return self._L.az_mcts_get_lanes(self._h)
 
+    def set_env_base(self, base):
+        """Global index of env 0 (keeps RNG streams sharding-invariant across GPUs)."""
+        self._ck(self._L.az_mcts_set_env_base(self._h, int(base)))
+
     def reserve(self, slots_per_tree):
         self._ck(self._L.az_mcts_reserve(self._h, int(slots_per_tree)))
 

@@ -150,6 +150,9 @@ int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream);
  * fewer replicated instructions; fewer means more warps to hide latency when n_envs is small. */
 int az_mcts_set_lanes(az_mcts *h, int lanes);
 int az_mcts_get_lanes(const az_mcts *h);
+/* Global index of env 0 of this handle: all RNG streams are keyed by (seed, global env index), so a game's result does
+ * not depend on how games are sharded over GPUs. */
+int az_mcts_set_env_base(az_mcts *h, uint64_t base);
 /* Pre-size every tree arena (slots of 32 bytes per tree) so no reallocation happens later (e.g. under graph capture). */
 int az_mcts_reserve(az_mcts *h, int slots_per_tree);
 
