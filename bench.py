@@ -193,6 +193,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-split", action="store_true")
+    ap.add_argument("--no-selfplay", action="store_true")
+    ap.add_argument("--selfplay-slots", type=int, default=16384)
+    ap.add_argument("--selfplay-plies", type=int, default=30)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (Connect4: 1/2/4/8, 0 = auto)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -356,6 +359,45 @@ def main():
                          "ms_per_step": 1e3 * dts,
                          "api": "mcts_cpp.search_batch[_vl]/backprop_batch[_vl] with numpy leaf buffers + numpy evaluator on the host"}
             del engs
+    # ---- self-play games/s: the on-device driver (search + sample + record + env step + re-root + training tuples) ----
+    selfplay = None
+    if not args.no_selfplay:
+        sp_mod = importlib.import_module("alphazero-al_b200.selfplay")
+        n_slots = min(G, args.selfplay_slots)
+        lo, _ = sp_mod.shard_range(world * n_slots, rank, world)
+        sp = sp_mod.SelfPlay("Connect4", n_slots, n_playout, K, ds.SyntheticEvaluator("Connect4", "constant"), search_cfg=SERVER_DEFAULTS,
+                             temperature=1.0, temp_decay_moves=20, temp_endgame=0.0, td_steps=10, seed=0, uid_base=lo,
+                             uid_stride=world * n_slots, device=local_rank, out_capacity=4 * n_slots)
+        sp.engine.reserve(16384)
+        for _ in range(12):                       # reach the steady state of continuously restarting games
+            sp.ply()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        g0, p0 = int(sp.out_count.item()), sp.plies
+        t0 = time.perf_counter()
+        for _ in range(args.selfplay_plies):
+            sp.ply()
+        g1 = int(sp.out_count.item())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        recs = sp.out[:min(g1, sp.out_capacity)]
+        t1 = time.perf_counter()
+        gathered, gcounts = sp_mod.all_gather_records(recs, recs.shape[0], sp.out_capacity)
+        torch.cuda.synchronize()
+        t_gather = time.perf_counter() - t1
+        tot = torch.tensor([g1 - g0, dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            tot[1] = mx[1]
+        games, dt = float(tot[0].item()), float(tot[1].item())
+        selfplay = {"games_per_sec": games / dt, "sims_per_sec": world * n_slots * n_playout * (sp.plies - p0) / dt,
+                    "slots_per_gpu": n_slots, "plies_timed": sp.plies - p0, "games_finished": games,
+                    "record_bytes": sp.layout.record_bytes, "allgather_ms": 1e3 * t_gather, "gathered_records": int(gathered.shape[0]),
+                    "note": "continuous self-play with tree reuse, temp 1 for 20 plies then 0, td_steps 10, constant evaluator; "
+                            "every finished game becomes one packed training record, all-gathered over NCCL when world > 1"}
+        del sp
     clk = clocks.stop() if rank == 0 else None
 
     if rank != 0:
@@ -390,7 +432,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(config, l2="working set (tree arenas touched per step) > 126 MB L2, no flush"),
-            "clocks": clk, "e2e": e2e, "e2e_split_api": e2e_split, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": clk, "e2e": e2e, "e2e_split_api": e2e_split, "selfplay": selfplay, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
