@@ -62,7 +62,7 @@ struct __align__(64) TreeRec {   // per tree: the root's own statistics + alloca
 };
 static_assert(sizeof(TreeRec) == 64, "TreeRec is one 64-byte record");
 
-struct __align__(16) LeafRec {   // what backprop needs to know about a pending leaf (MCTS.h:56-64), un-symmetrised
+struct __align__(16) LeafHead {  // what backprop needs to know about a pending leaf (MCTS.h:56-64), un-symmetrised
     uint64_t bb0, bb1;
     int32_t turn;
     int16_t passes;
@@ -71,7 +71,13 @@ struct __align__(16) LeafRec {   // what backprop needs to know about a pending 
     uint32_t path_len;
     uint32_t sym;                // symmetry id handed to the evaluator for this leaf
 };
-static_assert(sizeof(LeafRec) == 32, "LeafRec is 32 bytes");
+static_assert(sizeof(LeafHead) == 32, "LeafHead is 32 bytes");
+constexpr int PATH8 = 8;
+struct __align__(64) LeafRec {   // head + the first 8 path entries: one 64-byte record gives backprop everything for depth <= 8
+    LeafHead h;
+    uint32_t path8[PATH8];
+};
+static_assert(sizeof(LeafRec) == 64, "LeafRec is 64 bytes");
 static_assert(sizeof(az_root) == 32 && sizeof(az_leaf) == 32, "public records are one sector");
 constexpr uint8_t LF_VALID = 1, LF_VLPENDING = 2, LF_TERM = 4, LF_WIN_P1 = 8, LF_WIN_P2 = 16;
 
@@ -411,12 +417,12 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
         if (lane == 0) {
             const uint8_t tflags = (uint8_t)(leaf_term ? (AZ_LEAF_TERMINAL | ((cur.meta & F_WIN_P1) ? AZ_LEAF_P1_WINS : 0u) |
                                                           ((cur.meta & F_WIN_P2) ? AZ_LEAF_P2_WINS : 0u)) : 0u);
-            LeafRec L;     // remembered for backprop
+            LeafHead L;    // remembered for backprop
             L.bb0 = st.bb[0]; L.bb1 = st.bb[1]; L.turn = st.turn; L.passes = (int16_t)st.passes; L.last = (int8_t)st.last;
             L.flags = (uint8_t)(LF_VALID | ((VL && plen > 0) ? LF_VLPENDING : 0) | (leaf_term ? LF_TERM : 0) |
                                 ((tflags & AZ_LEAF_P1_WINS) ? LF_WIN_P1 : 0) | ((tflags & AZ_LEAF_P2_WINS) ? LF_WIN_P2 : 0));
             L.path_len = plen; L.sym = (uint32_t)sym;
-            st32(VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env, L);
+            st32(&(VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env)->h, L);
             az_leaf P;     // handed to the evaluator
             P.bb0 = ex.bb[0]; P.bb1 = ex.bb[1]; P.turn = (int8_t)st.turn; P.flags = tflags; P.sym = (uint8_t)sym; P.passes = (uint8_t)st.passes;
             P.reserved[0] = P.reserved[1] = P.reserved[2] = 0;
@@ -440,7 +446,7 @@ __device__ __forceinline__ void remove_vl_group(const Dev &d, const az_search_co
                                                 Slot *arena, Slot &root) {
     const int vl = cfg.vl_count;
     for (int k = 0; k < K; ++k) {
-        LeafRec *L = d.leaf_vl + (size_t)env * d.kcap + k;
+        LeafHead *L = &(d.leaf_vl + (size_t)env * d.kcap + k)->h;
         const uint8_t fl = L->flags;
         if (!(fl & LF_VLPENDING)) continue;
         const uint32_t plen = L->path_len;
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
     gsync<W>(gm);
 
     for (int k = 0; k < K; ++k) {
-        const LeafRec L = ld32(VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env);
+        const LeafHead L = ld32(&(VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env)->h);
         if (!(L.flags & LF_VALID)) continue;             // current_leaf_idx == -1 (MCTS.h:409,599)
         const size_t flat = (size_t)env * K + k;
         const bool term = is_term ? (is_term[flat] != 0) : ((L.flags & LF_TERM) != 0);
@@ -601,6 +607,327 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
     if (d.stats && lane == 0) { atomicAdd(d.stats + 3, st_created); atomicAdd(d.stats + 4, st_expanded); }
 }
 
+// ================================================================================================
+// Thread-per-tree variants (Connect4, lanes = 1) for large batches.
+//
+// With one thread per tree every warp instruction serves 32 trees, but naive per-thread loads of a tree's
+// 224-byte node block touch 32 different cache lines per instruction (L1TEX wavefront bound).  k_select_t
+// therefore gathers the 32 node blocks of a warp COOPERATIVELY: instruction i moves the 16-byte chunks of trees
+// 2i and 2i+1 with consecutive lanes on consecutive chunks (2-4 lines per instruction instead of 32), stages
+// them in shared memory (272-byte rows: conflict-free for 16-byte accesses), and each lane then reads its own
+// block from shared memory.  The arithmetic is the same as k_select's, so results are bit-identical.
+// ================================================================================================
+template <class G, bool VL>
+__global__ void __launch_bounds__(CTA, 4) k_select_t(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
+                                                  az_leaf *__restrict__ leaves) {
+    constexpr int NE = G::MAX_EDGES;       // 7
+    constexpr int ROW = 17;                // uint4 per staged tree (16 + 1 pad)
+    __shared__ uint4 stage[CTA / 32][32][ROW];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int tid = blockIdx.x * CTA + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool valid = tid < d.n_envs;
+    const int env = valid ? tid : d.n_envs - 1;        // clamped: inactive lanes only help with the gather
+    Slot *arena = d.pool + (size_t)env * d.cap;
+    TreeRec *tr = d.trees + env;
+    const int vl = VL ? cfg.vl_count : 0;
+    const bool use_aux = aux_enabled<G>(cfg);
+    const float ne_eps = cfg.noise_epsilon;
+
+    State start;
+    { const az_root r = ld32(roots + env); start.bb[0] = r.bb0; start.bb[1] = r.bb1; G::finish_import(start, r.turn); }
+    Slot root = ld_slot(&tr->root);
+    const uint32_t root_meta_in = root.meta;
+    float nz[NE];                           // the root's Dirichlet noise, read once
+#pragma unroll
+    for (int e = 0; e < NE; ++e) nz[e] = ne_eps > 0.0f ? d.noise[(size_t)env * d.noise_stride + e] : 0.0f;
+    unsigned long long st_depth = 0, st_edges = 0;
+
+    for (int k = 0; k < K; ++k) {
+        State st = start;
+        Slot cur = root;
+        bool is_root = true, root_vl = false;
+        uint32_t plen = 0;
+        uint32_t *path = VL ? d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH : d.path_nv + (size_t)env * G::MAX_DEPTH;
+        uint32_t p8[PATH8];
+#pragma unroll
+        for (int j = 0; j < PATH8; ++j) p8[j] = 0;
+        int winner = 0; bool full = false;
+        uint32_t last_slot = 0;
+        bool descending = valid && cur.child != NONE && !(cur.meta & F_TERM) && (cur.child & 63u) != 0;
+
+        while (__any_sync(FULL, descending)) {
+            // ---- cooperative gather of the warp's node blocks into shared memory ----
+            const int ne = descending ? (int)(cur.child & 63u) : 0;
+            const uint32_t off = descending ? (cur.child >> 6) : 0u;
+            // 32-byte aligned block address with the chunk count packed into its low bits
+            const unsigned long long src = (unsigned long long)(uintptr_t)(arena + off) | (unsigned long long)(2 * ne);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int t = 2 * i + (lane >> 4), part = lane & 15;
+                const uint32_t lo = __shfl_sync(FULL, (uint32_t)src, t), hi = __shfl_sync(FULL, (uint32_t)(src >> 32), t);
+                const int n_t = (int)(lo & 31u);
+                if (part < n_t) {     // asynchronous 16-byte global->shared copy: all 16 rounds are in flight together
+                    const uint4 *gp = reinterpret_cast<const uint4 *>((uintptr_t)(((unsigned long long)hi << 32) | (lo & ~31u))) + part;
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(&stage[warp][t][part]);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gp) : "memory");
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            if (descending) {
+                Slot s[NE];
+#pragma unroll
+                for (int c = 0; c < NE; ++c) {
+                    if (c < ne) {
+                        const uint4 a = stage[warp][lane][2 * c], b = stage[warp][lane][2 * c + 1];
+                        s[c].prior = __uint_as_float(a.x); s[c].n = (int)a.y; s[c].meta = a.z; s[c].child = a.w;
+                        s[c].wd = __uint_as_float(b.x); s[c].wp1 = __uint_as_float(b.y); s[c].wp2 = __uint_as_float(b.z); s[c].msum = __uint_as_float(b.w);
+                    } else { s[c].prior = 0.f; s[c].n = 0; s[c].meta = 0; s[c].child = NONE; s[c].wd = s[c].wp1 = s[c].wp2 = s[c].msum = 0.f; }
+                }
+                st_edges += (unsigned long long)ne;
+                // ---- compute_fpu (MCTS.h:140-156) ----
+                const int cur_infl = (int)(cur.meta & INFL_MASK);
+                const float parent_q = mean_q(cur.n, cur.wp1, cur.wp2, (cur.meta & F_TURN_P1) != 0);
+                float seen_policy = 0.0f;
+#pragma unroll
+                for (int c = 0; c < NE; ++c) seen_policy += (c < ne && s[c].n > 0) ? s[c].prior : 0.0f;   // + 0.0f is exact
+                const float fscale = (1.0f + parent_q) / 2.0f;
+                const float eff_fpu = cfg.fpu_reduction * fscale;
+                float fpu = parent_q - eff_fpu * sqrtf(seen_policy);
+                fpu = (-1.0f < fpu) ? fpu : -1.0f;
+                // ---- select_edge (MCTS.h:163-234) ----
+                const int pn_i = cur.n + cur_infl;
+                const float parent_n = (float)pn_i;
+                const float parent_M = use_aux ? mean_m(cur.n, cur.msum) : 0.0f;
+                const float lg = (pn_i >= 0 && pn_i < d.log_lut_n) ? d.log_lut[pn_i] : logf((parent_n + cfg.c_base + 1.0f) / cfg.c_base);
+                const float c_puct = cfg.c_init + lg;
+                const float sqrt_pn = sqrtf(parent_n);
+                const bool mix_noise = is_root && ne_eps > 0.0f;
+                float best_s = -INFINITY; int best_e = -1;
+#pragma unroll
+                for (int c = 0; c < NE; ++c) {
+                    if (c >= ne) continue;
+                    float eff_prior = s[c].prior;
+                    if (mix_noise) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * nz[c];
+                    const int cn = s[c].n, cinf = (int)(s[c].meta & INFL_MASK);
+                    float q_value = fpu, m_utility = 0.0f; int visits = cinf;
+                    if (cn > 0) {
+                        visits = cn + cinf;
+                        const float child_Q = mean_q(cn, s[c].wp1, s[c].wp2, (s[c].meta & F_TURN_P1) != 0);
+                        q_value = -child_Q;
+                        if (use_aux) {
+                            float child_M = mean_m(cn, s[c].msum);
+                            if (G::AUX_NEGATE) child_M = -child_M;
+                            m_utility = aux_utility<G>(child_M, parent_M, child_Q, cfg);
+                        }
+                    }
+                    const float u_score = c_puct * eff_prior * sqrt_pn / (1.0f + (float)visits);
+                    const float score = q_value + u_score + m_utility;
+                    if (score > best_s) { best_s = score; best_e = c; }
+                }
+                if (best_e < 0) descending = false;
+                else {
+                    if (VL && !root_vl) { root_vl = true; root.meta += (uint32_t)vl; }
+                    Slot ch = s[0];
+#pragma unroll
+                    for (int c = 1; c < NE; ++c) if (best_e == c) ch = s[c];
+                    G::step(st, (int)((ch.meta >> 16) & 0xFFu));
+                    uint32_t nmeta = ch.meta;
+                    if (!(nmeta & F_ALLOC)) {
+                        nmeta |= F_ALLOC;
+                        nmeta = st.turn == 1 ? (nmeta | F_TURN_P1) : (nmeta & ~F_TURN_P1);
+                    }
+                    nmeta += (uint32_t)vl;
+                    winner = G::winner(st);
+                    full = G::full(st);
+                    const bool term_now = winner != 0 || full;
+                    if (term_now) nmeta = (nmeta & ~(F_WIN_P1 | F_WIN_P2)) | F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+                    last_slot = off + (uint32_t)best_e;
+                    if (nmeta != ch.meta) arena[last_slot].meta = nmeta;
+                    path[plen] = last_slot;
+#pragma unroll
+                    for (int j = 0; j < PATH8; ++j) if (plen == (uint32_t)j) p8[j] = last_slot;
+                    ++plen;
+                    cur = ch; cur.meta = nmeta; is_root = false;
+                    descending = !term_now && cur.child != NONE && !(cur.meta & F_TERM) && (cur.child & 63u) != 0 && plen < (uint32_t)G::MAX_DEPTH;
+                }
+            }
+            __syncwarp();      // the staging rows are reused by the next level
+        }
+        if (valid) {
+            st_depth += plen;
+            bool leaf_term = (cur.meta & F_TERM) != 0;
+            if (plen == 0) leaf_term = (root.meta & F_TERM) != 0;
+            if (!leaf_term) {
+                if (winner == 0 && !full) { winner = G::winner(st); full = G::full(st); }
+                if (winner != 0 || full) {
+                    leaf_term = true;
+                    const uint32_t tf = F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+                    if (plen == 0) { root.meta = (root.meta & ~(F_WIN_P1 | F_WIN_P2)) | tf; cur.meta = root.meta; }
+                    else { cur.meta = (cur.meta & ~(F_WIN_P1 | F_WIN_P2)) | tf; arena[last_slot].meta = cur.meta; }
+                }
+            }
+            int sym = 0;
+            State ex = st;
+            if (!leaf_term && cfg.use_symmetry) {
+                const uint64_t h = az_rand(d.seed, d.epoch, STREAM_SYM, d.env_base + (uint64_t)env, (uint64_t)k);
+                sym = (int)(h & 1);
+                G::symmetry(ex, sym);
+            }
+            const uint8_t tflags = (uint8_t)(leaf_term ? (AZ_LEAF_TERMINAL | ((cur.meta & F_WIN_P1) ? AZ_LEAF_P1_WINS : 0u) |
+                                                          ((cur.meta & F_WIN_P2) ? AZ_LEAF_P2_WINS : 0u)) : 0u);
+            LeafRec R;
+            R.h.bb0 = st.bb[0]; R.h.bb1 = st.bb[1]; R.h.turn = st.turn; R.h.passes = (int16_t)st.passes; R.h.last = (int8_t)st.last;
+            R.h.flags = (uint8_t)(LF_VALID | ((VL && plen > 0) ? LF_VLPENDING : 0) | (leaf_term ? LF_TERM : 0) |
+                                  ((tflags & AZ_LEAF_P1_WINS) ? LF_WIN_P1 : 0) | ((tflags & AZ_LEAF_P2_WINS) ? LF_WIN_P2 : 0));
+            R.h.path_len = plen; R.h.sym = (uint32_t)sym;
+#pragma unroll
+            for (int j = 0; j < PATH8; ++j) R.path8[j] = p8[j];
+            LeafRec *dst = VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env;
+            st32(&dst->h, R.h);
+            uint4 *pq = reinterpret_cast<uint4 *>(dst->path8);
+            pq[0] = make_uint4(p8[0], p8[1], p8[2], p8[3]); pq[1] = make_uint4(p8[4], p8[5], p8[6], p8[7]);
+            az_leaf P;
+            P.bb0 = ex.bb[0]; P.bb1 = ex.bb[1]; P.turn = (int8_t)st.turn; P.flags = tflags; P.sym = (uint8_t)sym; P.passes = (uint8_t)st.passes;
+            P.reserved[0] = P.reserved[1] = P.reserved[2] = 0;
+            st32(leaves + (size_t)env * K + k, P);
+        }
+    }
+    if (valid && root.meta != root_meta_in) tr->root.meta = root.meta;
+    if (d.stats && valid) {
+        atomicAdd(d.stats + 0, (unsigned long long)K);
+        atomicAdd(d.stats + 1, st_depth);
+        atomicAdd(d.stats + 2, st_edges);
+    }
+}
+
+// Thread-per-tree back-propagation.  The virtual loss of path k is removed in the same read-modify-write that adds
+// simulation k's result to each node (the order is unobservable: nothing in back-prop reads in-flight counts, and
+// by the end of the kernel every pending loss is gone, exactly as after remove_all_vl + K backprop_vl calls).  The
+// first 8 path entries travel inside the 64-byte LeafRec, and path nodes are updated four at a time so their loads
+// overlap instead of forming a dependent chain.
+template <class G, bool VL>
+__global__ void __launch_bounds__(CTA, 4) k_backprop_t(Dev d, az_search_config cfg, int K, int removeK, int use_sym, const float *__restrict__ policy,
+                                                    const float *__restrict__ dv, const float *__restrict__ p1v, const float *__restrict__ p2v,
+                                                    const float *__restrict__ mlv, const uint8_t *__restrict__ is_term,
+                                                    const int32_t *__restrict__ sym_ids) {
+    static_assert(G::GAME == GAME_C4, "thread-per-tree back-prop is specialised for Connect4 (terminal aux = 0, <= 7 edges)");
+    const int env = blockIdx.x * CTA + threadIdx.x;
+    if (env >= d.n_envs) return;
+    constexpr int A = G::A;
+    Slot *arena = d.pool + (size_t)env * d.cap;
+    TreeRec *tr = d.trees + env;
+    Slot root = ld_slot(&tr->root);
+    uint32_t bump = tr->bump, noise_ctr = tr->noise_ctr;
+    const int vl = cfg.vl_count;
+    unsigned long long st_created = 0, st_expanded = 0;
+    LeafRec *recs = VL ? d.leaf_vl + (size_t)env * d.kcap : d.leaf_nv + env;
+    for (int k = 0; k < K; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + k));
+
+    for (int k = 0; k < K; ++k) {
+        LeafRec *rp = recs + k;
+        const LeafHead L = ld32(&rp->h);
+        if (!(L.flags & LF_VALID)) continue;
+        uint32_t p8[PATH8];
+        { const uint4 *pq = reinterpret_cast<const uint4 *>(rp->path8); const uint4 a = pq[0], b = pq[1];
+          p8[0] = a.x; p8[1] = a.y; p8[2] = a.z; p8[3] = a.w; p8[4] = b.x; p8[5] = b.y; p8[6] = b.z; p8[7] = b.w; }
+        const size_t flat = (size_t)env * K + k;
+        const bool term = is_term ? (is_term[flat] != 0) : ((L.flags & LF_TERM) != 0);
+        const uint32_t plen = L.path_len;
+        const uint32_t *path = VL ? d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH : d.path_nv + (size_t)env * G::MAX_DEPTH;
+        const bool pending = VL && (L.flags & LF_VLPENDING) && k < removeK;
+        const uint32_t dec = pending ? (uint32_t)vl : 0u;
+        State st; st.bb[0] = L.bb0; st.bb[1] = L.bb1; st.turn = L.turn; st.passes = L.passes; st.last = L.last;
+        auto path_at = [&](uint32_t j) -> uint32_t {             // j-th path entry (0 = first edge below the root)
+            uint32_t v = p8[0];
+#pragma unroll
+            for (int q = 1; q < PATH8; ++q) if (j == (uint32_t)q) v = p8[q];
+            return j < (uint32_t)PATH8 ? v : path[j];
+        };
+        if (pending) { const int infl = (int)(root.meta & INFL_MASK) - vl; root.meta = (root.meta & ~INFL_MASK) | (uint32_t)max(infl, 0); }
+        Slot leaf = root; Slot *leaf_ptr = nullptr;
+        if (plen > 0) { leaf_ptr = arena + path_at(plen - 1); leaf = ld_slot(leaf_ptr); }
+
+        // ---- expand_leaf (MCTS.h:329-375) ----
+        if (!term && (!VL || leaf.child == NONE)) {
+            const int sym = use_sym ? (sym_ids ? sym_ids[flat] : (int)L.sym) : 0;
+            const uint64_t legal = G::legal(st);
+            const int ne = popc64(legal);
+            const float *prow = policy + flat * A;
+            float pm[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) pm[a] = prow[G::sym_action(sym, a)];
+            float psum = 0.0f;
+#pragma unroll
+            for (int a = 0; a < A; ++a) psum += ((legal >> a) & 1ULL) ? pm[a] : 0.0f;     // ascending legal order; + 0.0f exact
+            const float denom = psum + 1e-8f;
+            if (bump + (uint32_t)ne > d.cap) atomicExch(d.err, 1);
+            else {
+                const uint32_t off = bump;
+                Slot ns; ns.n = 0; ns.child = NONE; ns.wd = ns.wp1 = ns.wp2 = ns.msum = 0.0f;
+                int eidx = 0;
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    if (!((legal >> a) & 1ULL)) continue;
+                    ns.prior = pm[a] / denom;
+                    ns.meta = (uint32_t)a << 16;
+                    st_slot(arena + off + eidx, ns);
+                    ++eidx;
+                }
+                bump += (uint32_t)ne;
+                leaf.child = (off << 6) | (uint32_t)ne;
+                if (plen == 0) {
+                    float *nrow = d.noise + (size_t)env * d.noise_stride;
+                    if (cfg.dirichlet_alpha > 0.0f) draw_root_noise(d.seed, d.env_base + (uint64_t)env, noise_ctr, cfg.dirichlet_alpha, ne, nrow);
+                    else for (int e = 0; e < ne; ++e) nrow[e] = 0.0f;
+                }
+                st_created += (unsigned long long)ne; st_expanded += 1;
+            }
+        }
+        // ---- propagate (MCTS.h:381-402) fused with the removal of this path's virtual loss ----
+        float wd = dv[flat], w1 = p1v[flat], w2 = p2v[flat];
+        float ml = term ? 0.0f : mlv[flat];                       // Connect4 terminal_aux = 0
+        const float gamma = cfg.value_decay;
+        const bool decay = gamma < 1.0f;
+        const float u3 = 1.0f / 3.0f;
+        auto advance = [&]() {
+            if (G::AUX_PLUS_ONE) ml += 1.0f;
+            if (G::AUX_NEGATE) ml = -ml;
+            if (decay) { wd = gamma * wd + (1 - gamma) * u3; w1 = gamma * w1 + (1 - gamma) * u3; w2 = gamma * w2 + (1 - gamma) * u3; }
+        };
+        auto apply = [&](Slot &s) {
+            s.n += 1; s.wd += wd; s.wp1 += w1; s.wp2 += w2; s.msum += ml;
+            const int infl = (int)(s.meta & INFL_MASK) - (int)dec;
+            s.meta = (s.meta & ~INFL_MASK) | (uint32_t)max(infl, 0);
+        };
+        if (plen == 0) {                                          // the leaf is the root
+            root.child = leaf.child;
+            root.n += 1; root.wd += wd; root.wp1 += w1; root.wp2 += w2; root.msum += ml;
+        } else {
+            apply(leaf);
+            st_slot(leaf_ptr, leaf);
+            advance();
+            uint32_t t = 1;                                       // t-th node counted from the leaf
+            while (t < plen) {
+                const uint32_t cnt = min(4u, plen - t);
+                Slot *sp[4]; Slot sv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if ((uint32_t)q < cnt) sp[q] = arena + path_at(plen - 1 - (t + q));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if ((uint32_t)q < cnt) sv[q] = ld_slot(sp[q]);       // independent loads in flight together
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if ((uint32_t)q < cnt) { apply(sv[q]); st_slot(sp[q], sv[q]); advance(); }
+                t += cnt;
+            }
+            root.n += 1; root.wd += wd; root.wp1 += w1; root.wp2 += w2; root.msum += ml;
+        }
+        if (pending) rp->h.flags = (uint8_t)(L.flags & ~LF_VLPENDING);
+    }
+    st_slot(&tr->root, root); tr->bump = bump; tr->noise_ctr = noise_ctr;
+    if (d.stats) { atomicAdd(d.stats + 3, st_created); atomicAdd(d.stats + 4, st_expanded); }
+}
+
 // remove_all_vl without backprop (BatchedMCTS.h:209-216)
 template <class G, int W>
 __global__ void __launch_bounds__(CTA) k_remove_vl(Dev d, az_search_config cfg, int K) {
@@ -661,7 +988,7 @@ __global__ void k_reset(Dev d, int env /* -1 = all */) {
 }
 __global__ void k_init_leaf(LeafRec *leaf, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) { leaf[i].flags = 0; leaf[i].path_len = 0; leaf[i].sym = 0; }
+    if (i < n) { leaf[i].h.flags = 0; leaf[i].h.path_len = 0; leaf[i].h.sym = 0; }
 }
 __global__ void k_max_bump(Dev d, unsigned int *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -738,7 +1065,7 @@ __global__ void k_eval_builtin(Dev d, int kind, int playout, float *__restrict__
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= d.n_envs) return;
     float *prow = policy + (size_t)env * G::A;
-    const LeafRec L = ld32(d.leaf_nv + env);
+    const LeafHead L = ld32(&d.leaf_nv[env].h);
     mlv[env] = 0.0f;
     if (L.flags & LF_TERM) {
         for (int a = 0; a < G::A; ++a) prow[a] = 0.0f;
@@ -981,6 +1308,12 @@ static int auto_lanes(int game, int n) {
 
 static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s) {
     const int g = grid_groups(h->n, h->W);
+    if (h->game == GAME_C4 && h->W == 1) {       // thread-per-tree kernels with cooperative block gather
+        if (vl) k_select_t<C4, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, roots, leaves);
+        else k_select_t<C4, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, roots, leaves);
+        h->launches++;
+        return;
+    }
     if (vl) AZ_DISPATCH_W(h, k_select, true, g, s, h->d, h->cfg, K, roots, leaves);
     else AZ_DISPATCH_W(h, k_select, false, g, s, h->d, h->cfg, 1, roots, leaves);
     h->launches++;
@@ -988,6 +1321,12 @@ static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_l
 static void launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym, const float *pol, const float *d, const float *p1,
                             const float *p2, const float *ml, const uint8_t *it, const int32_t *sym, cudaStream_t s) {
     const int g = grid_groups(h->n, h->W);
+    if (h->game == GAME_C4 && h->W == 1) {
+        if (vl) k_backprop_t<C4, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, removeK, use_sym, pol, d, p1, p2, ml, it, sym);
+        else k_backprop_t<C4, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, 0, use_sym, pol, d, p1, p2, ml, it, sym);
+        h->launches++;
+        return;
+    }
     if (vl) AZ_DISPATCH_W(h, k_backprop, true, g, s, h->d, h->cfg, K, removeK, use_sym, pol, d, p1, p2, ml, it, sym);
     else AZ_DISPATCH_W(h, k_backprop, false, g, s, h->d, h->cfg, 1, 0, use_sym, pol, d, p1, p2, ml, it, sym);
     h->launches++;
