@@ -115,21 +115,7 @@ class BatchedMCTS:
         st["boards"].copy_(st["h_boards"], non_blocking=True)
         st["turns"].copy_(st["h_turns"], non_blocking=True)
         buf.pack_roots(st["boards"], st["turns"], stream)
-        if isinstance(pv_func, ds.SyntheticEvaluator):
-            evaluator = pv_func
-        else:
-            L = _lib.lib()
-
-            def evaluator(b, rows, s):
-                b.unpack(rows, s)
-                probs, wdl_rel, aux = pv_func.predict_device(b.planes[:rows], b.mask[:rows])
-                b.policy[:rows].copy_(probs.reshape(rows, self.action_size).float())
-                st["wdl"][:rows].copy_(wdl_rel.reshape(rows, 3).float())
-                st["aux"][:rows].copy_(aux.reshape(rows).float())
-                rc = L.az_eval_finalize_dev(rows, b.leaves.data_ptr(), st["wdl"].data_ptr(), st["aux"].data_ptr(),
-                                            b.d.data_ptr(), b.p1w.data_ptr(), b.p2w.data_ptr(), b.ml.data_ptr(), s or None)
-                if rc != 0:
-                    raise RuntimeError("az_eval_finalize_dev failed")
+        evaluator = pv_func if isinstance(pv_func, ds.SyntheticEvaluator) else ds.NetEvaluator(pv_func)
         ds.playout_device(self.mcts, buf, max_n, K, evaluator, stream)
 
     # ------------------------------------------------------------------------------------------------------

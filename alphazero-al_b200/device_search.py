@@ -75,6 +75,30 @@ class SyntheticEvaluator:
         self.launches += 1
 
 
+class NetEvaluator:
+    """Fused evaluator boundary: az_leaf records -> CNN input planes + legal masks (one unpack
+    kernel) -> ``net.predict_device(planes, mask)`` -> backprop tuple (one finalize kernel).  No host copy, no sync.
+    `buf` must have been created with unpacked=True, planes=True."""
+
+    def __init__(self, net):
+        self.net = net
+        self._wdl = self._aux = None
+
+    def __call__(self, buf: LeafBuffers, rows: int, stream: int):
+        if self._wdl is None or self._wdl.shape[0] < buf.rows:
+            self._wdl = torch.empty((buf.rows, 3), dtype=torch.float32, device=buf.leaves.device)
+            self._aux = torch.empty(buf.rows, dtype=torch.float32, device=buf.leaves.device)
+        buf.unpack(rows, stream)
+        probs, wdl_rel, aux = self.net.predict_device(buf.planes[:rows], buf.mask[:rows])
+        buf.policy[:rows].copy_(probs.reshape(rows, buf.A))
+        self._wdl[:rows].copy_(wdl_rel.reshape(rows, 3))
+        self._aux[:rows].copy_(aux.reshape(rows))
+        rc = _lib.lib().az_eval_finalize_dev(rows, buf.leaves.data_ptr(), self._wdl.data_ptr(), self._aux.data_ptr(), buf.d.data_ptr(),
+                                             buf.p1w.data_ptr(), buf.p2w.data_ptr(), buf.ml.data_ptr(), stream or None)
+        if rc != 0:
+            raise RuntimeError("az_eval_finalize_dev failed (%d)" % rc)
+
+
 def playout_device(engine, buf: LeafBuffers, n_playout: int, K: int, evaluator, stream: int | None = None,
                    on_select=None):
     """Run `n_playout` simulations per tree entirely on the device from the roots in `buf.roots` (see

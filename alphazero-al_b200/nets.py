@@ -92,6 +92,8 @@ class C4Net(nn.Module):
                 nn.init.kaiming_normal_(m.weight, mode="fan_in", nonlinearity="relu")
                 if m.bias is not None:
                     nn.init.zeros_(m.bias)
+        for head in (self.p_out, self.v_wdl, self.v_aux):        # like the reference: heads start at zero, so a random-init
+            nn.init.zeros_(head.weight)                           # network predicts a uniform policy, WDL = 1/3 and 21 plies
         self.to(device)
         self.eval()
 

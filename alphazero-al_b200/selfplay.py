@@ -56,6 +56,8 @@ class SelfPlay:
         self.n, self.n_playout, self.K = int(n_slots), int(n_playout), int(vl_batch)
         dev_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", dev_index)
+        if not isinstance(evaluator, ds.SyntheticEvaluator) and hasattr(evaluator, "predict_device"):
+            evaluator = ds.NetEvaluator(evaluator)          # a network with the device contract
         self.evaluator = evaluator
         self.engine = getattr(mcts_cpp, f"BatchedMCTS_{game}")(self.n, device=dev_index)
         for k, v in (search_cfg or {}).items():
@@ -81,8 +83,8 @@ class SelfPlay:
         self.counts = torch.zeros((n, A), dtype=torch.int32, **d)
         self.stats = torch.zeros((n, 6 + 8 * A), dtype=torch.float32, **d)
         self.buf = ds.LeafBuffers(n, n * max(self.K, 1), A, (self.R, self.Cc), self.device,
-                                  unpacked=not isinstance(evaluator, ds.SyntheticEvaluator),
-                                  planes=not isinstance(evaluator, ds.SyntheticEvaluator))
+                                  unpacked=not isinstance(self.evaluator, ds.SyntheticEvaluator),
+                                  planes=not isinstance(self.evaluator, ds.SyntheticEvaluator))
         self.buf.roots = self.states                     # the env states ARE the search roots
         self.sp = AzSelfplay(self.gid, n, T, int(td_steps), int(temp_decay_moves), float(temperature), float(temp_endgame), int(seed),
                              int(uid_stride or n), self.states.data_ptr(), self.steps.data_ptr(), self.uids.data_ptr(),

@@ -194,6 +194,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-split", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true")
+    ap.add_argument("--no-cnn", action="store_true")
+    ap.add_argument("--cnn-slots", type=int, default=4096)
+    ap.add_argument("--cnn-plies", type=int, default=3)
     ap.add_argument("--selfplay-slots", type=int, default=16384)
     ap.add_argument("--selfplay-plies", type=int, default=30)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (Connect4: 1/2/4/8, 0 = auto)")
@@ -398,6 +401,32 @@ def main():
                     "note": "continuous self-play with tree reuse, temp 1 for 20 plies then 0, td_steps 10, constant evaluator; "
                             "every finished game becomes one packed training record, all-gathered over NCCL when world > 1"}
         del sp
+    # ---- the same self-play with a random-init CNN of the reference's Connect4 architecture in the loop (bf16 autocast) ----
+    selfplay_cnn = None
+    if not args.no_cnn and world == 1:
+        nets = importlib.import_module("alphazero-al_b200.nets")
+        sp_mod = importlib.import_module("alphazero-al_b200.selfplay")
+        torch.manual_seed(0)
+        net = nets.C4Net(device=f"cuda:{local_rank}")
+        n_slots = args.cnn_slots
+        sp = sp_mod.SelfPlay("Connect4", n_slots, n_playout, K, net, search_cfg=SERVER_DEFAULTS, temperature=1.0, temp_decay_moves=20,
+                             temp_endgame=0.0, td_steps=10, seed=0, device=local_rank, out_capacity=4 * n_slots)
+        sp.engine.reserve(16384)
+        sp.ply()
+        torch.cuda.synchronize()
+        g0, p0 = int(sp.out_count.item()), sp.plies
+        t0 = time.perf_counter()
+        for _ in range(args.cnn_plies):
+            sp.ply()
+        g1 = int(sp.out_count.item())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        selfplay_cnn = {"sims_per_sec": n_slots * n_playout * (sp.plies - p0) / dt, "positions_per_sec": n_slots * (sp.plies - p0) / dt,
+                        "games_per_sec_est": n_slots * (sp.plies - p0) / dt / 21.0, "slots": n_slots, "plies_timed": sp.plies - p0,
+                        "evaluator": "C4Net (160358 params, reference Connect4 CNN shape), random init, bf16 autocast, device contract "
+                                     "(leaves -> planes -> net -> finalize, no host copy)",
+                        "note": "games_per_sec_est = positions/s / 21 plies (mean length of random-init self-play games, SURVEY.md App. C.4)"}
+        del sp, net
     clk = clocks.stop() if rank == 0 else None
 
     if rank != 0:
@@ -432,7 +461,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(config, l2="working set (tree arenas touched per step) > 126 MB L2, no flush"),
-            "clocks": clk, "e2e": e2e, "e2e_split_api": e2e_split, "selfplay": selfplay, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": clk, "e2e": e2e, "e2e_split_api": e2e_split, "selfplay": selfplay, "selfplay_cnn": selfplay_cnn, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -281,5 +281,6 @@ def test_cnn_in_the_loop_visit_distribution_l1():
     playout(ref_engine, host_eval, boards, turns, npl, K)
     theirs = counts(ref_engine, n, 7).astype(np.float64)
     l1 = np.abs(mine / mine.sum(1, keepdims=True) - theirs / theirs.sum(1, keepdims=True)).sum(1)
-    assert l1.max() <= 1e-3 + 1e-12 or np.mean(l1 == 0) > 0.9, f"max L1 {l1.max()}, {np.mean(l1 == 0):.2f} trees identical"
-    assert np.median(l1) <= 1e-3
+    print(f"CNN-in-the-loop: max L1 {l1.max():.4g}, mean L1 {l1.mean():.4g}, {np.mean(l1 == 0):.3f} of trees identical")
+    # one visit moved between two actions is already L1 = 2/199; the tolerance is on the distribution over the batch
+    assert np.mean(l1 <= 1e-3) >= 0.95 and l1.mean() <= 1e-3, f"max L1 {l1.max()}, mean {l1.mean()}"
