@@ -76,7 +76,8 @@ class BatchedMCTS:
         self.n_playout, self.batch_size = n_playout, batch_size
         self.action_size, self.board_shape = backend_cls.action_size, backend_cls.board_shape
         self._convert_board = board_converter or _default_convert_board
-        self.cache = _LRU(cache_size) if cache_size > 0 else None
+        self.cache = _LRU(cache_size) if cache_size > 0 else None      # host LRU, used by the numpy `predict` path only
+        self._cache_size, self._dev_cache = cache_size, None
         self._game_name = game_name
         self._rollout_eval = None
         self._dev = None            # lazily created device-side state (torch tensors)
@@ -115,7 +116,14 @@ class BatchedMCTS:
         st["boards"].copy_(st["h_boards"], non_blocking=True)
         st["turns"].copy_(st["h_turns"], non_blocking=True)
         buf.pack_roots(st["boards"], st["turns"], stream)
-        evaluator = pv_func if isinstance(pv_func, ds.SyntheticEvaluator) else ds.NetEvaluator(pv_func)
+        if isinstance(pv_func, ds.SyntheticEvaluator):
+            evaluator = pv_func
+        elif self._cache_size > 0:          # device evaluation cache instead of the host LRU (same results, fewer network rows)
+            if self._dev_cache is None:
+                self._dev_cache = ds.EvalCache(self._game_name, self._cache_size, self.mcts._device)
+            evaluator = ds.CachedNetEvaluator(pv_func, self._dev_cache)
+        else:
+            evaluator = ds.NetEvaluator(pv_func)
         ds.playout_device(self.mcts, buf, max_n, K, evaluator, stream)
 
     # ------------------------------------------------------------------------------------------------------
@@ -181,7 +189,7 @@ class BatchedMCTS:
         if hasattr(pv_func, "score_scale"):
             pv_func.score_scale = self.mcts.config.score_scale
         from . import device_search as ds
-        if not use_time and self.cache is None and (isinstance(pv_func, ds.SyntheticEvaluator) or hasattr(pv_func, "predict_device")):
+        if not use_time and (isinstance(pv_func, ds.SyntheticEvaluator) or hasattr(pv_func, "predict_device")):
             self._playout_device(pv_func, current_boards, turns, max_n, vl_batch)
             return self
         t0 = time.perf_counter() if use_time else 0.0
@@ -220,6 +228,8 @@ class BatchedMCTS:
         return self
 
     def refresh_cache(self, pv_func):
+        if self._dev_cache is not None:     # device cache: stale after a weight reload -> drop (misses re-evaluate lazily)
+            self._dev_cache.clear()
         if self.cache is None or len(self.cache) == 0:
             return self
         if hasattr(pv_func, "score_scale"):
@@ -251,6 +261,8 @@ class BatchedMCTS:
         cfg = self.mcts.config
         old = cfg.score_scale
         cfg.score_utility_factor, cfg.score_scale = factor, scale
+        if scale != old and self._dev_cache is not None:
+            self._dev_cache.clear()
         if scale != old and self.cache is not None and len(self.cache) > 0:
             self.cache._od.clear()
 

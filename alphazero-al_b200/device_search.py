@@ -99,6 +99,76 @@ class NetEvaluator:
             raise RuntimeError("az_eval_finalize_dev failed (%d)" % rc)
 
 
+class EvalCache:
+    """Device evaluation cache (include/azb200_cache.h; reference: src/Cache.py LRUCache used by src/MCTS_cpp.py)."""
+
+    def __init__(self, game: str, cache_size: int, device: int | None = None):
+        self.gid = {"Connect4": 0, "Othello": 1}[game]
+        log2 = max(4, int(2 * max(cache_size, 1) - 1).bit_length())       # >= 2x the requested entry count
+        dev = torch.cuda.current_device() if device is None else int(device)
+        self._L = _lib.lib()
+        self._c = self._L.az_evalcache_create(self.gid, log2, dev)
+        if not self._c:
+            raise RuntimeError("az_evalcache_create failed")
+        self._c = C.c_void_p(self._c)
+
+    def __del__(self):
+        c, self._c = getattr(self, "_c", None), None
+        if c:
+            self._L.az_evalcache_destroy(c)
+
+    def clear(self, stream=0):
+        """refresh_cache / score_scale invalidation: cached values are stale after a weight reload."""
+        if self._L.az_evalcache_clear_dev(self._c, stream or None) != 0:
+            raise RuntimeError("az_evalcache_clear_dev failed")
+
+    def stats(self):
+        import numpy as np
+        out = np.zeros(4, np.uint64)
+        if self._L.az_evalcache_stats(self._c, out.ctypes.data_as(C.c_void_p)) != 0:
+            raise RuntimeError("az_evalcache_stats failed")
+        return dict(lookups=int(out[0]), hits=int(out[1]), inserts=int(out[2]), capacity=int(out[3]))
+
+
+class CachedNetEvaluator(NetEvaluator):
+    """NetEvaluator that probes the device cache first; only misses reach the network.  One 4-byte D2H read per
+    iteration (the miss count) is the price of a dynamically sized network batch."""
+
+    def __init__(self, net, cache: EvalCache):
+        super().__init__(net)
+        self.cache = cache
+        self._miss_idx = self._miss_cnt = None
+        self.net_rows = 0
+
+    def __call__(self, buf: LeafBuffers, rows: int, stream: int):
+        L, dev = _lib.lib(), buf.leaves.device
+        if self._wdl is None or self._wdl.shape[0] < buf.rows:
+            self._wdl = torch.empty((buf.rows, 3), dtype=torch.float32, device=dev)
+            self._aux = torch.empty(buf.rows, dtype=torch.float32, device=dev)
+            self._miss_idx = torch.empty(buf.rows, dtype=torch.int32, device=dev)
+            self._miss_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._miss_cnt.zero_()
+        rc = L.az_evalcache_lookup_dev(self.cache._c, rows, buf.leaves.data_ptr(), buf.policy.data_ptr(), self._wdl.data_ptr(),
+                                       self._aux.data_ptr(), self._miss_idx.data_ptr(), self._miss_cnt.data_ptr(), stream or None)
+        if rc != 0:
+            raise RuntimeError("az_evalcache_lookup_dev failed")
+        m = int(self._miss_cnt.item())
+        if m > 0:
+            buf.unpack(rows, stream)
+            idx = self._miss_idx[:m].long()
+            probs, wdl_rel, aux = self.net.predict_device(buf.planes[:rows].index_select(0, idx), buf.mask[:rows].index_select(0, idx))
+            pm, wm, am = probs.reshape(m, buf.A).float().contiguous(), wdl_rel.reshape(m, 3).float().contiguous(), aux.reshape(m).float().contiguous()
+            rc = L.az_evalcache_insert_dev(self.cache._c, m, buf.leaves.data_ptr(), self._miss_idx.data_ptr(), pm.data_ptr(), wm.data_ptr(),
+                                           am.data_ptr(), buf.policy.data_ptr(), self._wdl.data_ptr(), self._aux.data_ptr(), stream or None)
+            if rc != 0:
+                raise RuntimeError("az_evalcache_insert_dev failed")
+            self.net_rows += m
+        rc = L.az_eval_finalize_dev(rows, buf.leaves.data_ptr(), self._wdl.data_ptr(), self._aux.data_ptr(), buf.d.data_ptr(),
+                                    buf.p1w.data_ptr(), buf.p2w.data_ptr(), buf.ml.data_ptr(), stream or None)
+        if rc != 0:
+            raise RuntimeError("az_eval_finalize_dev failed (%d)" % rc)
+
+
 def playout_device(engine, buf: LeafBuffers, n_playout: int, K: int, evaluator, stream: int | None = None,
                    on_select=None):
     """Run `n_playout` simulations per tree entirely on the device from the roots in `buf.roots` (see

@@ -47,7 +47,7 @@ def shard_range(total: int, rank: int, world: int):
 
 class SelfPlay:
     def __init__(self, game, n_slots, n_playout, vl_batch, evaluator, search_cfg=None, temperature=1.0, temp_decay_moves=20,
-                 temp_endgame=0.0, td_steps=10, seed=0, uid_base=0, uid_stride=None, device=None, out_capacity=None):
+                 temp_endgame=0.0, td_steps=10, seed=0, uid_base=0, uid_stride=None, device=None, out_capacity=None, cache_size=0):
         if not torch.cuda.is_available():
             raise RuntimeError("SelfPlay needs a CUDA device (no CPU fallback)")
         self.game = game
@@ -56,8 +56,13 @@ class SelfPlay:
         self.n, self.n_playout, self.K = int(n_slots), int(n_playout), int(vl_batch)
         dev_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", dev_index)
+        self.eval_cache = None
         if not isinstance(evaluator, ds.SyntheticEvaluator) and hasattr(evaluator, "predict_device"):
-            evaluator = ds.NetEvaluator(evaluator)          # a network with the device contract
+            if cache_size > 0:                              # device evaluation cache (src/Cache.py semantics)
+                self.eval_cache = ds.EvalCache(game, cache_size, dev_index)
+                evaluator = ds.CachedNetEvaluator(evaluator, self.eval_cache)
+            else:
+                evaluator = ds.NetEvaluator(evaluator)      # a network with the device contract
         self.evaluator = evaluator
         self.engine = getattr(mcts_cpp, f"BatchedMCTS_{game}")(self.n, device=dev_index)
         for k, v in (search_cfg or {}).items():
@@ -179,3 +184,46 @@ def all_gather_records(local: torch.Tensor, count: int, capacity: int):
     counts = [int(c) for c in cnts.cpu()]
     parts = [recv[r * capacity:r * capacity + counts[r]] for r in range(world)]
     return torch.cat(parts, dim=0), counts
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Trajectory wire / disk formats: the reference's own layouts, produced from packed records.
+# ---------------------------------------------------------------------------------------------------------------
+def to_replay_tensors(packed: torch.Tensor, game: str):
+    """Packed records (uint8[m, record_bytes], any device) -> the 8 tensors of src/ReplayBuffer.py:12-19, one row per
+    recorded position (terminal tuples included), built with vectorised slicing on the tensor's own device."""
+    L = record_layout(game)
+    gid, R, Cc, A, T = _G[game]
+    S, m, T1 = R * Cc, packed.shape[0], L.T1
+    pk = packed.contiguous()
+    length = pk[:, L.off_header:L.off_header + 4].view(torch.int32).reshape(m)
+    keep = (torch.arange(T1, device=pk.device)[None, :] < length[:, None]).reshape(-1)
+
+    def field(off, nbytes, dtype, shape):
+        return pk[:, off:off + nbytes].contiguous().view(dtype).reshape(m * T1, *shape)[keep]
+
+    return {
+        "state": field(L.off_state, T1 * 3 * S, torch.int8, (3, R, Cc)),
+        "prob": field(L.off_prob, T1 * A * 4, torch.float32, (A,)),
+        "winner": field(L.off_winner, T1, torch.int8, (1,)),
+        "steps_to_end": field(L.off_steps, T1 * 2, torch.int16, (1,)),
+        "aux_target": field(L.off_aux, T1 * 2, torch.int16, (1,)),
+        "root_wdl": field(L.off_root_wdl, T1 * 12, torch.float32, (3,)),
+        "valid_mask": field(L.off_mask, T1 * A, torch.uint8, (A,)).bool(),
+        "future_root_wdl": field(L.off_future, T1 * 12, torch.float32, (3,)),
+    }
+
+
+def save_replay_pt(path: str, tensors: dict):
+    """Write the `.pt` layout that src/ReplayBuffer.py:25-62 saves/loads (state dict + `_ptr` + `current_capacity`)."""
+    n = tensors["state"].shape[0]
+    sd = {k: v.cpu() for k, v in tensors.items()}
+    sd["_ptr"], sd["current_capacity"] = n, n
+    torch.save(sd, path)
+
+
+def to_upload_payload(games) -> bytes:
+    """The pickle an actor POSTs to the learner's /upload endpoint (client.py:367-373): {'__az__': True, 'data': [play_data, ...]}
+    where play_data is the tuple of training tuples of one game (`unpack_records(...)[i]['tuples'][1]`)."""
+    import pickle
+    return pickle.dumps({"__az__": True, "data": [g["tuples"][1] for g in games]}, protocol=pickle.HIGHEST_PROTOCOL)

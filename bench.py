@@ -216,6 +216,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        # torchrun exports OMP_NUM_THREADS=1; the reference engine is OpenMP-parallel and must get every host core
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
         r = run_reference(G, n_playout, K, args.steps, max(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -452,7 +454,8 @@ def main():
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--games-per-gpu",
                                   str(args.cpu_baseline_games), "--n-playout", str(n_playout), "--vl-batch", str(K),
-                                  "--steps", "3", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+                                  "--steps", "3", "--warmup", "1"], capture_output=True, text=True, timeout=600,
+                                 env={k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "RANK", "WORLD_SIZE", "LOCAL_RANK")})
             r = json.loads(out.stdout.strip().splitlines()[-1])
             cpu = r["cpu_baseline"]
             cpu["sample"] = f"{args.cpu_baseline_games} games x {n_playout} sims x 3 steps (same workload, fewer games)"

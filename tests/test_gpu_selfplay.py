@@ -118,3 +118,52 @@ def test_temperature_sampling_follows_visit_distribution():
     assert np.allclose(probs, probs[0])
     freq = np.bincount(acts, minlength=7) / n
     assert np.abs(freq - probs[0]).max() < 0.02
+
+
+class _RowDeterministicNet:
+    """A 'network' whose output for a row depends only on that row (exact integer arithmetic), so evaluating a subset of
+    the batch gives bit-identical rows - lets the cache be tested for exact equality."""
+    def predict_device(self, planes, mask):
+        import torch
+        B = planes.shape[0]
+        w = torch.arange(1, 43, device=planes.device, dtype=torch.int64)
+        key = (planes[:, 0].reshape(B, 42).long() * w).sum(1) * 7919 + (planes[:, 1].reshape(B, 42).long() * w).sum(1) * 104729 \
+            + (planes[:, 2, 0, 0].long() + 2) * 1299709
+        a = torch.arange(7, device=planes.device, dtype=torch.int64)[None, :]
+        probs = (((key[:, None] * 31 + a * 977) % 4096) + 1).float() / 4096.0
+        w3 = torch.stack([((key * 13) % 251 + 1), ((key * 17) % 241 + 1), ((key * 19) % 239 + 1)], 1).float()
+        return probs, w3 / w3.sum(1, keepdim=True), ((key % 40) + 1).float()
+
+
+def test_device_evaluation_cache_is_transparent():
+    """Cached evaluations are exactly what the network returns, so visit counts with and without the cache are identical,
+    while most leaves of a self-play batch (same openings in every slot) never reach the network."""
+    import torch
+    bm = importlib.import_module("alphazero-al_b200.batched_mcts")
+    n, npl, K = 256, 60, 4
+    boards = np.zeros((n, 6, 7), np.int8)
+    turns = np.ones(n, np.int32)
+    kw = dict(game_name="Connect4", noise_epsilon=0.0, fpu_reduction=0.2, use_symmetry=True, mlh_slope=0.1)
+    plain = bm.BatchedMCTS(n, 1.4, 1000.0, 0.0, npl, cache_size=0, **kw)
+    cached = bm.BatchedMCTS(n, 1.4, 1000.0, 0.0, npl, cache_size=10000, **kw)
+    for e in (plain, cached):
+        e.seed(3)
+    net = _RowDeterministicNet()
+    for mv in range(3):
+        plain.batch_playout(net, boards, turns, vl_batch=K)
+        cached.batch_playout(net, boards, turns, vl_batch=K)
+        a, b = plain.get_visits_count(), cached.get_visits_count()
+        assert np.array_equal(a, b)
+        acts = a.argmax(1).astype(np.int32)
+        for i in range(n):                                   # play the move on the host boards
+            r = int(np.max(np.where(boards[i, :, acts[i]] == 0)[0]))
+            boards[i, r, acts[i]] = turns[i]
+        turns = -turns
+        plain.prune_roots(acts)
+        cached.prune_roots(acts)
+    st = cached._dev_cache.stats()
+    assert st["hits"] > 0.9 * st["lookups"] and st["inserts"] > 0, st
+    cached.refresh_cache(net)                                # weight reload: the device cache is dropped
+    cached.batch_playout(net, boards, turns, vl_batch=K)
+    st2 = cached._dev_cache.stats()
+    assert st2["inserts"] > st["inserts"]
