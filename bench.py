@@ -442,8 +442,14 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = (sel_rows * bytes_select_sim) / (sel_ms * 1e-3) / 1e9 if sel_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": f"az::k_select<C4,{eng.get_lanes()},VL>", "lanes_per_tree": eng.get_lanes(), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+    # DRAM bytes per select launch from the committed `ncu --set full` capture of the same workload (profiles/)
+    traffic, traffic_src = None, None
+    if G == 65536 and K == 4 and eng.get_lanes() == 1:
+        traffic = 147.69792e6 + 34.587648e6
+        traffic_src = ("profiles/r1c_ncu_full_select_t_backprop_t_n65536.csv: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                       "k_select_t launch (262144 simulations); algorithmic bytes of that launch = %.1f MB" % (G * K * bytes_select_sim / 1e6))
+    roofline = {"bound": "hbm", "kernel": "az::k_select_t<C4,VL>" if eng.get_lanes() == 1 else f"az::k_select<C4,{eng.get_lanes()},VL>", "lanes_per_tree": eng.get_lanes(), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "bytes_per_sim_select": bytes_select_sim, "bytes_per_sim_whole_path": bytes_total_sim,
                 "tree_stats": {"depth": d_bar, "edges_scanned": E_bar, "edges_created": b_bar, "expansions": x_bar},
