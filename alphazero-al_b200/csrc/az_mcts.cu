@@ -36,68 +36,31 @@
 namespace az {
 
 // ------------------------------------------------------------------------------------------------
-// HBM layout.  A tree arena is an array of 16-byte chunks.  An expanded node owns one BLOCK:
-//
-//     hot  [ne] x 16 B   {prior, n<<8 | in-flight, Q, M}      everything the PUCT scan needs - and nothing else
-//     link [ne] x  4 B   child block word (offset << 6 | num_edges) or NONE            (padded to 16 B)
-//     cold [ne] x 16 B   {W_d, W_p1w, W_p2w, M_sum}           the running sums back-propagation accumulates
-//     meta [ne] x  2 B   action | flags (allocated, terminal, result, child side to move) (padded to 16 B)
-//
-// Edge e of the block describes the edge AND the child it leads to (Edge + MCTSNode, MCTSNode.h:69-140): a node
-// has no record of its own, its statistics live in its parent's block (the root's in TreeRec).  Q = child.mean_q()
-// and M = child.mean_M() are CACHED in the hot record by back-propagation (same formulas, same operands, hence the
-// same bits the reference recomputes for every scanned edge in MCTS.h:190-199): one update per visited node
-// instead of two IEEE divisions per scanned edge, and the scan reads 16 instead of 32 bytes per edge.
+// HBM layout
 // ------------------------------------------------------------------------------------------------
-typedef uint4 Chunk;
-struct __align__(16) Hot { float prior; uint32_t nv; float q; float m; };      // nv = n_visits << 8 | n_inflight
-struct __align__(16) Cold { float wd, wp1, wp2, msum; };
-static_assert(sizeof(Hot) == 16 && sizeof(Cold) == 16, "hot / cold records are one 16-byte chunk");
-constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr uint32_t INFL_MASK = 0xFFu;
-constexpr uint32_t M_ALLOC = 1u << 8;     // child node exists (Edge.child != -1)
-constexpr uint32_t M_TERM = 1u << 9;      // child is_terminal
-constexpr uint32_t M_WIN_P1 = 1u << 10;   // cached terminal result: neither bit = draw
-constexpr uint32_t M_WIN_P2 = 1u << 11;
-constexpr uint32_t M_TURN_P1 = 1u << 12;  // child node.turn == +1
-__host__ __device__ __forceinline__ int link_chunks(int ne) { return (ne + 3) >> 2; }
-__host__ __device__ __forceinline__ int meta_chunks(int ne) { return (ne + 7) >> 3; }
-__host__ __device__ __forceinline__ int block_chunks(int ne) { return 2 * ne + link_chunks(ne) + meta_chunks(ne); }
-// path entry: block offset (20 bits) | num_edges (6) | edge index (6)
-__device__ __forceinline__ uint32_t path_entry(uint32_t off, int ne, int e) { return (off << 12) | ((uint32_t)ne << 6) | (uint32_t)e; }
-struct EdgeRef {
-    uint32_t off; int ne, e;
-    __device__ __forceinline__ explicit EdgeRef(uint32_t p) : off(p >> 12), ne((int)((p >> 6) & 63u)), e((int)(p & 63u)) {}
-    __device__ __forceinline__ Hot *hot(Chunk *arena) const { return reinterpret_cast<Hot *>(arena + off + e); }
-    __device__ __forceinline__ uint32_t *link(Chunk *arena) const { return reinterpret_cast<uint32_t *>(arena + off + ne) + e; }
-    __device__ __forceinline__ Cold *cold(Chunk *arena) const { return reinterpret_cast<Cold *>(arena + off + ne + link_chunks(ne) + e); }
-    __device__ __forceinline__ uint16_t *meta(Chunk *arena) const { return reinterpret_cast<uint16_t *>(arena + off + 2 * ne + link_chunks(ne)) + e; }
+struct __align__(32) Slot {   // one edge + the statistics of the child it leads to (Edge + MCTSNode, MCTSNode.h:69-140)
+    float prior;              // Edge.prior
+    int n;                    // child n_visits
+    uint32_t meta;            // [0,16) child n_inflight | [16,24) Edge.action | [24,32) flags
+    uint32_t child;           // NONE = child not expanded, else (block offset in slots << 6) | num_edges
+    float wd, wp1, wp2, msum; // child W_d, W_p1w, W_p2w, M_sum
 };
+static_assert(sizeof(Slot) == 32, "Slot must be one 32-byte sector");
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t F_ALLOC = 1u << 24;    // child node exists (Edge.child != -1)
+constexpr uint32_t F_TERM = 1u << 25;     // child is_terminal
+constexpr uint32_t F_WIN_P1 = 1u << 26;   // cached terminal result: neither bit = draw
+constexpr uint32_t F_WIN_P2 = 1u << 27;
+constexpr uint32_t F_TURN_P1 = 1u << 28;  // child node.turn == +1
+constexpr uint32_t INFL_MASK = 0xFFFFu;
 
 struct __align__(64) TreeRec {   // per tree: the root's own statistics + allocator state
-    int32_t n; uint32_t infl;    // root n_visits / n_inflight
-    float wd, wp1, wp2, msum;    // root W_d, W_p1w, W_p2w, M_sum
-    uint32_t child;              // root block word or NONE
-    uint32_t flags;              // M_TERM | M_WIN_* | M_TURN_P1 of the root node
-    uint32_t bump;               // chunks used in this tree's arena
+    Slot root;                   // root.prior unused
+    uint32_t bump;               // slots used in this tree's arena
     uint32_t noise_ctr;          // Dirichlet draw counter
     uint32_t pad[6];
 };
 static_assert(sizeof(TreeRec) == 64, "TreeRec is one 64-byte record");
-__device__ __forceinline__ TreeRec ld_tree(const TreeRec *p) {
-    TreeRec t; const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    uint4 a = q[0], b = q[1], c = q[2];
-    t.n = (int)a.x; t.infl = a.y; t.wd = __uint_as_float(a.z); t.wp1 = __uint_as_float(a.w);
-    t.wp2 = __uint_as_float(b.x); t.msum = __uint_as_float(b.y); t.child = b.z; t.flags = b.w;
-    t.bump = c.x; t.noise_ctr = c.y;
-    return t;
-}
-__device__ __forceinline__ void st_tree(TreeRec *p, const TreeRec &t) {
-    uint4 *q = reinterpret_cast<uint4 *>(p);
-    q[0] = make_uint4((uint32_t)t.n, t.infl, __float_as_uint(t.wd), __float_as_uint(t.wp1));
-    q[1] = make_uint4(__float_as_uint(t.wp2), __float_as_uint(t.msum), t.child, t.flags);
-    q[2] = make_uint4(t.bump, t.noise_ctr, 0u, 0u);
-}
 
 struct __align__(16) LeafHead {  // what backprop needs to know about a pending leaf (MCTS.h:56-64), un-symmetrised
     uint64_t bb0, bb1;
@@ -119,7 +82,7 @@ static_assert(sizeof(az_root) == 32 && sizeof(az_leaf) == 32, "public records ar
 constexpr uint8_t LF_VALID = 1, LF_VLPENDING = 2, LF_TERM = 4, LF_WIN_P1 = 8, LF_WIN_P2 = 16;
 
 struct Dev {   // kernel-visible view of an engine
-    Chunk *pool; uint32_t cap;           // cap = arena capacity (16-byte chunks per tree)
+    Slot *pool; uint32_t cap;            // cap = arena capacity (slots per tree)
     TreeRec *trees;
     float *noise; int noise_stride;      // root Dirichlet noise, [n_envs][noise_stride]
     LeafRec *leaf_vl; uint32_t *path_vl; int kcap;   // [n_envs][kcap], [n_envs][kcap][MAX_DEPTH]
@@ -147,10 +110,19 @@ template <int W> __device__ __forceinline__ int gshfl(unsigned gm, int v, int sr
 template <int W> __device__ __forceinline__ uint32_t gshfl(unsigned gm, uint32_t v, int src) { return W == 1 ? v : __shfl_sync(gm, v, src, W); }
 template <int W> __device__ __forceinline__ void gsync(unsigned gm) { if (W > 1) __syncwarp(gm); }
 
-__device__ __forceinline__ Hot ld_hot(const Hot *p) { const uint4 v = *reinterpret_cast<const uint4 *>(p); Hot h; h.prior = __uint_as_float(v.x); h.nv = v.y; h.q = __uint_as_float(v.z); h.m = __uint_as_float(v.w); return h; }
-__device__ __forceinline__ void st_hot(Hot *p, const Hot &h) { *reinterpret_cast<uint4 *>(p) = make_uint4(__float_as_uint(h.prior), h.nv, __float_as_uint(h.q), __float_as_uint(h.m)); }
-__device__ __forceinline__ Cold ld_cold(const Cold *p) { const float4 v = *reinterpret_cast<const float4 *>(p); Cold c; c.wd = v.x; c.wp1 = v.y; c.wp2 = v.z; c.msum = v.w; return c; }
-__device__ __forceinline__ void st_cold(Cold *p, const Cold &c) { *reinterpret_cast<float4 *>(p) = make_float4(c.wd, c.wp1, c.wp2, c.msum); }
+__device__ __forceinline__ Slot ld_slot(const Slot *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    Slot s;
+    s.prior = __uint_as_float(a.x); s.n = (int)a.y; s.meta = a.z; s.child = a.w;
+    s.wd = __uint_as_float(b.x); s.wp1 = __uint_as_float(b.y); s.wp2 = __uint_as_float(b.z); s.msum = __uint_as_float(b.w);
+    return s;
+}
+__device__ __forceinline__ void st_slot(Slot *p, const Slot &s) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(__float_as_uint(s.prior), (uint32_t)s.n, s.meta, s.child);
+    q[1] = make_uint4(__float_as_uint(s.wd), __float_as_uint(s.wp1), __float_as_uint(s.wp2), __float_as_uint(s.msum));
+}
 template <class T> __device__ __forceinline__ T ld32(const T *p) {      // 32-byte record as two 16-byte loads
     T v;
     const uint4 *q = reinterpret_cast<const uint4 *>(p);
@@ -185,12 +157,6 @@ template <class G> __device__ __forceinline__ float aux_utility(float child_M, f
     }
     if (cfg.score_utility_factor <= 0.0f) return 0.0f;   // Othello.h:268-274
     return cfg.score_utility_factor * child_M;
-}
-// e-th legal action in ascending order (edges are created in that order, MCTS.h:366-370)
-template <class G> __device__ __forceinline__ int nth_legal(uint64_t legal, bool pass_only, int e) {
-    if (G::GAME == GAME_OTH && pass_only) return Oth::PASS;
-    for (int i = 0; i < e; ++i) legal &= legal - 1;
-    return ctz64(legal);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -291,8 +257,6 @@ __global__ void k_unpack_leaves(int rows, const az_leaf *__restrict__ leaves, in
 // SELECT: simulate / simulate_vl (MCTS.h:242-322, 443-545) + leaf export (BatchedMCTS.h:119-171, 227-286)
 // W lanes cooperate on one tree; lane l owns edges l, l+W, l+2W, ... of the node being scanned.
 // ------------------------------------------------------------------------------------------------
-struct Cur { int n; uint32_t infl; float q, m; uint32_t child; };   // the node being scanned (identical in every lane)
-
 template <class G, int W, bool VL>
 __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
                                                 az_leaf *__restrict__ leaves) {
@@ -302,58 +266,48 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
     const int lane = threadIdx.x & (W - 1);
     const unsigned gm = group_mask<W>();
     const int env = gid;
-    Chunk *arena = d.pool + (size_t)env * d.cap;
+    Slot *arena = d.pool + (size_t)env * d.cap;
     TreeRec *tr = d.trees + env;
     const float *noise = d.noise + (size_t)env * d.noise_stride;
     const int vl = VL ? cfg.vl_count : 0;
     const bool use_aux = aux_enabled<G>(cfg);
-    const float ne_eps = cfg.noise_epsilon;
 
     State start;
     { const az_root r = ld32(roots + env); start.bb[0] = r.bb0; start.bb[1] = r.bb1; G::finish_import(start, r.turn); }
-    TreeRec root = ld_tree(tr);            // identical copy in every lane of the group, written back once
-    const uint32_t root_infl_in = root.infl, root_flags_in = root.flags;
-    float nz[NCH];                         // the root's Dirichlet noise for my edges, read once
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) nz[c] = (ne_eps > 0.0f && c * W + lane < d.noise_stride) ? noise[c * W + lane] : 0.0f;
+    Slot root = ld_slot(&tr->root);        // identical copy in every lane of the group, written back once
+    const uint32_t root_meta_in = root.meta;
     unsigned long long st_depth = 0, st_edges = 0;
 
     for (int k = 0; k < K; ++k) {
         State st = start;
-        Cur cur;
-        cur.n = root.n; cur.infl = root.infl; cur.child = root.child;
-        cur.q = mean_q(root.n, root.wp1, root.wp2, (root.flags & M_TURN_P1) != 0);
-        cur.m = use_aux ? mean_m(root.n, root.msum) : 0.0f;
-        bool is_root = true, root_vl = false, cur_term = (root.flags & M_TERM) != 0;
+        Slot cur = root;
+        bool is_root = true, root_vl = false;
         uint32_t plen = 0;
         uint32_t *path = VL ? d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH : d.path_nv + (size_t)env * G::MAX_DEPTH;
-        uint32_t p8[PATH8];
-#pragma unroll
-        for (int j = 0; j < PATH8; ++j) p8[j] = 0;
         int winner = 0; bool full = false;
-        uint32_t last_entry = 0;         // path entry of the edge that leads to `cur` (valid when plen > 0)
+        uint32_t last_slot = 0;          // arena offset of the slot that leads to `cur` (valid when plen > 0)
 
-        while (cur.child != NONE && !cur_term) {      // while (node.is_expanded) { if (is_terminal) break; ...
+        while (cur.child != NONE) {      // while (node.is_expanded)
+            if (cur.meta & F_TERM) break;
             const int ne = (int)(cur.child & 63u);
             if (ne == 0 || plen >= (uint32_t)G::MAX_DEPTH) break;
             const uint32_t off = cur.child >> 6;
-            const Hot *hot = reinterpret_cast<const Hot *>(arena + off);
-            const uint32_t *link = reinterpret_cast<const uint32_t *>(arena + off + ne);
-            Hot s[NCH]; uint32_t lk[NCH]; bool has[NCH];
+            Slot s[NCH]; bool has[NCH];
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const int e = c * W + lane;
                 has[c] = e < ne;
-                if (has[c]) { s[c] = ld_hot(hot + e); lk[c] = link[e]; }
-                else { s[c].prior = 0.f; s[c].nv = 0; s[c].q = 0.f; s[c].m = 0.f; lk[c] = NONE; }
+                if (has[c]) s[c] = ld_slot(arena + off + e);
+                else { s[c].prior = 0.f; s[c].n = 0; s[c].meta = 0; s[c].child = NONE; s[c].wd = s[c].wp1 = s[c].wp2 = s[c].msum = 0.f; }
             }
             st_edges += (unsigned long long)ne;
             // ---- compute_fpu (MCTS.h:140-156): seen_policy summed sequentially in edge order ----
-            const float parent_q = cur.q;
+            const int cur_infl = (int)(cur.meta & INFL_MASK);
+            const float parent_q = mean_q(cur.n, cur.wp1, cur.wp2, (cur.meta & F_TURN_P1) != 0);
             float seen_policy = 0.0f;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                const float pv = (has[c] && (s[c].nv >> 8) > 0) ? s[c].prior : 0.0f;   // + 0.0f is exact
+                const float pv = (has[c] && s[c].n > 0) ? s[c].prior : 0.0f;   // + 0.0f is exact
                 if (G::GAME == GAME_C4) {
 #pragma unroll
                     for (int l = 0; l < W; ++l) if (c * W + l < G::MAX_EDGES) seen_policy += gshfl<W>(gm, pv, l);
@@ -367,12 +321,13 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
             float fpu = parent_q - eff_fpu * sqrtf(seen_policy);
             fpu = (-1.0f < fpu) ? fpu : -1.0f;
             // ---- select_edge (MCTS.h:163-234) ----
-            const int pn_i = cur.n + (int)cur.infl;
+            const int pn_i = cur.n + cur_infl;
             const float parent_n = (float)pn_i;
-            const float parent_M = cur.m;
+            const float parent_M = use_aux ? mean_m(cur.n, cur.msum) : 0.0f;
             const float lg = (pn_i >= 0 && pn_i < d.log_lut_n) ? d.log_lut[pn_i] : logf((parent_n + cfg.c_base + 1.0f) / cfg.c_base);
             const float c_puct = cfg.c_init + lg;
             const float sqrt_pn = sqrtf(parent_n);
+            const float ne_eps = cfg.noise_epsilon;
             const bool mix_noise = is_root && ne_eps > 0.0f;
             float best_s = -INFINITY; int best_e = -1;
 #pragma unroll
@@ -380,13 +335,18 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
                 if (!has[c]) continue;
                 const int e = c * W + lane;
                 float eff_prior = s[c].prior;
-                if (mix_noise) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * nz[c];
-                const int cn = (int)(s[c].nv >> 8), cinf = (int)(s[c].nv & INFL_MASK);
+                if (mix_noise) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * noise[e];
+                const int cn = s[c].n, cinf = (int)(s[c].meta & INFL_MASK);
                 float q_value = fpu, m_utility = 0.0f; int visits = cinf;     // unvisited: FPU, in-flight only
                 if (cn > 0) {
                     visits = cn + cinf;
-                    q_value = -s[c].q;                                      // cached child.mean_q(), flipped to the parent's view
-                    if (use_aux) m_utility = aux_utility<G>(G::AUX_NEGATE ? -s[c].m : s[c].m, parent_M, s[c].q, cfg);
+                    const float child_Q = mean_q(cn, s[c].wp1, s[c].wp2, (s[c].meta & F_TURN_P1) != 0);
+                    q_value = -child_Q;
+                    if (use_aux) {
+                        float child_M = mean_m(cn, s[c].msum);
+                        if (G::AUX_NEGATE) child_M = -child_M;
+                        m_utility = aux_utility<G>(child_M, parent_M, child_Q, cfg);
+                    }
                 }
                 const float u_score = c_puct * eff_prior * sqrt_pn / (1.0f + (float)visits);
                 const float score = q_value + u_score + m_utility;
@@ -401,55 +361,50 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
                 if (take) { best_s = os; best_e = oe; }
             }
             if (best_e < 0) break;
-            if (VL && !root_vl) { root_vl = true; root.infl += (uint32_t)vl; }   // root virtual loss (MCTS.h:471-475)
+            if (VL && !root_vl) { root_vl = true; root.meta += (uint32_t)vl; }   // root virtual loss (MCTS.h:471-475)
             // broadcast the chosen child to the whole group
             const int bl = best_e & (W - 1), bc = best_e / W;
-            Hot ch = s[0]; uint32_t chl = lk[0];
+            Slot ch = s[0];
 #pragma unroll
-            for (int c = 1; c < NCH; ++c) if (bc == c) { ch = s[c]; chl = lk[c]; }
-            ch.nv = gshfl<W>(gm, ch.nv, bl); ch.q = gshfl<W>(gm, ch.q, bl); ch.m = gshfl<W>(gm, ch.m, bl); chl = gshfl<W>(gm, chl, bl);
-            // the action of edge e is the e-th legal move of the position (edges are created in ascending order)
-            uint64_t legal = G::legal(st);
-            bool pass_only = false;
-            if (G::GAME == GAME_OTH) pass_only = legal == 0ULL && !Oth::over(st);
-            const int action = nth_legal<G>(legal, pass_only, best_e);
-            G::step(st, action);
-            const bool first_visit = (ch.nv >> 8) == 0 && (ch.nv & INFL_MASK) == 0;
-            const uint32_t nnv = ch.nv + (uint32_t)vl;              // child virtual loss (MCTS.h:492)
+            for (int c = 1; c < NCH; ++c) if (bc == c) ch = s[c];
+            ch.n = gshfl<W>(gm, ch.n, bl);
+            ch.meta = gshfl<W>(gm, ch.meta, bl);
+            ch.child = gshfl<W>(gm, ch.child, bl);
+            ch.wp1 = gshfl<W>(gm, ch.wp1, bl);
+            ch.wp2 = gshfl<W>(gm, ch.wp2, bl);
+            ch.msum = gshfl<W>(gm, ch.msum, bl);
+            G::step(st, (int)((ch.meta >> 16) & 0xFFu));
+            uint32_t nmeta = ch.meta;
+            if (!(nmeta & F_ALLOC)) {      // lazy child allocation (MCTS.h:481-488): remember the child's side to move
+                nmeta |= F_ALLOC;
+                nmeta = st.turn == 1 ? (nmeta | F_TURN_P1) : (nmeta & ~F_TURN_P1);
+            }
+            nmeta += (uint32_t)vl;         // child virtual loss (MCTS.h:492)
             winner = G::winner(st);
             full = G::full(st);
             const bool term_now = winner != 0 || full;
-            last_entry = path_entry(off, ne, best_e);
+            if (term_now) nmeta = (nmeta & ~(F_WIN_P1 | F_WIN_P2)) | F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+            last_slot = off + (uint32_t)best_e;
             if (lane == 0) {
-                const EdgeRef r(last_entry);
-                if (VL && vl != 0) r.hot(arena)->nv = nnv;
-                if (first_visit || term_now) {   // lazy child allocation (MCTS.h:481-488) / terminal caching (:499-509)
-                    uint32_t mt = (uint32_t)action | M_ALLOC | (st.turn == 1 ? M_TURN_P1 : 0u);
-                    if (term_now) mt |= M_TERM | (winner == 1 ? M_WIN_P1 : (winner == -1 ? M_WIN_P2 : 0u));
-                    *r.meta(arena) = (uint16_t)mt;
-                }
-                path[plen] = last_entry;
+                if (nmeta != ch.meta) arena[last_slot].meta = nmeta;
+                path[plen] = last_slot;
             }
-#pragma unroll
-            for (int j = 0; j < PATH8; ++j) if (plen == (uint32_t)j) p8[j] = last_entry;
             ++plen;
-            cur.n = (int)(nnv >> 8); cur.infl = nnv & INFL_MASK; cur.q = ch.q; cur.m = ch.m; cur.child = chl;
-            cur_term = term_now; is_root = false;
+            cur = ch; cur.meta = nmeta; is_root = false;
             if (term_now) break;
         }
         st_depth += plen;
         // ---- leaf classification (MCTS.h:512-544) ----
-        bool leaf_term = cur_term;
+        bool leaf_term = (cur.meta & F_TERM) != 0;
+        if (plen == 0) leaf_term = (root.meta & F_TERM) != 0;
         if (!leaf_term) {
             if (winner == 0 && !full) { winner = G::winner(st); full = G::full(st); }
-            if (winner != 0 || full) {          // first-time detection (only reachable for the root or a broken tree)
+            if (winner != 0 || full) {
                 leaf_term = true;
-                const uint32_t tf = M_TERM | (winner == 1 ? M_WIN_P1 : (winner == -1 ? M_WIN_P2 : 0u));
-                if (plen == 0) root.flags = (root.flags & ~(M_WIN_P1 | M_WIN_P2)) | tf;
-                else if (lane == 0) { uint16_t *mp = EdgeRef(last_entry).meta(arena); *mp = (uint16_t)((*mp & ~(M_WIN_P1 | M_WIN_P2)) | tf); }
+                const uint32_t tf = F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+                if (plen == 0) { root.meta = (root.meta & ~(F_WIN_P1 | F_WIN_P2)) | tf; cur.meta = root.meta; }
+                else { cur.meta = (cur.meta & ~(F_WIN_P1 | F_WIN_P2)) | tf; if (lane == 0) arena[last_slot].meta = cur.meta; }
             }
-        } else if (plen == 0) {                 // flagged terminal root: cached result
-            winner = (root.flags & M_WIN_P1) ? 1 : ((root.flags & M_WIN_P2) ? -1 : 0);
         }
         // ---- random symmetry for non-terminal leaves (BatchedMCTS.h:148-158 / 261-271) ----
         int sym = 0;
@@ -460,16 +415,14 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
             G::symmetry(ex, sym);
         }
         if (lane == 0) {
-            const uint8_t tflags = (uint8_t)(leaf_term ? (AZ_LEAF_TERMINAL | (winner == 1 ? AZ_LEAF_P1_WINS : 0u) | (winner == -1 ? AZ_LEAF_P2_WINS : 0u)) : 0u);
-            LeafRec *dst = VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env;
-            LeafHead L;     // remembered for backprop
+            const uint8_t tflags = (uint8_t)(leaf_term ? (AZ_LEAF_TERMINAL | ((cur.meta & F_WIN_P1) ? AZ_LEAF_P1_WINS : 0u) |
+                                                          ((cur.meta & F_WIN_P2) ? AZ_LEAF_P2_WINS : 0u)) : 0u);
+            LeafHead L;    // remembered for backprop
             L.bb0 = st.bb[0]; L.bb1 = st.bb[1]; L.turn = st.turn; L.passes = (int16_t)st.passes; L.last = (int8_t)st.last;
             L.flags = (uint8_t)(LF_VALID | ((VL && plen > 0) ? LF_VLPENDING : 0) | (leaf_term ? LF_TERM : 0) |
                                 ((tflags & AZ_LEAF_P1_WINS) ? LF_WIN_P1 : 0) | ((tflags & AZ_LEAF_P2_WINS) ? LF_WIN_P2 : 0));
             L.path_len = plen; L.sym = (uint32_t)sym;
-            st32(&dst->h, L);
-            uint4 *pq = reinterpret_cast<uint4 *>(dst->path8);
-            pq[0] = make_uint4(p8[0], p8[1], p8[2], p8[3]); pq[1] = make_uint4(p8[4], p8[5], p8[6], p8[7]);
+            st32(&(VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env)->h, L);
             az_leaf P;     // handed to the evaluator
             P.bb0 = ex.bb[0]; P.bb1 = ex.bb[1]; P.turn = (int8_t)st.turn; P.flags = tflags; P.sym = (uint8_t)sym; P.passes = (uint8_t)st.passes;
             P.reserved[0] = P.reserved[1] = P.reserved[2] = 0;
@@ -477,10 +430,7 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
         }
         gsync<W>(gm);   // order this descent's in-flight updates before the next descent of the same tree
     }
-    if (lane == 0) {
-        if (root.infl != root_infl_in) tr->infl = root.infl;
-        if (root.flags != root_flags_in) tr->flags = root.flags;
-    }
+    if (lane == 0 && root.meta != root_meta_in) tr->root.meta = root.meta;
     if (d.stats && lane == 0) {
         atomicAdd(d.stats + 0, (unsigned long long)K);
         atomicAdd(d.stats + 1, st_depth);
@@ -490,15 +440,27 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
 
 // ------------------------------------------------------------------------------------------------
 // BACKPROP: remove_all_vl + expand_leaf + propagate (MCTS.h:329-402, 561-609; BatchedMCTS.h:176-199, 296-332)
-//
-// The virtual loss of path k is removed in the same read-modify-write that adds simulation k's result to each
-// node.  The order is unobservable: nothing in back-propagation reads in-flight counts, and at the end of the
-// kernel every pending loss of the first removeK paths is gone - exactly the state after remove_all_vl(K) followed
-// by K backprop_vl calls.  Each update also refreshes the cached Q / M of the node.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t dec_infl(uint32_t nv, uint32_t dec) {
-    const uint32_t infl = nv & INFL_MASK;
-    return (nv & ~INFL_MASK) | (infl > dec ? infl - dec : 0u);
+template <class G, int W>
+__device__ __forceinline__ void remove_vl_group(const Dev &d, const az_search_config &cfg, int env, int K, int lane, unsigned gm,
+                                                Slot *arena, Slot &root) {
+    const int vl = cfg.vl_count;
+    for (int k = 0; k < K; ++k) {
+        LeafHead *L = &(d.leaf_vl + (size_t)env * d.kcap + k)->h;
+        const uint8_t fl = L->flags;
+        if (!(fl & LF_VLPENDING)) continue;
+        const uint32_t plen = L->path_len;
+        const uint32_t *path = d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH;
+        { int infl = (int)(root.meta & INFL_MASK) - vl; root.meta = (root.meta & ~INFL_MASK) | (uint32_t)max(infl, 0); }
+        for (uint32_t j = lane; j < plen; j += W) {
+            uint32_t *m = &arena[path[j]].meta;
+            uint32_t v = *m;
+            int infl = (int)(v & INFL_MASK) - vl;
+            *m = (v & ~INFL_MASK) | (uint32_t)max(infl, 0);
+        }
+        gsync<W>(gm);
+        if (lane == 0) L->flags = (uint8_t)(fl & ~LF_VLPENDING);
+    }
 }
 
 template <class G, int W, bool VL>
@@ -512,37 +474,25 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
     const int lane = threadIdx.x & (W - 1);
     const unsigned gm = group_mask<W>();
     const int env = gid;
-    Chunk *arena = d.pool + (size_t)env * d.cap;
+    Slot *arena = d.pool + (size_t)env * d.cap;
     TreeRec *tr = d.trees + env;
-    TreeRec root = ld_tree(tr);         // kept in registers (identical in every lane), written back once
-    const int vl = cfg.vl_count;
+    Slot root = ld_slot(&tr->root);     // kept in registers (identical in every lane), written back once
+    uint32_t bump = tr->bump, noise_ctr = tr->noise_ctr;
     unsigned long long st_created = 0, st_expanded = 0;
-    LeafRec *recs = VL ? d.leaf_vl + (size_t)env * d.kcap : d.leaf_nv + env;
+
+    if (VL) remove_vl_group<G, W>(d, cfg, env, removeK, lane, gm, arena, root);
+    gsync<W>(gm);
 
     for (int k = 0; k < K; ++k) {
-        LeafRec *rp = recs + k;
-        const LeafHead L = ld32(&rp->h);
+        const LeafHead L = ld32(&(VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env)->h);
         if (!(L.flags & LF_VALID)) continue;             // current_leaf_idx == -1 (MCTS.h:409,599)
-        uint32_t p8[PATH8];
-        { const uint4 *pq = reinterpret_cast<const uint4 *>(rp->path8); const uint4 a = pq[0], b = pq[1];
-          p8[0] = a.x; p8[1] = a.y; p8[2] = a.z; p8[3] = a.w; p8[4] = b.x; p8[5] = b.y; p8[6] = b.z; p8[7] = b.w; }
         const size_t flat = (size_t)env * K + k;
         const bool term = is_term ? (is_term[flat] != 0) : ((L.flags & LF_TERM) != 0);
         const uint32_t plen = L.path_len;
         const uint32_t *path = VL ? d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH : d.path_nv + (size_t)env * G::MAX_DEPTH;
-        auto path_at = [&](uint32_t j) -> uint32_t {             // j-th path entry (0 = first edge below the root)
-            uint32_t v = p8[0];
-#pragma unroll
-            for (int q = 1; q < PATH8; ++q) if (j == (uint32_t)q) v = p8[q];
-            return j < (uint32_t)PATH8 ? v : path[j];
-        };
-        const bool pending = VL && (L.flags & LF_VLPENDING) && k < removeK;
-        const uint32_t dec = pending ? (uint32_t)vl : 0u;
-        if (pending) root.infl = root.infl > (uint32_t)vl ? root.infl - (uint32_t)vl : 0u;
         State st; st.bb[0] = L.bb0; st.bb[1] = L.bb1; st.turn = L.turn; st.passes = L.passes; st.last = L.last;
-        const uint32_t leaf_entry = plen > 0 ? path_at(plen - 1) : 0u;
-        uint32_t *leaf_link = plen > 0 ? EdgeRef(leaf_entry).link(arena) : nullptr;
-        const uint32_t leaf_child = plen > 0 ? *leaf_link : root.child;
+        Slot *leaf_slot = plen > 0 ? arena + path[plen - 1] : nullptr;
+        const uint32_t leaf_child = plen > 0 ? leaf_slot->child : root.child;
 
         // ---- expand_leaf (MCTS.h:329-375); VL: skipped when an earlier k already expanded it (MCTS.h:601-607) ----
         if (!term && (!VL || leaf_child == NONE)) {
@@ -583,15 +533,11 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
                 }
             }
             const float denom = psum + 1e-8f;
-            const uint32_t need = (uint32_t)block_chunks(ne);
-            if (root.bump + need > d.cap || root.bump + need >= (1u << 20)) {
+            if (bump + (uint32_t)ne > d.cap) {
                 if (lane == 0) atomicExch(d.err, 1);              // host sizes the arenas so this never fires
             } else {
-                const uint32_t off = root.bump;
-                Hot *hot = reinterpret_cast<Hot *>(arena + off);
-                uint32_t *link = reinterpret_cast<uint32_t *>(arena + off + ne);
-                Cold *cold = reinterpret_cast<Cold *>(arena + off + ne + link_chunks(ne));
-                uint16_t *meta = reinterpret_cast<uint16_t *>(arena + off + 2 * ne + link_chunks(ne));
+                const uint32_t off = bump;
+                Slot ns; ns.n = 0; ns.child = NONE; ns.wd = ns.wp1 = ns.wp2 = ns.msum = 0.0f;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     const int a = j * W + lane;
@@ -600,23 +546,20 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
                     if (G::GAME == GAME_OTH && a == Oth::PASS) { ok = pass_only; eidx = 0; }
                     else { ok = (legal >> (a & 63)) & 1ULL; eidx = popc64(legal & ((1ULL << (a & 63)) - 1ULL)); }
                     if (!ok) continue;
-                    Hot h; h.prior = pmine[j] / denom; h.nv = 0; h.q = 0.0f; h.m = 0.0f;
-                    st_hot(hot + eidx, h);
-                    link[eidx] = NONE;
-                    Cold z; z.wd = z.wp1 = z.wp2 = z.msum = 0.0f;
-                    st_cold(cold + eidx, z);
-                    meta[eidx] = (uint16_t)a;
+                    ns.prior = pmine[j] / denom;
+                    ns.meta = (uint32_t)a << 16;
+                    st_slot(arena + off + eidx, ns);
                 }
-                root.bump += need;
+                bump += (uint32_t)ne;
                 const uint32_t cw = (off << 6) | (uint32_t)ne;
-                if (plen > 0) { if (lane == 0) *leaf_link = cw; }
+                if (plen > 0) { if (lane == 0) leaf_slot->child = cw; }
                 else {
                     root.child = cw;
                     // root expansion draws Dirichlet noise when alpha > 0 (MCTS.h:347-363, leaf.parent == -1)
                     float *nrow = d.noise + (size_t)env * d.noise_stride;
                     if (cfg.dirichlet_alpha > 0.0f) {
-                        if (lane == 0) draw_root_noise(d.seed, d.env_base + (uint64_t)env, root.noise_ctr, cfg.dirichlet_alpha, ne, nrow);
-                        root.noise_ctr = gshfl<W>(gm, root.noise_ctr, 0);
+                        if (lane == 0) draw_root_noise(d.seed, d.env_base + (uint64_t)env, noise_ctr, cfg.dirichlet_alpha, ne, nrow);
+                        noise_ctr = gshfl<W>(gm, noise_ctr, 0);
                     } else {
                         for (int e = lane; e < ne; e += W) nrow[e] = 0.0f;
                     }
@@ -634,47 +577,355 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
         const float gamma = cfg.value_decay;
         const bool decay = gamma < 1.0f;
         const float u3 = 1.0f / 3.0f;
+        for (uint32_t base = 0; base < plen; base += W) {
+            const uint32_t t = base + lane;                      // t-th node counted from the leaf
+            const bool mine = t < plen;
+            Slot *sp = nullptr; int n = 0; float4 w = make_float4(0, 0, 0, 0);
+            if (mine) {
+                sp = arena + path[plen - 1 - t];
+                n = sp->n;
+                w = *reinterpret_cast<const float4 *>(&sp->wd);
+            }
+            float mwd = 0, mw1 = 0, mw2 = 0, mml = 0;
+            const uint32_t lim = min((uint32_t)W, plen - base);
+            for (uint32_t i = 0; i < lim; ++i) {                 // the value sequence is inherently sequential
+                if (i == (uint32_t)lane) { mwd = wd; mw1 = w1; mw2 = w2; mml = ml; }
+                if (G::AUX_PLUS_ONE) ml += 1.0f;
+                if (G::AUX_NEGATE) ml = -ml;
+                if (decay) { wd = gamma * wd + (1 - gamma) * u3; w1 = gamma * w1 + (1 - gamma) * u3; w2 = gamma * w2 + (1 - gamma) * u3; }
+            }
+            if (mine) {
+                sp->n = n + 1;
+                w.x += mwd; w.y += mw1; w.z += mw2; w.w += mml;
+                *reinterpret_cast<float4 *>(&sp->wd) = w;
+            }
+        }
+        root.n += 1; root.wd += wd; root.wp1 += w1; root.wp2 += w2; root.msum += ml;
+        gsync<W>(gm);   // the next k of this tree must see these updates (duplicate leaves, shared ancestors)
+    }
+    if (lane == 0) { st_slot(&tr->root, root); tr->bump = bump; tr->noise_ctr = noise_ctr; }
+    if (d.stats && lane == 0) { atomicAdd(d.stats + 3, st_created); atomicAdd(d.stats + 4, st_expanded); }
+}
+
+// ================================================================================================
+// Thread-per-tree variants (Connect4, lanes = 1) for large batches.
+//
+// With one thread per tree every warp instruction serves 32 trees, but naive per-thread loads of a tree's
+// 224-byte node block touch 32 different cache lines per instruction (L1TEX wavefront bound).  k_select_t
+// therefore gathers the 32 node blocks of a warp COOPERATIVELY: instruction i moves the 16-byte chunks of trees
+// 2i and 2i+1 with consecutive lanes on consecutive chunks (2-4 lines per instruction instead of 32), stages
+// them in shared memory (272-byte rows: conflict-free for 16-byte accesses), and each lane then reads its own
+// block from shared memory.  The arithmetic is the same as k_select's, so results are bit-identical.
+// ================================================================================================
+template <class G, bool VL>
+__global__ void __launch_bounds__(CTA, 4) k_select_t(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
+                                                  az_leaf *__restrict__ leaves) {
+    constexpr int NE = G::MAX_EDGES;       // 7
+    constexpr int ROW = 17;                // uint4 per staged tree (16 + 1 pad)
+    __shared__ uint4 stage[CTA / 32][32][ROW];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int tid = blockIdx.x * CTA + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool valid = tid < d.n_envs;
+    const int env = valid ? tid : d.n_envs - 1;        // clamped: inactive lanes only help with the gather
+    Slot *arena = d.pool + (size_t)env * d.cap;
+    TreeRec *tr = d.trees + env;
+    const int vl = VL ? cfg.vl_count : 0;
+    const bool use_aux = aux_enabled<G>(cfg);
+    const float ne_eps = cfg.noise_epsilon;
+
+    State start;
+    { const az_root r = ld32(roots + env); start.bb[0] = r.bb0; start.bb[1] = r.bb1; G::finish_import(start, r.turn); }
+    Slot root = ld_slot(&tr->root);
+    const uint32_t root_meta_in = root.meta;
+    float nz[NE];                           // the root's Dirichlet noise, read once
+#pragma unroll
+    for (int e = 0; e < NE; ++e) nz[e] = ne_eps > 0.0f ? d.noise[(size_t)env * d.noise_stride + e] : 0.0f;
+    unsigned long long st_depth = 0, st_edges = 0;
+
+    for (int k = 0; k < K; ++k) {
+        State st = start;
+        Slot cur = root;
+        bool is_root = true, root_vl = false;
+        uint32_t plen = 0;
+        uint32_t *path = VL ? d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH : d.path_nv + (size_t)env * G::MAX_DEPTH;
+        uint32_t p8[PATH8];
+#pragma unroll
+        for (int j = 0; j < PATH8; ++j) p8[j] = 0;
+        int winner = 0; bool full = false;
+        uint32_t last_slot = 0;
+        bool descending = valid && cur.child != NONE && !(cur.meta & F_TERM) && (cur.child & 63u) != 0;
+
+        while (__any_sync(FULL, descending)) {
+            // ---- cooperative gather of the warp's node blocks into shared memory ----
+            const int ne = descending ? (int)(cur.child & 63u) : 0;
+            const uint32_t off = descending ? (cur.child >> 6) : 0u;
+            // 32-byte aligned block address with the chunk count packed into its low bits
+            const unsigned long long src = (unsigned long long)(uintptr_t)(arena + off) | (unsigned long long)(2 * ne);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int t = 2 * i + (lane >> 4), part = lane & 15;
+                const uint32_t lo = __shfl_sync(FULL, (uint32_t)src, t), hi = __shfl_sync(FULL, (uint32_t)(src >> 32), t);
+                const int n_t = (int)(lo & 31u);
+                if (part < n_t) {     // asynchronous 16-byte global->shared copy: all 16 rounds are in flight together
+                    const uint4 *gp = reinterpret_cast<const uint4 *>((uintptr_t)(((unsigned long long)hi << 32) | (lo & ~31u))) + part;
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(&stage[warp][t][part]);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gp) : "memory");
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            if (descending) {
+                Slot s[NE];
+#pragma unroll
+                for (int c = 0; c < NE; ++c) {
+                    if (c < ne) {
+                        const uint4 a = stage[warp][lane][2 * c], b = stage[warp][lane][2 * c + 1];
+                        s[c].prior = __uint_as_float(a.x); s[c].n = (int)a.y; s[c].meta = a.z; s[c].child = a.w;
+                        s[c].wd = __uint_as_float(b.x); s[c].wp1 = __uint_as_float(b.y); s[c].wp2 = __uint_as_float(b.z); s[c].msum = __uint_as_float(b.w);
+                    } else { s[c].prior = 0.f; s[c].n = 0; s[c].meta = 0; s[c].child = NONE; s[c].wd = s[c].wp1 = s[c].wp2 = s[c].msum = 0.f; }
+                }
+                st_edges += (unsigned long long)ne;
+                // ---- compute_fpu (MCTS.h:140-156) ----
+                const int cur_infl = (int)(cur.meta & INFL_MASK);
+                const float parent_q = mean_q(cur.n, cur.wp1, cur.wp2, (cur.meta & F_TURN_P1) != 0);
+                float seen_policy = 0.0f;
+#pragma unroll
+                for (int c = 0; c < NE; ++c) seen_policy += (c < ne && s[c].n > 0) ? s[c].prior : 0.0f;   // + 0.0f is exact
+                const float fscale = (1.0f + parent_q) / 2.0f;
+                const float eff_fpu = cfg.fpu_reduction * fscale;
+                float fpu = parent_q - eff_fpu * sqrtf(seen_policy);
+                fpu = (-1.0f < fpu) ? fpu : -1.0f;
+                // ---- select_edge (MCTS.h:163-234) ----
+                const int pn_i = cur.n + cur_infl;
+                const float parent_n = (float)pn_i;
+                const float parent_M = use_aux ? mean_m(cur.n, cur.msum) : 0.0f;
+                const float lg = (pn_i >= 0 && pn_i < d.log_lut_n) ? d.log_lut[pn_i] : logf((parent_n + cfg.c_base + 1.0f) / cfg.c_base);
+                const float c_puct = cfg.c_init + lg;
+                const float sqrt_pn = sqrtf(parent_n);
+                const bool mix_noise = is_root && ne_eps > 0.0f;
+                float best_s = -INFINITY; int best_e = -1;
+#pragma unroll
+                for (int c = 0; c < NE; ++c) {
+                    if (c >= ne) continue;
+                    float eff_prior = s[c].prior;
+                    if (mix_noise) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * nz[c];
+                    const int cn = s[c].n, cinf = (int)(s[c].meta & INFL_MASK);
+                    float q_value = fpu, m_utility = 0.0f; int visits = cinf;
+                    if (cn > 0) {
+                        visits = cn + cinf;
+                        const float child_Q = mean_q(cn, s[c].wp1, s[c].wp2, (s[c].meta & F_TURN_P1) != 0);
+                        q_value = -child_Q;
+                        if (use_aux) {
+                            float child_M = mean_m(cn, s[c].msum);
+                            if (G::AUX_NEGATE) child_M = -child_M;
+                            m_utility = aux_utility<G>(child_M, parent_M, child_Q, cfg);
+                        }
+                    }
+                    const float u_score = c_puct * eff_prior * sqrt_pn / (1.0f + (float)visits);
+                    const float score = q_value + u_score + m_utility;
+                    if (score > best_s) { best_s = score; best_e = c; }
+                }
+                if (best_e < 0) descending = false;
+                else {
+                    if (VL && !root_vl) { root_vl = true; root.meta += (uint32_t)vl; }
+                    Slot ch = s[0];
+#pragma unroll
+                    for (int c = 1; c < NE; ++c) if (best_e == c) ch = s[c];
+                    G::step(st, (int)((ch.meta >> 16) & 0xFFu));
+                    uint32_t nmeta = ch.meta;
+                    if (!(nmeta & F_ALLOC)) {
+                        nmeta |= F_ALLOC;
+                        nmeta = st.turn == 1 ? (nmeta | F_TURN_P1) : (nmeta & ~F_TURN_P1);
+                    }
+                    nmeta += (uint32_t)vl;
+                    winner = G::winner(st);
+                    full = G::full(st);
+                    const bool term_now = winner != 0 || full;
+                    if (term_now) nmeta = (nmeta & ~(F_WIN_P1 | F_WIN_P2)) | F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+                    last_slot = off + (uint32_t)best_e;
+                    if (nmeta != ch.meta) arena[last_slot].meta = nmeta;
+                    path[plen] = last_slot;
+#pragma unroll
+                    for (int j = 0; j < PATH8; ++j) if (plen == (uint32_t)j) p8[j] = last_slot;
+                    ++plen;
+                    cur = ch; cur.meta = nmeta; is_root = false;
+                    descending = !term_now && cur.child != NONE && !(cur.meta & F_TERM) && (cur.child & 63u) != 0 && plen < (uint32_t)G::MAX_DEPTH;
+                }
+            }
+            __syncwarp();      // the staging rows are reused by the next level
+        }
+        if (valid) {
+            st_depth += plen;
+            bool leaf_term = (cur.meta & F_TERM) != 0;
+            if (plen == 0) leaf_term = (root.meta & F_TERM) != 0;
+            if (!leaf_term) {
+                if (winner == 0 && !full) { winner = G::winner(st); full = G::full(st); }
+                if (winner != 0 || full) {
+                    leaf_term = true;
+                    const uint32_t tf = F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+                    if (plen == 0) { root.meta = (root.meta & ~(F_WIN_P1 | F_WIN_P2)) | tf; cur.meta = root.meta; }
+                    else { cur.meta = (cur.meta & ~(F_WIN_P1 | F_WIN_P2)) | tf; arena[last_slot].meta = cur.meta; }
+                }
+            }
+            int sym = 0;
+            State ex = st;
+            if (!leaf_term && cfg.use_symmetry) {
+                const uint64_t h = az_rand(d.seed, d.epoch, STREAM_SYM, d.env_base + (uint64_t)env, (uint64_t)k);
+                sym = (int)(h & 1);
+                G::symmetry(ex, sym);
+            }
+            const uint8_t tflags = (uint8_t)(leaf_term ? (AZ_LEAF_TERMINAL | ((cur.meta & F_WIN_P1) ? AZ_LEAF_P1_WINS : 0u) |
+                                                          ((cur.meta & F_WIN_P2) ? AZ_LEAF_P2_WINS : 0u)) : 0u);
+            LeafRec R;
+            R.h.bb0 = st.bb[0]; R.h.bb1 = st.bb[1]; R.h.turn = st.turn; R.h.passes = (int16_t)st.passes; R.h.last = (int8_t)st.last;
+            R.h.flags = (uint8_t)(LF_VALID | ((VL && plen > 0) ? LF_VLPENDING : 0) | (leaf_term ? LF_TERM : 0) |
+                                  ((tflags & AZ_LEAF_P1_WINS) ? LF_WIN_P1 : 0) | ((tflags & AZ_LEAF_P2_WINS) ? LF_WIN_P2 : 0));
+            R.h.path_len = plen; R.h.sym = (uint32_t)sym;
+#pragma unroll
+            for (int j = 0; j < PATH8; ++j) R.path8[j] = p8[j];
+            LeafRec *dst = VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env;
+            st32(&dst->h, R.h);
+            uint4 *pq = reinterpret_cast<uint4 *>(dst->path8);
+            pq[0] = make_uint4(p8[0], p8[1], p8[2], p8[3]); pq[1] = make_uint4(p8[4], p8[5], p8[6], p8[7]);
+            az_leaf P;
+            P.bb0 = ex.bb[0]; P.bb1 = ex.bb[1]; P.turn = (int8_t)st.turn; P.flags = tflags; P.sym = (uint8_t)sym; P.passes = (uint8_t)st.passes;
+            P.reserved[0] = P.reserved[1] = P.reserved[2] = 0;
+            st32(leaves + (size_t)env * K + k, P);
+        }
+    }
+    if (valid && root.meta != root_meta_in) tr->root.meta = root.meta;
+    if (d.stats && valid) {
+        atomicAdd(d.stats + 0, (unsigned long long)K);
+        atomicAdd(d.stats + 1, st_depth);
+        atomicAdd(d.stats + 2, st_edges);
+    }
+}
+
+// Thread-per-tree back-propagation.  The virtual loss of path k is removed in the same read-modify-write that adds
+// simulation k's result to each node (the order is unobservable: nothing in back-prop reads in-flight counts, and
+// by the end of the kernel every pending loss is gone, exactly as after remove_all_vl + K backprop_vl calls).  The
+// first 8 path entries travel inside the 64-byte LeafRec, and path nodes are updated four at a time so their loads
+// overlap instead of forming a dependent chain.
+template <class G, bool VL>
+__global__ void __launch_bounds__(CTA, 4) k_backprop_t(Dev d, az_search_config cfg, int K, int removeK, int use_sym, const float *__restrict__ policy,
+                                                    const float *__restrict__ dv, const float *__restrict__ p1v, const float *__restrict__ p2v,
+                                                    const float *__restrict__ mlv, const uint8_t *__restrict__ is_term,
+                                                    const int32_t *__restrict__ sym_ids) {
+    static_assert(G::GAME == GAME_C4, "thread-per-tree back-prop is specialised for Connect4 (terminal aux = 0, <= 7 edges)");
+    const int env = blockIdx.x * CTA + threadIdx.x;
+    if (env >= d.n_envs) return;
+    constexpr int A = G::A;
+    Slot *arena = d.pool + (size_t)env * d.cap;
+    TreeRec *tr = d.trees + env;
+    Slot root = ld_slot(&tr->root);
+    uint32_t bump = tr->bump, noise_ctr = tr->noise_ctr;
+    const int vl = cfg.vl_count;
+    unsigned long long st_created = 0, st_expanded = 0;
+    LeafRec *recs = VL ? d.leaf_vl + (size_t)env * d.kcap : d.leaf_nv + env;
+    for (int k = 0; k < K; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + k));
+
+    for (int k = 0; k < K; ++k) {
+        LeafRec *rp = recs + k;
+        const LeafHead L = ld32(&rp->h);
+        if (!(L.flags & LF_VALID)) continue;
+        uint32_t p8[PATH8];
+        { const uint4 *pq = reinterpret_cast<const uint4 *>(rp->path8); const uint4 a = pq[0], b = pq[1];
+          p8[0] = a.x; p8[1] = a.y; p8[2] = a.z; p8[3] = a.w; p8[4] = b.x; p8[5] = b.y; p8[6] = b.z; p8[7] = b.w; }
+        const size_t flat = (size_t)env * K + k;
+        const bool term = is_term ? (is_term[flat] != 0) : ((L.flags & LF_TERM) != 0);
+        const uint32_t plen = L.path_len;
+        const uint32_t *path = VL ? d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH : d.path_nv + (size_t)env * G::MAX_DEPTH;
+        const bool pending = VL && (L.flags & LF_VLPENDING) && k < removeK;
+        const uint32_t dec = pending ? (uint32_t)vl : 0u;
+        State st; st.bb[0] = L.bb0; st.bb[1] = L.bb1; st.turn = L.turn; st.passes = L.passes; st.last = L.last;
+        auto path_at = [&](uint32_t j) -> uint32_t {             // j-th path entry (0 = first edge below the root)
+            uint32_t v = p8[0];
+#pragma unroll
+            for (int q = 1; q < PATH8; ++q) if (j == (uint32_t)q) v = p8[q];
+            return j < (uint32_t)PATH8 ? v : path[j];
+        };
+        if (pending) { const int infl = (int)(root.meta & INFL_MASK) - vl; root.meta = (root.meta & ~INFL_MASK) | (uint32_t)max(infl, 0); }
+        Slot leaf = root; Slot *leaf_ptr = nullptr;
+        if (plen > 0) { leaf_ptr = arena + path_at(plen - 1); leaf = ld_slot(leaf_ptr); }
+
+        // ---- expand_leaf (MCTS.h:329-375) ----
+        if (!term && (!VL || leaf.child == NONE)) {
+            const int sym = use_sym ? (sym_ids ? sym_ids[flat] : (int)L.sym) : 0;
+            const uint64_t legal = G::legal(st);
+            const int ne = popc64(legal);
+            const float *prow = policy + flat * A;
+            float pm[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) pm[a] = prow[G::sym_action(sym, a)];
+            float psum = 0.0f;
+#pragma unroll
+            for (int a = 0; a < A; ++a) psum += ((legal >> a) & 1ULL) ? pm[a] : 0.0f;     // ascending legal order; + 0.0f exact
+            const float denom = psum + 1e-8f;
+            if (bump + (uint32_t)ne > d.cap) atomicExch(d.err, 1);
+            else {
+                const uint32_t off = bump;
+                Slot ns; ns.n = 0; ns.child = NONE; ns.wd = ns.wp1 = ns.wp2 = ns.msum = 0.0f;
+                int eidx = 0;
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    if (!((legal >> a) & 1ULL)) continue;
+                    ns.prior = pm[a] / denom;
+                    ns.meta = (uint32_t)a << 16;
+                    st_slot(arena + off + eidx, ns);
+                    ++eidx;
+                }
+                bump += (uint32_t)ne;
+                leaf.child = (off << 6) | (uint32_t)ne;
+                if (plen == 0) {
+                    float *nrow = d.noise + (size_t)env * d.noise_stride;
+                    if (cfg.dirichlet_alpha > 0.0f) draw_root_noise(d.seed, d.env_base + (uint64_t)env, noise_ctr, cfg.dirichlet_alpha, ne, nrow);
+                    else for (int e = 0; e < ne; ++e) nrow[e] = 0.0f;
+                }
+                st_created += (unsigned long long)ne; st_expanded += 1;
+            }
+        }
+        // ---- propagate (MCTS.h:381-402) fused with the removal of this path's virtual loss ----
+        float wd = dv[flat], w1 = p1v[flat], w2 = p2v[flat];
+        float ml = term ? 0.0f : mlv[flat];                       // Connect4 terminal_aux = 0
+        const float gamma = cfg.value_decay;
+        const bool decay = gamma < 1.0f;
+        const float u3 = 1.0f / 3.0f;
         auto advance = [&]() {
             if (G::AUX_PLUS_ONE) ml += 1.0f;
             if (G::AUX_NEGATE) ml = -ml;
             if (decay) { wd = gamma * wd + (1 - gamma) * u3; w1 = gamma * w1 + (1 - gamma) * u3; w2 = gamma * w2 + (1 - gamma) * u3; }
         };
-        constexpr int UNR = W == 1 ? 4 : 1;                      // a single lane overlaps the loads of 4 path nodes
-        for (uint32_t base = 0; base < plen; base += W * UNR) {
-            Hot *hp[UNR]; Cold *cp[UNR]; Hot hv[UNR]; Cold cv[UNR]; bool mine[UNR];
+        auto apply = [&](Slot &s) {
+            s.n += 1; s.wd += wd; s.wp1 += w1; s.wp2 += w2; s.msum += ml;
+            const int infl = (int)(s.meta & INFL_MASK) - (int)dec;
+            s.meta = (s.meta & ~INFL_MASK) | (uint32_t)max(infl, 0);
+        };
+        if (plen == 0) {                                          // the leaf is the root
+            root.child = leaf.child;
+            root.n += 1; root.wd += wd; root.wp1 += w1; root.wp2 += w2; root.msum += ml;
+        } else {
+            apply(leaf);
+            st_slot(leaf_ptr, leaf);
+            advance();
+            uint32_t t = 1;                                       // t-th node counted from the leaf
+            while (t < plen) {
+                const uint32_t cnt = min(4u, plen - t);
+                Slot *sp[4]; Slot sv[4];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const uint32_t t = base + (uint32_t)(u * W + lane);          // t-th node counted from the leaf
-                mine[u] = t < plen;
-                if (mine[u]) { const EdgeRef r(path_at(plen - 1 - t)); hp[u] = r.hot(arena); cp[u] = r.cold(arena); }
+                for (int q = 0; q < 4; ++q) if ((uint32_t)q < cnt) sp[q] = arena + path_at(plen - 1 - (t + q));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if ((uint32_t)q < cnt) sv[q] = ld_slot(sp[q]);       // independent loads in flight together
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if ((uint32_t)q < cnt) { apply(sv[q]); st_slot(sp[q], sv[q]); advance(); }
+                t += cnt;
             }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) if (mine[u]) { hv[u] = ld_hot(hp[u]); cv[u] = ld_cold(cp[u]); }
-            const uint32_t lim = min((uint32_t)(W * UNR), plen - base);
-            for (uint32_t i = 0; i < lim; ++i) {                 // the value sequence is inherently sequential
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    if (i == (uint32_t)(u * W + lane)) {         // my node: add the value and refresh the cached means
-                        const int n = (int)(hv[u].nv >> 8) + 1;
-                        cv[u].wd += wd; cv[u].wp1 += w1; cv[u].wp2 += w2; cv[u].msum += ml;
-                        hv[u].nv = dec_infl(((uint32_t)n << 8) | (hv[u].nv & INFL_MASK), dec);
-                        // the node's own side to move: turns alternate along the path, the leaf's is known
-                        const bool turn_p1 = (((base + i) & 1u) ? -L.turn : L.turn) == 1;
-                        hv[u].q = mean_q(n, cv[u].wp1, cv[u].wp2, turn_p1);
-                        hv[u].m = mean_m(n, cv[u].msum);
-                    }
-                }
-                advance();
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) if (mine[u]) { st_hot(hp[u], hv[u]); st_cold(cp[u], cv[u]); }
+            root.n += 1; root.wd += wd; root.wp1 += w1; root.wp2 += w2; root.msum += ml;
         }
-        root.n += 1; root.wd += wd; root.wp1 += w1; root.wp2 += w2; root.msum += ml;
-        if (pending && lane == 0) rp->h.flags = (uint8_t)(L.flags & ~LF_VLPENDING);
-        gsync<W>(gm);   // the next k of this tree must see these updates (duplicate leaves, shared ancestors)
+        if (pending) rp->h.flags = (uint8_t)(L.flags & ~LF_VLPENDING);
     }
-    if (lane == 0) st_tree(tr, root);
-    if (d.stats && lane == 0) { atomicAdd(d.stats + 3, st_created); atomicAdd(d.stats + 4, st_expanded); }
+    st_slot(&tr->root, root); tr->bump = bump; tr->noise_ctr = noise_ctr;
+    if (d.stats) { atomicAdd(d.stats + 3, st_created); atomicAdd(d.stats + 4, st_expanded); }
 }
 
 // remove_all_vl without backprop (BatchedMCTS.h:209-216)
@@ -684,32 +935,20 @@ __global__ void __launch_bounds__(CTA) k_remove_vl(Dev d, az_search_config cfg, 
     if (gid >= d.n_envs) return;
     const int lane = threadIdx.x & (W - 1);
     const unsigned gm = group_mask<W>();
-    const int env = gid;
-    Chunk *arena = d.pool + (size_t)env * d.cap;
-    TreeRec *tr = d.trees + env;
-    uint32_t infl = tr->infl;
-    const uint32_t infl_in = infl, vl = (uint32_t)cfg.vl_count;
-    for (int k = 0; k < K; ++k) {
-        LeafHead *L = &(d.leaf_vl + (size_t)env * d.kcap + k)->h;
-        const uint8_t fl = L->flags;
-        if (!(fl & LF_VLPENDING)) continue;
-        const uint32_t plen = L->path_len;
-        const uint32_t *path = d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH;
-        infl = infl > vl ? infl - vl : 0u;
-        for (uint32_t j = lane; j < plen; j += W) { Hot *h = EdgeRef(path[j]).hot(arena); h->nv = dec_infl(h->nv, vl); }
-        gsync<W>(gm);
-        if (lane == 0) L->flags = (uint8_t)(fl & ~LF_VLPENDING);
-    }
-    if (lane == 0 && infl != infl_in) tr->infl = infl;
+    TreeRec *tr = d.trees + gid;
+    Slot root = ld_slot(&tr->root);
+    const uint32_t before = root.meta;
+    remove_vl_group<G, W>(d, cfg, gid, K, lane, gm, d.pool + (size_t)gid * d.cap, root);
+    if (lane == 0 && root.meta != before) tr->root.meta = root.meta;
 }
 
 // ------------------------------------------------------------------------------------------------
 // prune_root / apply_root_noise / reset (MCTS.h:77-132), one thread per tree
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void reset_tree(TreeRec *tr, float *nrow, int noise_stride) {
-    TreeRec r; r.n = 0; r.infl = 0; r.wd = r.wp1 = r.wp2 = r.msum = 0.f; r.child = NONE; r.flags = M_TURN_P1;   // fresh root: turn = +1
-    r.bump = 0; r.noise_ctr = tr->noise_ctr;
-    st_tree(tr, r);
+    Slot r; r.prior = 0.f; r.n = 0; r.meta = F_TURN_P1; r.child = NONE; r.wd = r.wp1 = r.wp2 = r.msum = 0.f;   // fresh root: turn = +1
+    st_slot(&tr->root, r);
+    tr->bump = 0;
     for (int e = 0; e < noise_stride; ++e) nrow[e] = 0.0f;
 }
 template <class G>
@@ -717,27 +956,25 @@ __global__ void k_prune(Dev d, az_search_config cfg, const int32_t *__restrict__
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= d.n_envs) return;
     TreeRec *tr = d.trees + env;
-    Chunk *arena = d.pool + (size_t)env * d.cap;
+    Slot *arena = d.pool + (size_t)env * d.cap;
     float *nrow = d.noise + (size_t)env * d.noise_stride;
-    TreeRec root = ld_tree(tr);
+    const Slot root = ld_slot(&tr->root);
     const int action = actions[env];
     if (root.child != NONE) {
         const int ne = (int)(root.child & 63u); const uint32_t off = root.child >> 6;
         for (int e = 0; e < ne; ++e) {
-            const EdgeRef r(path_entry(off, ne, e));
-            const uint32_t mt = *r.meta(arena);
-            if ((int)(mt & 0xFFu) == action && (mt & M_ALLOC)) {
-                const Hot h = ld_hot(r.hot(arena)); const Cold c = ld_cold(r.cold(arena));
-                root.n = (int)(h.nv >> 8); root.infl = h.nv & INFL_MASK;       // promoted child becomes the root (parent = -1)
-                root.wd = c.wd; root.wp1 = c.wp1; root.wp2 = c.wp2; root.msum = c.msum;
-                root.child = *r.link(arena);
-                root.flags = mt & (M_TERM | M_WIN_P1 | M_WIN_P2 | M_TURN_P1);
-                const int cne = root.child == NONE ? 0 : (int)(root.child & 63u);
-                if (cfg.dirichlet_alpha > 0.0f && cne > 0)      // apply_root_noise (MCTS.h:113-132)
-                    draw_root_noise(d.seed, d.env_base + (uint64_t)env, root.noise_ctr, cfg.dirichlet_alpha, cne, nrow);
-                else
+            Slot s = ld_slot(arena + off + e);
+            if ((int)((s.meta >> 16) & 0xFFu) == action && (s.meta & F_ALLOC)) {
+                s.prior = 0.f;
+                st_slot(&tr->root, s);                      // promoted child becomes the root (parent = -1)
+                const int cne = s.child == NONE ? 0 : (int)(s.child & 63u);
+                if (cfg.dirichlet_alpha > 0.0f && cne > 0) {  // apply_root_noise (MCTS.h:113-132)
+                    uint32_t ctr = tr->noise_ctr;
+                    draw_root_noise(d.seed, d.env_base + (uint64_t)env, ctr, cfg.dirichlet_alpha, cne, nrow);
+                    tr->noise_ctr = ctr;
+                } else {
                     for (int i = 0; i < d.noise_stride; ++i) nrow[i] = 0.0f;   // the promoted node's edges never had noise
-                st_tree(tr, root);
+                }
                 return;
             }
         }
@@ -747,12 +984,6 @@ __global__ void k_prune(Dev d, az_search_config cfg, const int32_t *__restrict__
 __global__ void k_reset(Dev d, int env /* -1 = all */) {
     const int i = env >= 0 ? env : (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= d.n_envs || (env >= 0 && (blockIdx.x | threadIdx.x) != 0)) return;
-    reset_tree(d.trees + i, d.noise + (size_t)i * d.noise_stride, d.noise_stride);
-}
-__global__ void k_init_trees(Dev d) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.n_envs) return;
-    d.trees[i].noise_ctr = 0;
     reset_tree(d.trees + i, d.noise + (size_t)i * d.noise_stride, d.noise_stride);
 }
 __global__ void k_init_leaf(LeafRec *leaf, size_t n) {
@@ -765,13 +996,13 @@ __global__ void k_max_bump(Dev d, unsigned int *out) {
     v = __reduce_max_sync(0xFFFFFFFFu, v);
     if ((threadIdx.x & 31) == 0) atomicMax(out, v);
 }
-__global__ void k_grow(const Chunk *__restrict__ src, Chunk *__restrict__ dst, const TreeRec *__restrict__ trees, uint32_t old_cap,
+__global__ void k_grow(const Slot *__restrict__ src, Slot *__restrict__ dst, const TreeRec *__restrict__ trees, uint32_t old_cap,
                        uint32_t new_cap) {   // one CTA per tree copies the used prefix of its arena
     const int env = blockIdx.x;
     const uint32_t used = trees[env].bump;
-    const Chunk *s = src + (size_t)env * old_cap;
-    Chunk *t = dst + (size_t)env * new_cap;
-    for (uint32_t i = threadIdx.x; i < used; i += blockDim.x) t[i] = s[i];
+    const uint4 *s = reinterpret_cast<const uint4 *>(src + (size_t)env * old_cap);
+    uint4 *t = reinterpret_cast<uint4 *>(dst + (size_t)env * new_cap);
+    for (uint32_t i = threadIdx.x; i < used * 2; i += blockDim.x) t[i] = s[i];
 }
 
 // get_counts / get_root_stats (MCTS.h:617-673)
@@ -781,14 +1012,13 @@ __global__ void k_counts(Dev d, int32_t *__restrict__ out) {
     if (env >= d.n_envs) return;
     int32_t *o = out + (size_t)env * G::A;
     for (int a = 0; a < G::A; ++a) o[a] = 0;
-    const uint32_t child = d.trees[env].child;
-    if (child == NONE) return;
-    Chunk *arena = d.pool + (size_t)env * d.cap;
-    const int ne = (int)(child & 63u); const uint32_t off = child >> 6;
+    const Slot root = ld_slot(&d.trees[env].root);
+    if (root.child == NONE) return;
+    const Slot *blk = d.pool + (size_t)env * d.cap + (root.child >> 6);
+    const int ne = (int)(root.child & 63u);
     for (int e = 0; e < ne; ++e) {
-        const EdgeRef r(path_entry(off, ne, e));
-        const uint32_t mt = *r.meta(arena);
-        if (mt & M_ALLOC) o[mt & 0xFFu] = (int32_t)(r.hot(arena)->nv >> 8);
+        const Slot s = ld_slot(blk + e);
+        if (s.meta & F_ALLOC) o[(s.meta >> 16) & 0xFFu] = s.n;
     }
 }
 template <class G>
@@ -797,34 +1027,30 @@ __global__ void k_root_stats(Dev d, float *__restrict__ out) {
     if (env >= d.n_envs) return;
     constexpr int SZ = 6 + 8 * G::A;
     float *o = out + (size_t)env * SZ;
-    const TreeRec root = ld_tree(d.trees + env);
+    const Slot root = ld_slot(&d.trees[env].root);
     const float third = 1.f / 3;
     if (root.n == 0) { o[3] = o[4] = o[5] = third; }
     else { float inv = 1.0f / (float)root.n; o[3] = root.wd * inv; o[4] = root.wp1 * inv; o[5] = root.wp2 * inv; }
     o[0] = (float)root.n;
-    o[1] = mean_q(root.n, root.wp1, root.wp2, (root.flags & M_TURN_P1) != 0);
+    o[1] = mean_q(root.n, root.wp1, root.wp2, (root.meta & F_TURN_P1) != 0);
     o[2] = mean_m(root.n, root.msum);
     for (int j = 6; j < SZ; ++j) o[j] = 0.0f;
     if (root.child == NONE) return;
-    Chunk *arena = d.pool + (size_t)env * d.cap;
+    const Slot *blk = d.pool + (size_t)env * d.cap + (root.child >> 6);
     const float *nrow = d.noise + (size_t)env * d.noise_stride;
-    const int ne = (int)(root.child & 63u); const uint32_t off = root.child >> 6;
+    const int ne = (int)(root.child & 63u);
     for (int e = 0; e < ne; ++e) {
-        const EdgeRef r(path_entry(off, ne, e));
-        const uint32_t mt = *r.meta(arena);
-        const Hot h = ld_hot(r.hot(arena));
-        float *sl = o + 6 + (mt & 0xFFu) * 8;
-        sl[2] = h.prior; sl[3] = nrow[e];
-        if (mt & M_ALLOC) {
-            const Cold c = ld_cold(r.cold(arena));
-            const int n = (int)(h.nv >> 8);
-            float cm = mean_m(n, c.msum);
+        const Slot s = ld_slot(blk + e);
+        float *sl = o + 6 + ((s.meta >> 16) & 0xFFu) * 8;
+        sl[2] = s.prior; sl[3] = nrow[e];
+        if (s.meta & F_ALLOC) {
+            float cm = mean_m(s.n, s.msum);
             if (G::AUX_NEGATE) cm = -cm;
-            sl[0] = (float)n;
-            sl[1] = mean_q(n, c.wp1, c.wp2, (mt & M_TURN_P1) != 0);
+            sl[0] = (float)s.n;
+            sl[1] = mean_q(s.n, s.wp1, s.wp2, (s.meta & F_TURN_P1) != 0);
             sl[4] = cm;
-            if (n == 0) { sl[5] = sl[6] = sl[7] = third; }
-            else { float inv = 1.0f / (float)n; sl[5] = c.wd * inv; sl[6] = c.wp1 * inv; sl[7] = c.wp2 * inv; }
+            if (s.n == 0) { sl[5] = sl[6] = sl[7] = third; }
+            else { float inv = 1.0f / (float)s.n; sl[5] = s.wd * inv; sl[6] = s.wp1 * inv; sl[7] = s.wp2 * inv; }
         }
     }
 }
@@ -1020,9 +1246,9 @@ static int ensure_io(az_mcts *h, int rows) {
 }
 
 static int grow_arena(az_mcts *h, uint64_t ncap, cudaStream_t st) {
-    if (ncap > (1ull << 20)) AZ_FAIL(h, AZ_ERR_NOMEM, "tree arena would exceed 2^20 chunks (16 MB) per tree");
-    Chunk *np = nullptr;
-    cudaError_t e = cudaMalloc((void **)&np, sizeof(Chunk) * (size_t)h->n * ncap);
+    if (ncap >= (1ull << 26)) AZ_FAIL(h, AZ_ERR_NOMEM, "tree arena would exceed 2^26 slots per tree");
+    Slot *np = nullptr;
+    cudaError_t e = cudaMalloc((void **)&np, sizeof(Slot) * (size_t)h->n * ncap);
     if (e != cudaSuccess) AZ_FAIL(h, AZ_ERR_NOMEM, "cannot grow tree arenas to %llu slots/tree: %s", (unsigned long long)ncap, cudaGetErrorString(e));
     CU(h, cudaDeviceSynchronize());
     k_grow<<<h->n, 256, 0, st>>>(h->d.pool, np, h->d.trees, h->cap, (uint32_t)ncap);
@@ -1034,7 +1260,7 @@ static int grow_arena(az_mcts *h, uint64_t ncap, cudaStream_t st) {
 
 // Make sure no tree can overflow its arena during a back-prop of `sims` simulations per tree.
 static int ensure_arena(az_mcts *h, int sims, cudaStream_t st) {
-    const uint64_t need = (uint64_t)sims * (uint64_t)(h->game == GAME_C4 ? block_chunks(7) : block_chunks(34));
+    const uint64_t need = (uint64_t)sims * (uint64_t)(h->game == GAME_C4 ? 7 : 34);
     if (h->bump_bound + need <= h->cap) { h->bump_bound += need; return AZ_OK; }
     // refresh the bound from the device
     CU(h, cudaMemsetAsync(h->d_scratch_u32, 0, sizeof(unsigned int), st));
@@ -1053,8 +1279,8 @@ static int ensure_arena(az_mcts *h, int sims, cudaStream_t st) {
 }
 
 static int check_cfg(az_mcts *h, int K) {
-    if (h->cfg.vl_count < 0 || (int64_t)h->cfg.vl_count * std::max(K, 1) > 255)    // in-flight counts live in 8 bits of the hot record
-        AZ_FAIL(h, AZ_ERR_INVALID, "vl_count * K must be in [0, 255] (got vl_count=%d, K=%d)", h->cfg.vl_count, K);
+    if (h->cfg.vl_count < 0 || (int64_t)h->cfg.vl_count * std::max(K, 1) > 65535)
+        AZ_FAIL(h, AZ_ERR_INVALID, "vl_count * K must be in [0, 65535] (got vl_count=%d, K=%d)", h->cfg.vl_count, K);
     return ensure_luts(h);
 }
 
@@ -1082,6 +1308,12 @@ static int auto_lanes(int game, int n) {
 
 static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s) {
     const int g = grid_groups(h->n, h->W);
+    if (h->game == GAME_C4 && h->W == 1) {       // thread-per-tree kernels with cooperative block gather
+        if (vl) k_select_t<C4, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, roots, leaves);
+        else k_select_t<C4, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, roots, leaves);
+        h->launches++;
+        return;
+    }
     if (vl) AZ_DISPATCH_W(h, k_select, true, g, s, h->d, h->cfg, K, roots, leaves);
     else AZ_DISPATCH_W(h, k_select, false, g, s, h->d, h->cfg, 1, roots, leaves);
     h->launches++;
@@ -1089,6 +1321,12 @@ static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_l
 static void launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym, const float *pol, const float *d, const float *p1,
                             const float *p2, const float *ml, const uint8_t *it, const int32_t *sym, cudaStream_t s) {
     const int g = grid_groups(h->n, h->W);
+    if (h->game == GAME_C4 && h->W == 1) {
+        if (vl) k_backprop_t<C4, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, removeK, use_sym, pol, d, p1, p2, ml, it, sym);
+        else k_backprop_t<C4, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, 0, use_sym, pol, d, p1, p2, ml, it, sym);
+        h->launches++;
+        return;
+    }
     if (vl) AZ_DISPATCH_W(h, k_backprop, true, g, s, h->d, h->cfg, K, removeK, use_sym, pol, d, p1, p2, ml, it, sym);
     else AZ_DISPATCH_W(h, k_backprop, false, g, s, h->d, h->cfg, 1, 0, use_sym, pol, d, p1, p2, ml, it, sym);
     h->launches++;
@@ -1159,7 +1397,7 @@ template <class G> static void launch_unpack(int rows, const az_leaf *l, int8_t 
 
 extern "C" {
 
-const char *az_version(void) { return "azb200 0.3 (sm_100a)"; }
+const char *az_version(void) { return "azb200 0.2 (sm_100a)"; }
 const char *az_global_last_error(void) { return g_global_err.c_str(); }
 int az_game_action_size(int g) { return g == GAME_C4 ? C4::A : (g == GAME_OTH ? Oth::A : -1); }
 int az_game_board_size(int g) { return g == GAME_C4 ? C4::S : (g == GAME_OTH ? Oth::S : -1); }
@@ -1213,8 +1451,8 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail("create"); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "stream create failed"; return fail("create"); }
     if (cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming) != cudaSuccess) { h->err = "event create failed"; return fail("create"); }
-    const char *ce = getenv("AZB200_ARENA_CHUNKS");
-    h->cap = ce ? (uint32_t)std::max(256, atoi(ce)) : (game == GAME_C4 ? 4096u : 8192u);     // 16-byte chunks per tree
+    const char *ce = getenv("AZB200_ARENA_SLOTS");
+    h->cap = ce ? (uint32_t)std::max(256, atoi(ce)) : (game == GAME_C4 ? 2048u : 4096u);
     h->d.n_envs = n_envs; h->d.cap = h->cap; h->d.noise_stride = h->max_edges;
     h->d.seed = 0x243F6A8885A308D3ULL; h->d.epoch = 0;
     int rc = 0;
@@ -1232,7 +1470,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     h->d.err = h->d_err;
     cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream);
     cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
-    k_init_trees<<<grid_threads((size_t)n_envs), 128, 0, h->stream>>>(h->d);
+    k_reset<<<grid_threads((size_t)n_envs), 128, 0, h->stream>>>(h->d, -1);
     k_init_leaf<<<grid_threads((size_t)n_envs), 128, 0, h->stream>>>(h->d.leaf_nv, (size_t)n_envs);
     if (ensure_io(h, n_envs) != AZ_OK) return fail("io allocation");
     if (ensure_luts(h) != AZ_OK) return fail("LUT upload");
