@@ -284,3 +284,57 @@ def test_cnn_in_the_loop_visit_distribution_l1():
     print(f"CNN-in-the-loop: max L1 {l1.max():.4g}, mean L1 {l1.mean():.4g}, {np.mean(l1 == 0):.3f} of trees identical")
     # one visit moved between two actions is already L1 = 2/199; the tolerance is on the distribution over the batch
     assert np.mean(l1 <= 1e-3) >= 0.95 and l1.mean() <= 1e-3, f"max L1 {l1.max()}, mean {l1.mean()}"
+
+
+# ---- search() with built-in evaluators, and the RNG-dependent features (distributional: parity unpinned) ----
+@pytest.mark.parametrize("game", ["Connect4", "Othello"])
+def test_rollout_search_matches_restatement(game):
+    """search(RolloutEvaluator) runs the whole playout loop on the device.  The integer rollout RNG is shared with the C
+    restatement (not with the reference's mt19937), so visit counts match the restatement bit for bit."""
+    m = importlib.import_module("alphazero-al_b200.mcts_cpp")
+    n, npl = 64, 60
+    boards, turns = random_positions(game, n, 12, 51)
+    cfg = dict(c_init=1.0, c_base=500.0, dirichlet_alpha=0.0, noise_epsilon=0.0, fpu_reduction=0.0, use_symmetry=False)   # MCTSPlayer, src/player.py:81-88
+    a, b = _cuda(game, n), _orc(game, n)
+    for e in (a, b):
+        set_config(e, **cfg)
+        e.set_seed(77)
+    a.search(getattr(m, f"RolloutEvaluator_{game}")(), boards, turns, npl)
+    b.search(oracle.EVAL_ROLLOUT, boards, turns, npl)
+    A = oracle.ACTION_SIZE[game]
+    assert np.array_equal(counts(a, n, A), counts(b, n, A))
+    assert a.get_all_root_stats().tobytes() == b.get_all_root_stats().tobytes()
+    assert (counts(a, n, A).sum(1) == npl - 1).all()
+
+
+def test_dirichlet_noise_and_symmetry_ids_are_well_formed():
+    n = 4096
+    e = _cuda("Connect4", n)
+    set_config(e, **dict(SERVER_DEFAULTS, dirichlet_alpha=0.3, noise_epsilon=0.25, use_symmetry=True))
+    e.set_seed(5)
+    boards = np.zeros((n, 6, 7), np.int8)
+    boards[:, 5, 3] = 1
+    boards[:, :, 0] = np.array([1, -1, 1, -1, 1, -1])[None, :]          # column 0 full: 6 legal moves
+    turns = np.ones(n, np.int32)
+    ev = importlib.import_module("alphazero-al_b200.evaluators").HashEvaluator("Connect4", "constant")
+    playout(e, ev, boards, turns, 2, 1)
+    st = e.get_all_root_stats()[:, 6:].reshape(n, 7, 8)
+    noise, prior = st[:, :, 3], st[:, :, 2]
+    assert np.allclose(noise.sum(1), 1.0, atol=1e-5) and (noise[:, 0] == 0).all() and (noise[:, 1:] > 0).all()
+    assert np.allclose(prior[:, 1:], 1 / 6, atol=1e-6) and (prior[:, 0] == 0).all()
+    # Dirichlet(0.3 x 6): each marginal has mean 1/6 and variance (1/6)(5/6)/(1.8+1)
+    assert abs(noise[:, 1:].mean() - 1 / 6) < 5e-3 and abs(noise[:, 1].var() - (1 / 6) * (5 / 6) / 2.8) < 8e-3
+    e.prune_roots(np.full(n, 3, np.int32))                               # promoted root: noise is re-drawn (MCTS.h:102)
+    st2 = e.get_all_root_stats()[:, 6:].reshape(n, 7, 8)
+    # symmetry ids: Connect4 uniform over {0,1}; Othello uniform over {0,2,6,7} (Othello.h:45)
+    _, _, _, _, _, _, sym, _ = e.search_batch_vl(4, boards, turns)
+    e.remove_all_vl(4)
+    assert set(np.unique(sym)) <= {0, 1} and abs(sym.mean() - 0.5) < 0.03
+    o = _cuda("Othello", 1024)
+    set_config(o, dirichlet_alpha=0.0, use_symmetry=True)
+    ob, ot = random_positions("Othello", 1, 0, 0)
+    ob, ot = np.tile(ob, (1024, 1, 1)), np.tile(ot, 1024)
+    playout(o, importlib.import_module("alphazero-al_b200.evaluators").HashEvaluator("Othello", "constant"), ob, ot, 1, 1)
+    _, _, _, _, _, _, osym, _ = o.search_batch_vl(4, ob, ot)
+    vals, cnt = np.unique(osym, return_counts=True)
+    assert set(vals) == {0, 2, 6, 7} and (np.abs(cnt / osym.size - 0.25) < 0.04).all()
