@@ -480,12 +480,18 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
     uint32_t bump = tr->bump, noise_ctr = tr->noise_ctr;
     unsigned long long st_created = 0, st_expanded = 0;
 
-    if (VL) remove_vl_group<G, W>(d, cfg, env, removeK, lane, gm, arena, root);
-    gsync<W>(gm);
+    const int vl = cfg.vl_count;
 
     for (int k = 0; k < K; ++k) {
-        const LeafHead L = ld32(&(VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env)->h);
+        LeafRec *rp = VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env;
+        const LeafHead L = ld32(&rp->h);
         if (!(L.flags & LF_VALID)) continue;             // current_leaf_idx == -1 (MCTS.h:409,599)
+        // The virtual loss of path k is removed in the same read-modify-write that adds simulation k's result to each
+        // node (unobservable reordering: nothing in back-prop reads in-flight counts; at the end of the kernel every
+        // pending loss of the first removeK paths is gone, as after remove_all_vl + K backprop_vl calls).
+        const bool pending = VL && (L.flags & LF_VLPENDING) && k < removeK;
+        const int dec = pending ? vl : 0;
+        if (pending) { const int infl = (int)(root.meta & INFL_MASK) - vl; root.meta = (root.meta & ~INFL_MASK) | (uint32_t)max(infl, 0); }
         const size_t flat = (size_t)env * K + k;
         const bool term = is_term ? (is_term[flat] != 0) : ((L.flags & LF_TERM) != 0);
         const uint32_t plen = L.path_len;
@@ -580,10 +586,10 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
         for (uint32_t base = 0; base < plen; base += W) {
             const uint32_t t = base + lane;                      // t-th node counted from the leaf
             const bool mine = t < plen;
-            Slot *sp = nullptr; int n = 0; float4 w = make_float4(0, 0, 0, 0);
+            Slot *sp = nullptr; int n = 0; uint32_t mt = 0; float4 w = make_float4(0, 0, 0, 0);
             if (mine) {
                 sp = arena + path[plen - 1 - t];
-                n = sp->n;
+                n = sp->n; mt = sp->meta;
                 w = *reinterpret_cast<const float4 *>(&sp->wd);
             }
             float mwd = 0, mw1 = 0, mw2 = 0, mml = 0;
@@ -595,12 +601,15 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
                 if (decay) { wd = gamma * wd + (1 - gamma) * u3; w1 = gamma * w1 + (1 - gamma) * u3; w2 = gamma * w2 + (1 - gamma) * u3; }
             }
             if (mine) {
+                const int infl = (int)(mt & INFL_MASK) - dec;
                 sp->n = n + 1;
+                if (dec) sp->meta = (mt & ~INFL_MASK) | (uint32_t)max(infl, 0);
                 w.x += mwd; w.y += mw1; w.z += mw2; w.w += mml;
                 *reinterpret_cast<float4 *>(&sp->wd) = w;
             }
         }
         root.n += 1; root.wd += wd; root.wp1 += w1; root.wp2 += w2; root.msum += ml;
+        if (pending && lane == 0) rp->h.flags = (uint8_t)(L.flags & ~LF_VLPENDING);
         gsync<W>(gm);   // the next k of this tree must see these updates (duplicate leaves, shared ancestors)
     }
     if (lane == 0) { st_slot(&tr->root, root); tr->bump = bump; tr->noise_ctr = noise_ctr; }
