@@ -1294,8 +1294,11 @@ static int check_cfg(az_mcts *h, int K) {
 }
 
 static int auto_lanes(int game, int n) {
-    if (game == GAME_OTH) return 16;
     const char *e = getenv("AZB200_LANES");
+    if (game == GAME_OTH) {
+        if (e) { int w = atoi(e); if (w == 8 || w == 16) return w; }
+        return n >= 16384 ? 8 : 16;
+    }
     if (e) { int w = atoi(e); if (w == 1 || w == 2 || w == 4 || w == 8) return w; }
     if (n < 12288) return 8;
     if (n < 24576) return 4;
@@ -1306,8 +1309,10 @@ static int auto_lanes(int game, int n) {
 // ---- kernel dispatch over (game, lanes, VL) ----
 #define AZ_DISPATCH_W(h, KERNEL, VLFLAG, GRID, STREAM, ...)                                                          \
     do {                                                                                                             \
-        if ((h)->game == GAME_OTH) KERNEL<Oth, 16, VLFLAG><<<GRID, CTA, 0, STREAM>>>(__VA_ARGS__);                   \
-        else switch ((h)->W) {                                                                                       \
+        if ((h)->game == GAME_OTH) {                                                                                 \
+            if ((h)->W == 8) KERNEL<Oth, 8, VLFLAG><<<GRID, CTA, 0, STREAM>>>(__VA_ARGS__);                          \
+            else KERNEL<Oth, 16, VLFLAG><<<GRID, CTA, 0, STREAM>>>(__VA_ARGS__);                                     \
+        } else switch ((h)->W) {                                                                                       \
             case 1: KERNEL<C4, 1, VLFLAG><<<GRID, CTA, 0, STREAM>>>(__VA_ARGS__); break;                             \
             case 2: KERNEL<C4, 2, VLFLAG><<<GRID, CTA, 0, STREAM>>>(__VA_ARGS__); break;                             \
             case 4: KERNEL<C4, 4, VLFLAG><<<GRID, CTA, 0, STREAM>>>(__VA_ARGS__); break;                             \
@@ -1507,7 +1512,11 @@ int az_mcts_set_config(az_mcts *h, const az_search_config *c) { h->cfg = *c; ret
 int az_mcts_get_config(const az_mcts *h, az_search_config *c) { *c = h->cfg; return AZ_OK; }
 int az_mcts_set_lanes(az_mcts *h, int lanes) {
     if (lanes == 0) { h->W = auto_lanes(h->game, h->n); return AZ_OK; }
-    if (h->game == GAME_OTH) { if (lanes != 16) AZ_FAIL(h, AZ_ERR_INVALID, "Othello trees use 16 lanes"); return AZ_OK; }
+    if (h->game == GAME_OTH) {
+        if (lanes != 8 && lanes != 16) AZ_FAIL(h, AZ_ERR_INVALID, "Othello lanes must be 8 or 16");
+        h->W = lanes;
+        return AZ_OK;
+    }
     if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8) AZ_FAIL(h, AZ_ERR_INVALID, "Connect4 lanes must be 1, 2, 4 or 8");
     h->W = lanes;
     return AZ_OK;
@@ -1626,8 +1635,10 @@ int az_mcts_remove_all_vl(az_mcts *h, int K) {
     const int safeK = std::min(K, h->prepared_K);
     if (safeK <= 0) return AZ_OK;
     const int g = grid_groups(h->n, h->W);
-    if (h->game == GAME_OTH) k_remove_vl<Oth, 16><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK);
-    else switch (h->W) {
+    if (h->game == GAME_OTH) {
+        if (h->W == 8) k_remove_vl<Oth, 8><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK);
+        else k_remove_vl<Oth, 16><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK);
+    } else switch (h->W) {
         case 1: k_remove_vl<C4, 1><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK); break;
         case 2: k_remove_vl<C4, 2><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK); break;
         case 4: k_remove_vl<C4, 4><<<g, CTA, 0, h->stream>>>(h->d, h->cfg, safeK); break;

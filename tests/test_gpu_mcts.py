@@ -338,3 +338,12 @@ def test_dirichlet_noise_and_symmetry_ids_are_well_formed():
     _, _, _, _, _, _, osym, _ = o.search_batch_vl(4, ob, ot)
     vals, cnt = np.unique(osym, return_counts=True)
     assert set(vals) == {0, 2, 6, 7} and (np.abs(cnt / osym.size - 0.25) < 0.04).all()
+
+
+@pytest.mark.parametrize("lanes", [8, 16])
+def test_othello_lane_widths_are_bit_exact(lanes):
+    e = _cuda("Othello", 40)
+    e.set_lanes(lanes)
+    cfg = dict(OTH_CFG, use_symmetry=True, value_decay=0.99)
+    boards, turns = random_positions("Othello", 40, 50, 61)
+    compare_engines(e, _orc("Othello", 40), "Othello", 40, 70, 4, cfg, boards=boards, turns=turns, moves=6, seed=8)
