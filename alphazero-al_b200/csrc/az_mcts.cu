@@ -88,6 +88,7 @@ struct Dev {   // kernel-visible view of an engine
     LeafRec *leaf_vl; uint32_t *path_vl; int kcap;   // [n_envs][kcap], [n_envs][kcap][MAX_DEPTH]
     LeafRec *leaf_nv; uint32_t *path_nv;             // non-VL search_batch state
     const float *log_lut; int log_lut_n;
+    const float2 *ls_lut;                // {log((n + c_base + 1) / c_base), sqrt(n)} interleaved, same length
     const float *atan_lut;               // 129 entries: disc difference -64..64
     unsigned long long *stats;           // nullptr = counters off
     int *err;                            // sticky device error flag (arena overflow)
@@ -937,6 +938,10 @@ __global__ void __launch_bounds__(CTA, 4) k_backprop_t(Dev d, az_search_config c
     if (d.stats) { atomicAdd(d.stats + 3, st_created); atomicAdd(d.stats + 4, st_expanded); }
 }
 
+}  // namespace az
+#include "az_mcts_fast.cuh"
+namespace az {
+
 // remove_all_vl without backprop (BatchedMCTS.h:209-216)
 template <class G, int W>
 __global__ void __launch_bounds__(CTA) k_remove_vl(Dev d, az_search_config cfg, int K) {
@@ -1117,6 +1122,7 @@ struct az_mcts {
     int game = 0, n = 0, device = 0;
     int A = 0, S = 0, W = 0, max_depth = 0, max_edges = 0;
     bool lanes_fixed = false;
+    size_t bp_smem_set = 0;           // dynamic shared memory already granted to k_backprop_f
     az_search_config cfg;
     Dev d{};
     cudaStream_t stream = nullptr;
@@ -1128,6 +1134,8 @@ struct az_mcts {
     float lut_c_base = -1.0f, lut_scale = -1.0f;
     int lut_n = 0;
     float *d_log_lut = nullptr, *d_atan_lut = nullptr;
+    float2 *d_ls_lut = nullptr;
+    int variant = 1;                  // thread-per-tree kernels: 0 = first generation (k_*_t), 1 = lean (k_*_f), 2 = lean + bulk-copy gather
     // VL bookkeeping
     int kcap = 0;
     int prepared_K = 0;               // vl_paths_.size() (MCTS.h:421-429)
@@ -1199,9 +1207,15 @@ static int ensure_luts(az_mcts *h) {
             h->lut_n = e ? std::max(1024, atoi(e)) : (1 << 18);
         }
         std::vector<float> lut((size_t)h->lut_n);
-        for (int i = 0; i < h->lut_n; ++i) lut[(size_t)i] = logf(((float)i + c.c_base + 1.0f) / c.c_base);   // MCTS.h:213-214, host libm
+        std::vector<float2> ls((size_t)h->lut_n);
+        for (int i = 0; i < h->lut_n; ++i) {
+            lut[(size_t)i] = logf(((float)i + c.c_base + 1.0f) / c.c_base);   // MCTS.h:213-214, host libm
+            ls[(size_t)i] = make_float2(lut[(size_t)i], sqrtf((float)i));     // MCTS.h:216 (sqrt is correctly rounded everywhere)
+        }
         if (!h->d_log_lut) { int r = dev_alloc(h, &h->d_log_lut, (size_t)h->lut_n); if (r) return r; }
+        if (!h->d_ls_lut) { int r = dev_alloc(h, &h->d_ls_lut, (size_t)h->lut_n); if (r) return r; }
         CU(h, cudaMemcpyAsync(h->d_log_lut, lut.data(), sizeof(float) * (size_t)h->lut_n, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(h->d_ls_lut, ls.data(), sizeof(float2) * (size_t)h->lut_n, cudaMemcpyHostToDevice, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
         h->lut_c_base = c.c_base;
     }
@@ -1213,13 +1227,14 @@ static int ensure_luts(az_mcts *h) {
         CU(h, cudaStreamSynchronize(h->stream));
         h->lut_scale = c.score_scale;
     }
-    h->d.log_lut = h->d_log_lut; h->d.log_lut_n = h->lut_n; h->d.atan_lut = h->d_atan_lut;
+    h->d.log_lut = h->d_log_lut; h->d.log_lut_n = h->lut_n; h->d.atan_lut = h->d_atan_lut; h->d.ls_lut = h->d_ls_lut;
     return AZ_OK;
 }
 
 static int ensure_kcap(az_mcts *h, int K) {
     if (K <= h->kcap) return AZ_OK;
-    int nk = std::max(K, std::max(4, h->kcap * 2));
+    int nk = std::max(4, h->kcap * 2);           // a power of two: the staged back-prop addresses records with shifts
+    while (nk < K) nk *= 2;
     LeafRec *nl = nullptr; uint32_t *np = nullptr;
     CU(h, cudaDeviceSynchronize());
     CU(h, cudaMalloc((void **)&nl, sizeof(LeafRec) * (size_t)h->n * nk));
@@ -1322,6 +1337,23 @@ static int auto_lanes(int game, int n) {
 
 static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s) {
     const int g = grid_groups(h->n, h->W);
+    if (h->game == GAME_C4 && h->W == 1 && h->variant != 0 && (uint64_t)(h->n + 32) * h->cap < (1ull << 31) &&
+        ((uintptr_t)leaves & 31) == 0) {         // lean thread-per-tree kernel (32-bit chunk indices, 256-bit record stores)
+        const int gf = (h->n + CTA_F - 1) / CTA_F;
+        const int kk = vl ? K : 1;
+        const bool aux = h->cfg.mlh_slope > 0.0f;            // aux_enabled<C4>
+#define AZ_SELECT_F(VLF, GA, AX) k_select_f<C4, VLF, GA, AX><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves)
+        if (h->variant == 2) {
+            if (vl) { if (aux) AZ_SELECT_F(true, 1, true); else AZ_SELECT_F(true, 1, false); }
+            else { if (aux) AZ_SELECT_F(false, 1, true); else AZ_SELECT_F(false, 1, false); }
+        } else {
+            if (vl) { if (aux) AZ_SELECT_F(true, 0, true); else AZ_SELECT_F(true, 0, false); }
+            else { if (aux) AZ_SELECT_F(false, 0, true); else AZ_SELECT_F(false, 0, false); }
+        }
+#undef AZ_SELECT_F
+        h->launches++;
+        return;
+    }
     if (h->game == GAME_C4 && h->W == 1) {       // thread-per-tree kernels with cooperative block gather
         if (vl) k_select_t<C4, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, roots, leaves);
         else k_select_t<C4, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, roots, leaves);
@@ -1335,6 +1367,25 @@ static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_l
 static void launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym, const float *pol, const float *d, const float *p1,
                             const float *p2, const float *ml, const uint8_t *it, const int32_t *sym, cudaStream_t s) {
     const int g = grid_groups(h->n, h->W);
+    if (h->game == GAME_C4 && h->W == 1 && h->variant != 0 && ((uintptr_t)pol & 15) == 0) {
+        // staged back-prop: leaf records + policy rows of a warp in shared memory (dynamic, sized by K and the record stride)
+        const int kk = vl ? K : 1;
+        int rec_shift = 2;                                   // non-VL: one 64-byte record (4 chunks) per tree
+        if (vl) { rec_shift = 0; while ((1 << rec_shift) < 4 * h->kcap) ++rec_shift; }
+        const size_t smem = backprop_f_smem_per_warp(kk, rec_shift) * (CTA_F / 32);
+        if ((!vl || (1 << rec_shift) == 4 * h->kcap) && smem <= 200 * 1024) {
+            const int gf = (h->n + CTA_F - 1) / CTA_F;
+            if (smem > h->bp_smem_set) {
+                cudaFuncSetAttribute(k_backprop_f<C4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(k_backprop_f<C4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                h->bp_smem_set = smem;
+            }
+            if (vl) k_backprop_f<C4, true><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, kk, removeK, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);
+            else k_backprop_f<C4, false><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, 1, 0, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);
+            h->launches++;
+            return;
+        }
+    }
     if (h->game == GAME_C4 && h->W == 1) {
         if (vl) k_backprop_t<C4, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, removeK, use_sym, pol, d, p1, p2, ml, it, sym);
         else k_backprop_t<C4, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, 0, use_sym, pol, d, p1, p2, ml, it, sym);
@@ -1454,6 +1505,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     h->game = game; h->n = n_envs; h->device = device;
     h->A = az_game_action_size(game); h->S = az_game_board_size(game);
     h->W = auto_lanes(game, n_envs);
+    { const char *ve = getenv("AZB200_VARIANT"); if (ve) { int v = atoi(ve); if (v >= 0 && v <= 2) h->variant = v; } }
     h->max_depth = game == GAME_C4 ? C4::MAX_DEPTH : Oth::MAX_DEPTH;
     h->max_edges = game == GAME_C4 ? 8 : 48;
     az_search_config_defaults(&h->cfg);
@@ -1496,7 +1548,7 @@ void az_mcts_destroy(az_mcts *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {h->d.pool, h->d.trees, h->d.noise, h->d.leaf_vl, h->d.path_vl, h->d.leaf_nv, h->d.path_nv, h->d_log_lut,
+    void *ptrs[] = {h->d.pool, h->d.trees, h->d.noise, h->d.leaf_vl, h->d.path_vl, h->d.leaf_nv, h->d.path_nv, h->d_log_lut, h->d_ls_lut,
                     h->d_atan_lut, h->d_stats, h->d_err, h->d_scratch_u32, h->io_boards_in, h->io_turns_in, h->io_roots, h->io_leaves,
                     h->io_out, h->io_in, h->io_actions, h->io_counts, h->io_stats};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -1522,6 +1574,24 @@ int az_mcts_set_lanes(az_mcts *h, int lanes) {
     return AZ_OK;
 }
 int az_mcts_get_lanes(const az_mcts *h) { return h->W; }
+int az_mcts_set_variant(az_mcts *h, int variant) {
+    if (variant < 0 || variant > 2) AZ_FAIL(h, AZ_ERR_INVALID, "kernel variant must be 0, 1 or 2");
+    h->variant = variant;
+    return AZ_OK;
+}
+int az_mcts_get_variant(const az_mcts *h) { return h->variant; }
+int az_selftest_div(int mode, uint64_t count, uint64_t seed, uint64_t *mismatches) {
+    unsigned long long *dm = nullptr, hm = 0;
+    if (mode < 0 || mode > 2 || !mismatches) return AZ_ERR_INVALID;
+    if (cudaMalloc((void **)&dm, sizeof(hm)) != cudaSuccess) return AZ_ERR_CUDA;
+    cudaMemset(dm, 0, sizeof(hm));
+    k_selftest_div<<<148 * 8, 256>>>(mode, (unsigned long long)count, (unsigned long long)seed, dm);
+    cudaError_t e = cudaMemcpy(&hm, dm, sizeof(hm), cudaMemcpyDeviceToHost);
+    cudaFree(dm);
+    if (e != cudaSuccess) return AZ_ERR_CUDA;
+    *mismatches = hm;
+    return AZ_OK;
+}
 int az_mcts_set_env_base(az_mcts *h, uint64_t base) { h->d.env_base = base; return AZ_OK; }
 int az_mcts_reserve(az_mcts *h, int slots_per_tree) {
     CU(h, cudaSetDevice(h->device));

@@ -290,6 +290,13 @@ class _BatchedMCTS:
     def get_lanes(self):
         return self._L.az_mcts_get_lanes(self._h)
 
+    def set_variant(self, variant):
+        """Generation of the thread-per-tree Connect4 kernels (0 first, 1 lean, 2 lean + bulk-copy gather); bit-identical results."""
+        self._ck(self._L.az_mcts_set_variant(self._h, int(variant)))
+
+    def get_variant(self):
+        return self._L.az_mcts_get_variant(self._h)
+
     def set_env_base(self, base):
         """Global index of env 0 (keeps RNG streams sharding-invariant across GPUs)."""
         self._ck(self._L.az_mcts_set_env_base(self._h, int(base)))

@@ -150,6 +150,15 @@ int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream);
  * fewer replicated instructions; fewer means more warps to hide latency when n_envs is small. */
 int az_mcts_set_lanes(az_mcts *h, int lanes);
 int az_mcts_get_lanes(const az_mcts *h);
+/* Generation of the thread-per-tree Connect4 kernels (lanes == 1): 0 = first generation, 1 = lean kernels (branch-free
+ * IEEE divisions, staged back-prop, 256-bit slot accesses; default), 2 = lean + bulk-copy (TMA) gather.  All variants
+ * compute bit-identical results; the setting exists for A/B measurements and the parity tests.  Env: AZB200_VARIANT. */
+int az_mcts_set_variant(az_mcts *h, int variant);
+int az_mcts_get_variant(const az_mcts *h);
+/* Self-test of the branch-free division sequences against the compiler's IEEE division: mode 0 = 1/n for n = 1..count,
+ * mode 1 = random a/b over the covered range, mode 2 = small-integer ratios (exact results and ties).  Writes the number
+ * of bit mismatches (expected 0). */
+int az_selftest_div(int mode, uint64_t count, uint64_t seed, uint64_t *mismatches);
 /* Global index of env 0 of this handle: all RNG streams are keyed by (seed, global env index), so a game's result does
  * not depend on how games are sharded over GPUs. */
 int az_mcts_set_env_base(az_mcts *h, uint64_t base);

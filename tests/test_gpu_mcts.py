@@ -174,6 +174,44 @@ def test_c4_every_lane_width_is_bit_exact(lanes):
     compare_engines(e, _orc("Connect4", 80), "Connect4", 80, 90, 4, cfg, boards=boards, turns=turns, moves=6, seed=5)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("n,K,decay", [(80, 4, 0.98), (131, 3, 1.0), (64, 8, 1.0), (40, 1, 1.0)])
+def test_c4_thread_per_tree_kernel_generations_are_bit_exact(variant, n, K, decay):
+    """lanes = 1 runs the thread-per-tree kernels; every generation (first, lean, lean + bulk-copy gather) must match the
+    oracle bit for bit: full warps, a ragged tail warp (131 = 4 warps + 3 trees), K = 8 (record stride 8) and K = 1."""
+    e = _cuda("Connect4", n)
+    e.set_lanes(1)
+    e.set_variant(variant)
+    assert e.get_variant() == variant
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True, value_decay=decay)
+    boards, turns = random_positions("Connect4", n, 30, 21 + n)
+    compare_engines(e, _orc("Connect4", n), "Connect4", n, 90, K, cfg, boards=boards, turns=turns, moves=6, seed=5)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_c4_lean_kernels_fall_back_to_plain_division_on_tiny_numerators(variant):
+    """Priors of 1e-30 and WDL sums of 1e-35 push the PUCT numerators below the range the branch-free division covers:
+    the kernel must notice and redo the level with the plain IEEE operators (same bits as the oracle)."""
+    n, K = 64, 4
+    tiny = importlib.import_module("alphazero-al_b200.evaluators").HashEvaluator("Connect4", "hash")
+
+    class Tiny:
+        def __call__(self, *a, **kw):
+            probs, d, p1, p2, ml = tiny(*a, **kw)
+            probs = probs.copy(); probs[:, ::2] *= np.float32(1e-30)
+            return probs, d, (p1 * np.float32(1e-35)).astype(np.float32), p2, (ml * np.float32(1e-33)).astype(np.float32)
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=False)
+    boards, turns = random_positions("Connect4", n, 12, 77)
+    a, b = _cuda("Connect4", n), _orc("Connect4", n)
+    a.set_lanes(1); a.set_variant(variant)
+    for e in (a, b):
+        set_config(e, **cfg); e.set_seed(3)
+    playout(a, Tiny(), boards, turns, 120, K)
+    playout(b, Tiny(), boards, turns, 120, K)
+    assert np.array_equal(counts(a, n, 7), counts(b, n, 7))
+    assert a.get_all_root_stats().tobytes() == b.get_all_root_stats().tobytes()
+
+
 @pytest.mark.parametrize("game,mode,K", [("Connect4", "hash", 4), ("Connect4", "equivariant", 8), ("Othello", "hash", 4)])
 def test_device_resident_loop_equals_host_buffer_loop(game, mode, K):
     """search_dev -> az_eval_synthetic_dev -> backprop_dev (no host round trip, flags/sym ids remembered inside the
