@@ -93,11 +93,14 @@ struct Dev {   // kernel-visible view of an engine
     unsigned long long *stats;           // nullptr = counters off
     int *err;                            // sticky device error flag (arena overflow)
     int n_envs;
+    int env_lo, env_cnt;                 // trees [env_lo, env_lo + env_cnt) are processed by the select / back-prop launch
+    int hints;                           // bit 0: streaming stores for new edge blocks (experiment switch, AZB200_HINTS)
     uint64_t seed, epoch;
     uint64_t env_base;                   // global index of env 0 (RNG keys are sharding-invariant)
 };
 
 constexpr int CTA = 128;
+constexpr int AZ_DBG_WARPS = 4096;   // stats mode: per-warp start/end timestamps of the last thread-per-tree select launch
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -263,10 +266,10 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
                                                 az_leaf *__restrict__ leaves) {
     constexpr int NCH = (G::MAX_EDGES + W - 1) / W;
     const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
-    if (gid >= d.n_envs) return;
+    if (gid >= d.env_cnt) return;
     const int lane = threadIdx.x & (W - 1);
     const unsigned gm = group_mask<W>();
-    const int env = gid;
+    const int env = d.env_lo + gid;
     Slot *arena = d.pool + (size_t)env * d.cap;
     TreeRec *tr = d.trees + env;
     const float *noise = d.noise + (size_t)env * d.noise_stride;
@@ -471,10 +474,10 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
                                                   const int32_t *__restrict__ sym_ids) {
     constexpr int NJ = (G::A + W - 1) / W;
     const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
-    if (gid >= d.n_envs) return;
+    if (gid >= d.env_cnt) return;
     const int lane = threadIdx.x & (W - 1);
     const unsigned gm = group_mask<W>();
-    const int env = gid;
+    const int env = d.env_lo + gid;
     Slot *arena = d.pool + (size_t)env * d.cap;
     TreeRec *tr = d.trees + env;
     Slot root = ld_slot(&tr->root);     // kept in registers (identical in every lane), written back once
@@ -636,8 +639,8 @@ __global__ void __launch_bounds__(CTA, 4) k_select_t(Dev d, az_search_config cfg
     const unsigned FULL = 0xFFFFFFFFu;
     const int tid = blockIdx.x * CTA + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool valid = tid < d.n_envs;
-    const int env = valid ? tid : d.n_envs - 1;        // clamped: inactive lanes only help with the gather
+    const bool valid = tid < d.env_cnt;
+    const int env = d.env_lo + (valid ? tid : d.env_cnt - 1);        // clamped: inactive lanes only help with the gather
     Slot *arena = d.pool + (size_t)env * d.cap;
     TreeRec *tr = d.trees + env;
     const int vl = VL ? cfg.vl_count : 0;
@@ -823,8 +826,8 @@ __global__ void __launch_bounds__(CTA, 4) k_backprop_t(Dev d, az_search_config c
                                                     const float *__restrict__ mlv, const uint8_t *__restrict__ is_term,
                                                     const int32_t *__restrict__ sym_ids) {
     static_assert(G::GAME == GAME_C4, "thread-per-tree back-prop is specialised for Connect4 (terminal aux = 0, <= 7 edges)");
-    const int env = blockIdx.x * CTA + threadIdx.x;
-    if (env >= d.n_envs) return;
+    if ((int)(blockIdx.x * CTA + threadIdx.x) >= d.env_cnt) return;
+    const int env = d.env_lo + (int)(blockIdx.x * CTA + threadIdx.x);
     constexpr int A = G::A;
     Slot *arena = d.pool + (size_t)env * d.cap;
     TreeRec *tr = d.trees + env;
@@ -1128,14 +1131,20 @@ struct az_mcts {
     cudaStream_t stream = nullptr;
     // pools
     uint32_t cap = 0;
-    uint64_t bump_bound = 0;          // conservative upper bound of max(TreeRec.bump)
+    uint64_t bump_bound = 0;          // conservative upper bound of max(TreeRec.bump) at the last refresh ...
+    struct Bound { int lo, hi; uint64_t b; };
+    std::vector<Bound> bounds;        // ... and of the tree ranges [lo, hi) that back-propagated since then
+    cudaStream_t side[8] = {};        // shard streams of az_mcts_playout_synthetic_dev
+    bool time_select = false;         // az_mcts_time_select: CUDA events around every select launch
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sel_ev; size_t sel_used = 0; uint64_t sel_rows = 0;
+    cudaEvent_t side_ev[8] = {};
     unsigned int *d_scratch_u32 = nullptr;
     // LUT state
     float lut_c_base = -1.0f, lut_scale = -1.0f;
     int lut_n = 0;
     float *d_log_lut = nullptr, *d_atan_lut = nullptr;
     float2 *d_ls_lut = nullptr;
-    int variant = 1;                  // thread-per-tree kernels: 0 = first generation (k_*_t), 1 = lean (k_*_f), 2 = lean + bulk-copy gather
+    int variant = 1;                  // thread-per-tree kernels: 0 = first generation (k_*_t), 1 = lean (k_*_f)
     // VL bookkeeping
     int kcap = 0;
     int prepared_K = 0;               // vl_paths_.size() (MCTS.h:421-429)
@@ -1282,23 +1291,37 @@ static int grow_arena(az_mcts *h, uint64_t ncap, cudaStream_t st) {
     return AZ_OK;
 }
 
-// Make sure no tree can overflow its arena during a back-prop of `sims` simulations per tree.
+// Make sure no tree of the current range can overflow its arena during a back-prop of `sims` simulations per tree.
+// The host keeps conservative upper bounds of max(TreeRec.bump) per tree range (shards of one batch advance independently).
 static int ensure_arena(az_mcts *h, int sims, cudaStream_t st) {
     const uint64_t need = (uint64_t)sims * (uint64_t)(h->game == GAME_C4 ? 7 : 34);
-    if (h->bump_bound + need <= h->cap) { h->bump_bound += need; return AZ_OK; }
-    // refresh the bound from the device
-    CU(h, cudaMemsetAsync(h->d_scratch_u32, 0, sizeof(unsigned int), st));
-    k_max_bump<<<grid_threads((size_t)h->n, 256), 256, 0, st>>>(h->d, h->d_scratch_u32);
-    unsigned int mx = 0;
-    CU(h, cudaMemcpyAsync(&mx, h->d_scratch_u32, sizeof(mx), cudaMemcpyDeviceToHost, st));
-    CU(h, cudaStreamSynchronize(st));
-    h->bump_bound = mx;
-    if (h->bump_bound + need > h->cap) {
-        uint64_t ncap = h->cap;
-        while (h->bump_bound + need > ncap) ncap *= 2;
-        int rc = grow_arena(h, ncap, st); if (rc) return rc;
+    const int lo = h->d.env_lo, hi = lo + h->d.env_cnt;
+    auto current = [&]() {
+        uint64_t b = h->bump_bound;
+        for (const auto &r : h->bounds) if (r.lo < hi && lo < r.hi) b = std::max(b, r.b);
+        return b;
+    };
+    uint64_t b = current();
+    if (b + need > h->cap) {
+        // refresh the bound from the device (all streams: other shards of the batch may still be growing their trees)
+        CU(h, cudaDeviceSynchronize());
+        CU(h, cudaMemsetAsync(h->d_scratch_u32, 0, sizeof(unsigned int), st));
+        k_max_bump<<<grid_threads((size_t)h->n, 256), 256, 0, st>>>(h->d, h->d_scratch_u32);
+        unsigned int mx = 0;
+        CU(h, cudaMemcpyAsync(&mx, h->d_scratch_u32, sizeof(mx), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        h->bump_bound = mx; h->bounds.clear();
+        b = mx;
+        if (b + need > h->cap) {
+            uint64_t ncap = h->cap;
+            while (b + need > ncap) ncap *= 2;
+            int rc = grow_arena(h, ncap, st); if (rc) return rc;
+        }
     }
-    h->bump_bound += need;
+    b += need;
+    h->bounds.erase(std::remove_if(h->bounds.begin(), h->bounds.end(), [&](const az_mcts::Bound &r) { return r.lo < hi && lo < r.hi; }),
+                    h->bounds.end());
+    h->bounds.push_back({lo, hi, b});
     return AZ_OK;
 }
 
@@ -1336,20 +1359,16 @@ static int auto_lanes(int game, int n) {
     } while (0)
 
 static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s) {
-    const int g = grid_groups(h->n, h->W);
+    const int cnt = h->d.env_cnt;                             // trees of this launch (a whole batch or one shard)
+    const int g = grid_groups(cnt, h->W);
     if (h->game == GAME_C4 && h->W == 1 && h->variant != 0 && (uint64_t)(h->n + 32) * h->cap < (1ull << 31) &&
         ((uintptr_t)leaves & 31) == 0) {         // lean thread-per-tree kernel (32-bit chunk indices, 256-bit record stores)
-        const int gf = (h->n + CTA_F - 1) / CTA_F;
+        const int gf = (cnt + CTA_F - 1) / CTA_F;
         const int kk = vl ? K : 1;
         const bool aux = h->cfg.mlh_slope > 0.0f;            // aux_enabled<C4>
-#define AZ_SELECT_F(VLF, GA, AX) k_select_f<C4, VLF, GA, AX><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves)
-        if (h->variant == 2) {
-            if (vl) { if (aux) AZ_SELECT_F(true, 1, true); else AZ_SELECT_F(true, 1, false); }
-            else { if (aux) AZ_SELECT_F(false, 1, true); else AZ_SELECT_F(false, 1, false); }
-        } else {
-            if (vl) { if (aux) AZ_SELECT_F(true, 0, true); else AZ_SELECT_F(true, 0, false); }
-            else { if (aux) AZ_SELECT_F(false, 0, true); else AZ_SELECT_F(false, 0, false); }
-        }
+#define AZ_SELECT_F(VLF, AX) k_select_f<C4, VLF, AX><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves)
+        if (vl) { if (aux) AZ_SELECT_F(true, true); else AZ_SELECT_F(true, false); }
+        else { if (aux) AZ_SELECT_F(false, true); else AZ_SELECT_F(false, false); }
 #undef AZ_SELECT_F
         h->launches++;
         return;
@@ -1366,7 +1385,8 @@ static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_l
 }
 static void launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym, const float *pol, const float *d, const float *p1,
                             const float *p2, const float *ml, const uint8_t *it, const int32_t *sym, cudaStream_t s) {
-    const int g = grid_groups(h->n, h->W);
+    const int cnt = h->d.env_cnt;
+    const int g = grid_groups(cnt, h->W);
     if (h->game == GAME_C4 && h->W == 1 && h->variant != 0 && ((uintptr_t)pol & 15) == 0) {
         // staged back-prop: leaf records + policy rows of a warp in shared memory (dynamic, sized by K and the record stride)
         const int kk = vl ? K : 1;
@@ -1374,7 +1394,7 @@ static void launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym
         if (vl) { rec_shift = 0; while ((1 << rec_shift) < 4 * h->kcap) ++rec_shift; }
         const size_t smem = backprop_f_smem_per_warp(kk, rec_shift) * (CTA_F / 32);
         if ((!vl || (1 << rec_shift) == 4 * h->kcap) && smem <= 200 * 1024) {
-            const int gf = (h->n + CTA_F - 1) / CTA_F;
+            const int gf = (cnt + CTA_F - 1) / CTA_F;
             if (smem > h->bp_smem_set) {
                 cudaFuncSetAttribute(k_backprop_f<C4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 cudaFuncSetAttribute(k_backprop_f<C4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1397,21 +1417,41 @@ static void launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym
     h->launches++;
 }
 
-static int do_search(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, cudaStream_t s) {
+static int set_range(az_mcts *h, int first, int count) {
+    if (first < 0 || count <= 0 || first + count > h->n || (first & 31))
+        AZ_FAIL(h, AZ_ERR_INVALID, "tree range [%d, %d) must lie inside [0, %d) and start at a multiple of 32", first, first + count, h->n);
+    h->d.env_lo = first; h->d.env_cnt = count;
+    return AZ_OK;
+}
+static int do_search(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, cudaStream_t s, int first = 0, int count = -1,
+                     bool new_epoch = true) {
     int rc = check_cfg(h, K); if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
+    rc = set_range(h, first, count < 0 ? h->n : count); if (rc) return rc;
     const bool vl = K > 0;
     if (vl) { rc = ensure_kcap(h, K); if (rc) return rc; h->prepared_K = K; }
-    h->d.epoch++;
+    if (new_epoch) h->d.epoch++;
     h->d.stats = h->stats_on ? h->d_stats : nullptr;
+    if (h->time_select) {
+        if (h->sel_used == h->sel_ev.size()) {
+            cudaEvent_t a, b; CU(h, cudaEventCreate(&a)); CU(h, cudaEventCreate(&b));
+            h->sel_ev.push_back({a, b});
+        }
+        CU(h, cudaEventRecord(h->sel_ev[h->sel_used].first, s));
+    }
     launch_select(h, vl, K, d_roots, d_leaves, s);
+    if (h->time_select) {
+        CU(h, cudaEventRecord(h->sel_ev[h->sel_used].second, s));
+        h->sel_used++; h->sel_rows += (uint64_t)h->d.env_cnt * (uint64_t)std::max(K, 1);
+    }
     CU(h, cudaGetLastError());
     return AZ_OK;
 }
 static int do_backprop(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
-                       const uint8_t *it, const int32_t *sym, cudaStream_t s) {
+                       const uint8_t *it, const int32_t *sym, cudaStream_t s, int first = 0, int count = -1) {
     int rc = check_cfg(h, K); if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
+    rc = set_range(h, first, count < 0 ? h->n : count); if (rc) return rc;
     const bool vl = K > 0;
     if (vl && K > h->prepared_K) AZ_FAIL(h, AZ_ERR_INVALID, "backprop_batch_vl: K (%d) exceeds the K of the last search_batch_vl (%d)", K, h->prepared_K);
     rc = ensure_arena(h, vl ? K : 1, s); if (rc) return rc;
@@ -1505,7 +1545,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     h->game = game; h->n = n_envs; h->device = device;
     h->A = az_game_action_size(game); h->S = az_game_board_size(game);
     h->W = auto_lanes(game, n_envs);
-    { const char *ve = getenv("AZB200_VARIANT"); if (ve) { int v = atoi(ve); if (v >= 0 && v <= 2) h->variant = v; } }
+    { const char *ve = getenv("AZB200_VARIANT"); if (ve) { int v = atoi(ve); if (v >= 0 && v <= 1) h->variant = v; } }
     h->max_depth = game == GAME_C4 ? C4::MAX_DEPTH : Oth::MAX_DEPTH;
     h->max_edges = game == GAME_C4 ? 8 : 48;
     az_search_config_defaults(&h->cfg);
@@ -1519,7 +1559,8 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     if (cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming) != cudaSuccess) { h->err = "event create failed"; return fail("create"); }
     const char *ce = getenv("AZB200_ARENA_SLOTS");
     h->cap = ce ? (uint32_t)std::max(256, atoi(ce)) : (game == GAME_C4 ? 2048u : 4096u);
-    h->d.n_envs = n_envs; h->d.cap = h->cap; h->d.noise_stride = h->max_edges;
+    h->d.n_envs = n_envs; h->d.env_lo = 0; h->d.env_cnt = n_envs; h->d.cap = h->cap; h->d.noise_stride = h->max_edges;
+    { const char *he = getenv("AZB200_HINTS"); h->d.hints = he ? atoi(he) : 1; }
     h->d.seed = 0x243F6A8885A308D3ULL; h->d.epoch = 0;
     int rc = 0;
     rc |= dev_alloc(h, &h->d.pool, (size_t)n_envs * h->cap);
@@ -1527,14 +1568,14 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     rc |= dev_alloc(h, &h->d.noise, (size_t)n_envs * h->d.noise_stride);
     rc |= dev_alloc(h, &h->d.leaf_nv, (size_t)n_envs);
     rc |= dev_alloc(h, &h->d.path_nv, (size_t)n_envs * h->max_depth);
-    rc |= dev_alloc(h, &h->d_stats, 8); rc |= dev_alloc(h, &h->d_err, 1); rc |= dev_alloc(h, &h->d_scratch_u32, 4);
+    rc |= dev_alloc(h, &h->d_stats, 8 + 2 * AZ_DBG_WARPS); rc |= dev_alloc(h, &h->d_err, 1); rc |= dev_alloc(h, &h->d_scratch_u32, 4);
     rc |= dev_alloc(h, &h->io_boards_in, (size_t)n_envs * h->S); rc |= dev_alloc(h, &h->io_turns_in, (size_t)n_envs);
     rc |= dev_alloc(h, &h->io_roots, (size_t)n_envs);
     rc |= dev_alloc(h, &h->io_actions, (size_t)n_envs); rc |= dev_alloc(h, &h->io_counts, (size_t)n_envs * h->A);
     rc |= dev_alloc(h, &h->io_stats, (size_t)n_envs * (6 + 8 * h->A));
     if (rc) return fail("device allocation");
     h->d.err = h->d_err;
-    cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream);
+    cudaMemsetAsync(h->d_stats, 0, (8 + 2 * AZ_DBG_WARPS) * sizeof(unsigned long long), h->stream);
     cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
     k_reset<<<grid_threads((size_t)n_envs), 128, 0, h->stream>>>(h->d, -1);
     k_init_leaf<<<grid_threads((size_t)n_envs), 128, 0, h->stream>>>(h->d.leaf_nv, (size_t)n_envs);
@@ -1555,6 +1596,8 @@ void az_mcts_destroy(az_mcts *h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->ev) cudaEventDestroy(h->ev);
+    for (auto &pr : h->sel_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (int j = 0; j < 8; ++j) { if (h->side_ev[j]) cudaEventDestroy(h->side_ev[j]); if (h->side[j]) cudaStreamDestroy(h->side[j]); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1575,7 +1618,7 @@ int az_mcts_set_lanes(az_mcts *h, int lanes) {
 }
 int az_mcts_get_lanes(const az_mcts *h) { return h->W; }
 int az_mcts_set_variant(az_mcts *h, int variant) {
-    if (variant < 0 || variant > 2) AZ_FAIL(h, AZ_ERR_INVALID, "kernel variant must be 0, 1 or 2");
+    if (variant < 0 || variant > 1) AZ_FAIL(h, AZ_ERR_INVALID, "kernel variant must be 0 or 1");
     h->variant = variant;
     return AZ_OK;
 }
@@ -1732,6 +1775,64 @@ int az_mcts_backprop_dev(az_mcts *h, int K, const float *pol, const float *d, co
     return do_backprop(h, K, pol, d, p1, p2, ml, it, sym, (cudaStream_t)stream);
 }
 
+int az_mcts_search_range_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, int first, int count, int new_epoch, void *stream) {
+    if (K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "search_range_dev: K must be >= 0");
+    { int rc = enter_dev(h, (cudaStream_t)stream); if (rc) return rc; }
+    return do_search(h, K, d_roots, d_leaves, (cudaStream_t)stream, first, count, new_epoch != 0);
+}
+int az_mcts_backprop_range_dev(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
+                               const uint8_t *it, const int32_t *sym, int first, int count, void *stream) {
+    if (K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "backprop_range_dev: K must be >= 0");
+    { int rc = enter_dev(h, (cudaStream_t)stream); if (rc) return rc; }
+    return do_backprop(h, K, pol, d, p1, p2, ml, it, sym, (cudaStream_t)stream, first, count);
+}
+int az_mcts_stream_handover_dev(az_mcts *h, void *stream) { return enter_dev(h, (cudaStream_t)stream); }
+
+// The whole playout loop of src/MCTS_cpp.py:217-357 with a synthetic evaluator, driven natively (no per-launch Python
+// cost) and optionally pipelined over `shards` independent tree ranges on internal streams.
+int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, int shards, const az_root *d_roots, az_leaf *d_leaves,
+                                  float *pol, float *d, float *p1, float *p2, float *ml, void *stream, int *launches_out) {
+    if (n_playout < 0 || K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "playout: n_playout and K must be >= 0");
+    cudaStream_t main = (cudaStream_t)stream;
+    int rc = enter_dev(h, main); if (rc) return rc;
+    const int per = (((h->n + std::max(shards, 1) - 1) / std::max(shards, 1)) + 31) / 32 * 32;
+    const int ns = std::min(8, std::max(1, (h->n + per - 1) / per));
+    std::vector<int> iters;
+    if (K <= 1) iters.assign((size_t)n_playout, 0);
+    else if (n_playout > 0) {
+        iters.push_back(0);
+        for (int rem = n_playout - 1; rem > 0; rem -= std::min(K, rem)) iters.push_back(std::min(K, rem));
+    }
+    cudaStream_t lanes[8];
+    if (ns > 1) {
+        for (int j = 0; j < ns; ++j) {
+            if (!h->side[j]) { CU(h, cudaStreamCreateWithFlags(&h->side[j], cudaStreamNonBlocking)); CU(h, cudaEventCreateWithFlags(&h->side_ev[j], cudaEventDisableTiming)); }
+            lanes[j] = h->side[j];
+        }
+        CU(h, cudaEventRecord(h->ev, main));
+        for (int j = 0; j < ns; ++j) CU(h, cudaStreamWaitEvent(lanes[j], h->ev, 0));
+    } else lanes[0] = main;
+    int launches = 0;
+    for (size_t it = 0; it < iters.size(); ++it) {
+        const int k = iters[it], kk = std::max(k, 1);
+        for (int j = 0; j < ns; ++j) {
+            const int lo = j * per, cnt = std::min(per, h->n - lo);
+            const size_t r0 = (size_t)lo * kk;
+            rc = do_search(h, k, d_roots, d_leaves, lanes[j], lo, cnt, j == 0); if (rc) return rc;
+            rc = az_eval_synthetic_dev(h->game, mode, cnt * kk, d_leaves + r0, pol + r0 * h->A, d + r0, p1 + r0, p2 + r0, ml + r0, lanes[j]);
+            if (rc) AZ_FAIL(h, rc, "synthetic evaluator launch failed");
+            rc = do_backprop(h, k, pol, d, p1, p2, ml, nullptr, nullptr, lanes[j], lo, cnt); if (rc) return rc;
+            launches += 3;
+        }
+    }
+    if (ns > 1) {
+        for (int j = 0; j < ns; ++j) { CU(h, cudaEventRecord(h->side_ev[j], lanes[j])); CU(h, cudaStreamWaitEvent(main, h->side_ev[j], 0)); }
+    }
+    h->user_stream = main; h->user_pending = true;
+    if (launches_out) *launches_out = launches;
+    return AZ_OK;
+}
+
 int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const az_root *d_roots, int n_playout, void *stream) {
     if (evaluator != AZ_EVAL_UNIFORM && evaluator != AZ_EVAL_ROLLOUT) AZ_FAIL(h, AZ_ERR_INVALID, "unknown evaluator kind %d", evaluator);
     int rc = check_cfg(h, 1); if (rc) return rc;
@@ -1739,6 +1840,7 @@ int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const az_root *d_roots, i
     rc = enter_dev(h, s); if (rc) return rc;
     rc = ensure_io(h, h->n); if (rc) return rc;
     h->d.epoch++;                          // one epoch per search() call, like orc_search
+    h->d.env_lo = 0; h->d.env_cnt = h->n;
     const InLayout L = in_layout((size_t)h->n, h->A);
     uint8_t *q = h->io_in;
     float *pol = (float *)(q + L.policy), *dv = (float *)(q + L.d), *p1 = (float *)(q + L.p1), *p2 = (float *)(q + L.p2), *ml = (float *)(q + L.ml);
@@ -1802,6 +1904,25 @@ int az_mcts_enable_stats(az_mcts *h, int on) {
     CU(h, cudaDeviceSynchronize());
     CU(h, cudaMemset(h->d_stats, 0, 8 * sizeof(unsigned long long)));
     return AZ_OK;
+}
+int az_mcts_time_select(az_mcts *h, int on) { h->time_select = on != 0; h->sel_used = 0; h->sel_rows = 0; return AZ_OK; }
+int az_mcts_get_select_time(az_mcts *h, float *ms_out, int *launches_out, uint64_t *rows_out) {
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());
+    float tot = 0.0f;
+    for (size_t i = 0; i < h->sel_used; ++i) { float ms = 0.0f; CU(h, cudaEventElapsedTime(&ms, h->sel_ev[i].first, h->sel_ev[i].second)); tot += ms; }
+    if (ms_out) *ms_out = tot;
+    if (launches_out) *launches_out = (int)h->sel_used;
+    if (rows_out) *rows_out = h->sel_rows;
+    h->sel_used = 0; h->sel_rows = 0;
+    return AZ_OK;
+}
+int az_mcts_get_warp_times(az_mcts *h, uint64_t *out, int max_warps) {
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());
+    const int nw = std::min(std::min(max_warps, AZ_DBG_WARPS), (h->n + 31) / 32);
+    CU(h, cudaMemcpy(out, h->d_stats + 8, sizeof(uint64_t) * 2 * (size_t)nw, cudaMemcpyDeviceToHost));
+    return nw;
 }
 int az_mcts_get_stats(az_mcts *h, uint64_t *out8) {
     CU(h, cudaSetDevice(h->device));

@@ -48,10 +48,10 @@ class LeafBuffers:
         if rc != 0:
             raise RuntimeError("az_pack_roots_dev failed (%d)" % rc)
 
-    def unpack(self, rows: int, stream: int):
-        """az_leaf[rows] -> whichever reference-format arrays / CNN planes were allocated."""
-        p = lambda t: t.data_ptr() if t is not None else None
-        rc = _lib.lib().az_unpack_leaves_dev(self.gid, rows, self.leaves.data_ptr(), p(self.boards), p(self.td), p(self.tp1),
+    def unpack(self, rows: int, stream: int, row0: int = 0):
+        """az_leaf[row0 : row0 + rows] -> whichever reference-format arrays / CNN planes were allocated."""
+        p = lambda t: t[row0:].data_ptr() if t is not None else None
+        rc = _lib.lib().az_unpack_leaves_dev(self.gid, rows, p(self.leaves), p(self.boards), p(self.td), p(self.tp1),
                                              p(self.tp2), p(self.is_term), p(self.turns), p(self.sym), p(self.mask),
                                              p(self.planes), stream or None)
         if rc != 0:
@@ -66,10 +66,10 @@ class SyntheticEvaluator:
         self.mode = SYN_MODES[mode]
         self.launches = 0
 
-    def __call__(self, buf: LeafBuffers, rows: int, stream: int):
+    def __call__(self, buf: LeafBuffers, rows: int, stream: int, row0: int = 0):
         rc = _lib.lib().az_eval_synthetic_dev(
-            self.gid, self.mode, rows, buf.leaves.data_ptr(), buf.policy.data_ptr(), buf.d.data_ptr(),
-            buf.p1w.data_ptr(), buf.p2w.data_ptr(), buf.ml.data_ptr(), stream or None)
+            self.gid, self.mode, rows, buf.leaves[row0:].data_ptr(), buf.policy[row0:].data_ptr(), buf.d[row0:].data_ptr(),
+            buf.p1w[row0:].data_ptr(), buf.p2w[row0:].data_ptr(), buf.ml[row0:].data_ptr(), stream or None)
         if rc != 0:
             raise RuntimeError("az_eval_synthetic_dev failed (%d)" % rc)
         self.launches += 1
@@ -84,17 +84,19 @@ class NetEvaluator:
         self.net = net
         self._wdl = self._aux = None
 
-    def __call__(self, buf: LeafBuffers, rows: int, stream: int):
+    def __call__(self, buf: LeafBuffers, rows: int, stream: int, row0: int = 0):
         if self._wdl is None or self._wdl.shape[0] < buf.rows:
             self._wdl = torch.empty((buf.rows, 3), dtype=torch.float32, device=buf.leaves.device)
             self._aux = torch.empty(buf.rows, dtype=torch.float32, device=buf.leaves.device)
-        buf.unpack(rows, stream)
-        probs, wdl_rel, aux = self.net.predict_device(buf.planes[:rows], buf.mask[:rows])
-        buf.policy[:rows].copy_(probs.reshape(rows, buf.A))
-        self._wdl[:rows].copy_(wdl_rel.reshape(rows, 3))
-        self._aux[:rows].copy_(aux.reshape(rows))
-        rc = _lib.lib().az_eval_finalize_dev(rows, buf.leaves.data_ptr(), self._wdl.data_ptr(), self._aux.data_ptr(), buf.d.data_ptr(),
-                                             buf.p1w.data_ptr(), buf.p2w.data_ptr(), buf.ml.data_ptr(), stream or None)
+        r = slice(row0, row0 + rows)
+        buf.unpack(rows, stream, row0)
+        probs, wdl_rel, aux = self.net.predict_device(buf.planes[r], buf.mask[r])
+        buf.policy[r].copy_(probs.reshape(rows, buf.A))
+        self._wdl[r].copy_(wdl_rel.reshape(rows, 3))
+        self._aux[r].copy_(aux.reshape(rows))
+        rc = _lib.lib().az_eval_finalize_dev(rows, buf.leaves[row0:].data_ptr(), self._wdl[row0:].data_ptr(), self._aux[row0:].data_ptr(),
+                                             buf.d[row0:].data_ptr(), buf.p1w[row0:].data_ptr(), buf.p2w[row0:].data_ptr(),
+                                             buf.ml[row0:].data_ptr(), stream or None)
         if rc != 0:
             raise RuntimeError("az_eval_finalize_dev failed (%d)" % rc)
 
@@ -140,7 +142,10 @@ class CachedNetEvaluator(NetEvaluator):
         self._miss_idx = self._miss_cnt = None
         self.net_rows = 0
 
-    def __call__(self, buf: LeafBuffers, rows: int, stream: int):
+    shardable = False       # one miss counter / index buffer per evaluator: drive it on the whole batch
+
+    def __call__(self, buf: LeafBuffers, rows: int, stream: int, row0: int = 0):
+        assert row0 == 0, "CachedNetEvaluator evaluates the whole batch at once"
         L, dev = _lib.lib(), buf.leaves.device
         if self._wdl is None or self._wdl.shape[0] < buf.rows:
             self._wdl = torch.empty((buf.rows, 3), dtype=torch.float32, device=dev)
@@ -169,49 +174,96 @@ class CachedNetEvaluator(NetEvaluator):
             raise RuntimeError("az_eval_finalize_dev failed (%d)" % rc)
 
 
+_SHARD_STREAMS = {}
+
+
+def auto_shards(n: int) -> int:
+    """Independent tree shards driven on their own streams (measured on B200, Connect4 n=200 K=4, 65 536 trees:
+    1 shard 2.07, 2 shards 2.23, 4 shards 2.29 G simulations/s).  Small batches stay whole: they are launch bound."""
+    return 4 if n >= 32768 else (2 if n >= 16384 else 1)
+
+
 def playout_device(engine, buf: LeafBuffers, n_playout: int, K: int, evaluator, stream: int | None = None,
-                   on_select=None):
+                   on_select=None, shards: int | None = None):
     """Run `n_playout` simulations per tree entirely on the device from the roots in `buf.roots` (see
     LeafBuffers.pack_roots).  `on_select(rows, fn)` (optional) wraps each select launch (bench.py times the dominant
-    kernel with CUDA events through it).  Returns the number of kernels launched."""
+    kernel with CUDA events through it).  Returns the number of kernels launched.
+
+    `shards` > 1 splits the batch into that many independent tree ranges, each running its own
+    select -> evaluate -> backprop chain on its own stream, so that the latency-bound tree kernels of one shard overlap
+    the evaluation of another.  Trees are independent and the RNG keys do not depend on the split, so the result is
+    identical to the unsharded loop (tests/test_gpu_mcts.py).  None = auto_shards(n)."""
     if stream is None:
         stream = torch.cuda.current_stream().cuda_stream
     n = engine.get_num_envs()
+    if shards is None:
+        shards = auto_shards(n)
+    if not getattr(evaluator, "shardable", True) or n < 64 * shards:
+        shards = 1
+    iters = []                              # K of every iteration: warm-up (non-VL), then virtual-loss batches
+    if K <= 1:
+        iters = [0] * n_playout
+    elif n_playout > 0:
+        rem = n_playout - 1
+        iters = [0] + [K] * (rem // K) + ([rem % K] if rem % K else [])
+    if isinstance(evaluator, SyntheticEvaluator) and on_select is None:
+        # everything is inside the library: let it drive the loop (no per-launch Python / ctypes cost)
+        assert n * max(K, 1) <= buf.rows
+        return engine.playout_synthetic_dev(evaluator.mode, n_playout, K, shards, buf.roots.data_ptr(), buf.leaves.data_ptr(),
+                                            buf.policy.data_ptr(), buf.d.data_ptr(), buf.p1w.data_ptr(), buf.p2w.data_ptr(),
+                                            buf.ml.data_ptr(), stream)
+    if shards > 1:
+        return _playout_sharded(engine, buf, iters, evaluator, stream, shards, on_select)
     launches = 0
-
-    def select(k):
+    for k in iters:
         rows = n * max(k, 1)
         assert rows <= buf.rows
         if on_select is not None:
             on_select(rows, lambda: engine.search_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), stream))
         else:
             engine.search_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), stream)
-        return rows
-
-    def backprop(k):
+        evaluator(buf, rows, stream)
         # is_term / sym ids: the engine uses what it remembered from the matching search
         engine.backprop_dev(k, buf.policy.data_ptr(), buf.d.data_ptr(), buf.p1w.data_ptr(), buf.p2w.data_ptr(),
                             buf.ml.data_ptr(), 0, 0, stream)
+        launches += 3
+    return launches
 
-    remaining = n_playout
-    if K <= 1:
-        for _ in range(n_playout):
-            rows = select(0)
-            evaluator(buf, rows, stream)
-            backprop(0)
+
+def _playout_sharded(engine, buf, iters, evaluator, stream, shards, on_select=None):
+    n = engine.get_num_envs()
+    dev = buf.leaves.device
+    key = (dev.index, shards)
+    if key not in _SHARD_STREAMS:
+        _SHARD_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(shards)]
+    side = _SHARD_STREAMS[key]
+    per = ((n + shards - 1) // shards + 31) // 32 * 32            # shard starts are multiples of 32
+    ranges = [(lo, min(per, n - lo)) for lo in range(0, n, per)]
+    main = torch.cuda.ExternalStream(stream, device=dev)
+    engine.stream_handover_dev(stream)                           # main stream now follows everything queued so far
+    fork = torch.cuda.Event()
+    fork.record(main)
+    for st in side[:len(ranges)]:
+        st.wait_event(fork)
+    ptrs = (buf.policy.data_ptr(), buf.d.data_ptr(), buf.p1w.data_ptr(), buf.p2w.data_ptr(), buf.ml.data_ptr())
+    launches = 0
+    for it, k in enumerate(iters):
+        kk = max(k, 1)
+        assert n * kk <= buf.rows
+        for j, (lo, cnt) in enumerate(ranges):
+            st = side[j]
+            cs = st.cuda_stream
+            if on_select is not None:
+                on_select(cnt * kk, lambda: engine.search_range_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), lo, cnt, j == 0, cs), st)
+            else:
+                engine.search_range_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), lo, cnt, j == 0, cs)
+            with torch.cuda.stream(st):                          # torch evaluators launch on the current stream
+                evaluator(buf, cnt * kk, cs, lo * kk)
+            engine.backprop_range_dev(k, *ptrs, lo, cnt, 0, 0, cs)
             launches += 3
-        return launches
-    if remaining > 0:                      # warm-up: make sure every root is expanded (src/MCTS_cpp.py:217-248)
-        rows = select(0)
-        evaluator(buf, rows, stream)
-        backprop(0)
-        remaining -= 1
-        launches += 3
-    while remaining > 0:
-        cur = min(K, remaining)
-        remaining -= cur
-        rows = select(cur)
-        evaluator(buf, rows, stream)
-        backprop(cur)
-        launches += 3
+    for st in side[:len(ranges)]:
+        ev = torch.cuda.Event()
+        ev.record(st)
+        main.wait_event(ev)
+    engine.stream_handover_dev(stream)
     return launches

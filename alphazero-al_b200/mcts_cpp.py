@@ -269,6 +269,38 @@ class _BatchedMCTS:
         self._ck(self._L.az_mcts_backprop_dev(self._h, int(K), policy, d, p1w, p2w, ml, is_term or None, sym or None,
                                               stream or None))
 
+    def search_range_dev(self, K, roots_ptr, leaves_ptr, first, count, new_epoch=True, stream=0):
+        """search_dev restricted to trees [first, first + count); pointers are whole-batch bases (include/azb200.h)."""
+        self._push_cfg()
+        self._ck(self._L.az_mcts_search_range_dev(self._h, int(K), roots_ptr, leaves_ptr, int(first), int(count),
+                                                  1 if new_epoch else 0, stream or None))
+
+    def backprop_range_dev(self, K, policy, d, p1w, p2w, ml, first, count, is_term=0, sym=0, stream=0):
+        self._push_cfg()
+        self._ck(self._L.az_mcts_backprop_range_dev(self._h, int(K), policy, d, p1w, p2w, ml, is_term or None, sym or None,
+                                                    int(first), int(count), stream or None))
+
+    def playout_synthetic_dev(self, mode, n_playout, K, shards, roots_ptr, leaves_ptr, policy, d, p1w, p2w, ml, stream=0):
+        """The whole playout loop with a synthetic evaluator, driven natively (include/azb200.h).  Returns kernel launches."""
+        self._push_cfg()
+        out = C.c_int(0)
+        self._ck(self._L.az_mcts_playout_synthetic_dev(self._h, int(mode), int(n_playout), int(K), int(shards), roots_ptr, leaves_ptr,
+                                                       policy, d, p1w, p2w, ml, stream or None, C.byref(out)))
+        return out.value
+
+    def time_select(self, on=True):
+        """CUDA events around every select launch (measurement, include/azb200.h)."""
+        self._ck(self._L.az_mcts_time_select(self._h, 1 if on else 0))
+
+    def get_select_time(self):
+        """(summed select ms, launches, leaf rows) since the last call; synchronises the device."""
+        ms, n, rows = C.c_float(0), C.c_int(0), C.c_uint64(0)
+        self._ck(self._L.az_mcts_get_select_time(self._h, C.byref(ms), C.byref(n), C.byref(rows)))
+        return ms.value, n.value, rows.value
+
+    def stream_handover_dev(self, stream=0):
+        self._ck(self._L.az_mcts_stream_handover_dev(self._h, stream or None))
+
     def prune_roots_dev(self, actions_ptr, stream=0):
         self._push_cfg()
         self._ck(self._L.az_mcts_prune_roots_dev(self._h, actions_ptr, stream or None))
@@ -291,7 +323,7 @@ class _BatchedMCTS:
         return self._L.az_mcts_get_lanes(self._h)
 
     def set_variant(self, variant):
-        """Generation of the thread-per-tree Connect4 kernels (0 first, 1 lean, 2 lean + bulk-copy gather); bit-identical results."""
+        """Generation of the thread-per-tree Connect4 kernels (0 first, 1 lean); bit-identical results."""
         self._ck(self._L.az_mcts_set_variant(self._h, int(variant)))
 
     def get_variant(self):

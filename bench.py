@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--selfplay-slots", type=int, default=16384)
     ap.add_argument("--selfplay-plies", type=int, default=30)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (Connect4: 1/2/4/8, 0 = auto)")
+    ap.add_argument("--shards", type=int, default=0, help="independent tree shards on their own streams (0 = auto)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -211,6 +212,7 @@ def main():
               "search_params": "server defaults (c_init 1.4, c_base 1000, fpu 0.2, alpha 0.3, eps 0.25, mlh 0.1/0.2, symmetry on)",
               "evaluator": "constant (uniform prior, fixed WDL/aux; stands in for the random-init CNN)",
               "parallelism": f"{world} x independent game shards, no data-path collective"}
+    
     
 
     if args.impl == "reference":
@@ -255,10 +257,12 @@ def main():
     ev = ds.SyntheticEvaluator("Connect4", "constant")
     stream = torch.cuda.current_stream().cuda_stream
 
-    def dev_step(on_select=None):
+    shards = args.shards if args.shards > 0 else ds.auto_shards(G)
+
+    def dev_step(n_shards=None):
         eng.prune_roots_dev(reset_actions.data_ptr(), stream)
         buf.pack_roots(boards, turns, stream)
-        return 2 + ds.playout_device(eng, buf, n_playout, K, ev, stream, on_select)
+        return 2 + ds.playout_device(eng, buf, n_playout, K, ev, stream, shards=n_shards or shards)
 
     # ---- untimed pass with counters on: tree statistics for the roofline model ----
     eng.enable_stats(True)
@@ -277,13 +281,6 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sel_events = []
-
-    def on_select(rows, fn):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record()
-        sel_events.append((rows, e0, e1))
-
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -291,16 +288,27 @@ def main():
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     launches = 0
+    eng.time_select(True)               # CUDA events around every select launch, on the stream it is launched on
     for _ in range(args.steps):
-        launches += dev_step(on_select)
+        launches += dev_step()
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ms = t_start.elapsed_time(t_end)
-    sel_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in sel_events)
-    sel_rows = sum(r for r, _, _ in sel_events)
+    sel_ms, sel_launches, sel_rows = eng.get_select_time()
+    # the dominant kernel timed ALONE: two more steps with the whole batch per launch on one stream (no overlap with other
+    # shards' kernels)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(2):
+        dev_step(n_shards=1)
+    a1.record()
+    torch.cuda.synchronize()
+    alone_step_ms = a0.elapsed_time(a1) / 2
+    alone_sel_ms, alone_sel_launches, alone_sel_rows = eng.get_select_time()
+    eng.time_select(False)
     if world > 1:
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -442,6 +450,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = (sel_rows * bytes_select_sim) / (sel_ms * 1e-3) / 1e9 if sel_ms > 0 else 0.0
+    achieved_alone = (alone_sel_rows * bytes_select_sim) / (alone_sel_ms * 1e-3) / 1e9 if alone_sel_ms > 0 else 0.0
     # DRAM bytes per select launch from the committed `ncu --set full` capture of the same workload (profiles/)
     traffic, traffic_src = None, None
     if G == 65536 and K == 4 and eng.get_lanes() == 1:
@@ -449,11 +458,17 @@ def main():
         traffic_src = ("profiles/r1c_ncu_full_select_t_backprop_t_n65536.csv: dram__bytes_read.sum + dram__bytes_write.sum of one "
                        "k_select_t launch (262144 simulations); algorithmic bytes of that launch = %.1f MB" % (G * K * bytes_select_sim / 1e6))
     roofline = {"bound": "hbm", "kernel": "az::k_select_t<C4,VL>" if eng.get_lanes() == 1 else f"az::k_select<C4,{eng.get_lanes()},VL>", "lanes_per_tree": eng.get_lanes(), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "frac": achieved / peak, "shards": shards,
+                "note": ("achieved = algorithmic select bytes / CUDA-event time of the select launches inside the timed region, on their "
+                         "own streams; with shards > 1 those launches share the GPU with the other shards' evaluate / back-prop kernels, "
+                         "so achieved_alone (whole batch per launch, one stream, 2 extra steps) is the kernel's own rate"),
+                "achieved_alone": achieved_alone, "frac_alone": achieved_alone / peak,
+                "select_us_per_launch_alone": 1e3 * alone_sel_ms / max(alone_sel_launches, 1), "select_launches_timed": sel_launches, "ms_per_step_one_stream": alone_step_ms,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "bytes_per_sim_select": bytes_select_sim, "bytes_per_sim_whole_path": bytes_total_sim,
                 "tree_stats": {"depth": d_bar, "edges_scanned": E_bar, "edges_created": b_bar, "expansions": x_bar},
-                "select_share_of_step": sel_ms / ms if world == 1 else None,
+                "select_share_of_step": alone_sel_ms / (2 * alone_step_ms) if alone_step_ms > 0 else None,
                 "whole_path_frac": value / world * bytes_total_sim / 1e9 / peak}
     cpu = None
     if not args.no_cpu_baseline and world == 1:

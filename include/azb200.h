@@ -142,6 +142,28 @@ int az_mcts_search_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_lea
 int az_mcts_backprop_dev(az_mcts *h, int K, const float *d_policy, const float *d_d, const float *d_p1w,
                          const float *d_p2w, const float *d_moves_left, const uint8_t *d_is_term,
                          const int32_t *d_sym_ids, void *stream);
+/* Shard variants: the same launches restricted to trees [first, first + count) (first a multiple of 32).  All pointers
+ * are still the bases of the whole-batch arrays (row of tree i, simulation k = i*K + k).  Independent shards may be
+ * driven on different streams so that the select of one overlaps the evaluation / back-prop of another (the kernels
+ * are DRAM-latency bound and leave issue slots idle; a CNN evaluator is compute bound - they overlap well).  Pass
+ * new_epoch = 1 for the first shard of a search iteration and 0 for the others: every shard then draws its leaf
+ * symmetries from the same epoch as an unsharded az_mcts_search_dev call, so results do not depend on the sharding.
+ * az_mcts_stream_handover_dev orders the stream after everything queued through this handle so far (call it on the
+ * stream the shards fork from, and again on the stream that joined them). */
+int az_mcts_search_range_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, int first, int count, int new_epoch,
+                             void *stream);
+int az_mcts_backprop_range_dev(az_mcts *h, int K, const float *d_policy, const float *d_d, const float *d_p1w,
+                               const float *d_p2w, const float *d_moves_left, const uint8_t *d_is_term,
+                               const int32_t *d_sym_ids, int first, int count, void *stream);
+int az_mcts_stream_handover_dev(az_mcts *h, void *stream);
+/* The per-move playout loop of the reference wrapper (src/MCTS_cpp.py:217-357: one non-VL warm-up simulation, then
+ * ceil((n-1)/K) virtual-loss iterations) with one of the synthetic evaluators of az_eval_synthetic_dev, driven natively:
+ * 3 launches per iteration and shard, no per-launch host-language cost.  shards > 1 pipelines that many tree ranges on
+ * internal streams (forked from and joined back into `stream`).  Buffers: az_leaf[n*max(K,1)], policy f32[n*max(K,1)*A],
+ * d/p1w/p2w/moves_left f32[n*max(K,1)].  *launches_out (optional) = kernels launched. */
+int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, int shards, const az_root *d_roots,
+                                  az_leaf *d_leaves, float *d_policy, float *d_d, float *d_p1w, float *d_p2w,
+                                  float *d_moves_left, void *stream, int *launches_out);
 int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const az_root *d_roots, int n_playout, void *stream);
 int az_mcts_get_counts_dev(az_mcts *h, int32_t *d_out, void *stream);
 int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream);
@@ -151,8 +173,8 @@ int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream);
 int az_mcts_set_lanes(az_mcts *h, int lanes);
 int az_mcts_get_lanes(const az_mcts *h);
 /* Generation of the thread-per-tree Connect4 kernels (lanes == 1): 0 = first generation, 1 = lean kernels (branch-free
- * IEEE divisions, staged back-prop, 256-bit slot accesses; default), 2 = lean + bulk-copy (TMA) gather.  All variants
- * compute bit-identical results; the setting exists for A/B measurements and the parity tests.  Env: AZB200_VARIANT. */
+ * IEEE divisions, software-pipelined block gather, staged back-prop, 256-bit slot accesses; default).  Both compute
+ * bit-identical results; the setting exists for A/B measurements and the parity tests.  Env: AZB200_VARIANT. */
 int az_mcts_set_variant(az_mcts *h, int variant);
 int az_mcts_get_variant(const az_mcts *h);
 /* Self-test of the branch-free division sequences against the compiler's IEEE division: mode 0 = 1/n for n = 1..count,
@@ -169,6 +191,14 @@ int az_mcts_reserve(az_mcts *h, int slots_per_tree);
  * scanned, edges created, expansions, max arena use (slots), arena capacity (slots/tree), kernel launches */
 int az_mcts_enable_stats(az_mcts *h, int on);
 int az_mcts_get_stats(az_mcts *h, uint64_t *out8);
+/* Measurement: with timing on, every select launch is bracketed by CUDA events on the stream it is launched on;
+ * az_mcts_get_select_time synchronises the device and returns the summed elapsed time (ms), the number of launches and
+ * the leaf rows (trees x simulations) they produced since the last call (bench.py: roofline of the dominant kernel). */
+int az_mcts_time_select(az_mcts *h, int on);
+int az_mcts_get_select_time(az_mcts *h, float *ms_out, int *launches_out, uint64_t *rows_out);
+/* Diagnostics (stats mode, thread-per-tree Connect4 select): out[2w], out[2w+1] = %globaltimer (ns) at the start / end of
+ * warp w of the most recent select launch.  Returns the number of warps written (<= max_warps) or a negative error. */
+int az_mcts_get_warp_times(az_mcts *h, uint64_t *out, int max_warps);
 
 /* Synthetic deterministic evaluators on device pointers (twins of alphazero-al_b200/evaluators.py): turn the leaves
  * of az_mcts_search_dev into the backprop tuple.  mode: 0 hash, 1 flip-equivariant hash (Connect4), 2 constant. */
