@@ -55,6 +55,8 @@ def lib() -> C.CDLL:
     L.az_mcts_destroy.restype = None
     L.az_mcts_destroy.argtypes = [_vp]
     L.az_search_config_defaults.restype = None
+    L.az_mcts_compactions.restype = C.c_uint64
+    L.az_mcts_compactions.argtypes = [_vp]
     sig = {
         "az_mcts_num_envs": [_vp],
         "az_mcts_set_config": [_vp, _vp], "az_mcts_get_config": [_vp, _vp],
@@ -65,7 +67,7 @@ def lib() -> C.CDLL:
         "az_mcts_search_batch_vl": [_vp, _i] + [_vp] * 10,
         "az_mcts_backprop_batch_vl": [_vp, _i] + [_vp] * 7,
         "az_mcts_search": [_vp, _i, _vp, _vp, _i],
-        "az_mcts_get_counts": [_vp, _vp], "az_mcts_get_root_stats": [_vp, _vp],
+        "az_mcts_get_counts": [_vp, _vp], "az_mcts_get_counts64": [_vp, _vp], "az_mcts_get_root_stats": [_vp, _vp],
         "az_mcts_prune_roots_dev": [_vp, _vp, _vp],
         "az_mcts_search_dev": [_vp, _i, _vp, _vp, _vp],
         "az_pack_roots_dev": [_i, _i, _vp, _vp, _vp, _vp],
@@ -81,7 +83,7 @@ def lib() -> C.CDLL:
         "az_mcts_playout_synthetic_dev": [_vp, _i, _i, _i, _i] + [_vp] * 9,
         "az_mcts_search_eval_dev": [_vp, _i, _vp, _i, _vp],
         "az_mcts_get_counts_dev": [_vp, _vp, _vp], "az_mcts_get_root_stats_dev": [_vp, _vp, _vp],
-        "az_mcts_enable_stats": [_vp, _i], "az_mcts_get_stats": [_vp, _vp], "az_mcts_get_warp_times": [_vp, _vp, _i], "az_mcts_time_select": [_vp, _i], "az_mcts_get_select_time": [_vp, _vp, _vp, _vp],
+        "az_mcts_enable_stats": [_vp, _i], "az_mcts_get_stats": [_vp, _vp], "az_mcts_get_warp_times": [_vp, _vp, _i], "az_mcts_time_select": [_vp, _i], "az_mcts_set_compaction": [_vp, _i], "az_mcts_get_select_time": [_vp, _vp, _vp, _vp],
         "az_eval_synthetic_dev": [_i, _i, _i] + [_vp] * 7,
         "az_eval_finalize_dev": [_i] + [_vp] * 8,
         "az_game_action_size": [_i], "az_game_board_size": [_i], "az_game_board_rows": [_i], "az_game_board_cols": [_i],

@@ -103,6 +103,8 @@ class BatchedMCTS:
                 h_counts=torch.empty((n, self.action_size), dtype=torch.int32).pin_memory(),
                 wdl=torch.empty((rows, 3), dtype=torch.float32, device=dev),
                 aux=torch.empty(rows, dtype=torch.float32, device=dev))
+            self._dev["h_boards_np"] = self._dev["h_boards"].numpy()
+            self._dev["h_turns_np"] = self._dev["h_turns"].numpy()
         return self._dev
 
     def _playout_device(self, pv_func, current_boards, turns, max_n, K):
@@ -111,8 +113,9 @@ class BatchedMCTS:
         st = self._device_state(K)
         buf = st["buf"]
         stream = torch.cuda.current_stream().cuda_stream
-        st["h_boards"].copy_(torch.from_numpy(np.ascontiguousarray(current_boards, dtype=np.int8)))
-        st["h_turns"].copy_(torch.from_numpy(np.ascontiguousarray(turns, dtype=np.int32)))
+        # one pass from the caller's arrays (any dtype: Env.board is float32, src/MCTS_cpp.py:101-102) into pinned staging
+        np.copyto(st["h_boards_np"], current_boards, casting="unsafe")
+        np.copyto(st["h_turns_np"], turns, casting="unsafe")
         st["boards"].copy_(st["h_boards"], non_blocking=True)
         st["turns"].copy_(st["h_turns"], non_blocking=True)
         buf.pack_roots(st["boards"], st["turns"], stream)
@@ -182,16 +185,16 @@ class BatchedMCTS:
         return f32(probs), f32(d_vals), f32(p1w_vals), f32(p2w_vals), f32(moves_left)
 
     def batch_playout(self, pv_func, current_boards, turns, n_playout=None, vl_batch=1, time_budget=None):
-        current_boards = np.asarray(current_boards).astype(np.int8)
-        turns = np.asarray(turns).astype(np.int32)
         max_n = n_playout if n_playout is not None else self.n_playout
         use_time = time_budget is not None and time_budget > 0
         if hasattr(pv_func, "score_scale"):
             pv_func.score_scale = self.mcts.config.score_scale
         from . import device_search as ds
         if not use_time and (isinstance(pv_func, ds.SyntheticEvaluator) or hasattr(pv_func, "predict_device")):
-            self._playout_device(pv_func, current_boards, turns, max_n, vl_batch)
+            self._playout_device(pv_func, np.asarray(current_boards), np.asarray(turns), max_n, vl_batch)
             return self
+        current_boards = np.asarray(current_boards).astype(np.int8)
+        turns = np.asarray(turns).astype(np.int32)
         t0 = time.perf_counter() if use_time else 0.0
         if vl_batch <= 1:
             for step in range(max_n):
@@ -296,7 +299,7 @@ class BatchedMCTS:
         return self
 
     def get_visits_count(self):
-        return self.mcts.get_all_counts_array().astype(np.int64)
+        return self.mcts.get_all_counts_array64()
 
     def get_mcts_probs(self):
         counts = self.get_visits_count()

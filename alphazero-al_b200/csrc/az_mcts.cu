@@ -543,7 +543,8 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
                 }
             }
             const float denom = psum + 1e-8f;
-            if (bump + (uint32_t)ne > d.cap) {
+            const uint32_t alloc = (uint32_t)ne;
+            if (bump + alloc > d.cap) {
                 if (lane == 0) atomicExch(d.err, 1);              // host sizes the arenas so this never fires
             } else {
                 const uint32_t off = bump;
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
                     ns.meta = (uint32_t)a << 16;
                     st_slot(arena + off + eidx, ns);
                 }
-                bump += (uint32_t)ne;
+                bump += alloc;
                 const uint32_t cw = (off << 6) | (uint32_t)ne;
                 if (plen > 0) { if (lane == 0) leaf_slot->child = cw; }
                 else {
@@ -875,7 +876,8 @@ __global__ void __launch_bounds__(CTA, 4) k_backprop_t(Dev d, az_search_config c
 #pragma unroll
             for (int a = 0; a < A; ++a) psum += ((legal >> a) & 1ULL) ? pm[a] : 0.0f;     // ascending legal order; + 0.0f exact
             const float denom = psum + 1e-8f;
-            if (bump + (uint32_t)ne > d.cap) atomicExch(d.err, 1);
+            const uint32_t alloc = (uint32_t)ne;
+            if (bump + alloc > d.cap) atomicExch(d.err, 1);
             else {
                 const uint32_t off = bump;
                 Slot ns; ns.n = 0; ns.child = NONE; ns.wd = ns.wp1 = ns.wp2 = ns.msum = 0.0f;
@@ -888,7 +890,7 @@ __global__ void __launch_bounds__(CTA, 4) k_backprop_t(Dev d, az_search_config c
                     st_slot(arena + off + eidx, ns);
                     ++eidx;
                 }
-                bump += (uint32_t)ne;
+                bump += alloc;
                 leaf.child = (off << 6) | (uint32_t)ne;
                 if (plen == 0) {
                     float *nrow = d.noise + (size_t)env * d.noise_stride;
@@ -997,6 +999,65 @@ __global__ void k_prune(Dev d, az_search_config cfg, const int32_t *__restrict__
         }
     }
     reset_tree(tr, nrow, d.noise_stride);
+}
+// ------------------------------------------------------------------------------------------------
+// Arena compaction (new; the reference's node pools only ever grow within a game, MCTSNode.h:149-199).  After a re-root
+// only the subtree below the played move is reachable, but the bump allocator never reclaims the rest: over a 40-ply
+// self-play game a Connect4 arena grows to ~43 000 slots (1.4 MB per tree) of which a few hundred are live.  k_compact
+// copies the live tree of every env breadth-first into a second pool and rewrites the child pointers; the pools are then
+// swapped.  The copied blocks themselves are the BFS queue, so no extra memory is needed.  W lanes per tree: W slots of
+// the queue are examined per step and their child blocks copied cooperatively.  Nothing observable depends on where a
+// block lives, so search results are unchanged (tests/test_gpu_mcts.py).  Pending leaf records (a search without its
+// back-prop) refer to the old offsets: they are invalidated.
+// ------------------------------------------------------------------------------------------------
+template <class G, int W>
+__global__ void __launch_bounds__(CTA) k_compact(Dev d, Slot *__restrict__ dst_pool, unsigned int *max_bump_out) {
+    const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
+    if (gid >= d.n_envs) return;
+    const int lane = threadIdx.x & (W - 1);
+    const unsigned gm = group_mask<W>();
+    const int env = gid;
+    TreeRec *tr = d.trees + env;
+    const Slot *src = d.pool + (size_t)env * d.cap;
+    Slot *dst = dst_pool + (size_t)env * d.cap;
+    if (lane == 0) {                                             // stale path offsets must never be back-propagated
+        d.leaf_nv[env].h.flags = 0;
+        for (int k = 0; k < d.kcap; ++k) d.leaf_vl[(size_t)env * d.kcap + k].h.flags = 0;
+    }
+    const uint32_t rc = tr->root.child;
+    uint32_t nb = 0;
+    if (rc != NONE) {
+        const uint32_t ne = rc & 63u, off = rc >> 6;
+        for (uint32_t e = lane; e < ne; e += W) st_slot(dst + e, ld_slot(src + off + e));
+        nb = ne;
+        gsync<W>(gm);
+        uint32_t i = 0;
+        while (i < nb) {
+            const uint32_t lim = min(i + (uint32_t)W, nb), idx = i + (uint32_t)lane;
+            const uint32_t c = idx < lim ? dst[idx].child : NONE;
+            const uint32_t n2 = c != NONE ? (c & 63u) : 0u;
+            uint32_t pre = n2;                                   // inclusive prefix sum over the lane group
+#pragma unroll
+            for (int o = 1; o < W; o <<= 1) { const uint32_t v = __shfl_up_sync(gm, pre, o, W); if (lane >= o) pre += v; }
+            const uint32_t total = gshfl<W>(gm, pre, W - 1);
+            const uint32_t my_off = nb + pre - n2;
+            for (int l = 0; l < W; ++l) {                        // all lanes copy the child block of queue slot i + l
+                const uint32_t cl = gshfl<W>(gm, c, l), ol = gshfl<W>(gm, my_off, l);
+                if (cl == NONE) continue;
+                const uint32_t nl = cl & 63u, sl = cl >> 6;
+                for (uint32_t e = lane; e < nl; e += W) st_slot(dst + ol + e, ld_slot(src + sl + e));
+            }
+            if (c != NONE) dst[idx].child = (my_off << 6) | n2;
+            nb += total;
+            i = lim;
+            gsync<W>(gm);
+        }
+    }
+    if (lane == 0) {
+        if (rc != NONE) tr->root.child = rc & 63u;               // the root's block now starts at offset 0
+        tr->bump = nb;
+        atomicMax(max_bump_out, nb);
+    }
 }
 __global__ void k_reset(Dev d, int env /* -1 = all */) {
     const int i = env >= 0 ? env : (int)(blockIdx.x * blockDim.x + threadIdx.x);
@@ -1135,6 +1196,11 @@ struct az_mcts {
     struct Bound { int lo, hi; uint64_t b; };
     std::vector<Bound> bounds;        // ... and of the tree ranges [lo, hi) that back-propagated since then
     cudaStream_t side[8] = {};        // shard streams of az_mcts_playout_synthetic_dev
+    Slot *pool_alt = nullptr;         // second arena pool (compaction target), allocated on first use, same capacity
+    int compaction = 1;               // 0 never, 1 when the arenas are more than half full at a re-root, 2 at every re-root
+    bool bound_stale = false;         // arena use changed on the device (compaction): refresh the host bound before the next back-prop
+    uint64_t compactions = 0;
+    uint64_t base_after_prune = 0, growth_est = 0; bool base_pending = false;   // arena-use bookkeeping between re-roots
     bool time_select = false;         // az_mcts_time_select: CUDA events around every select launch
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sel_ev; size_t sel_used = 0; uint64_t sel_rows = 0;
     cudaEvent_t side_ev[8] = {};
@@ -1155,6 +1221,7 @@ struct az_mcts {
     uint8_t *io_in = nullptr;         // packed eval arrays: policy | d | p1 | p2 | ml | sym | is_term
     int32_t *io_actions = nullptr; int32_t *io_counts = nullptr; float *io_stats = nullptr;
     uint8_t *h_out = nullptr, *h_in = nullptr;   // pinned mirrors of io_out / io_in
+    int32_t *h_counts = nullptr;                 // pinned staging of the visit counts
     unsigned long long *d_stats = nullptr; int *d_err = nullptr;
     uint64_t launches = 0;
     bool stats_on = false;
@@ -1287,6 +1354,7 @@ static int grow_arena(az_mcts *h, uint64_t ncap, cudaStream_t st) {
     k_grow<<<h->n, 256, 0, st>>>(h->d.pool, np, h->d.trees, h->cap, (uint32_t)ncap);
     CU(h, cudaStreamSynchronize(st));
     cudaFree(h->d.pool);
+    if (h->pool_alt) { cudaFree(h->pool_alt); h->pool_alt = nullptr; }     // re-created with the new capacity on demand
     h->d.pool = np; h->cap = (uint32_t)ncap; h->d.cap = h->cap;
     return AZ_OK;
 }
@@ -1302,7 +1370,8 @@ static int ensure_arena(az_mcts *h, int sims, cudaStream_t st) {
         return b;
     };
     uint64_t b = current();
-    if (b + need > h->cap) {
+    if (h->bound_stale || b + need > h->cap) {
+        h->bound_stale = false;
         // refresh the bound from the device (all streams: other shards of the batch may still be growing their trees)
         CU(h, cudaDeviceSynchronize());
         CU(h, cudaMemsetAsync(h->d_scratch_u32, 0, sizeof(unsigned int), st));
@@ -1311,6 +1380,7 @@ static int ensure_arena(az_mcts *h, int sims, cudaStream_t st) {
         CU(h, cudaMemcpyAsync(&mx, h->d_scratch_u32, sizeof(mx), cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));
         h->bump_bound = mx; h->bounds.clear();
+        if (h->base_pending) { h->base_after_prune = mx; h->base_pending = false; }
         b = mx;
         if (b + need > h->cap) {
             uint64_t ncap = h->cap;
@@ -1546,6 +1616,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     h->A = az_game_action_size(game); h->S = az_game_board_size(game);
     h->W = auto_lanes(game, n_envs);
     { const char *ve = getenv("AZB200_VARIANT"); if (ve) { int v = atoi(ve); if (v >= 0 && v <= 1) h->variant = v; } }
+    { const char *ce2 = getenv("AZB200_COMPACTION"); if (ce2) { int v = atoi(ce2); if (v >= 0 && v <= 2) h->compaction = v; } }
     h->max_depth = game == GAME_C4 ? C4::MAX_DEPTH : Oth::MAX_DEPTH;
     h->max_edges = game == GAME_C4 ? 8 : 48;
     az_search_config_defaults(&h->cfg);
@@ -1589,12 +1660,13 @@ void az_mcts_destroy(az_mcts *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {h->d.pool, h->d.trees, h->d.noise, h->d.leaf_vl, h->d.path_vl, h->d.leaf_nv, h->d.path_nv, h->d_log_lut, h->d_ls_lut,
+    void *ptrs[] = {h->d.pool, h->pool_alt, h->d.trees, h->d.noise, h->d.leaf_vl, h->d.path_vl, h->d.leaf_nv, h->d.path_nv, h->d_log_lut, h->d_ls_lut,
                     h->d_atan_lut, h->d_stats, h->d_err, h->d_scratch_u32, h->io_boards_in, h->io_turns_in, h->io_roots, h->io_leaves,
                     h->io_out, h->io_in, h->io_actions, h->io_counts, h->io_stats};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->ev) cudaEventDestroy(h->ev);
     for (auto &pr : h->sel_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (int j = 0; j < 8; ++j) { if (h->side_ev[j]) cudaEventDestroy(h->side_ev[j]); if (h->side[j]) cudaStreamDestroy(h->side[j]); }
@@ -1669,8 +1741,35 @@ int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream) 
     else k_prune<Oth><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, h->cfg, d_actions);
     h->launches++;
     CU(h, cudaGetLastError());
+    // compaction: copy the surviving subtrees into the other pool when the arenas are filling up
+    // ... i.e. when one more move's growth (estimated from the growth since the previous re-root) might not fit any more
+    uint64_t bound = h->bump_bound;
+    for (const auto &r : h->bounds) bound = std::max(bound, r.b);
+    const uint64_t growth = bound > h->base_after_prune ? bound - h->base_after_prune : 0;
+    h->growth_est = std::max(h->growth_est - h->growth_est / 4, growth);
+    const bool due = h->compaction == 2 || (h->compaction == 1 && bound + h->growth_est + h->growth_est / 4 > h->cap && bound > 0);
+    h->base_after_prune = bound;
+    if (due) {
+        if (!h->pool_alt) {
+            cudaError_t e = cudaMalloc((void **)&h->pool_alt, sizeof(Slot) * (size_t)h->n * h->cap);
+            if (e != cudaSuccess) { h->pool_alt = nullptr; cudaGetLastError(); return AZ_OK; }   // no room for a second pool: keep growing instead
+        }
+        CU(h, cudaMemsetAsync(h->d_scratch_u32 + 1, 0, sizeof(unsigned int), s));
+        const int g = grid_groups(h->n, 8);
+        if (h->game == GAME_C4) k_compact<C4, 8><<<g, CTA, 0, s>>>(h->d, h->pool_alt, h->d_scratch_u32 + 1);
+        else k_compact<Oth, 8><<<g, CTA, 0, s>>>(h->d, h->pool_alt, h->d_scratch_u32 + 1);
+        std::swap(h->d.pool, h->pool_alt);
+        h->bound_stale = true; h->base_pending = true; h->compactions++; h->launches++;
+        CU(h, cudaGetLastError());
+    }
     return AZ_OK;
 }
+int az_mcts_set_compaction(az_mcts *h, int mode) {
+    if (mode < 0 || mode > 2) AZ_FAIL(h, AZ_ERR_INVALID, "compaction mode must be 0 (never), 1 (auto) or 2 (every re-root)");
+    h->compaction = mode;
+    return AZ_OK;
+}
+uint64_t az_mcts_compactions(const az_mcts *h) { return h->compactions; }
 int az_mcts_prune_roots(az_mcts *h, const int32_t *actions) {
     { int rc = enter_host(h); if (rc) return rc; }
     CU(h, cudaMemcpyAsync(h->io_actions, actions, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
@@ -1881,6 +1980,19 @@ int az_mcts_get_counts(az_mcts *h, int32_t *out) {
     rc = az_mcts_get_counts_dev(h, h->io_counts, h->stream); if (rc) return rc;
     CU(h, cudaMemcpyAsync(out, h->io_counts, sizeof(int32_t) * (size_t)h->n * h->A, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    return AZ_OK;
+}
+// Visit counts widened to int64 (what callers of the reference build from get_all_counts(): np.array(list of int)): one D2H
+// copy into pinned memory, widened on the host.
+int az_mcts_get_counts64(az_mcts *h, int64_t *out) {
+    int rc = enter_host(h); if (rc) return rc;
+    const size_t cnt = (size_t)h->n * h->A;
+    if (!h->h_counts) CU(h, cudaMallocHost((void **)&h->h_counts, sizeof(int32_t) * cnt));
+    rc = az_mcts_get_counts_dev(h, h->io_counts, h->stream); if (rc) return rc;
+    CU(h, cudaMemcpyAsync(h->h_counts, h->io_counts, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    const int32_t *src = h->h_counts;
+    for (size_t i = 0; i < cnt; ++i) out[i] = (int64_t)src[i];
     return AZ_OK;
 }
 int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream) {

@@ -180,6 +180,9 @@ _SHARD_STREAMS = {}
 def auto_shards(n: int) -> int:
     """Independent tree shards driven on their own streams (measured on B200, Connect4 n=200 K=4, 65 536 trees:
     1 shard 2.07, 2 shards 2.23, 4 shards 2.29 G simulations/s).  Small batches stay whole: they are launch bound."""
+    import os
+    if os.environ.get("AZB200_SHARDS"):
+        return max(1, int(os.environ["AZB200_SHARDS"]))
     return 4 if n >= 32768 else (2 if n >= 16384 else 1)
 
 

@@ -253,6 +253,12 @@ class _BatchedMCTS:
         self._ck(self._L.az_mcts_get_counts(self._h, _ptr(out)))
         return out
 
+    def get_all_counts_array64(self):
+        """The counts as int64 [n_envs, A] - the dtype np.array(get_all_counts()) has in the reference wrapper."""
+        out = np.empty((self._n, self._A), np.int64)
+        self._ck(self._L.az_mcts_get_counts64(self._h, _ptr(out)))
+        return out
+
     def get_all_root_stats(self):
         out = np.empty((self._n, 6 + 8 * self._A), np.float32)
         self._ck(self._L.az_mcts_get_root_stats(self._h, _ptr(out)))
@@ -287,6 +293,13 @@ class _BatchedMCTS:
         self._ck(self._L.az_mcts_playout_synthetic_dev(self._h, int(mode), int(n_playout), int(K), int(shards), roots_ptr, leaves_ptr,
                                                        policy, d, p1w, p2w, ml, stream or None, C.byref(out)))
         return out.value
+
+    def set_compaction(self, mode):
+        """Arena compaction at re-roots: 0 never, 1 auto (default), 2 always (include/azb200.h)."""
+        self._ck(self._L.az_mcts_set_compaction(self._h, int(mode)))
+
+    def compactions(self):
+        return int(self._L.az_mcts_compactions(self._h))
 
     def time_select(self, on=True):
         """CUDA events around every select launch (measurement, include/azb200.h)."""

@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--no-cnn", action="store_true")
     ap.add_argument("--cnn-slots", type=int, default=4096)
     ap.add_argument("--cnn-plies", type=int, default=3)
-    ap.add_argument("--selfplay-slots", type=int, default=16384)
+    ap.add_argument("--selfplay-slots", type=int, default=65536)
     ap.add_argument("--selfplay-plies", type=int, default=30)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (Connect4: 1/2/4/8, 0 = auto)")
     ap.add_argument("--shards", type=int, default=0, help="independent tree shards on their own streams (0 = auto)")
@@ -381,7 +381,7 @@ def main():
         sp = sp_mod.SelfPlay("Connect4", n_slots, n_playout, K, ds.SyntheticEvaluator("Connect4", "constant"), search_cfg=SERVER_DEFAULTS,
                              temperature=1.0, temp_decay_moves=20, temp_endgame=0.0, td_steps=10, seed=0, uid_base=lo,
                              uid_stride=world * n_slots, device=local_rank, out_capacity=4 * n_slots)
-        sp.engine.reserve(16384)
+        sp.engine.reserve(8192)                   # arena compaction at re-roots keeps every game inside 8192 slots (2 x 256 KB)
         for _ in range(12):                       # reach the steady state of continuously restarting games
             sp.ply()
         torch.cuda.synchronize()

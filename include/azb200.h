@@ -102,6 +102,8 @@ int az_mcts_backprop_batch_vl(az_mcts *h, int K, const float *policy, const floa
 int az_mcts_search(az_mcts *h, int evaluator, const int8_t *boards, const int32_t *turns, int n_playout);
 /* get_all_counts - BatchedMCTS.h:413-427: int32[n*A] */
 int az_mcts_get_counts(az_mcts *h, int32_t *out);
+/* the same counts widened to int64[n*A] - what src/MCTS_cpp.py:81,442-443 builds with np.array(get_all_counts()) */
+int az_mcts_get_counts64(az_mcts *h, int64_t *out);
 /* get_all_root_stats - BatchedMCTS.h:435-441, layout MCTS.h:634-636: f32[n, 6+8A] */
 int az_mcts_get_root_stats(az_mcts *h, float *out);
 
@@ -184,6 +186,14 @@ int az_selftest_div(int mode, uint64_t count, uint64_t seed, uint64_t *mismatche
 /* Global index of env 0 of this handle: all RNG streams are keyed by (seed, global env index), so a game's result does
  * not depend on how games are sharded over GPUs. */
 int az_mcts_set_env_base(az_mcts *h, uint64_t base);
+/* Arena compaction.  The reference's node pools only grow within a game (MCTSNode.h:149-199); after a re-root only the
+ * subtree below the played move is reachable.  mode 1 (default): when the growth of one more move might no longer fit at a
+ * re-root, the live tree of every env is copied breadth-first into a second pool of the same size and the pools are swapped
+ * (bounded memory per game: many more concurrent self-play games fit in HBM).  0 = never, 2 = at every re-root.  Search
+ * results do not depend on it; leaf records of a search whose back-prop has not run yet are invalidated by a compaction.
+ * Env: AZB200_COMPACTION.  az_mcts_compactions = compactions performed so far. */
+int az_mcts_set_compaction(az_mcts *h, int mode);
+uint64_t az_mcts_compactions(const az_mcts *h);
 /* Pre-size every tree arena (slots of 32 bytes per tree) so no reallocation happens later (e.g. under graph capture). */
 int az_mcts_reserve(az_mcts *h, int slots_per_tree);
 

@@ -212,6 +212,20 @@ def test_c4_lean_kernels_fall_back_to_plain_division_on_tiny_numerators(variant)
     assert a.get_all_root_stats().tobytes() == b.get_all_root_stats().tobytes()
 
 
+@pytest.mark.parametrize("game,lanes", [("Connect4", 1), ("Connect4", 8), ("Othello", 16)])
+def test_arena_compaction_at_every_reroot_changes_nothing(game, lanes):
+    """k_compact copies the surviving subtree into the second pool after every re-root (mode 2); the search that follows
+    must be bit-identical to the oracle's (which, like the reference, never moves a node), over a whole game of tree reuse."""
+    n = 96
+    e = _cuda(game, n)
+    e.set_lanes(lanes)
+    e.set_compaction(2)
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True) if game == "Connect4" else dict(OTH_CFG, use_symmetry=True)
+    boards, turns = random_positions(game, n, 6, 91)
+    compare_engines(e, _orc(game, n), game, n, 80, 4, cfg, boards=boards, turns=turns, moves=16, seed=12)
+    assert e.compactions() >= 15
+
+
 @pytest.mark.parametrize("game,n,lanes,shards", [("Connect4", 1000, 1, 4), ("Connect4", 512, 8, 2), ("Connect4", 200, 1, 3), ("Othello", 256, 16, 2)])
 def test_sharded_device_loop_equals_unsharded_loop(game, n, lanes, shards):
     """Tree shards on their own streams (az_mcts_search_range_dev / backprop_range_dev) must build exactly the trees of
