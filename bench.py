@@ -453,17 +453,22 @@ def main():
     achieved_alone = (alone_sel_rows * bytes_select_sim) / (alone_sel_ms * 1e-3) / 1e9 if alone_sel_ms > 0 else 0.0
     # DRAM bytes per select launch from the committed `ncu --set full` capture of the same workload (profiles/)
     traffic, traffic_src = None, None
-    if G == 65536 and K == 4 and eng.get_lanes() == 1:
-        traffic = 147.69792e6 + 34.587648e6
-        traffic_src = ("profiles/r1c_ncu_full_select_t_backprop_t_n65536.csv: dram__bytes_read.sum + dram__bytes_write.sum of one "
-                       "k_select_t launch (262144 simulations); algorithmic bytes of that launch = %.1f MB" % (G * K * bytes_select_sim / 1e6))
-    roofline = {"bound": "hbm", "kernel": "az::k_select_t<C4,VL>" if eng.get_lanes() == 1 else f"az::k_select<C4,{eng.get_lanes()},VL>", "lanes_per_tree": eng.get_lanes(), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "shards": shards,
-                "note": ("achieved = algorithmic select bytes / CUDA-event time of the select launches inside the timed region, on their "
-                         "own streams; with shards > 1 those launches share the GPU with the other shards' evaluate / back-prop kernels, "
-                         "so achieved_alone (whole batch per launch, one stream, 2 extra steps) is the kernel's own rate"),
-                "achieved_alone": achieved_alone, "frac_alone": achieved_alone / peak,
-                "select_us_per_launch_alone": 1e3 * alone_sel_ms / max(alone_sel_launches, 1), "select_launches_timed": sel_launches, "ms_per_step_one_stream": alone_step_ms,
+    if G == 65536 and K == 4 and eng.get_lanes() == 1 and eng.get_variant() == 1:
+        traffic = 101.218e6 + 16.894e6
+        traffic_src = ("profiles/r1g_per_kernel_traffic_n65536.csv: dram__bytes_read.sum + dram__bytes_write.sum per k_select_f launch, mean over "
+                       "the 50 launches of one step (ncu flushes the caches before every replay, so this is cold-L2 traffic); algorithmic "
+                       "bytes of one launch (262144 simulations) = %.1f MB" % (G * K * bytes_select_sim / 1e6))
+    kname = ("az::k_select_f<C4,VL,AUX>" if eng.get_variant() == 1 else "az::k_select_t<C4,VL>") if eng.get_lanes() == 1 else f"az::k_select<C4,{eng.get_lanes()},VL>"
+    roofline = {"bound": "hbm", "kernel": kname, "lanes_per_tree": eng.get_lanes(), "achieved": achieved_alone, "peak": peak, "unit": "GB/s",
+                "frac": achieved_alone / peak, "shards": shards,
+                "note": ("achieved = algorithmic select bytes / CUDA-event time of the select launches (events on the launching stream, "
+                         "az_mcts_time_select), taken in 2 extra steps right after the timed region with the whole batch per launch on ONE "
+                         "stream.  Inside the timed region the batch runs as `shards` tree ranges on their own streams, so a select launch "
+                         "shares the SMs with other shards' evaluate / back-prop kernels and its elapsed time is not the kernel's own: "
+                         "those numbers are under in_timed_region"),
+                "in_timed_region": {"achieved": achieved, "frac": achieved / peak, "select_launches": sel_launches,
+                                    "select_us_per_launch": 1e3 * sel_ms / max(sel_launches, 1), "trees_per_launch": G // max(shards, 1)},
+                "select_us_per_launch": 1e3 * alone_sel_ms / max(alone_sel_launches, 1), "ms_per_step_one_stream": alone_step_ms,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "bytes_per_sim_select": bytes_select_sim, "bytes_per_sim_whole_path": bytes_total_sim,
