@@ -1408,10 +1408,10 @@ static int auto_lanes(int game, int n) {
         return n >= 16384 ? 8 : 16;
     }
     if (e) { int w = atoi(e); if (w == 1 || w == 2 || w == 4 || w == 8) return w; }
-    if (n < 12288) return 8;
-    if (n < 24576) return 4;
-    if (n < 49152) return 2;
-    return 1;
+    // measured with the lean thread-per-tree kernels (tools/bench_configs.py, B200): one lane per tree wins from 8192 trees
+    // up (16384 trees: 0.97 vs 0.89 G sims/s with 4 lanes; 32768: 1.58 vs 1.24 with 2 lanes); smaller batches are latency
+    // bound and a little faster with 8 lanes (more warps, shorter per-level chains)
+    return n >= 8192 ? 1 : 8;
 }
 
 // ---- kernel dispatch over (game, lanes, VL) ----

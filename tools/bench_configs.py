@@ -75,7 +75,16 @@ if __name__ == "__main__":
     c4 = dict(c_init=1.4, c_base=4000.0, fpu_reduction=0.2, dirichlet_alpha=0.3, noise_epsilon=0.25, mlh_slope=0.1, mlh_cap=0.2, use_symmetry=True)
     oth = dict(c_init=1.4, c_base=2000.0, fpu_reduction=0.2, dirichlet_alpha=0.3, noise_epsilon=0.25, use_symmetry=True,
                score_utility_factor=0.15, score_scale=8.0)
+    c1 = dict(c4, c_base=1000.0)
+    if "--small" in sys.argv:
+        for n in (100, 1024, 2048, 4096):
+            for ln in (1, 4, 8):
+                run("Connect4", n, 200, 4, c1, "hash", steps=5, label=f"C4 N={n} n=200 K=4, {ln} lanes", lanes=ln)
+        sys.exit(0)
+    run("Connect4", 100, 200, 4, c1, "hash", steps=10, label="config 1 search: C4 N=100 n=200 K=4")
     run("Connect4", 8192, 800, 8, c4, "equivariant", label="config 3: C4 N=8192 n=800 K=8 sym+MLH")
+    run("Connect4", 16384, 200, 4, c1, "hash", label="C4 N=16384 n=200 K=4")
+    run("Connect4", 32768, 200, 4, c1, "hash", label="C4 N=32768 n=200 K=4")
     run("Connect4", 65536, 800, 8, c4, "equivariant", label="config 3 shape at N=65536")
     run("Othello", 4096, 400, 4, oth, "hash", label="config 4: Othello N=4096 n=400 K=4 score utility")
     run("Othello", 4096, 400, 4, oth, "hash", label="config 4, 8 lanes", lanes=8)
