@@ -25,20 +25,22 @@ __global__ void k_eval_synth(int mode, int n, const az_leaf *__restrict__ leaves
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     constexpr int A = G::A;
+    const uint64_t keep = l2_keep_policy();          // leaves / policy / value rows live in L2 (az_rng.cuh)
     az_leaf L;
-    *reinterpret_cast<uint4 *>(&L) = *reinterpret_cast<const uint4 *>(leaves + i);
-    *(reinterpret_cast<uint4 *>(&L) + 1) = *(reinterpret_cast<const uint4 *>(leaves + i) + 1);
+    *reinterpret_cast<uint4 *>(&L) = ld_u4_keep(leaves + i, keep);
+    *(reinterpret_cast<uint4 *>(&L) + 1) = ld_u4_keep(reinterpret_cast<const uint4 *>(leaves + i) + 1, keep);
     float *prow = policy + (size_t)i * A;
     if (L.flags & AZ_LEAF_TERMINAL) {
-        for (int a = 0; a < A; ++a) prow[a] = 0.0f;
+        for (int a = 0; a < A; ++a) st_f32_keep(prow + a, 0.0f, keep);
         const bool w1 = (L.flags & AZ_LEAF_P1_WINS) != 0, w2 = (L.flags & AZ_LEAF_P2_WINS) != 0;
-        dv[i] = (!w1 && !w2) ? 1.0f : 0.0f; p1v[i] = w1 ? 1.0f : 0.0f; p2v[i] = w2 ? 1.0f : 0.0f; mlv[i] = 0.0f;
+        st_f32_keep(dv + i, (!w1 && !w2) ? 1.0f : 0.0f, keep); st_f32_keep(p1v + i, w1 ? 1.0f : 0.0f, keep);
+        st_f32_keep(p2v + i, w2 ? 1.0f : 0.0f, keep); st_f32_keep(mlv + i, 0.0f, keep);
         return;
     }
     const int turn = L.turn;
     float wdl0, wdl1, wdl2, aux;
     if (mode == 2) {   // constant
-        for (int a = 0; a < A; ++a) prow[a] = 1.0f;
+        for (int a = 0; a < A; ++a) st_f32_keep(prow + a, 1.0f, keep);
         wdl0 = 0.25f; wdl1 = 0.5f; wdl2 = 0.25f;
         aux = G::GAME == GAME_C4 ? 10.0f : 0.125f;
     } else {
@@ -59,7 +61,7 @@ __global__ void k_eval_synth(int mode, int n, const az_leaf *__restrict__ leaves
                 if (selfsym) ac = min(ac, A - 1 - ac);
             }
             const uint64_t ph = splitmix64(h + (uint64_t)ac + 1ULL);
-            prow[a] = ((float)((ph >> 40) & 0xFFFFULL) + 1.0f) * (1.0f / 65536.0f);
+            st_f32_keep(prow + a, ((float)((ph >> 40) & 0xFFFFULL) + 1.0f) * (1.0f / 65536.0f), keep);
         }
         const float w0 = (float)((splitmix64(h ^ 0x1111ULL) >> 40) & 0xFFULL) + 1.0f;
         const float w1 = (float)((splitmix64(h ^ 0x2222ULL) >> 40) & 0xFFULL) + 1.0f;
@@ -69,10 +71,10 @@ __global__ void k_eval_synth(int mode, int n, const az_leaf *__restrict__ leaves
         if (G::GAME == GAME_C4) aux = (float)((h >> 20) & 31ULL);
         else aux = (float)((h >> 20) & 63ULL) * (1.0f / 32.0f) - 1.0f;
     }
-    dv[i] = wdl0;
-    p1v[i] = turn == 1 ? wdl1 : wdl2;
-    p2v[i] = turn == 1 ? wdl2 : wdl1;
-    mlv[i] = aux;
+    st_f32_keep(dv + i, wdl0, keep);
+    st_f32_keep(p1v + i, turn == 1 ? wdl1 : wdl2, keep);
+    st_f32_keep(p2v + i, turn == 1 ? wdl2 : wdl1, keep);
+    st_f32_keep(mlv + i, aux, keep);
 }
 
 // CNN.predict outputs -> backprop tuple: relative WDL [draw, win(to move), loss(to move)] to absolute [draw, p1w, p2w]

@@ -65,15 +65,17 @@ struct C4 {
         s.last = n > 0 ? ((n & 1) ? 0 : 1) : -1;
         s.turn = turn; s.passes = 0;
     }
+    // (bb[] is only ever indexed with constants: a run-time index would move the boards to local memory in a kernel)
     AZ_HD static void step(State &s, int col) {                       // :159-172 (no legality check)
         uint64_t occ = s.bb[0] | s.bb[1];
-        int p = s.turn == 1 ? 0 : 1;
-        s.bb[p] |= 1ULL << (col * 7 + col_height(occ, col));
-        s.last = p; s.turn = -s.turn;
+        const bool p1 = s.turn == 1;
+        const uint64_t bit = 1ULL << (col * 7 + col_height(occ, col));
+        s.bb[0] |= p1 ? bit : 0ULL; s.bb[1] |= p1 ? 0ULL : bit;
+        s.last = p1 ? 0 : 1; s.turn = -s.turn;
     }
     AZ_HD static int winner(const State &s) {                         // :182-203 (last mover only)
         if (s.last < 0) return 0;
-        uint64_t b = s.bb[s.last], t;
+        uint64_t b = s.last == 0 ? s.bb[0] : s.bb[1], t;
         int res = s.last == 0 ? 1 : -1;
         t = b & (b >> 1); if (t & (t >> 2))  return res;
         t = b & (b >> 7); if (t & (t >> 14)) return res;
@@ -148,8 +150,8 @@ struct Oth {
         return shift<D>(c) & empty;
     }
     AZ_HD static uint64_t valid_positions(const State &s) {             // :155-171
-        int p = s.turn == 1 ? 0 : 1;
-        uint64_t own = s.bb[p], opp = s.bb[1 - p], empty = ~(own | opp);
+        const bool p1 = s.turn == 1;
+        uint64_t own = p1 ? s.bb[0] : s.bb[1], opp = p1 ? s.bb[1] : s.bb[0], empty = ~(own | opp);
         return valid_dir<0>(own, opp, empty) | valid_dir<1>(own, opp, empty) | valid_dir<2>(own, opp, empty) |
                valid_dir<3>(own, opp, empty) | valid_dir<4>(own, opp, empty) | valid_dir<5>(own, opp, empty) |
                valid_dir<6>(own, opp, empty) | valid_dir<7>(own, opp, empty);
@@ -165,19 +167,20 @@ struct Oth {
         return (sq & own) ? cand : 0;
     }
     AZ_HD static uint64_t flips(const State &s, int pos) {              // :177-198
-        int p = s.turn == 1 ? 0 : 1;
-        uint64_t own = s.bb[p], opp = s.bb[1 - p], pl = 1ULL << pos;
+        const bool p1 = s.turn == 1;
+        uint64_t own = p1 ? s.bb[0] : s.bb[1], opp = p1 ? s.bb[1] : s.bb[0], pl = 1ULL << pos;
         return flips_dir<0>(pl, own, opp) | flips_dir<1>(pl, own, opp) | flips_dir<2>(pl, own, opp) |
                flips_dir<3>(pl, own, opp) | flips_dir<4>(pl, own, opp) | flips_dir<5>(pl, own, opp) |
                flips_dir<6>(pl, own, opp) | flips_dir<7>(pl, own, opp);
     }
     AZ_HD static void step(State &s, int a) {                           // :206-235
         if (a == PASS) { s.passes++; s.turn = -s.turn; return; }
-        int p = s.turn == 1 ? 0 : 1;
+        const bool p1 = s.turn == 1;
         uint64_t f = flips(s, a);
-        s.bb[p] |= (1ULL << a) | f;
-        s.bb[1 - p] &= ~f;
-        s.passes = 0; s.last = p; s.turn = -s.turn;
+        const uint64_t add = (1ULL << a) | f;
+        s.bb[0] = p1 ? (s.bb[0] | add) : (s.bb[0] & ~f);
+        s.bb[1] = p1 ? (s.bb[1] & ~f) : (s.bb[1] | add);
+        s.passes = 0; s.last = p1 ? 0 : 1; s.turn = -s.turn;
     }
     AZ_HD static bool over(const State &s) { return n_pieces(s) == 64 || s.passes >= 2; }   // :241-244
     AZ_HD static int winner(const State &s) {                           // :250-258

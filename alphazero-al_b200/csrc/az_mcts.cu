@@ -94,7 +94,7 @@ struct Dev {   // kernel-visible view of an engine
     int *err;                            // sticky device error flag (arena overflow)
     int n_envs;
     int env_lo, env_cnt;                 // trees [env_lo, env_lo + env_cnt) are processed by the select / back-prop launch
-    int hints;                           // bit 0: streaming stores for new edge blocks (experiment switch, AZB200_HINTS)
+    int hints;                           // bit 0: streaming (.cs) stores for new edge blocks (on; AZB200_HINTS=0 turns it off for A/B runs)
     uint64_t seed, epoch;
     uint64_t env_base;                   // global index of env 0 (RNG keys are sharding-invariant)
 };

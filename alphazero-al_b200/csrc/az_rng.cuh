@@ -28,4 +28,38 @@ AZ_HD uint64_t rollout_hash(uint64_t seed, uint64_t gidx, uint64_t ply) {
     return splitmix64(splitmix64(seed ^ 0xA5A5A5A55A5A5A5AULL) ^ (gidx << 8) ^ ply);
 }
 
+#if defined(__CUDACC__)
+// ---- L2 residency hints --------------------------------------------------------------------------------------------
+// The leaf records, az_leaf rows, policy rows and value rows are producer -> consumer buffers rewritten in place every
+// iteration (select -> evaluator -> back-prop), ~37 MB at 65 536 trees x K = 4.  Accessed with the evict_last policy they
+// stay resident in the 126 MB L2, so neither their write-back nor their re-read reaches HBM.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_f32_keep(float *p, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float ld_f32_keep(const float *p, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_u4_keep(const void *p, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_words256_keep(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t dd, uint32_t e, uint32_t f, uint32_t g,
+                                                 uint32_t h, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(dd), "r"(e), "r"(f),
+                 "r"(g), "r"(h), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async16_keep(void *smem_dst, const void *gsrc, uint64_t pol) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "l"(pol) : "memory");
+}
+#endif
+
 }  // namespace az

@@ -61,11 +61,11 @@ template <class G> __global__ void k_sp_ply(az_selfplay sp, const int32_t *__res
     if (step < T) {
         const size_t o = (size_t)g * T + step;
         int8_t *ps = sp.st_state + o * 3 * S;
-        const int own = s.turn == 1 ? 0 : 1;
+        const uint64_t own_bb = s.turn == 1 ? s.bb[0] : s.bb[1], opp_bb = s.turn == 1 ? s.bb[1] : s.bb[0];
         for (int j = 0; j < S; ++j) {
             const int bit = G::cell_bit(j);
-            ps[j] = (int8_t)((s.bb[own] >> bit) & 1ULL);
-            ps[S + j] = (int8_t)((s.bb[1 - own] >> bit) & 1ULL);
+            ps[j] = (int8_t)((own_bb >> bit) & 1ULL);
+            ps[S + j] = (int8_t)((opp_bb >> bit) & 1ULL);
             ps[2 * S + j] = (int8_t)s.turn;
         }
         float *pp = sp.st_prob + o * A;
@@ -131,11 +131,11 @@ template <class G> __global__ void k_sp_flush(az_selfplay sp) {
             reinterpret_cast<int16_t *>(rec + L.off_aux)[t] = (int16_t)(G::GAME == GAME_OTH ? diff * (int)sp.st_player[base + t] : ste);   // src/game.py:17-23
         }
         // terminal tuple (src/game.py:135-148): end state, zero prob, winner, 0, terminal aux, zero wdl, all-ones mask
-        const int own = s.turn == 1 ? 0 : 1;
+        const uint64_t own_bb = s.turn == 1 ? s.bb[0] : s.bb[1], opp_bb = s.turn == 1 ? s.bb[1] : s.bb[0];
         for (int j = threadIdx.x; j < S; j += blockDim.x) {
             const int bit = G::cell_bit(j);
             int8_t *ps = reinterpret_cast<int8_t *>(rec + L.off_state) + (size_t)Tn * 3 * S;
-            ps[j] = (int8_t)((s.bb[own] >> bit) & 1ULL); ps[S + j] = (int8_t)((s.bb[1 - own] >> bit) & 1ULL); ps[2 * S + j] = (int8_t)s.turn;
+            ps[j] = (int8_t)((own_bb >> bit) & 1ULL); ps[S + j] = (int8_t)((opp_bb >> bit) & 1ULL); ps[2 * S + j] = (int8_t)s.turn;
         }
         for (int a = threadIdx.x; a < A; a += blockDim.x) rec[L.off_mask + Tn * A + a] = 1;
         if (threadIdx.x == 0) {
