@@ -1012,10 +1012,12 @@ __global__ void k_prune(Dev d, az_search_config cfg, const int32_t *__restrict__
 // ------------------------------------------------------------------------------------------------
 template <class G, int W>
 __global__ void __launch_bounds__(CTA) k_compact(Dev d, Slot *__restrict__ dst_pool, unsigned int *max_bump_out) {
+    constexpr int J = 4;                                         // queue windows examined per step (independent: more loads in flight)
     const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
     if (gid >= d.n_envs) return;
     const int lane = threadIdx.x & (W - 1);
     const unsigned gm = group_mask<W>();
+    const int gshift = (threadIdx.x & 31) & ~(W - 1);            // first lane of this group inside the warp
     const int env = gid;
     TreeRec *tr = d.trees + env;
     const Slot *src = d.pool + (size_t)env * d.cap;
@@ -1033,22 +1035,48 @@ __global__ void __launch_bounds__(CTA) k_compact(Dev d, Slot *__restrict__ dst_p
         gsync<W>(gm);
         uint32_t i = 0;
         while (i < nb) {
-            const uint32_t lim = min(i + (uint32_t)W, nb), idx = i + (uint32_t)lane;
-            const uint32_t c = idx < lim ? dst[idx].child : NONE;
-            const uint32_t n2 = c != NONE ? (c & 63u) : 0u;
-            uint32_t pre = n2;                                   // inclusive prefix sum over the lane group
+            const uint32_t lim = min(i + (uint32_t)(J * W), nb);
+            uint32_t c[J], my_off[J];
+            uint32_t run = nb;                                   // next free slot of the new arena
 #pragma unroll
-            for (int o = 1; o < W; o <<= 1) { const uint32_t v = __shfl_up_sync(gm, pre, o, W); if (lane >= o) pre += v; }
-            const uint32_t total = gshfl<W>(gm, pre, W - 1);
-            const uint32_t my_off = nb + pre - n2;
-            for (int l = 0; l < W; ++l) {                        // all lanes copy the child block of queue slot i + l
-                const uint32_t cl = gshfl<W>(gm, c, l), ol = gshfl<W>(gm, my_off, l);
-                if (cl == NONE) continue;
-                const uint32_t nl = cl & 63u, sl = cl >> 6;
-                for (uint32_t e = lane; e < nl; e += W) st_slot(dst + ol + e, ld_slot(src + sl + e));
+            for (int j = 0; j < J; ++j) {
+                const uint32_t idx = i + (uint32_t)(j * W + lane);
+                c[j] = idx < lim ? dst[idx].child : NONE;
             }
-            if (c != NONE) dst[idx].child = (my_off << 6) | n2;
-            nb += total;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {                        // queue order: window j, then lane
+                const uint32_t n2 = c[j] != NONE ? (c[j] & 63u) : 0u;
+                uint32_t pre = n2;                               // inclusive prefix sum over the lane group
+#pragma unroll
+                for (int o = 1; o < W; o <<= 1) { const uint32_t v = __shfl_up_sync(gm, pre, o, W); if (lane >= o) pre += v; }
+                my_off[j] = run + pre - n2;
+                run += gshfl<W>(gm, pre, W - 1);
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) {                        // all lanes copy the child blocks of window j, four at a time
+                unsigned todo = (__ballot_sync(gm, c[j] != NONE) >> gshift) & ((1u << W) - 1u);
+                while (todo) {
+                    Slot tmp[4]; uint32_t to[4]; bool mine[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        mine[q] = false;
+                        if (!todo) continue;
+                        const int l = __ffs((int)todo) - 1; todo &= todo - 1;
+                        const uint32_t cl = gshfl<W>(gm, c[j], l), ol = gshfl<W>(gm, my_off[j], l);
+                        const uint32_t nl = cl & 63u, sl = cl >> 6;
+                        if (G::MAX_EDGES <= W) {                 // one slot per lane
+                            mine[q] = (uint32_t)lane < nl; to[q] = ol + (uint32_t)lane;
+                            if (mine[q]) tmp[q] = ld_slot(src + sl + lane);
+                        } else {
+                            for (uint32_t e = lane; e < nl; e += W) st_slot(dst + ol + e, ld_slot(src + sl + e));
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (mine[q]) st_slot(dst + to[q], tmp[q]);
+                }
+                if (c[j] != NONE) dst[i + (uint32_t)(j * W + lane)].child = (my_off[j] << 6) | (c[j] & 63u);
+            }
+            nb = run;
             i = lim;
             gsync<W>(gm);
         }

@@ -381,7 +381,7 @@ def main():
         sp = sp_mod.SelfPlay("Connect4", n_slots, n_playout, K, ds.SyntheticEvaluator("Connect4", "constant"), search_cfg=SERVER_DEFAULTS,
                              temperature=1.0, temp_decay_moves=20, temp_endgame=0.0, td_steps=10, seed=0, uid_base=lo,
                              uid_stride=world * n_slots, device=local_rank, out_capacity=4 * n_slots)
-        sp.engine.reserve(8192)                   # arena compaction at re-roots keeps every game inside 8192 slots (2 x 256 KB)
+        sp.engine.reserve(16384)                  # arena compaction at re-roots keeps every game inside 16384 slots (2 pools x 512 KB)
         for _ in range(12):                       # reach the steady state of continuously restarting games
             sp.ply()
         torch.cuda.synchronize()
