@@ -454,10 +454,11 @@ def main():
     # DRAM bytes per select launch from the committed `ncu --set full` capture of the same workload (profiles/)
     traffic, traffic_src = None, None
     if G == 65536 and K == 4 and eng.get_lanes() == 1 and eng.get_variant() == 1:
-        traffic = 101.218e6 + 16.894e6
-        traffic_src = ("profiles/r1g_per_kernel_traffic_n65536.csv: dram__bytes_read.sum + dram__bytes_write.sum per k_select_f launch, mean over "
-                       "the 50 launches of one step (ncu flushes the caches before every replay, so this is cold-L2 traffic); algorithmic "
-                       "bytes of one launch (262144 simulations) = %.1f MB" % (G * K * bytes_select_sim / 1e6))
+        traffic = 100.902e6 + 46.635e6
+        traffic_src = ("profiles/r1i_per_kernel_traffic_warm_l2_n65536.csv: dram__bytes_read.sum + dram__bytes_write.sum per k_select_f launch, mean "
+                       "over the 50 launches of one step, ncu --cache-control none (warm L2 as in a real run; the writes are mostly dirty sectors "
+                       "of the previous back-prop being evicted; cold-L2 capture: 101.2 + 16.9 MB, profiles/r1g_*); algorithmic bytes of one "
+                       "launch (262144 simulations) = %.1f MB" % (G * K * bytes_select_sim / 1e6))
     kname = ("az::k_select_f<C4,VL,AUX>" if eng.get_variant() == 1 else "az::k_select_t<C4,VL>") if eng.get_lanes() == 1 else f"az::k_select<C4,{eng.get_lanes()},VL>"
     roofline = {"bound": "hbm", "kernel": kname, "lanes_per_tree": eng.get_lanes(), "achieved": achieved_alone, "peak": peak, "unit": "GB/s",
                 "frac": achieved_alone / peak, "shards": shards,
