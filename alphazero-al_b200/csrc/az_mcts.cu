@@ -1238,6 +1238,7 @@ struct az_mcts {
     int lut_n = 0;
     float *d_log_lut = nullptr, *d_atan_lut = nullptr;
     float2 *d_ls_lut = nullptr;
+    bool last_select_ro = false;      // the last select launch was read-only: its back-prop applies the leaf flags, removes no virtual loss
     int variant = 1;                  // thread-per-tree kernels: 0 = first generation (k_*_t), 1 = lean (k_*_f)
     // VL bookkeeping
     int kcap = 0;
@@ -1464,13 +1465,22 @@ static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_l
         const int gf = (cnt + CTA_F - 1) / CTA_F;
         const int kk = vl ? K : 1;
         const bool aux = h->cfg.mlh_slope > 0.0f;            // aux_enabled<C4>
-#define AZ_SELECT_F(VLF, AX) k_select_f<C4, VLF, AX><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves)
+        // K <= RS_MAX: read-only select (launch-local virtual loss, leaf flags applied by back-prop); the matching back-prop
+        // launch must know (last_select_ro)
+        const bool ro = kk <= RS_MAX;
+        h->last_select_ro = ro;
+#define AZ_SELECT_F(VLF, AX)                                                                                             \
+    do {                                                                                                                 \
+        if (ro) k_select_f<C4, VLF, AX, true><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);                      \
+        else k_select_f<C4, VLF, AX, false><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);                        \
+    } while (0)
         if (vl) { if (aux) AZ_SELECT_F(true, true); else AZ_SELECT_F(true, false); }
         else { if (aux) AZ_SELECT_F(false, true); else AZ_SELECT_F(false, false); }
 #undef AZ_SELECT_F
         h->launches++;
         return;
     }
+    h->last_select_ro = false;
     if (h->game == GAME_C4 && h->W == 1) {       // thread-per-tree kernels with cooperative block gather
         if (vl) k_select_t<C4, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, roots, leaves);
         else k_select_t<C4, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, roots, leaves);
@@ -1481,7 +1491,7 @@ static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_l
     else AZ_DISPATCH_W(h, k_select, false, g, s, h->d, h->cfg, 1, roots, leaves);
     h->launches++;
 }
-static void launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym, const float *pol, const float *d, const float *p1,
+static int launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym, const float *pol, const float *d, const float *p1,
                             const float *p2, const float *ml, const uint8_t *it, const int32_t *sym, cudaStream_t s) {
     const int cnt = h->d.env_cnt;
     const int g = grid_groups(cnt, h->W);
@@ -1494,25 +1504,32 @@ static void launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym
         if ((!vl || (1 << rec_shift) == 4 * h->kcap) && smem <= 200 * 1024) {
             const int gf = (cnt + CTA_F - 1) / CTA_F;
             if (smem > h->bp_smem_set) {
-                cudaFuncSetAttribute(k_backprop_f<C4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                cudaFuncSetAttribute(k_backprop_f<C4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(k_backprop_f<C4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(k_backprop_f<C4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(k_backprop_f<C4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(k_backprop_f<C4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 h->bp_smem_set = smem;
             }
-            if (vl) k_backprop_f<C4, true><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, kk, removeK, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);
-            else k_backprop_f<C4, false><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, 1, 0, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);
+            const bool ro = h->last_select_ro;
+            if (vl) { if (ro) k_backprop_f<C4, true, true><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, kk, removeK, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);
+                      else k_backprop_f<C4, true, false><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, kk, removeK, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym); }
+            else { if (ro) k_backprop_f<C4, false, true><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, 1, 0, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);
+                   else k_backprop_f<C4, false, false><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, 1, 0, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym); }
             h->launches++;
-            return;
+            return AZ_OK;
         }
     }
+    if (h->last_select_ro) AZ_FAIL(h, AZ_ERR_INVALID, "back-prop after a read-only select needs a 16-byte aligned policy buffer");
     if (h->game == GAME_C4 && h->W == 1) {
         if (vl) k_backprop_t<C4, true><<<g, CTA, 0, s>>>(h->d, h->cfg, K, removeK, use_sym, pol, d, p1, p2, ml, it, sym);
         else k_backprop_t<C4, false><<<g, CTA, 0, s>>>(h->d, h->cfg, 1, 0, use_sym, pol, d, p1, p2, ml, it, sym);
         h->launches++;
-        return;
+        return AZ_OK;
     }
     if (vl) AZ_DISPATCH_W(h, k_backprop, true, g, s, h->d, h->cfg, K, removeK, use_sym, pol, d, p1, p2, ml, it, sym);
     else AZ_DISPATCH_W(h, k_backprop, false, g, s, h->d, h->cfg, 1, 0, use_sym, pol, d, p1, p2, ml, it, sym);
     h->launches++;
+    return AZ_OK;
 }
 
 static int set_range(az_mcts *h, int first, int count) {
@@ -1556,7 +1573,7 @@ static int do_backprop(az_mcts *h, int K, const float *pol, const float *d, cons
     h->d.stats = h->stats_on ? h->d_stats : nullptr;
     const int removeK = vl ? std::min(K, h->prepared_K) : 0;
     // non-VL: the symmetry id is the one search_batch remembered (pending_sym_ids_, BatchedMCTS.h:45,194)
-    launch_backprop(h, vl, K, removeK, 1, pol, d, p1, p2, ml, it, vl ? sym : nullptr, s);
+    rc = launch_backprop(h, vl, K, removeK, 1, pol, d, p1, p2, ml, it, vl ? sym : nullptr, s); if (rc) return rc;
     CU(h, cudaGetLastError());
     return AZ_OK;
 }
@@ -1979,7 +1996,7 @@ int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const az_root *d_roots, i
         launch_select(h, false, 1, d_roots, h->io_leaves, s);
         if (h->game == GAME_C4) k_eval_builtin<C4><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, evaluator, p, pol, dv, p1, p2, ml);
         else k_eval_builtin<Oth><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, evaluator, p, pol, dv, p1, p2, ml);
-        launch_backprop(h, false, 1, 0, 0, pol, dv, p1, p2, ml, nullptr, nullptr, s);
+        rc = launch_backprop(h, false, 1, 0, 0, pol, dv, p1, p2, ml, nullptr, nullptr, s); if (rc) { h->cfg = saved; return rc; }
         h->launches += 1;
     }
     h->cfg = saved;
