@@ -4,9 +4,10 @@
 //   src/cpp/MCTS.h:46-675 (single tree), src/cpp/BatchedMCTS.h:26-442 (batch manager), src/cpp/MCTSNode.h.
 // How it computes it is re-designed for the GPU:
 //
-//   * One LANE GROUP per tree (8 lanes for Connect4, 16 for Othello; 4 / 2 trees per warp).  Lane e owns edge e
-//     of the node being scanned, so FPU + PUCT for all children is one coalesced sweep and the arg-max is a
-//     shuffle reduction with lowest-index tie-break (the reference's strict `>` scan, MCTS.h:227).
+//   * One LANE GROUP per tree for small batches (8 lanes for Connect4, 16 for Othello; 4 / 2 trees per warp).  Lane e
+//     owns edge e of the node being scanned, so FPU + PUCT for all children is one coalesced sweep and the arg-max is a
+//     shuffle reduction with lowest-index tie-break (the reference's strict `>` scan, MCTS.h:227).  From 8192 Connect4
+//     trees up, one THREAD per tree (az_mcts_fast.cuh): every warp instruction then serves 32 trees.
 //   * A node has no record of its own.  Its statistics (N, in-flight, W_d/W_p1/W_p2, M_sum), its flags and the
 //     pointer to its edge block live in the 32-byte SLOT of the edge that leads to it, inside its parent's
 //     block; the root's live in the per-tree TreeRec.  Descending one level is therefore ONE dependent
