@@ -188,6 +188,26 @@ def test_c4_thread_per_tree_kernel_generations_are_bit_exact(variant, n, K, deca
     compare_engines(e, _orc("Connect4", n), "Connect4", n, 90, K, cfg, boards=boards, turns=turns, moves=6, seed=5)
 
 
+@pytest.mark.parametrize("K", [4, 3, 2])
+def test_c4_read_only_select_deep_paths_and_terminals(K):
+    """The read-only select (K <= 4) derives virtual loss from the earlier paths of the launch: entries beyond the 8 kept in
+    shared memory come from the global path array, terminal children are reached repeatedly, and with 400 simulations on
+    late-game roots most descents end in terminal or duplicate leaves.  Must match the oracle bit for bit, and the compiled
+    reference when it travelled with the snapshot."""
+    n = 96
+    e = _cuda("Connect4", n)
+    e.set_lanes(1)
+    assert e.get_variant() == 1
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True, c_init=3.0)         # a large c_init spreads visits: long, varied paths
+    boards, turns = random_positions("Connect4", n, 34, 1234 + K)
+    compare_engines(e, _orc("Connect4", n), "Connect4", n, 400, K, cfg, boards=boards, turns=turns, moves=3, seed=77)
+    if oracle.ref_available("parity"):
+        e2 = _cuda("Connect4", n)
+        e2.set_lanes(1)
+        cfg2 = dict(cfg, use_symmetry=False)
+        compare_engines(e2, _ref("Connect4", n), "Connect4", n, 200, K, cfg2, boards=boards, turns=turns, moves=2, compare_leaves=True)
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_c4_lean_kernels_fall_back_to_plain_division_on_tiny_numerators(variant):
     """Priors of 1e-30 and WDL sums of 1e-35 push the PUCT numerators below the range the branch-free division covers:
