@@ -1470,10 +1470,15 @@ static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_l
         // launch must know (last_select_ro)
         const bool ro = kk <= RS_MAX;
         h->last_select_ro = ro;
+        // launches that fill the machine on their own (more CTAs than 6 per SM) run the 128-register build, shard-sized
+        // launches the spill-free 144-register build (see az_mcts_fast.cuh)
+        const bool wide = gf > 6 * 148;
 #define AZ_SELECT_F(VLF, AX)                                                                                             \
     do {                                                                                                                 \
-        if (ro) k_select_f<C4, VLF, AX, true><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);                      \
-        else k_select_f<C4, VLF, AX, false><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);                        \
+        if (ro) { if (wide) k_select_f<C4, VLF, AX, true><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);           \
+                  else k_select_f_r<C4, VLF, AX, true><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves); }           \
+        else { if (wide) k_select_f<C4, VLF, AX, false><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);            \
+               else k_select_f_r<C4, VLF, AX, false><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves); }            \
     } while (0)
         if (vl) { if (aux) AZ_SELECT_F(true, true); else AZ_SELECT_F(true, false); }
         else { if (aux) AZ_SELECT_F(false, true); else AZ_SELECT_F(false, false); }
@@ -1505,17 +1510,24 @@ static int launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym,
         if ((!vl || (1 << rec_shift) == 4 * h->kcap) && smem <= 200 * 1024) {
             const int gf = (cnt + CTA_F - 1) / CTA_F;
             if (smem > h->bp_smem_set) {
-                cudaFuncSetAttribute(k_backprop_f<C4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                cudaFuncSetAttribute(k_backprop_f<C4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                cudaFuncSetAttribute(k_backprop_f<C4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                cudaFuncSetAttribute(k_backprop_f<C4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#define AZ_BP_ATTR(KF) cudaFuncSetAttribute(KF, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                AZ_BP_ATTR((k_backprop_f<C4, true, true>)); AZ_BP_ATTR((k_backprop_f<C4, true, false>));
+                AZ_BP_ATTR((k_backprop_f<C4, false, true>)); AZ_BP_ATTR((k_backprop_f<C4, false, false>));
+                AZ_BP_ATTR((k_backprop_f_r<C4, true, true>)); AZ_BP_ATTR((k_backprop_f_r<C4, true, false>));
+                AZ_BP_ATTR((k_backprop_f_r<C4, false, true>)); AZ_BP_ATTR((k_backprop_f_r<C4, false, false>));
+#undef AZ_BP_ATTR
                 h->bp_smem_set = smem;
             }
-            const bool ro = h->last_select_ro;
-            if (vl) { if (ro) k_backprop_f<C4, true, true><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, kk, removeK, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);
-                      else k_backprop_f<C4, true, false><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, kk, removeK, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym); }
-            else { if (ro) k_backprop_f<C4, false, true><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, 1, 0, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);
-                   else k_backprop_f<C4, false, false><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, 1, 0, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym); }
+            const bool ro = h->last_select_ro, wide = gf > 6 * 148;
+#define AZ_BP_F(KERNEL, VLF, ROF, KARG, RARG) KERNEL<C4, VLF, ROF><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, KARG, RARG, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym)
+            if (vl) {
+                if (ro) { if (wide) AZ_BP_F(k_backprop_f, true, true, kk, removeK); else AZ_BP_F(k_backprop_f_r, true, true, kk, removeK); }
+                else { if (wide) AZ_BP_F(k_backprop_f, true, false, kk, removeK); else AZ_BP_F(k_backprop_f_r, true, false, kk, removeK); }
+            } else {
+                if (ro) { if (wide) AZ_BP_F(k_backprop_f, false, true, 1, 0); else AZ_BP_F(k_backprop_f_r, false, true, 1, 0); }
+                else { if (wide) AZ_BP_F(k_backprop_f, false, false, 1, 0); else AZ_BP_F(k_backprop_f_r, false, false, 1, 0); }
+            }
+#undef AZ_BP_F
             h->launches++;
             return AZ_OK;
         }
