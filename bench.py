@@ -454,8 +454,8 @@ def main():
     # DRAM bytes per select launch from the committed `ncu --set full` capture of the same workload (profiles/)
     traffic, traffic_src = None, None
     if G == 65536 and K == 4 and eng.get_lanes() == 1 and eng.get_variant() == 1:
-        traffic = 100.893e6 + 25.097e6
-        traffic_src = ("profiles/r1k_per_kernel_traffic_warm_l2_n65536.csv: dram__bytes_read.sum + dram__bytes_write.sum per k_select_f launch, mean "
+        traffic = 99.600e6 + 24.502e6
+        traffic_src = ("profiles/r1m_per_kernel_traffic_warm_l2_n65536.csv: dram__bytes_read.sum + dram__bytes_write.sum per k_select_f launch, mean "
                        "over the 50 launches of one step, ncu --cache-control none (warm L2 as in a real run; the writes are mostly dirty sectors "
                        "of the previous back-prop being evicted; cold-L2 capture: 101.2 + 16.9 MB, profiles/r1g_*); algorithmic bytes of one "
                        "launch (262144 simulations) = %.1f MB" % (G * K * bytes_select_sim / 1e6))
