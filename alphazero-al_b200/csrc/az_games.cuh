@@ -219,4 +219,58 @@ struct Oth {
     AZ_HD static int cell_bit(int j) { return j; }
 };
 
+#if defined(__CUDACC__)
+// ---- Othello on a lane group (W >= 8 lanes per tree) ------------------------------------------------------------------
+// flips() and valid_positions() walk the 8 compass directions one after the other (8 x 6 masked shifts, ~480 instructions on
+// 64-bit boards); every lane of a tree's group would repeat all of it.  Here lane (l & 7) walks ONE direction, given as data
+// (shift amount, left/right, wrap mask - no divergence), and the eight partial masks are OR-reduced with three shuffles.
+struct OthDir { int sh; bool left; uint64_t mask; };
+__device__ __forceinline__ OthDir oth_dir(int dd) {          // same numbering as Oth::shift<D>
+    OthDir D;
+    const int q = dd & 3;
+    D.sh = q == 0 ? 8 : (q == 1 ? 7 : (q == 2 ? 1 : 9));
+    D.left = dd >= 2 && dd <= 5;
+    D.mask = q == 0 ? ~0ULL : ((dd >= 1 && dd <= 3) ? Oth::NOT_A : Oth::NOT_H);
+    return D;
+}
+__device__ __forceinline__ uint64_t oth_shift(uint64_t b, const OthDir &D) { return (D.left ? (b << D.sh) : (b >> D.sh)) & D.mask; }
+template <int W> __device__ __forceinline__ uint64_t oth_or8(uint64_t v, unsigned gm) {
+    v |= __shfl_xor_sync(gm, v, 1, W); v |= __shfl_xor_sync(gm, v, 2, W); v |= __shfl_xor_sync(gm, v, 4, W);
+    return v;
+}
+template <int W> __device__ __forceinline__ uint64_t oth_flips_group(const State &s, int pos, int lane, unsigned gm) {   // Othello.h:177-198
+    const bool p1 = s.turn == 1;
+    const uint64_t own = p1 ? s.bb[0] : s.bb[1], opp = p1 ? s.bb[1] : s.bb[0];
+    const OthDir D = oth_dir(lane & 7);
+    uint64_t cand = 0, sq = oth_shift(1ULL << pos, D);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const uint64_t hit = sq & opp; cand |= hit; sq = hit ? oth_shift(sq, D) : sq; }
+    return oth_or8<W>((sq & own) ? cand : 0ULL, gm);
+}
+template <int W> __device__ __forceinline__ uint64_t oth_valid_group(const State &s, int lane, unsigned gm) {             // Othello.h:155-171
+    const bool p1 = s.turn == 1;
+    const uint64_t own = p1 ? s.bb[0] : s.bb[1], opp = p1 ? s.bb[1] : s.bb[0], empty = ~(own | opp);
+    const OthDir D = oth_dir(lane & 7);
+    uint64_t c = oth_shift(own, D) & opp;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) c |= oth_shift(c, D) & opp;
+    return oth_or8<W>(oth_shift(c, D) & empty, gm);
+}
+// Game::step / legal moves for a lane group: group-uniform control flow required (every lane of the group calls it)
+template <class G, int W> __device__ __forceinline__ void step_group(State &s, int a, int lane, unsigned gm) {
+    if (G::GAME == GAME_OTH && W >= 8) {
+        if (a == Oth::PASS) { s.passes++; s.turn = -s.turn; return; }
+        const bool p1 = s.turn == 1;
+        const uint64_t f = oth_flips_group<W>(s, a, lane, gm), add = (1ULL << a) | f;
+        s.bb[0] = p1 ? (s.bb[0] | add) : (s.bb[0] & ~f);
+        s.bb[1] = p1 ? (s.bb[1] & ~f) : (s.bb[1] | add);
+        s.passes = 0; s.last = p1 ? 0 : 1; s.turn = -s.turn;
+    } else G::step(s, a);
+}
+template <class G, int W> __device__ __forceinline__ uint64_t legal_group(const State &s, int lane, unsigned gm) {
+    if (G::GAME == GAME_OTH && W >= 8) return Oth::over(s) ? 0ULL : oth_valid_group<W>(s, lane, gm);
+    return G::legal(s);
+}
+#endif
+
 }  // namespace az

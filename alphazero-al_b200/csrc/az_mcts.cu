@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
             ch.wp1 = gshfl<W>(gm, ch.wp1, bl);
             ch.wp2 = gshfl<W>(gm, ch.wp2, bl);
             ch.msum = gshfl<W>(gm, ch.msum, bl);
-            G::step(st, (int)((ch.meta >> 16) & 0xFFu));
+            step_group<G, W>(st, (int)((ch.meta >> 16) & 0xFFu), lane, gm);
             uint32_t nmeta = ch.meta;
             if (!(nmeta & F_ALLOC)) {      // lazy child allocation (MCTS.h:481-488): remember the child's side to move
                 nmeta |= F_ALLOC;
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
         if (!term && (!VL || leaf_child == NONE)) {
             // search() never symmetrises (BatchedMCTS.h:404): use_sym == 0
             const int sym = use_sym ? (sym_ids ? sym_ids[flat] : (int)L.sym) : 0;
-            const uint64_t legal = G::legal(st);
+            const uint64_t legal = legal_group<G, W>(st, lane, gm);
             int ne; bool pass_only = false;
             if (G::GAME == GAME_OTH) {
                 pass_only = legal == 0ULL && !Oth::over(st);
