@@ -97,6 +97,7 @@ struct Dev {   // kernel-visible view of an engine
     int env_lo, env_cnt;                 // trees [env_lo, env_lo + env_cnt) are processed by the select / back-prop launch
     int hints;                           // bit 0: streaming (.cs) stores for new edge blocks (on; AZB200_HINTS=0 turns it off for A/B runs)
     uint64_t seed, epoch;
+    const unsigned long long *epoch_add;   // graph replays: added to `epoch` (kernel parameters are frozen in a captured graph)
     uint64_t env_base;                   // global index of env 0 (RNG keys are sharding-invariant)
 };
 
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
         int sym = 0;
         State ex = st;
         if (!leaf_term && cfg.use_symmetry) {
-            const uint64_t h = az_rand(d.seed, d.epoch, STREAM_SYM, d.env_base + (uint64_t)env, (uint64_t)k);
+            const uint64_t h = az_rand(d.seed, d.epoch + (d.epoch_add ? *d.epoch_add : 0ULL), STREAM_SYM, d.env_base + (uint64_t)env, (uint64_t)k);
             sym = G::GAME == GAME_C4 ? (int)(h & 1) : ((0x7620 >> (4 * (int)(h & 3))) & 0xF);   // Othello {0,2,6,7}
             G::symmetry(ex, sym);
         }
@@ -786,7 +787,7 @@ __global__ void __launch_bounds__(CTA, 4) k_select_t(Dev d, az_search_config cfg
             int sym = 0;
             State ex = st;
             if (!leaf_term && cfg.use_symmetry) {
-                const uint64_t h = az_rand(d.seed, d.epoch, STREAM_SYM, d.env_base + (uint64_t)env, (uint64_t)k);
+                const uint64_t h = az_rand(d.seed, d.epoch + (d.epoch_add ? *d.epoch_add : 0ULL), STREAM_SYM, d.env_base + (uint64_t)env, (uint64_t)k);
                 sym = (int)(h & 1);
                 G::symmetry(ex, sym);
             }
@@ -1225,6 +1226,17 @@ struct az_mcts {
     struct Bound { int lo, hi; uint64_t b; };
     std::vector<Bound> bounds;        // ... and of the tree ranges [lo, hi) that back-propagated since then
     cudaStream_t side[8] = {};        // shard streams of az_mcts_playout_synthetic_dev
+    // CUDA graphs of whole playout loops (az_mcts_playout_synthetic_dev): the native loop issues ~600 launches per move at
+    // ~6.5 us of host time each; a captured graph replays them with one call.  Keyed by everything a launch bakes in.
+    struct GraphKey {
+        int mode, n_playout, K, ns, W, variant, hints, kcap; uint32_t cap; const void *ptrs[10]; az_search_config cfg; uint64_t seed, env_base;
+    };
+    struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t epoch0; int launches; uint64_t last_use; };
+    std::vector<GraphEntry> graphs;
+    unsigned long long *d_epoch_add = nullptr;
+    int use_graphs = 1;               // AZB200_GRAPHS=0 disables
+    bool capturing = false;           // inside a capture: no host-side arena accounting, no synchronising paths
+    uint64_t graph_clock = 0, graph_replays = 0;
     Slot *pool_alt = nullptr;         // second arena pool (compaction target), allocated on first use, same capacity
     int compaction = 1;               // 0 never, 1 when the arenas are more than half full at a re-root, 2 at every re-root
     bool bound_stale = false;         // arena use changed on the device (compaction): refresh the host bound before the next back-prop
@@ -1392,6 +1404,7 @@ static int grow_arena(az_mcts *h, uint64_t ncap, cudaStream_t st) {
 // Make sure no tree of the current range can overflow its arena during a back-prop of `sims` simulations per tree.
 // The host keeps conservative upper bounds of max(TreeRec.bump) per tree range (shards of one batch advance independently).
 static int ensure_arena(az_mcts *h, int sims, cudaStream_t st) {
+    if (h->capturing) return AZ_OK;        // the caller reserved the whole loop's growth up front
     const uint64_t need = (uint64_t)sims * (uint64_t)(h->game == GAME_C4 ? 7 : 34);
     const int lo = h->d.env_lo, hi = lo + h->d.env_cnt;
     auto current = [&]() {
@@ -1497,6 +1510,9 @@ static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_l
     else AZ_DISPATCH_W(h, k_select, false, g, s, h->d, h->cfg, 1, roots, leaves);
     h->launches++;
 }
+// Grants k_backprop_f its dynamic shared memory for K simulations per tree ahead of time (not allowed to happen lazily
+// inside a stream capture).
+static void bp_prepare(az_mcts *h, bool vl, int K);
 static int launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym, const float *pol, const float *d, const float *p1,
                             const float *p2, const float *ml, const uint8_t *it, const int32_t *sym, cudaStream_t s) {
     const int cnt = h->d.env_cnt;
@@ -1509,7 +1525,7 @@ static int launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym,
         const size_t smem = backprop_f_smem_per_warp(kk, rec_shift) * (CTA_F / 32);
         if ((!vl || (1 << rec_shift) == 4 * h->kcap) && smem <= 200 * 1024) {
             const int gf = (cnt + CTA_F - 1) / CTA_F;
-            if (smem > h->bp_smem_set) {
+            if (smem > h->bp_smem_set) {                     // (never inside a graph capture: the playout loop calls bp_prepare first)
 #define AZ_BP_ATTR(KF) cudaFuncSetAttribute(KF, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                 AZ_BP_ATTR((k_backprop_f<C4, true, true>)); AZ_BP_ATTR((k_backprop_f<C4, true, false>));
                 AZ_BP_ATTR((k_backprop_f<C4, false, true>)); AZ_BP_ATTR((k_backprop_f<C4, false, false>));
@@ -1545,17 +1561,37 @@ static int launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym,
     return AZ_OK;
 }
 
+static void bp_prepare(az_mcts *h, bool vl, int K) {
+    if (!(h->game == GAME_C4 && h->W == 1 && h->variant != 0)) return;
+    const int kk = vl ? K : 1;
+    int rec_shift = 2;
+    if (vl) { rec_shift = 0; while ((1 << rec_shift) < 4 * h->kcap) ++rec_shift; }
+    const size_t smem = backprop_f_smem_per_warp(kk, rec_shift) * (CTA_F / 32);
+    if (smem > h->bp_smem_set && smem <= 200 * 1024) {
+#define AZ_BP_ATTR(KF) cudaFuncSetAttribute(KF, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        AZ_BP_ATTR((k_backprop_f<C4, true, true>)); AZ_BP_ATTR((k_backprop_f<C4, true, false>));
+        AZ_BP_ATTR((k_backprop_f<C4, false, true>)); AZ_BP_ATTR((k_backprop_f<C4, false, false>));
+        AZ_BP_ATTR((k_backprop_f_r<C4, true, true>)); AZ_BP_ATTR((k_backprop_f_r<C4, true, false>));
+        AZ_BP_ATTR((k_backprop_f_r<C4, false, true>)); AZ_BP_ATTR((k_backprop_f_r<C4, false, false>));
+#undef AZ_BP_ATTR
+        h->bp_smem_set = smem;
+    }
+}
 static int set_range(az_mcts *h, int first, int count) {
     if (first < 0 || count <= 0 || first + count > h->n || (first & 31))
         AZ_FAIL(h, AZ_ERR_INVALID, "tree range [%d, %d) must lie inside [0, %d) and start at a multiple of 32", first, first + count, h->n);
     h->d.env_lo = first; h->d.env_cnt = count;
     return AZ_OK;
 }
+// Shards: rows of the caller's leaf / policy / value arrays that belong to tree range [first, first + count) start at row0
+// (row of tree i, simulation k = row0 + (i - first) * K + k).  The kernels index rows by the global tree number, so the
+// base pointers are shifted accordingly.  (row0 = first * K reproduces the whole-batch layout.)
 static int do_search(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, cudaStream_t s, int first = 0, int count = -1,
-                     bool new_epoch = true) {
+                     bool new_epoch = true, int64_t row0 = -1) {
     int rc = check_cfg(h, K); if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
     rc = set_range(h, first, count < 0 ? h->n : count); if (rc) return rc;
+    if (row0 >= 0) d_leaves += row0 - (int64_t)first * std::max(K, 1);
     const bool vl = K > 0;
     if (vl) { rc = ensure_kcap(h, K); if (rc) return rc; h->prepared_K = K; }
     if (new_epoch) h->d.epoch++;
@@ -1576,10 +1612,16 @@ static int do_search(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leave
     return AZ_OK;
 }
 static int do_backprop(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
-                       const uint8_t *it, const int32_t *sym, cudaStream_t s, int first = 0, int count = -1) {
+                       const uint8_t *it, const int32_t *sym, cudaStream_t s, int first = 0, int count = -1, int64_t row0 = -1) {
     int rc = check_cfg(h, K); if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
     rc = set_range(h, first, count < 0 ? h->n : count); if (rc) return rc;
+    if (row0 >= 0) {
+        const int64_t sh = row0 - (int64_t)first * std::max(K, 1);
+        pol += sh * h->A; d += sh; p1 += sh; p2 += sh; ml += sh;
+        if (it) it += sh;
+        if (sym) sym += sh;
+    }
     const bool vl = K > 0;
     if (vl && K > h->prepared_K) AZ_FAIL(h, AZ_ERR_INVALID, "backprop_batch_vl: K (%d) exceeds the K of the last search_batch_vl (%d)", K, h->prepared_K);
     rc = ensure_arena(h, vl ? K : 1, s); if (rc) return rc;
@@ -1674,6 +1716,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     h->A = az_game_action_size(game); h->S = az_game_board_size(game);
     h->W = auto_lanes(game, n_envs);
     { const char *ve = getenv("AZB200_VARIANT"); if (ve) { int v = atoi(ve); if (v >= 0 && v <= 1) h->variant = v; } }
+    { const char *ge = getenv("AZB200_GRAPHS"); if (ge) h->use_graphs = atoi(ge) != 0; }
     { const char *ce2 = getenv("AZB200_COMPACTION"); if (ce2) { int v = atoi(ce2); if (v >= 0 && v <= 2) h->compaction = v; } }
     h->max_depth = game == GAME_C4 ? C4::MAX_DEPTH : Oth::MAX_DEPTH;
     h->max_edges = game == GAME_C4 ? 8 : 48;
@@ -1690,7 +1733,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     h->cap = ce ? (uint32_t)std::max(256, atoi(ce)) : (game == GAME_C4 ? 2048u : 4096u);
     h->d.n_envs = n_envs; h->d.env_lo = 0; h->d.env_cnt = n_envs; h->d.cap = h->cap; h->d.noise_stride = h->max_edges;
     { const char *he = getenv("AZB200_HINTS"); h->d.hints = he ? atoi(he) : 1; }
-    h->d.seed = 0x243F6A8885A308D3ULL; h->d.epoch = 0;
+    h->d.seed = 0x243F6A8885A308D3ULL; h->d.epoch = 0; h->d.epoch_add = nullptr;
     int rc = 0;
     rc |= dev_alloc(h, &h->d.pool, (size_t)n_envs * h->cap);
     rc |= dev_alloc(h, &h->d.trees, (size_t)n_envs);
@@ -1727,6 +1770,8 @@ void az_mcts_destroy(az_mcts *h) {
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->ev) cudaEventDestroy(h->ev);
     for (auto &pr : h->sel_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
+    if (h->d_epoch_add) cudaFree(h->d_epoch_add);
     for (int j = 0; j < 8; ++j) { if (h->side_ev[j]) cudaEventDestroy(h->side_ev[j]); if (h->side[j]) cudaStreamDestroy(h->side[j]); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1932,21 +1977,58 @@ int az_mcts_backprop_dev(az_mcts *h, int K, const float *pol, const float *d, co
     return do_backprop(h, K, pol, d, p1, p2, ml, it, sym, (cudaStream_t)stream);
 }
 
-int az_mcts_search_range_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, int first, int count, int new_epoch, void *stream) {
-    if (K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "search_range_dev: K must be >= 0");
+int az_mcts_search_range_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, int first, int count, int64_t row0, int new_epoch,
+                             void *stream) {
+    if (K < 0 || row0 < 0) AZ_FAIL(h, AZ_ERR_INVALID, "search_range_dev: K and row0 must be >= 0");
     { int rc = enter_dev(h, (cudaStream_t)stream); if (rc) return rc; }
-    return do_search(h, K, d_roots, d_leaves, (cudaStream_t)stream, first, count, new_epoch != 0);
+    return do_search(h, K, d_roots, d_leaves, (cudaStream_t)stream, first, count, new_epoch != 0, row0);
 }
 int az_mcts_backprop_range_dev(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
-                               const uint8_t *it, const int32_t *sym, int first, int count, void *stream) {
-    if (K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "backprop_range_dev: K must be >= 0");
+                               const uint8_t *it, const int32_t *sym, int first, int count, int64_t row0, void *stream) {
+    if (K < 0 || row0 < 0) AZ_FAIL(h, AZ_ERR_INVALID, "backprop_range_dev: K and row0 must be >= 0");
     { int rc = enter_dev(h, (cudaStream_t)stream); if (rc) return rc; }
-    return do_backprop(h, K, pol, d, p1, p2, ml, it, sym, (cudaStream_t)stream, first, count);
+    return do_backprop(h, K, pol, d, p1, p2, ml, it, sym, (cudaStream_t)stream, first, count, row0);
 }
 int az_mcts_stream_handover_dev(az_mcts *h, void *stream) { return enter_dev(h, (cudaStream_t)stream); }
 
 // The whole playout loop of src/MCTS_cpp.py:217-357 with a synthetic evaluator, driven natively (no per-launch Python
 // cost) and optionally pipelined over `shards` independent tree ranges on internal streams.
+static int playout_issue(az_mcts *h, int mode, const std::vector<int> &iters, int ns, int per, const az_root *d_roots, az_leaf *d_leaves,
+                         float *pol, float *d, float *p1, float *p2, float *ml, cudaStream_t main, int *launches_out) {
+    cudaStream_t lanes[8];
+    if (ns > 1) {
+        for (int j = 0; j < ns; ++j) lanes[j] = h->side[j];
+        CU(h, cudaEventRecord(h->ev, main));
+        for (int j = 0; j < ns; ++j) CU(h, cudaStreamWaitEvent(lanes[j], h->ev, 0));
+    } else lanes[0] = main;
+    int launches = 0, rc;
+    // every shard keeps its own rows of the leaf / policy / value arrays for the whole loop ([lo * kmax, (lo + cnt) * kmax)):
+    // shards run ahead of each other, and with the whole-batch layout (row = tree * K + k) the rows of one shard's K = 4
+    // iteration would overlap another shard's K = 1 or remainder iteration
+    int kmax = 1;
+    for (int k : iters) kmax = std::max(kmax, k);
+    for (size_t it = 0; it < iters.size(); ++it) {
+        const int k = iters[it], kk = std::max(k, 1);
+        for (int j = 0; j < ns; ++j) {
+            const int lo = j * per, cnt = std::min(per, h->n - lo);
+            const size_t r0 = (size_t)lo * kmax;
+            rc = do_search(h, k, d_roots, d_leaves, lanes[j], lo, cnt, j == 0, (int64_t)r0); if (rc) return rc;
+            rc = az_eval_synthetic_dev(h->game, mode, cnt * kk, d_leaves + r0, pol + r0 * h->A, d + r0, p1 + r0, p2 + r0, ml + r0, lanes[j]);
+            if (rc) AZ_FAIL(h, rc, "synthetic evaluator launch failed");
+            rc = do_backprop(h, k, pol, d, p1, p2, ml, nullptr, nullptr, lanes[j], lo, cnt, (int64_t)r0); if (rc) return rc;
+            launches += 3;
+        }
+    }
+    if (ns > 1) {
+        for (int j = 0; j < ns; ++j) { CU(h, cudaEventRecord(h->side_ev[j], lanes[j])); CU(h, cudaStreamWaitEvent(main, h->side_ev[j], 0)); }
+    }
+    *launches_out = launches;
+    return AZ_OK;
+}
+
+// The whole playout loop of src/MCTS_cpp.py:217-357 with a synthetic evaluator, driven natively (no per-launch Python
+// cost), optionally pipelined over `shards` independent tree ranges on internal streams, and replayed from a CUDA graph
+// when the same loop was issued before (same buffers, configuration and arena pool).
 int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, int shards, const az_root *d_roots, az_leaf *d_leaves,
                                   float *pol, float *d, float *p1, float *p2, float *ml, void *stream, int *launches_out) {
     if (n_playout < 0 || K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "playout: n_playout and K must be >= 0");
@@ -1960,30 +2042,82 @@ int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, in
         iters.push_back(0);
         for (int rem = n_playout - 1; rem > 0; rem -= std::min(K, rem)) iters.push_back(std::min(K, rem));
     }
-    cudaStream_t lanes[8];
-    if (ns > 1) {
-        for (int j = 0; j < ns; ++j) {
+    if (ns > 1)
+        for (int j = 0; j < ns; ++j)
             if (!h->side[j]) { CU(h, cudaStreamCreateWithFlags(&h->side[j], cudaStreamNonBlocking)); CU(h, cudaEventCreateWithFlags(&h->side_ev[j], cudaEventDisableTiming)); }
-            lanes[j] = h->side[j];
-        }
-        CU(h, cudaEventRecord(h->ev, main));
-        for (int j = 0; j < ns; ++j) CU(h, cudaStreamWaitEvent(lanes[j], h->ev, 0));
-    } else lanes[0] = main;
     int launches = 0;
-    for (size_t it = 0; it < iters.size(); ++it) {
-        const int k = iters[it], kk = std::max(k, 1);
-        for (int j = 0; j < ns; ++j) {
-            const int lo = j * per, cnt = std::min(per, h->n - lo);
-            const size_t r0 = (size_t)lo * kk;
-            rc = do_search(h, k, d_roots, d_leaves, lanes[j], lo, cnt, j == 0); if (rc) return rc;
-            rc = az_eval_synthetic_dev(h->game, mode, cnt * kk, d_leaves + r0, pol + r0 * h->A, d + r0, p1 + r0, p2 + r0, ml + r0, lanes[j]);
-            if (rc) AZ_FAIL(h, rc, "synthetic evaluator launch failed");
-            rc = do_backprop(h, k, pol, d, p1, p2, ml, nullptr, nullptr, lanes[j], lo, cnt); if (rc) return rc;
-            launches += 3;
+    const bool graphable = h->use_graphs && !h->time_select && !h->stats_on && iters.size() >= 4;
+    if (!graphable) {
+        rc = playout_issue(h, mode, iters, ns, per, d_roots, d_leaves, pol, d, p1, p2, ml, main, &launches); if (rc) return rc;
+    } else {
+        rc = check_cfg(h, K); if (rc) return rc;
+        if (K > 0) { rc = ensure_kcap(h, K); if (rc) return rc; }
+        for (int k : iters) bp_prepare(h, k > 0, k);
+        // the legacy default stream cannot be captured: run on the internal stream, ordered after / before the caller's
+        cudaStream_t run = main;
+        if (!main) {
+            run = h->stream;
+            CU(h, cudaEventRecord(h->ev, main));
+            CU(h, cudaStreamWaitEvent(run, h->ev, 0));
         }
-    }
-    if (ns > 1) {
-        for (int j = 0; j < ns; ++j) { CU(h, cudaEventRecord(h->side_ev[j], lanes[j])); CU(h, cudaStreamWaitEvent(main, h->side_ev[j], 0)); }
+        if (!h->d_epoch_add) { CU(h, cudaMalloc((void **)&h->d_epoch_add, sizeof(unsigned long long))); }
+        // reserve the growth of the whole loop up front (may synchronise / grow the arenas: before any capture)
+        h->d.env_lo = 0; h->d.env_cnt = h->n;
+        rc = ensure_arena(h, n_playout, run); if (rc) return rc;
+        az_mcts::GraphKey key;
+        memset(&key, 0, sizeof(key));
+        key.mode = mode; key.n_playout = n_playout; key.K = K; key.ns = ns; key.W = h->W; key.variant = h->variant; key.hints = h->d.hints;
+        key.kcap = h->kcap; key.cap = h->cap; key.cfg = h->cfg; key.seed = h->d.seed; key.env_base = h->d.env_base;
+        const void *pp[10] = {d_roots, d_leaves, pol, d, p1, p2, ml, h->d.pool, h->d.leaf_vl, run};
+        memcpy(key.ptrs, pp, sizeof(pp));
+        az_mcts::GraphEntry *ge = nullptr;
+        for (auto &g : h->graphs) if (memcmp(&g.key, &key, sizeof(key)) == 0) { ge = &g; break; }
+        if (!ge) {
+            if (h->graphs.size() >= 6) {                      // drop the least recently used
+                size_t v = 0;
+                for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].last_use < h->graphs[v].last_use) v = i;
+                cudaGraphExecDestroy(h->graphs[v].exec);
+                h->graphs.erase(h->graphs.begin() + (long)v);
+            }
+            const uint64_t epoch0 = h->d.epoch;
+            h->d.epoch_add = h->d_epoch_add;
+            h->capturing = true;
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(run, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                rc = playout_issue(h, mode, iters, ns, per, d_roots, d_leaves, pol, d, p1, p2, ml, run, &launches);
+                e = cudaStreamEndCapture(run, &graph);
+            }
+            h->capturing = false;
+            h->d.epoch_add = nullptr;
+            h->d.epoch = epoch0;                              // the replay below accounts for it
+            cudaGraphExec_t exec = nullptr;
+            if (rc == AZ_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != AZ_OK || e != cudaSuccess || !exec) {       // no graph: issue the loop launch by launch from now on
+                cudaGetLastError();
+                h->use_graphs = 0;
+                h->bounds.clear();                               // (the growth reserved above is re-counted by the issued loop; harmless)
+                rc = playout_issue(h, mode, iters, ns, per, d_roots, d_leaves, pol, d, p1, p2, ml, run, &launches); if (rc) return rc;
+                if (!main) { CU(h, cudaEventRecord(h->ev, run)); CU(h, cudaStreamWaitEvent(main, h->ev, 0)); }
+                h->user_stream = main; h->user_pending = true;
+                if (launches_out) *launches_out = launches;
+                return AZ_OK;
+            }
+            h->graphs.push_back({key, exec, epoch0, launches, 0});
+            ge = &h->graphs.back();
+        }
+        const unsigned long long delta = (unsigned long long)(h->d.epoch - ge->epoch0);
+        CU(h, cudaMemcpyAsync(h->d_epoch_add, &delta, sizeof(delta), cudaMemcpyHostToDevice, run));
+        CU(h, cudaGraphLaunch(ge->exec, run));
+        if (!main) { CU(h, cudaEventRecord(h->ev, run)); CU(h, cudaStreamWaitEvent(main, h->ev, 0)); }
+        ge->last_use = ++h->graph_clock; h->graph_replays++;
+        launches = ge->launches;
+        // host-side state the issued loop would have left behind
+        h->d.epoch += (uint64_t)iters.size();
+        if (K > 0) h->prepared_K = iters.back() > 0 ? iters.back() : h->prepared_K;
+        h->last_select_ro = h->game == GAME_C4 && h->W == 1 && h->variant != 0 && std::max(iters.back(), 1) <= RS_MAX;
+        h->launches += (uint64_t)launches;
     }
     h->user_stream = main; h->user_pending = true;
     if (launches_out) *launches_out = launches;

@@ -250,19 +250,23 @@ def _playout_sharded(engine, buf, iters, evaluator, stream, shards, on_select=No
         st.wait_event(fork)
     ptrs = (buf.policy.data_ptr(), buf.d.data_ptr(), buf.p1w.data_ptr(), buf.p2w.data_ptr(), buf.ml.data_ptr())
     launches = 0
+    # every shard owns rows [lo * kmax, (lo + cnt) * kmax) for the whole loop: shards run ahead of each other, and with the
+    # whole-batch layout (row = tree * K + k) one shard's K = 4 rows would overlap another's K = 1 / remainder rows
+    kmax = max([1] + iters)
+    assert n * kmax <= buf.rows
     for it, k in enumerate(iters):
         kk = max(k, 1)
-        assert n * kk <= buf.rows
         for j, (lo, cnt) in enumerate(ranges):
             st = side[j]
             cs = st.cuda_stream
+            row0 = lo * kmax
             if on_select is not None:
-                on_select(cnt * kk, lambda: engine.search_range_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), lo, cnt, j == 0, cs), st)
+                on_select(cnt * kk, lambda: engine.search_range_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), lo, cnt, row0, j == 0, cs), st)
             else:
-                engine.search_range_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), lo, cnt, j == 0, cs)
+                engine.search_range_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), lo, cnt, row0, j == 0, cs)
             with torch.cuda.stream(st):                          # torch evaluators launch on the current stream
-                evaluator(buf, cnt * kk, cs, lo * kk)
-            engine.backprop_range_dev(k, *ptrs, lo, cnt, 0, 0, cs)
+                evaluator(buf, cnt * kk, cs, row0)
+            engine.backprop_range_dev(k, *ptrs, lo, cnt, row0, 0, 0, cs)
             launches += 3
     for st in side[:len(ranges)]:
         ev = torch.cuda.Event()

@@ -275,16 +275,16 @@ class _BatchedMCTS:
         self._ck(self._L.az_mcts_backprop_dev(self._h, int(K), policy, d, p1w, p2w, ml, is_term or None, sym or None,
                                               stream or None))
 
-    def search_range_dev(self, K, roots_ptr, leaves_ptr, first, count, new_epoch=True, stream=0):
-        """search_dev restricted to trees [first, first + count); pointers are whole-batch bases (include/azb200.h)."""
+    def search_range_dev(self, K, roots_ptr, leaves_ptr, first, count, row0, new_epoch=True, stream=0):
+        """search_dev restricted to trees [first, first + count); the shard's rows start at row0 (include/azb200.h)."""
         self._push_cfg()
-        self._ck(self._L.az_mcts_search_range_dev(self._h, int(K), roots_ptr, leaves_ptr, int(first), int(count),
+        self._ck(self._L.az_mcts_search_range_dev(self._h, int(K), roots_ptr, leaves_ptr, int(first), int(count), int(row0),
                                                   1 if new_epoch else 0, stream or None))
 
-    def backprop_range_dev(self, K, policy, d, p1w, p2w, ml, first, count, is_term=0, sym=0, stream=0):
+    def backprop_range_dev(self, K, policy, d, p1w, p2w, ml, first, count, row0, is_term=0, sym=0, stream=0):
         self._push_cfg()
         self._ck(self._L.az_mcts_backprop_range_dev(self._h, int(K), policy, d, p1w, p2w, ml, is_term or None, sym or None,
-                                                    int(first), int(count), stream or None))
+                                                    int(first), int(count), int(row0), stream or None))
 
     def playout_synthetic_dev(self, mode, n_playout, K, shards, roots_ptr, leaves_ptr, policy, d, p1w, p2w, ml, stream=0):
         """The whole playout loop with a synthetic evaluator, driven natively (include/azb200.h).  Returns kernel launches."""

@@ -144,24 +144,27 @@ int az_mcts_search_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_lea
 int az_mcts_backprop_dev(az_mcts *h, int K, const float *d_policy, const float *d_d, const float *d_p1w,
                          const float *d_p2w, const float *d_moves_left, const uint8_t *d_is_term,
                          const int32_t *d_sym_ids, void *stream);
-/* Shard variants: the same launches restricted to trees [first, first + count) (first a multiple of 32).  All pointers
- * are still the bases of the whole-batch arrays (row of tree i, simulation k = i*K + k).  Independent shards may be
- * driven on different streams so that the select of one overlaps the evaluation / back-prop of another (the kernels
- * are DRAM-latency bound and leave issue slots idle; a CNN evaluator is compute bound - they overlap well).  Pass
+/* Shard variants: the same launches restricted to trees [first, first + count) (first a multiple of 32).  d_roots is
+ * indexed by tree as always; the rows of the leaf / policy / value arrays that belong to the shard start at row0: row of
+ * tree i, simulation k = row0 + (i - first)*K + k (row0 = first*K reproduces the whole-batch layout; a loop whose K varies
+ * between iterations should give every shard a fixed region, row0 = first*Kmax, because shards run ahead of each other).
+ * Independent shards may be driven on different streams so that the select of one overlaps the evaluation / back-prop of
+ * another (the tree kernels are latency bound and leave issue slots idle; a CNN evaluator is compute bound).  Pass
  * new_epoch = 1 for the first shard of a search iteration and 0 for the others: every shard then draws its leaf
  * symmetries from the same epoch as an unsharded az_mcts_search_dev call, so results do not depend on the sharding.
  * az_mcts_stream_handover_dev orders the stream after everything queued through this handle so far (call it on the
  * stream the shards fork from, and again on the stream that joined them). */
-int az_mcts_search_range_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, int first, int count, int new_epoch,
-                             void *stream);
+int az_mcts_search_range_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, int first, int count, int64_t row0,
+                             int new_epoch, void *stream);
 int az_mcts_backprop_range_dev(az_mcts *h, int K, const float *d_policy, const float *d_d, const float *d_p1w,
                                const float *d_p2w, const float *d_moves_left, const uint8_t *d_is_term,
-                               const int32_t *d_sym_ids, int first, int count, void *stream);
+                               const int32_t *d_sym_ids, int first, int count, int64_t row0, void *stream);
 int az_mcts_stream_handover_dev(az_mcts *h, void *stream);
 /* The per-move playout loop of the reference wrapper (src/MCTS_cpp.py:217-357: one non-VL warm-up simulation, then
  * ceil((n-1)/K) virtual-loss iterations) with one of the synthetic evaluators of az_eval_synthetic_dev, driven natively:
  * 3 launches per iteration and shard, no per-launch host-language cost.  shards > 1 pipelines that many tree ranges on
- * internal streams (forked from and joined back into `stream`).  Buffers: az_leaf[n*max(K,1)], policy f32[n*max(K,1)*A],
+ * internal streams (forked from and joined back into `stream`); a loop issued before with the same buffers / configuration is
+ * replayed from a CUDA graph (AZB200_GRAPHS=0 disables).  With shards, shard j's rows live at [first_j*Kmax, ...).  Buffers: az_leaf[n*max(K,1)], policy f32[n*max(K,1)*A],
  * d/p1w/p2w/moves_left f32[n*max(K,1)].  *launches_out (optional) = kernels launched. */
 int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, int shards, const az_root *d_roots,
                                   az_leaf *d_leaves, float *d_policy, float *d_d, float *d_p1w, float *d_p2w,
