@@ -1225,7 +1225,7 @@ struct az_mcts {
     uint64_t bump_bound = 0;          // conservative upper bound of max(TreeRec.bump) at the last refresh ...
     struct Bound { int lo, hi; uint64_t b; };
     std::vector<Bound> bounds;        // ... and of the tree ranges [lo, hi) that back-propagated since then
-    cudaStream_t side[8] = {};        // shard streams of az_mcts_playout_synthetic_dev
+    cudaStream_t side[16] = {};        // shard streams of az_mcts_playout_synthetic_dev
     // CUDA graphs of whole playout loops (az_mcts_playout_synthetic_dev): the native loop issues ~600 launches per move at
     // ~6.5 us of host time each; a captured graph replays them with one call.  Keyed by everything a launch bakes in.
     struct GraphKey {
@@ -1244,7 +1244,7 @@ struct az_mcts {
     uint64_t base_after_prune = 0, growth_est = 0; bool base_pending = false;   // arena-use bookkeeping between re-roots
     bool time_select = false;         // az_mcts_time_select: CUDA events around every select launch
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sel_ev; size_t sel_used = 0; uint64_t sel_rows = 0;
-    cudaEvent_t side_ev[8] = {};
+    cudaEvent_t side_ev[16] = {};
     unsigned int *d_scratch_u32 = nullptr;
     // LUT state
     float lut_c_base = -1.0f, lut_scale = -1.0f;
@@ -1772,7 +1772,7 @@ void az_mcts_destroy(az_mcts *h) {
     for (auto &pr : h->sel_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
     if (h->d_epoch_add) cudaFree(h->d_epoch_add);
-    for (int j = 0; j < 8; ++j) { if (h->side_ev[j]) cudaEventDestroy(h->side_ev[j]); if (h->side[j]) cudaStreamDestroy(h->side[j]); }
+    for (int j = 0; j < 16; ++j) { if (h->side_ev[j]) cudaEventDestroy(h->side_ev[j]); if (h->side[j]) cudaStreamDestroy(h->side[j]); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1995,7 +1995,7 @@ int az_mcts_stream_handover_dev(az_mcts *h, void *stream) { return enter_dev(h, 
 // cost) and optionally pipelined over `shards` independent tree ranges on internal streams.
 static int playout_issue(az_mcts *h, int mode, const std::vector<int> &iters, int ns, int per, const az_root *d_roots, az_leaf *d_leaves,
                          float *pol, float *d, float *p1, float *p2, float *ml, cudaStream_t main, int *launches_out) {
-    cudaStream_t lanes[8];
+    cudaStream_t lanes[16];
     if (ns > 1) {
         for (int j = 0; j < ns; ++j) lanes[j] = h->side[j];
         CU(h, cudaEventRecord(h->ev, main));
@@ -2035,7 +2035,7 @@ int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, in
     cudaStream_t main = (cudaStream_t)stream;
     int rc = enter_dev(h, main); if (rc) return rc;
     const int per = (((h->n + std::max(shards, 1) - 1) / std::max(shards, 1)) + 31) / 32 * 32;
-    const int ns = std::min(8, std::max(1, (h->n + per - 1) / per));
+    const int ns = std::min(16, std::max(1, (h->n + per - 1) / per));
     std::vector<int> iters;
     if (K <= 1) iters.assign((size_t)n_playout, 0);
     else if (n_playout > 0) {

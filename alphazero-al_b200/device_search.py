@@ -178,12 +178,13 @@ _SHARD_STREAMS = {}
 
 
 def auto_shards(n: int) -> int:
-    """Independent tree shards driven on their own streams (measured on B200, Connect4 n=200 K=4, 65 536 trees:
-    1 shard 2.07, 2 shards 2.23, 4 shards 2.29 G simulations/s).  Small batches stay whole: they are launch bound."""
+    """Independent tree shards driven on their own streams: 8192 trees per shard, at most 8 (measured on B200, Connect4
+    n=200 K=4, 65 536 trees, loop replayed from its CUDA graph: 1 shard 2.25, 4 shards 2.80, 8 shards 3.31, 16 shards 3.30 G
+    simulations/s).  Small batches stay whole: they are latency bound."""
     import os
     if os.environ.get("AZB200_SHARDS"):
         return max(1, int(os.environ["AZB200_SHARDS"]))
-    return 4 if n >= 32768 else (2 if n >= 16384 else 1)
+    return max(1, min(8, n // 8192))
 
 
 def playout_device(engine, buf: LeafBuffers, n_playout: int, K: int, evaluator, stream: int | None = None,

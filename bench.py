@@ -288,17 +288,21 @@ def main():
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     launches = 0
-    eng.time_select(True)               # CUDA events around every select launch, on the stream it is launched on
     for _ in range(args.steps):
-        launches += dev_step()
+        launches += dev_step()           # native loop, tree shards on their own streams, replayed from a CUDA graph
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ms = t_start.elapsed_time(t_end)
+    # the dominant kernel with CUDA events around every select launch (az_mcts_time_select; the loop is then issued launch by
+    # launch instead of replayed from its graph): one more sharded step, then ...
+    eng.time_select(True)
+    dev_step()
+    torch.cuda.synchronize()
     sel_ms, sel_launches, sel_rows = eng.get_select_time()
-    # the dominant kernel timed ALONE: two more steps with the whole batch per launch on one stream (no overlap with other
+    # ... the dominant kernel timed ALONE: two more steps with the whole batch per launch on one stream (no overlap with other
     # shards' kernels)
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a0.record()
@@ -464,10 +468,10 @@ def main():
                 "frac": achieved_alone / peak, "shards": shards,
                 "note": ("achieved = algorithmic select bytes / CUDA-event time of the select launches (events on the launching stream, "
                          "az_mcts_time_select), taken in 2 extra steps right after the timed region with the whole batch per launch on ONE "
-                         "stream.  Inside the timed region the batch runs as `shards` tree ranges on their own streams, so a select launch "
-                         "shares the SMs with other shards' evaluate / back-prop kernels and its elapsed time is not the kernel's own: "
-                         "those numbers are under in_timed_region"),
-                "in_timed_region": {"achieved": achieved, "frac": achieved / peak, "select_launches": sel_launches,
+                         "stream.  The timed region itself replays the step from a CUDA graph with `shards` tree ranges on their own "
+                         "streams: there a select launch shares the SMs with other shards' evaluate / back-prop kernels and its elapsed "
+                         "time is not the kernel's own - one extra sharded step with events is reported under sharded_step"),
+                "sharded_step": {"achieved": achieved, "frac": achieved / peak, "select_launches": sel_launches,
                                     "select_us_per_launch": 1e3 * sel_ms / max(sel_launches, 1), "trees_per_launch": G // max(shards, 1)},
                 "select_us_per_launch": 1e3 * alone_sel_ms / max(alone_sel_launches, 1), "ms_per_step_one_stream": alone_step_ms,
                 "traffic": traffic, "traffic_source": traffic_src,

@@ -54,6 +54,6 @@ def test_iteration_schedule_is_the_reference_wrappers(n_playout, K, expect):
 def test_auto_shards(monkeypatch):
     monkeypatch.delenv("AZB200_SHARDS", raising=False)
     assert ds.auto_shards(100) == 1 and ds.auto_shards(8192) == 1
-    assert ds.auto_shards(16384) == 2 and ds.auto_shards(65536) == 4
+    assert ds.auto_shards(16384) == 2 and ds.auto_shards(32768) == 4 and ds.auto_shards(65536) == 8 and ds.auto_shards(1 << 20) == 8
     monkeypatch.setenv("AZB200_SHARDS", "3")
     assert ds.auto_shards(65536) == 3
