@@ -102,7 +102,9 @@ def lib() -> C.CDLL:
     L.az_evalcache_destroy.restype = None
     L.az_evalcache_destroy.argtypes = [_vp]
     sig.update({"az_evalcache_clear_dev": [_vp, _vp], "az_evalcache_lookup_dev": [_vp, _i] + [_vp] * 7,
-                "az_evalcache_insert_dev": [_vp, _i] + [_vp] * 9, "az_evalcache_stats": [_vp, _vp]})
+                "az_evalcache_insert_dev": [_vp, _i] + [_vp] * 9, "az_evalcache_stats": [_vp, _vp],
+                "az_evalcache_lookup_dedup_dev": [_vp, _i] + [_vp] * 8, "az_evalcache_resolve_dups_dev": [_vp, _i] + [_vp] * 5,
+                "az_evalcache_dups": [_vp, _vp]})
     for name, argt in (("az_env_reset", [_i, _vp]), ("az_env_import", [_i, _vp, _vp]), ("az_env_export", [_i, _vp, _vp]),
                        ("az_env_step", [_i, _vp, _i]), ("az_env_apply_symmetry", [_i, _vp, _i])):
         f = getattr(L, name)

@@ -127,6 +127,7 @@ class BatchedMCTS:
             evaluator = ds.CachedNetEvaluator(pv_func, self._dev_cache)
         else:
             evaluator = ds.NetEvaluator(pv_func)
+        self._last_evaluator = evaluator
         ds.playout_device(self.mcts, buf, max_n, K, evaluator, stream)
 
     # ------------------------------------------------------------------------------------------------------

@@ -129,17 +129,22 @@ class EvalCache:
         out = np.zeros(4, np.uint64)
         if self._L.az_evalcache_stats(self._c, out.ctypes.data_as(C.c_void_p)) != 0:
             raise RuntimeError("az_evalcache_stats failed")
-        return dict(lookups=int(out[0]), hits=int(out[1]), inserts=int(out[2]), capacity=int(out[3]))
+        dups = np.zeros(1, np.uint64)
+        if self._L.az_evalcache_dups(self._c, dups.ctypes.data_as(C.c_void_p)) != 0:
+            raise RuntimeError("az_evalcache_dups failed")
+        return dict(lookups=int(out[0]), hits=int(out[1]), inserts=int(out[2]), capacity=int(out[3]), dups=int(dups[0]))
 
 
 class CachedNetEvaluator(NetEvaluator):
-    """NetEvaluator that probes the device cache first; only misses reach the network.  One 4-byte D2H read per
+    """NetEvaluator that probes the device cache first; only misses reach the network, and of the missing leaves that hold
+    the same position only one does (`dedup`; self-play batches repeat openings in every slot).  One 4-byte D2H read per
     iteration (the miss count) is the price of a dynamically sized network batch."""
 
-    def __init__(self, net, cache: EvalCache):
+    def __init__(self, net, cache: EvalCache, dedup: bool = True):
         super().__init__(net)
         self.cache = cache
-        self._miss_idx = self._miss_cnt = None
+        self.dedup = dedup
+        self._miss_idx = self._miss_cnt = self._dup_of = None
         self.net_rows = 0
 
     shardable = False       # one miss counter / index buffer per evaluator: drive it on the whole batch
@@ -150,28 +155,50 @@ class CachedNetEvaluator(NetEvaluator):
         if self._wdl is None or self._wdl.shape[0] < buf.rows:
             self._wdl = torch.empty((buf.rows, 3), dtype=torch.float32, device=dev)
             self._aux = torch.empty(buf.rows, dtype=torch.float32, device=dev)
-            self._miss_idx = torch.empty(buf.rows, dtype=torch.int32, device=dev)
+            self._miss_idx = torch.zeros(buf.rows, dtype=torch.int32, device=dev)
             self._miss_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._dup_of = torch.empty(buf.rows, dtype=torch.int32, device=dev)
         self._miss_cnt.zero_()
-        rc = L.az_evalcache_lookup_dev(self.cache._c, rows, buf.leaves.data_ptr(), buf.policy.data_ptr(), self._wdl.data_ptr(),
-                                       self._aux.data_ptr(), self._miss_idx.data_ptr(), self._miss_cnt.data_ptr(), stream or None)
+        if self.dedup:
+            rc = L.az_evalcache_lookup_dedup_dev(self.cache._c, rows, buf.leaves.data_ptr(), buf.policy.data_ptr(), self._wdl.data_ptr(),
+                                                 self._aux.data_ptr(), self._miss_idx.data_ptr(), self._miss_cnt.data_ptr(),
+                                                 self._dup_of.data_ptr(), stream or None)
+        else:
+            rc = L.az_evalcache_lookup_dev(self.cache._c, rows, buf.leaves.data_ptr(), buf.policy.data_ptr(), self._wdl.data_ptr(),
+                                           self._aux.data_ptr(), self._miss_idx.data_ptr(), self._miss_cnt.data_ptr(), stream or None)
         if rc != 0:
             raise RuntimeError("az_evalcache_lookup_dev failed")
         m = int(self._miss_cnt.item())
         if m > 0:
             buf.unpack(rows, stream)
-            idx = self._miss_idx[:m].long()
-            probs, wdl_rel, aux = self.net.predict_device(buf.planes[:rows].index_select(0, idx), buf.mask[:rows].index_select(0, idx))
-            pm, wm, am = probs.reshape(m, buf.A).float().contiguous(), wdl_rel.reshape(m, 3).float().contiguous(), aux.reshape(m).float().contiguous()
+            # the network sees a few batch sizes only (every new shape costs cuDNN / SDPA plan selection: tens of ms): the index
+            # list is read up to the next bucket - the entries past m are older row numbers, their outputs are dropped
+            mb = _bucket(m, buf.rows)
+            idx = self._miss_idx[:mb].long()
+            probs, wdl_rel, aux = self.net.predict_device(buf.planes.index_select(0, idx), buf.mask.index_select(0, idx))
+            pm, wm, am = probs.reshape(mb, buf.A).float().contiguous(), wdl_rel.reshape(mb, 3).float().contiguous(), aux.reshape(mb).float().contiguous()
             rc = L.az_evalcache_insert_dev(self.cache._c, m, buf.leaves.data_ptr(), self._miss_idx.data_ptr(), pm.data_ptr(), wm.data_ptr(),
                                            am.data_ptr(), buf.policy.data_ptr(), self._wdl.data_ptr(), self._aux.data_ptr(), stream or None)
             if rc != 0:
                 raise RuntimeError("az_evalcache_insert_dev failed")
             self.net_rows += m
+            if self.dedup:                  # duplicates copy the row of the leaf that was evaluated for them
+                rc = L.az_evalcache_resolve_dups_dev(self.cache._c, rows, self._dup_of.data_ptr(), buf.policy.data_ptr(),
+                                                     self._wdl.data_ptr(), self._aux.data_ptr(), stream or None)
+                if rc != 0:
+                    raise RuntimeError("az_evalcache_resolve_dups_dev failed")
         rc = L.az_eval_finalize_dev(rows, buf.leaves.data_ptr(), self._wdl.data_ptr(), self._aux.data_ptr(), buf.d.data_ptr(),
                                     buf.p1w.data_ptr(), buf.p2w.data_ptr(), buf.ml.data_ptr(), stream or None)
         if rc != 0:
             raise RuntimeError("az_eval_finalize_dev failed (%d)" % rc)
+
+
+def _bucket(m: int, cap: int, floor: int = 256) -> int:
+    """Smallest batch size of the form {4,5,6,7} * 2^k >= max(m, floor), at most `cap` (<= 25 % padding, 4 shapes per octave)."""
+    m = max(m, min(floor, cap))
+    k = max(m.bit_length() - 3, 0)
+    b = -(-m // (1 << k)) << k
+    return min(b, cap)
 
 
 _SHARD_STREAMS = {}

@@ -28,6 +28,14 @@ int az_evalcache_clear_dev(az_evalcache *c, void *stream);
  * Terminal leaves are neither (az_eval_finalize_dev overrides them).  *d_miss_count must be zero on entry. */
 int az_evalcache_lookup_dev(az_evalcache *c, int n_leaves, const az_leaf *d_leaves, float *d_probs, float *d_wdl_rel,
                             float *d_aux, int32_t *d_miss_idx, int32_t *d_miss_count, void *stream);
+/* De-duplicating lookup ("dedup of identical leaves within a batch"; the reference evaluates in-batch
+ * duplicates separately, src/MCTS_cpp.py:299-339).  As az_evalcache_lookup_dev, but of all missing leaves that hold the same
+ * position only one is appended to d_miss_idx; the others get d_dup_of[i] = row of that leaf (-1 for every other row) and
+ * receive a copy of its outputs from az_evalcache_resolve_dups_dev, to be called after az_evalcache_insert_dev. */
+int az_evalcache_lookup_dedup_dev(az_evalcache *c, int n_leaves, const az_leaf *d_leaves, float *d_probs, float *d_wdl_rel,
+                                  float *d_aux, int32_t *d_miss_idx, int32_t *d_miss_count, int32_t *d_dup_of, void *stream);
+int az_evalcache_resolve_dups_dev(az_evalcache *c, int n_leaves, const int32_t *d_dup_of, float *d_probs, float *d_wdl_rel,
+                                  float *d_aux, void *stream);
 /* Network outputs of the misses (row j belongs to leaf d_miss_idx[j]) are stored in the table and scattered to rows
  * d_miss_idx[j] of the full outputs. */
 int az_evalcache_insert_dev(az_evalcache *c, int n_miss, const az_leaf *d_leaves, const int32_t *d_miss_idx,
@@ -35,6 +43,8 @@ int az_evalcache_insert_dev(az_evalcache *c, int n_miss, const az_leaf *d_leaves
                             float *d_wdl_rel, float *d_aux, void *stream);
 /* out[0..3] = lookups (non-terminal leaves probed), hits, inserts, capacity */
 int az_evalcache_stats(az_evalcache *c, uint64_t *out4);
+/* *out = leaves that shared another leaf's evaluation (az_evalcache_lookup_dedup_dev) */
+int az_evalcache_dups(az_evalcache *c, uint64_t *out);
 
 #ifdef __cplusplus
 }
