@@ -27,13 +27,6 @@ def _mirror_orbits():
     return torch.tensor([r * 4 + min(c, C - 1 - c) for r in range(R) for c in range(C)], dtype=torch.long)
 
 
-class _RMSNorm(nn.RMSNorm):
-    """nn.RMSNorm whose weight follows the input dtype: under bf16 autocast the stock module meets a bf16 input with its fp32
-    weight and falls back from the fused kernel to a chain of element-wise ones."""
-    def forward(self, x):
-        return F.rms_norm(x, self.normalized_shape, self.weight.to(x.dtype), self.eps)
-
-
 class _ConvBlock(nn.Module):
     def __init__(self, ch):
         super().__init__()
@@ -48,12 +41,12 @@ class _GatedSelfAttention(nn.Module):
     def __init__(self, dim, heads):
         super().__init__()
         self.h, self.hd = heads, dim // heads
-        self.pre = _RMSNorm(dim, eps=1e-5)
+        self.pre = nn.RMSNorm(dim, eps=1e-5)
         self.qkv = nn.Linear(dim, 3 * dim, bias=False)
         self.gate = nn.Linear(dim, heads, bias=False)
         self.out = nn.Linear(dim, dim, bias=False)
-        self.qn = _RMSNorm(self.hd, eps=1e-5)
-        self.kn = _RMSNorm(self.hd, eps=1e-5)
+        self.qn = nn.RMSNorm(self.hd, eps=1e-5)
+        self.kn = nn.RMSNorm(self.hd, eps=1e-5)
 
     def forward(self, x):                                   # x: [B, 42, dim]
         B, L, D = x.shape
@@ -80,16 +73,16 @@ class C4Net(nn.Module):
         self.body = nn.Sequential(*[_ConvBlock(width) for _ in range(blocks)])
         self.attn = _GatedSelfAttention(width, heads)
         # column policy head
-        self.p_norm = _RMSNorm(width, eps=1e-5)
+        self.p_norm = nn.RMSNorm(width, eps=1e-5)
         self.p_row = nn.Linear(width, 1)
         self.p_fc = nn.Linear(width, width)
         self.p_out = nn.Linear(width, 1)
         # WDL + moves-left head
-        self.v_pool_norm = _RMSNorm(width, eps=1e-5)
+        self.v_pool_norm = nn.RMSNorm(width, eps=1e-5)
         self.v_pool_fc = nn.Linear(width, width)
-        self.v_norm = _RMSNorm(width, eps=1e-5)
+        self.v_norm = nn.RMSNorm(width, eps=1e-5)
         self.v_fc = nn.Linear(width, width)
-        self.v_out_norm = _RMSNorm(width, eps=1e-5)
+        self.v_out_norm = nn.RMSNorm(width, eps=1e-5)
         self.v_wdl = nn.Linear(width, 3)
         self.v_aux = nn.Linear(width, 1)
         for m in self.modules():
