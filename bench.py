@@ -12,8 +12,9 @@ server-default search parameters (server.py:44-72) and a deterministic constant 
 random-init CNN (the CNN is outside the path: SURVEY.md 8d).  Simulations/s = G*n/step time, whole job over all GPUs.
 
   value : device-resident loop (inputs in HBM, CUDA-event timed, max over ranks)
-  e2e   : the same search through the reference-facing host-buffer API (mcts_cpp.search_batch[_vl] /
-          backprop_batch[_vl] with numpy arrays; H2D/D2H inside the timed region)
+  e2e   : the same search through the wrapper API with HOST buffers (BatchedMCTS.prune_roots + batch_playout(numpy boards)
+          + get_visits_count(), the calls src/player.py makes; H2D/D2H inside the timed region); e2e_split_api: the split
+          plugin API (mcts_cpp.search_batch[_vl] / backprop_batch[_vl]) with numpy leaf buffers every iteration
   roofline     : k_select (dominant kernel) algorithmic bytes / its CUDA-event time vs measured HBM peak
   cpu_baseline : the reference engine (oracle/_ref/timing) on this box's host cores, bounded sample
 """
@@ -197,6 +198,8 @@ def main():
     ap.add_argument("--no-cnn", action="store_true")
     ap.add_argument("--cnn-slots", type=int, default=4096)
     ap.add_argument("--cnn-plies", type=int, default=3)
+    ap.add_argument("--cnn-cached-plies", type=int, default=8)
+    ap.add_argument("--cnn-cached-warm-plies", type=int, default=22)
     ap.add_argument("--selfplay-slots", type=int, default=65536)
     ap.add_argument("--selfplay-plies", type=int, default=30)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (Connect4: 1/2/4/8, 0 = auto)")
@@ -440,7 +443,32 @@ def main():
                         "evaluator": "C4Net (160358 params, reference Connect4 CNN shape), random init, bf16 autocast, device contract "
                                      "(leaves -> planes -> net -> finalize, no host copy)",
                         "note": "games_per_sec_est = positions/s / 21 plies (mean length of random-init self-play games, SURVEY.md App. C.4)"}
-        del sp, net
+        del sp
+        # the same with the device evaluation cache + in-batch de-duplication: only distinct unseen positions
+        # reach the network.  Timed at steady state (slots at mixed plies), not on the opening, where nearly every leaf repeats.
+        if args.cnn_cached_plies > 0:
+            sp = sp_mod.SelfPlay("Connect4", n_slots, n_playout, K, net, search_cfg=SERVER_DEFAULTS, temperature=1.0, temp_decay_moves=20,
+                                 temp_endgame=0.0, td_steps=10, seed=0, device=local_rank, out_capacity=16 * n_slots, cache_size=1 << 22)
+            sp.engine.reserve(16384)
+            for _ in range(args.cnn_cached_warm_plies):
+                sp.ply()
+            torch.cuda.synchronize()
+            st0, r0, p0 = sp.eval_cache.stats(), sp.evaluator.net_rows, sp.plies
+            t0 = time.perf_counter()
+            for _ in range(args.cnn_cached_plies):
+                sp.ply()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            st1 = sp.eval_cache.stats()
+            look = max(st1["lookups"] - st0["lookups"], 1)
+            selfplay_cnn["cached"] = {
+                "sims_per_sec": n_slots * n_playout * (sp.plies - p0) / dt, "positions_per_sec": n_slots * (sp.plies - p0) / dt,
+                "games_per_sec_est": n_slots * (sp.plies - p0) / dt / 21.0, "plies_timed": sp.plies - p0, "plies_before": p0,
+                "cache_entries": st1["capacity"], "hit_frac": (st1["hits"] - st0["hits"]) / look, "dup_frac": (st1["dups"] - st0["dups"]) / look,
+                "net_rows_frac": (sp.evaluator.net_rows - r0) / look,
+                "note": "device evaluation cache + in-batch de-duplication; timed after the warm plies, slots at mixed game plies"}
+            del sp
+        del net
     clk = clocks.stop() if rank == 0 else None
 
     if rank != 0:
