@@ -78,6 +78,7 @@ class BatchedMCTS:
         self._convert_board = board_converter or _default_convert_board
         self.cache = _LRU(cache_size) if cache_size > 0 else None      # host LRU, used by the numpy `predict` path only
         self._cache_size, self._dev_cache = cache_size, None
+        self._evaluators = {}
         self._game_name = game_name
         self._rollout_eval = None
         self._dev = None            # lazily created device-side state (torch tensors)
@@ -121,12 +122,19 @@ class BatchedMCTS:
         buf.pack_roots(st["boards"], st["turns"], stream)
         if isinstance(pv_func, ds.SyntheticEvaluator):
             evaluator = pv_func
-        elif self._cache_size > 0:          # device evaluation cache instead of the host LRU (same results, fewer network rows)
-            if self._dev_cache is None:
-                self._dev_cache = ds.EvalCache(self._game_name, self._cache_size, self.mcts._device)
-            evaluator = ds.CachedNetEvaluator(pv_func, self._dev_cache)
-        else:
-            evaluator = ds.NetEvaluator(pv_func)
+        else:                               # one evaluator object per network: it owns the captured CUDA graphs of the forward pass
+            key = (id(pv_func), self._cache_size > 0)
+            evaluator = self._evaluators.get(key)
+            if evaluator is None or evaluator.net is not pv_func:
+                if self._cache_size > 0:    # device evaluation cache instead of the host LRU (same results, fewer network rows)
+                    if self._dev_cache is None:
+                        self._dev_cache = ds.EvalCache(self._game_name, self._cache_size, self.mcts._device)
+                    evaluator = ds.CachedNetEvaluator(pv_func, self._dev_cache)
+                else:
+                    evaluator = ds.NetEvaluator(pv_func)
+                self._evaluators = {key: evaluator}
+            elif self._cache_size > 0:
+                evaluator.net_rows = 0
         self._last_evaluator = evaluator
         ds.playout_device(self.mcts, buf, max_n, K, evaluator, stream)
 

@@ -78,22 +78,62 @@ class SyntheticEvaluator:
 class NetEvaluator:
     """Fused evaluator boundary: az_leaf records -> CNN input planes + legal masks (one unpack
     kernel) -> ``net.predict_device(planes, mask)`` -> backprop tuple (one finalize kernel).  No host copy, no sync.
-    `buf` must have been created with unpacked=True, planes=True."""
+    `buf` must have been created with unpacked=True, planes=True.
 
-    def __init__(self, net):
+    `graph_rows`: batches of at most this many rows replay the network from a CUDA graph captured per (buffer, row range):
+    a small batch (the reference's own 100-game configuration evaluates 100-400 leaves per iteration) is bound by the ~150
+    kernel launches of an eager forward pass, not by the GPU.  Larger batches run eagerly (nothing to gain, and a graph keeps
+    its activations allocated).  A network that cannot be captured falls back to eager calls for good."""
+
+    def __init__(self, net, graph_rows: int = 8192):
         self.net = net
         self._wdl = self._aux = None
+        self.graph_rows = int(graph_rows)
+        self._graphs = {}
+        self.graph_replays = 0
+
+    def _forward(self, buf, r, rows):
+        probs, wdl_rel, aux = self.net.predict_device(buf.planes[r], buf.mask[r])
+        buf.policy[r].copy_(probs.reshape(rows, buf.A))
+        self._wdl[r].copy_(wdl_rel.reshape(rows, 3))
+        self._aux[r].copy_(aux.reshape(rows))
+
+    def _captured(self, buf, r, rows):
+        """Graph of _forward for this row range (inputs and outputs are slices of persistent buffers), or None."""
+        key = (buf.planes.data_ptr(), buf.policy.data_ptr(), self._wdl.data_ptr(), r.start, rows)
+        g = self._graphs.get(key)
+        if g is None and self.graph_rows > 0:
+            cur = torch.cuda.current_stream(buf.leaves.device)
+            try:
+                side = torch.cuda.Stream(device=buf.leaves.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side), torch.no_grad():       # warm-up off the capture: cuDNN plans, lazy initialisation
+                    for _ in range(2):
+                        self._forward(buf, r, rows)
+                cur.wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g), torch.no_grad():
+                    self._forward(buf, r, rows)
+            except Exception:                                        # e.g. a predict_device that synchronises: stay eager
+                g = False
+                self.graph_rows = 0
+                torch.cuda.synchronize(buf.leaves.device)
+            self._graphs[key] = g
+        return g or None
 
     def __call__(self, buf: LeafBuffers, rows: int, stream: int, row0: int = 0):
         if self._wdl is None or self._wdl.shape[0] < buf.rows:
             self._wdl = torch.empty((buf.rows, 3), dtype=torch.float32, device=buf.leaves.device)
             self._aux = torch.empty(buf.rows, dtype=torch.float32, device=buf.leaves.device)
+            self._graphs.clear()
         r = slice(row0, row0 + rows)
         buf.unpack(rows, stream, row0)
-        probs, wdl_rel, aux = self.net.predict_device(buf.planes[r], buf.mask[r])
-        buf.policy[r].copy_(probs.reshape(rows, buf.A))
-        self._wdl[r].copy_(wdl_rel.reshape(rows, 3))
-        self._aux[r].copy_(aux.reshape(rows))
+        g = self._captured(buf, r, rows) if rows <= self.graph_rows else None
+        if g is not None:
+            g.replay()
+            self.graph_replays += 1
+        else:
+            self._forward(buf, r, rows)
         rc = _lib.lib().az_eval_finalize_dev(rows, buf.leaves[row0:].data_ptr(), self._wdl[row0:].data_ptr(), self._aux[row0:].data_ptr(),
                                              buf.d[row0:].data_ptr(), buf.p1w[row0:].data_ptr(), buf.p2w[row0:].data_ptr(),
                                              buf.ml[row0:].data_ptr(), stream or None)
@@ -141,7 +181,7 @@ class CachedNetEvaluator(NetEvaluator):
     iteration (the miss count) is the price of a dynamically sized network batch."""
 
     def __init__(self, net, cache: EvalCache, dedup: bool = True):
-        super().__init__(net)
+        super().__init__(net, graph_rows=0)             # dynamic batch sizes: eager
         self.cache = cache
         self.dedup = dedup
         self._miss_idx = self._miss_cnt = self._dup_of = None

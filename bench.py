@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--no-cnn", action="store_true")
     ap.add_argument("--cnn-slots", type=int, default=4096)
     ap.add_argument("--cnn-plies", type=int, default=3)
+    ap.add_argument("--cnn-plies-100", type=int, default=8)
     ap.add_argument("--cnn-cached-plies", type=int, default=8)
     ap.add_argument("--cnn-cached-warm-plies", type=int, default=22)
     ap.add_argument("--selfplay-slots", type=int, default=65536)
@@ -444,6 +445,25 @@ def main():
                                      "(leaves -> planes -> net -> finalize, no host copy)",
                         "note": "games_per_sec_est = positions/s / 21 plies (mean length of random-init self-play games, SURVEY.md App. C.4)"}
         del sp
+        # BASELINE config 1 itself: 100 games, n=200, K=4, random-init CNN - 100..400 leaves per evaluation, bound by the launches
+        # of the forward pass; NetEvaluator replays it from a CUDA graph (eager timed beside it)
+        c0 = {}
+        for name, graph_rows in (("eager", 0), ("graph", 8192)):
+            sp = sp_mod.SelfPlay("Connect4", 100, n_playout, K, net, search_cfg=SERVER_DEFAULTS, temperature=1.0, temp_decay_moves=20,
+                                 temp_endgame=0.0, td_steps=10, seed=0, device=local_rank, out_capacity=1024)
+            sp.evaluator.graph_rows = graph_rows
+            for _ in range(2):
+                sp.ply()
+            torch.cuda.synchronize()
+            p0, t0 = sp.plies, time.perf_counter()
+            for _ in range(args.cnn_plies_100):
+                sp.ply()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            c0[name] = {"sims_per_sec": 100 * n_playout * (sp.plies - p0) / dt, "ms_per_ply": 1e3 * dt / (sp.plies - p0),
+                        "games_per_sec_est": 100 * (sp.plies - p0) / dt / 21.0, "graph_replays": sp.evaluator.graph_replays}
+            del sp
+        selfplay_cnn["config1_100_games"] = c0
         # the same with the device evaluation cache + in-batch de-duplication: only distinct unseen positions
         # reach the network.  Timed at steady state (slots at mixed plies), not on the opening, where nearly every leaf repeats.
         if args.cnn_cached_plies > 0:

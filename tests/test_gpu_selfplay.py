@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
-from harness import SERVER_DEFAULTS, counts, playout, set_config
+from harness import SERVER_DEFAULTS, counts, playout, random_positions, set_config
 
 pytestmark = pytest.mark.gpu
 
@@ -236,3 +236,41 @@ def test_cache_dedup_on_leaf_records(log2cap):
     if log2cap == 12:
         assert st["hits"] >= int((~term).sum()) * 0.9        # second batch: nearly everything was stored by the first
     assert st["inserts"] <= st["lookups"] - st["hits"] - st["dups"]
+
+
+def test_net_evaluator_graph_replay_equals_eager():
+    """Small batches replay the network from a captured CUDA graph (NetEvaluator.graph_rows); the search must not notice."""
+    import torch
+    bm = importlib.import_module("alphazero-al_b200.batched_mcts")
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    nets = importlib.import_module("alphazero-al_b200.nets")
+    n, npl, K = 96, 41, 4
+    boards, turns = random_positions("Connect4", n, 12, seed=21)
+    kw = dict(game_name="Connect4", noise_epsilon=0.0, fpu_reduction=0.2, use_symmetry=True, mlh_slope=0.1)
+    for net in (_RowDeterministicNet(), None):
+        if net is None:
+            torch.manual_seed(4)
+            net = nets.C4Net(device="cuda:0")
+            for head in (net.p_out, net.v_wdl, net.v_aux):                     # non-trivial outputs
+                torch.nn.init.normal_(head.weight, std=0.5)
+        res = []
+        for graph_rows in (0, 8192):
+            eng = bm.BatchedMCTS(n, 1.4, 1000.0, 0.0, npl, **kw)
+            eng.seed(9)
+            for mv in range(2):
+                eng.batch_playout(net, boards, turns, vl_batch=K)
+                ev = eng._last_evaluator
+                if mv == 0:
+                    ev.graph_rows = graph_rows                                  # takes effect from the second move on
+                    if graph_rows == 0:
+                        ev._graphs.clear()
+                cnt = eng.get_visits_count()
+                eng.prune_roots(np.full(n, -1, np.int32))
+            res.append((cnt, ev.graph_replays))
+        (c0, r0), (c1, r1) = res
+        assert r1 > r0
+        if isinstance(net, _RowDeterministicNet):
+            assert np.array_equal(c0, c1)
+        else:                                                                   # same kernels, same inputs: equal in practice; L1 bound as in north_star
+            p0, p1 = c0 / c0.sum(1, keepdims=True), c1 / c1.sum(1, keepdims=True)
+            assert np.abs(p0 - p1).sum(1).max() <= 1e-3
