@@ -180,14 +180,55 @@ class CachedNetEvaluator(NetEvaluator):
     the same position only one does (`dedup`; self-play batches repeat openings in every slot).  One 4-byte D2H read per
     iteration (the miss count) is the price of a dynamically sized network batch."""
 
-    def __init__(self, net, cache: EvalCache, dedup: bool = True):
-        super().__init__(net, graph_rows=0)             # dynamic batch sizes: eager
+    def __init__(self, net, cache: EvalCache, dedup: bool = True, graph_rows: int = 8192):
+        super().__init__(net, graph_rows=graph_rows)    # graphs are captured per batch-size bucket here (see _net_rows)
         self.cache = cache
         self.dedup = dedup
-        self._miss_idx = self._miss_cnt = self._dup_of = None
+        self._miss_idx = self._miss_cnt = self._dup_of = self._stage = None
         self.net_rows = 0
 
     shardable = False       # one miss counter / index buffer per evaluator: drive it on the whole batch
+
+    def _eager_rows(self, planes, mask, mb, A):
+        probs, wdl_rel, aux = self.net.predict_device(planes, mask)
+        return probs.reshape(mb, A).float().contiguous(), wdl_rel.reshape(mb, 3).float().contiguous(), aux.reshape(mb).float().contiguous()
+
+    def _net_rows(self, buf, idx, mb):
+        """Network outputs (probs[mb,A], wdl_rel[mb,3], aux[mb]) of the leaves `idx`.  Small buckets gather the rows into static
+        staging tensors and replay the forward pass from a CUDA graph captured per bucket size (see NetEvaluator)."""
+        if mb <= self.graph_rows:
+            if self._stage is None or self._stage[0].shape[0] < min(self.graph_rows, buf.rows) or self._stage[2] != buf.planes.data_ptr():
+                cap = min(self.graph_rows, buf.rows)
+                self._stage = (torch.zeros((cap, *buf.planes.shape[1:]), dtype=buf.planes.dtype, device=buf.planes.device),
+                               torch.ones((cap, buf.A), dtype=buf.mask.dtype, device=buf.planes.device), buf.planes.data_ptr())
+                self._graphs.clear()
+            sp, sm = self._stage[0][:mb], self._stage[1][:mb]
+            g = self._graphs.get(mb)
+            if g is None:
+                cur = torch.cuda.current_stream(buf.leaves.device)
+                try:
+                    side = torch.cuda.Stream(device=buf.leaves.device)
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side), torch.no_grad():
+                        for _ in range(2):
+                            self._eager_rows(sp, sm, mb, buf.A)
+                    cur.wait_stream(side)
+                    cg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(cg), torch.no_grad():
+                        outs = self._eager_rows(sp, sm, mb, buf.A)
+                    g = (cg, outs)
+                except Exception:
+                    g = False
+                    self.graph_rows = 0
+                    torch.cuda.synchronize(buf.leaves.device)
+                self._graphs[mb] = g
+            if g:
+                torch.index_select(buf.planes, 0, idx, out=sp)
+                torch.index_select(buf.mask, 0, idx, out=sm)
+                g[0].replay()
+                self.graph_replays += 1
+                return g[1]
+        return self._eager_rows(buf.planes.index_select(0, idx), buf.mask.index_select(0, idx), mb, buf.A)
 
     def __call__(self, buf: LeafBuffers, rows: int, stream: int, row0: int = 0):
         assert row0 == 0, "CachedNetEvaluator evaluates the whole batch at once"
@@ -214,9 +255,7 @@ class CachedNetEvaluator(NetEvaluator):
             # the network sees a few batch sizes only (every new shape costs cuDNN / SDPA plan selection: tens of ms): the index
             # list is read up to the next bucket - the entries past m are older row numbers, their outputs are dropped
             mb = _bucket(m, buf.rows)
-            idx = self._miss_idx[:mb].long()
-            probs, wdl_rel, aux = self.net.predict_device(buf.planes.index_select(0, idx), buf.mask.index_select(0, idx))
-            pm, wm, am = probs.reshape(mb, buf.A).float().contiguous(), wdl_rel.reshape(mb, 3).float().contiguous(), aux.reshape(mb).float().contiguous()
+            pm, wm, am = self._net_rows(buf, self._miss_idx[:mb].long(), mb)
             rc = L.az_evalcache_insert_dev(self.cache._c, m, buf.leaves.data_ptr(), self._miss_idx.data_ptr(), pm.data_ptr(), wm.data_ptr(),
                                            am.data_ptr(), buf.policy.data_ptr(), self._wdl.data_ptr(), self._aux.data_ptr(), stream or None)
             if rc != 0:

@@ -448,11 +448,11 @@ def main():
         # BASELINE config 1 itself: 100 games, n=200, K=4, random-init CNN - 100..400 leaves per evaluation, bound by the launches
         # of the forward pass; NetEvaluator replays it from a CUDA graph (eager timed beside it)
         c0 = {}
-        for name, graph_rows in (("eager", 0), ("graph", 8192)):
+        for name, graph_rows, csize in (("eager", 0, 0), ("graph", 8192, 0), ("graph+cache", 8192, 1 << 20)):
             sp = sp_mod.SelfPlay("Connect4", 100, n_playout, K, net, search_cfg=SERVER_DEFAULTS, temperature=1.0, temp_decay_moves=20,
-                                 temp_endgame=0.0, td_steps=10, seed=0, device=local_rank, out_capacity=1024)
+                                 temp_endgame=0.0, td_steps=10, seed=0, device=local_rank, out_capacity=1024, cache_size=csize)
             sp.evaluator.graph_rows = graph_rows
-            for _ in range(2):
+            for _ in range(12 if csize else 2):     # the cache is timed past the opening (every game starts from the same position)
                 sp.ply()
             torch.cuda.synchronize()
             p0, t0 = sp.plies, time.perf_counter()
