@@ -95,3 +95,68 @@ def test_config3_8192_trees_n800_k8_symmetry_mlh():
 
 def test_config4_othello_4096_trees_n400_score_utility():
     _run("Othello", 4096, 400, 4, OTH_CFG, "hash", 16, None, _oth_roots(4096, 9))
+
+
+def test_selfplay_32768_slots_record_invariants():
+    """Continuous self-play at scale (tree reuse, arena compaction, slot restarts, temperature sampling): every position of every
+    finished game record must be a consistent Connect4 training tuple."""
+    import torch
+    sp_mod = importlib.import_module("alphazero-al_b200.selfplay")
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    n, npl, K = 32768, 64, 4
+    sp = sp_mod.SelfPlay("Connect4", n, npl, K, ds.SyntheticEvaluator("Connect4", "hash"), search_cfg=dict(SERVER_DEFAULTS, use_symmetry=True, dirichlet_alpha=0.3),
+                         temperature=1.0, temp_decay_moves=12, temp_endgame=0.0, td_steps=5, seed=3, out_capacity=3 * n)
+    sp.engine.reserve(4096)
+    for _ in range(46):
+        sp.ply()
+    torch.cuda.synchronize()
+    m = min(int(sp.out_count.item()), sp.out_capacity)
+    assert m >= n, "every slot finishes at least one game in 46 plies"
+    assert sp.engine.compactions() > 0
+    recs = sp.out[:m]
+    L = sp.layout
+    length = recs[:, L.off_header:L.off_header + 4].contiguous().view(torch.int32).reshape(m)
+    winner = recs[:, L.off_header + 4:L.off_header + 8].contiguous().view(torch.int32).reshape(m)
+    uid = recs[:, L.off_header + 8:L.off_header + 16].contiguous().view(torch.int64).reshape(m)
+    assert int(length.min()) >= 8 and int(length.max()) <= 43 and bool(((winner >= -1) & (winner <= 1)).all())
+    assert uid.unique().numel() == m, "game uids are unique"
+    t = sp_mod.to_replay_tensors(recs, "Connect4")
+    st, prob, mask = t["state"].to(torch.int32), t["prob"], t["valid_mask"]
+    P = st.shape[0]
+    assert P == int(length.sum())
+    own, opp, turn = st[:, 0], st[:, 1], st[:, 2]
+    assert bool(((own == 0) | (own == 1)).all()) and bool(((opp == 0) | (opp == 1)).all()) and bool((own * opp == 0).all())
+    assert bool((turn.reshape(P, -1).min(1).values == turn.reshape(P, -1).max(1).values).all()) and bool((turn.abs() == 1).all())
+    occ = own + opp
+    stones = occ.reshape(P, -1).sum(1)
+    tsign = turn[:, 0, 0]
+    assert bool((tsign == 1 - 2 * (stones % 2)).all()), "player +1 moves on even stone counts"
+    assert bool((occ[:, 1:, :] >= occ[:, :-1, :]).all()), "gravity: a stone never floats (row 0 is the top)"
+    ste = t["steps_to_end"].reshape(P).to(torch.int32)
+    term = ste == 0
+    assert int(term.sum()) == m                                                      # one terminal tuple per game
+    # non-terminal positions: the legal mask is "column not full", the policy target is a distribution over legal moves
+    col_open = occ[:, 0, :] == 0
+    assert bool((mask[~term] == col_open[~term]).all())
+    assert bool((prob[~term].sum(1) - 1.0).abs().max() < 1e-5) and bool((prob[~term][~mask[~term]] == 0).all())
+    assert bool((prob[term] == 0).all())
+    # terminal positions: the recorded winner has four in a row (the mover who just played = the opponent plane), else the board is full
+    def four(b):
+        h = b[:, :, 0:4] * b[:, :, 1:5] * b[:, :, 2:6] * b[:, :, 3:7]
+        v = b[:, 0:3] * b[:, 1:4] * b[:, 2:5] * b[:, 3:6]
+        d1 = b[:, 0:3, 0:4] * b[:, 1:4, 1:5] * b[:, 2:5, 2:6] * b[:, 3:6, 3:7]
+        d2 = b[:, 3:6, 0:4] * b[:, 2:5, 1:5] * b[:, 1:4, 2:6] * b[:, 0:3, 3:7]
+        return (h.reshape(len(b), -1).sum(1) + v.reshape(len(b), -1).sum(1) + d1.reshape(len(b), -1).sum(1) + d2.reshape(len(b), -1).sum(1)) > 0
+    wz = t["winner"].reshape(P).to(torch.int32)
+    last_mover_won = four(opp[term])
+    assert bool((~four(own[term])).all()), "the side to move at the end never has four in a row"
+    assert bool((last_mover_won == (wz[term] != 0)).all())
+    assert bool((wz[term][last_mover_won] == -tsign[term][last_mover_won]).all())
+    assert bool((stones[term][~last_mover_won] == 42).all()), "a draw is a full board"
+    # within a game, winner_z is constant and steps_to_end counts down to 0
+    starts = torch.cumsum(length, 0) - length
+    gidx = torch.repeat_interleave(torch.arange(m, device=recs.device), length)
+    assert bool((wz == winner[gidx]).all())
+    pos_in_game = torch.arange(P, device=recs.device) - starts[gidx]
+    assert bool((ste == length[gidx] - 1 - pos_in_game).all())
+    assert bool((stones[1:][pos_in_game[1:] > 0] == stones[:-1][pos_in_game[1:] > 0] + 1).all()), "one stone per ply"
