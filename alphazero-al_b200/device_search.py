@@ -90,7 +90,21 @@ class NetEvaluator:
         self._wdl = self._aux = None
         self.graph_rows = int(graph_rows)
         self._graphs = {}
+        self._fp, self._fp_params, self._fp_calls = None, None, 0
         self.graph_replays = 0
+
+    def _check_weights(self):
+        """Captured graphs read the parameter tensors that existed at capture time: in-place updates (load_state_dict) are seen,
+        re-created parameters (net.to(dtype), net.half(), a swapped module) are not - drop the graphs when the storage moved."""
+        self._fp_calls += 1
+        if self._fp_params is None or self._fp_calls % 256 == 0:      # walking the module tree costs ~90 us: not on every call
+            params = getattr(self.net, "parameters", None)
+            ps = list(params()) if callable(params) else []
+            self._fp_params = (ps[0], ps[-1], len(ps)) if ps else ()
+        fp = tuple((p.data_ptr(), p.dtype) if hasattr(p, "data_ptr") else p for p in self._fp_params)
+        if fp != self._fp:
+            self._graphs.clear()
+            self._fp = fp
 
     def _forward(self, buf, r, rows):
         probs, wdl_rel, aux = self.net.predict_device(buf.planes[r], buf.mask[r])
@@ -128,7 +142,10 @@ class NetEvaluator:
             self._graphs.clear()
         r = slice(row0, row0 + rows)
         buf.unpack(rows, stream, row0)
-        g = self._captured(buf, r, rows) if rows <= self.graph_rows else None
+        g = None
+        if rows <= self.graph_rows:
+            self._check_weights()
+            g = self._captured(buf, r, rows)
         if g is not None:
             g.replay()
             self.graph_replays += 1
@@ -197,6 +214,7 @@ class CachedNetEvaluator(NetEvaluator):
         """Network outputs (probs[mb,A], wdl_rel[mb,3], aux[mb]) of the leaves `idx`.  Small buckets gather the rows into static
         staging tensors and replay the forward pass from a CUDA graph captured per bucket size (see NetEvaluator)."""
         if mb <= self.graph_rows:
+            self._check_weights()
             if self._stage is None or self._stage[0].shape[0] < min(self.graph_rows, buf.rows) or self._stage[2] != buf.planes.data_ptr():
                 cap = min(self.graph_rows, buf.rows)
                 self._stage = (torch.zeros((cap, *buf.planes.shape[1:]), dtype=buf.planes.dtype, device=buf.planes.device),
