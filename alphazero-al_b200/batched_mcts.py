@@ -79,6 +79,7 @@ class BatchedMCTS:
         self.cache = _LRU(cache_size) if cache_size > 0 else None      # host LRU, used by the numpy `predict` path only
         self._cache_size, self._dev_cache = cache_size, None
         self._evaluators = {}
+        self._adapters = {}
         self._game_name = game_name
         self._rollout_eval = None
         self._dev = None            # lazily created device-side state (torch tensors)
@@ -199,6 +200,13 @@ class BatchedMCTS:
         if hasattr(pv_func, "score_scale"):
             pv_func.score_scale = self.mcts.config.score_scale
         from . import device_search as ds
+        if not use_time and ds.ReferenceNetAdapter.accepts(pv_func):
+            # an unmodified network of the reference on a CUDA device: same numbers as its predict(), but nothing leaves the device
+            ad = self._adapters.get(id(pv_func))
+            if ad is None or ad.net is not pv_func:
+                ad = ds.ReferenceNetAdapter(pv_func, self._game_name)
+                self._adapters = {id(pv_func): ad}
+            pv_func = ad
         if not use_time and (isinstance(pv_func, ds.SyntheticEvaluator) or hasattr(pv_func, "predict_device")):
             self._playout_device(pv_func, np.asarray(current_boards), np.asarray(turns), max_n, vl_batch)
             return self

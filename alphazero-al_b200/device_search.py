@@ -158,6 +158,49 @@ class NetEvaluator:
             raise RuntimeError("az_eval_finalize_dev failed (%d)" % rc)
 
 
+class ReferenceNetAdapter:
+    """Device contract for an UNMODIFIED network of the reference (src/environments/{Connect4,Othello}/Network.py::CNN): the
+    post-processing of its ``predict`` (Connect4/Network.py:267-288, Othello/Network.py:235-261 - bf16 autocast off the CPU,
+    exp of the log-policy and log-WDL, aux = steps_norm * aux_target_offset for Connect4, atan(disc_diff / score_scale) * 2/pi
+    for Othello) on tensors that stay where they are: no pinned staging, no ``.cpu()``, no ``torch.cuda.synchronize()``.
+    ``BatchedMCTS.batch_playout`` wraps such a network by itself, so ``src/player.py`` reaches the device-resident loop without
+    any change."""
+
+    def __init__(self, net, game: str):
+        self.net, self.game = net, game
+
+    @staticmethod
+    def accepts(net) -> bool:
+        """A torch module with the reference's forward contract whose weights live on a CUDA device."""
+        if not isinstance(net, torch.nn.Module) or not hasattr(net, "aux_target_offset") or hasattr(net, "predict_device"):
+            return False
+        p = next(net.parameters(), None)
+        return p is not None and p.is_cuda
+
+    def parameters(self):
+        return self.net.parameters()
+
+    @property
+    def score_scale(self):
+        return getattr(self.net, "score_scale", 8.0)
+
+    @score_scale.setter
+    def score_scale(self, v):
+        self.net.score_scale = v
+
+    @torch.no_grad()
+    def predict_device(self, planes, action_mask):
+        kind = planes.device.type
+        with torch.autocast(kind, dtype=torch.bfloat16, enabled=kind != "cpu"):
+            log_prob, value_log_prob, aux = self.net(planes, action_mask=action_mask.bool())
+        probs, wdl = log_prob.float().exp(), value_log_prob.float().exp()
+        aux = aux.float().reshape(-1) * float(self.net.aux_target_offset)
+        if self.game == "Othello":
+            import math
+            aux = torch.atan(aux / self.score_scale) * (2.0 / math.pi)
+        return probs, wdl, aux
+
+
 class EvalCache:
     """Device evaluation cache (include/azb200_cache.h; reference: src/Cache.py LRUCache used by src/MCTS_cpp.py)."""
 

@@ -274,3 +274,43 @@ def test_net_evaluator_graph_replay_equals_eager():
         else:                                                                   # same kernels, same inputs: equal in practice; L1 bound as in north_star
             p0, p1 = c0 / c0.sum(1, keepdims=True), c1 / c1.sum(1, keepdims=True)
             assert np.abs(p0 - p1).sum(1).max() <= 1e-3
+
+
+def test_reference_style_network_takes_the_device_path():
+    """A torch module with the reference networks' forward contract (forward(state, action_mask) -> log-policy, log-WDL,
+    normalised aux; `aux_target_offset`; numpy `predict`) and weights on the GPU is wrapped by batch_playout itself
+    (ReferenceNetAdapter) and gives the trees its own predict() gives through the host path."""
+    import torch
+    bm = importlib.import_module("alphazero-al_b200.batched_mcts")
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    nets = importlib.import_module("alphazero-al_b200.nets")
+
+    class RefLike(torch.nn.Module):
+        aux_target_offset = 42
+
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, x, action_mask=None):
+            return self.inner(x, action_mask)
+
+        def predict(self, state, action_mask=None):
+            return self.inner.predict(state, action_mask)
+
+    torch.manual_seed(6)
+    inner = nets.C4Net(device="cuda:0")
+    for head in (inner.p_out, inner.v_wdl, inner.v_aux):
+        torch.nn.init.normal_(head.weight, std=0.5)
+    ref_like = RefLike(inner).eval()
+    assert ds.ReferenceNetAdapter.accepts(ref_like) and not ds.ReferenceNetAdapter.accepts(inner)
+    n, npl, K = 64, 41, 4
+    boards, turns = random_positions("Connect4", n, 12, seed=8)
+    kw = dict(game_name="Connect4", noise_epsilon=0.0, fpu_reduction=0.2, use_symmetry=False, mlh_slope=0.1)
+    a, b = bm.BatchedMCTS(n, 1.4, 1000.0, 0.0, npl, **kw), bm.BatchedMCTS(n, 1.4, 1000.0, 0.0, npl, **kw)
+    a.batch_playout(ref_like, boards, turns, vl_batch=K)
+    assert isinstance(a._last_evaluator.net, ds.ReferenceNetAdapter)
+    b.batch_playout(inner, boards, turns, vl_batch=K)
+    ca, cb = a.get_visits_count(), b.get_visits_count()
+    pa, pb = ca / ca.sum(1, keepdims=True), cb / cb.sum(1, keepdims=True)
+    assert np.abs(pa - pb).sum(1).max() <= 1e-3
