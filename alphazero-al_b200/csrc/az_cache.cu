@@ -41,37 +41,51 @@ __device__ __forceinline__ int cache_claim(unsigned long long *lock, uint32_t ep
     }
 }
 
+// one atomic per warp and counter (a batch of 262 144 leaves would otherwise queue that many atomics on one address)
+__device__ __forceinline__ void warp_count(unsigned long long *ctr, bool flag) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, flag);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(ctr, (unsigned long long)__popc(m));
+}
+
 // DEDUP: dup_of[i] = row whose evaluation leaf i shares (or -1); only one leaf per distinct position is appended to miss_idx.
 template <int A, bool DEDUP>
 __global__ void k_cache_lookup(CacheEntry<A> *tab, uint64_t mask, uint32_t epoch, int n, const az_leaf *__restrict__ leaves, float *probs, float *wdl,
                                float *aux, int32_t *miss_idx, int32_t *miss_count, int32_t *dup_of, unsigned long long *stats) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const az_leaf L = leaves[i];
-    if (DEDUP) dup_of[i] = -1;
-    if (L.flags & AZ_LEAF_TERMINAL) return;
-    CacheEntry<A> *e = tab + (leaf_hash(L.bb0, L.bb1, L.turn) & mask);
-    const bool hit = e->turn == (int32_t)L.turn && e->bb0 == L.bb0 && e->bb1 == L.bb1;
-    atomicAdd(stats + 0, 1ULL);
-    if (hit) {
-        for (int a = 0; a < A; ++a) probs[(size_t)i * A + a] = e->probs[a];
-        wdl[3 * i] = e->wdl[0]; wdl[3 * i + 1] = e->wdl[1]; wdl[3 * i + 2] = e->wdl[2];
-        aux[i] = e->aux;
-        atomicAdd(stats + 1, 1ULL);
-        return;
-    }
-    if (DEDUP) {
-        const int owner = cache_claim(&e->lock, epoch, i);
-        if (owner != i) {
-            const az_leaf O = leaves[owner];
-            if (O.bb0 == L.bb0 && O.bb1 == L.bb1 && O.turn == L.turn && !(O.flags & AZ_LEAF_TERMINAL)) {
-                dup_of[i] = owner;
-                atomicAdd(stats + 3, 1ULL);
-                return;
+    bool looked = false, hit = false, dup = false, miss = false;
+    if (i < n) {
+        const az_leaf L = leaves[i];
+        if (DEDUP) dup_of[i] = -1;
+        if (!(L.flags & AZ_LEAF_TERMINAL)) {
+            looked = true;
+            CacheEntry<A> *e = tab + (leaf_hash(L.bb0, L.bb1, L.turn) & mask);
+            hit = e->turn == (int32_t)L.turn && e->bb0 == L.bb0 && e->bb1 == L.bb1;
+            if (hit) {
+                for (int a = 0; a < A; ++a) probs[(size_t)i * A + a] = e->probs[a];
+                wdl[3 * i] = e->wdl[0]; wdl[3 * i + 1] = e->wdl[1]; wdl[3 * i + 2] = e->wdl[2];
+                aux[i] = e->aux;
+            } else {
+                if (DEDUP) {
+                    const int owner = cache_claim(&e->lock, epoch, i);
+                    if (owner != i) {
+                        const az_leaf O = leaves[owner];
+                        dup = O.bb0 == L.bb0 && O.bb1 == L.bb1 && O.turn == L.turn && !(O.flags & AZ_LEAF_TERMINAL);
+                        if (dup) dup_of[i] = owner;
+                    }       // else a different position owns the entry in this batch: evaluate, do not store
+                }
+                miss = !dup;
             }
-        }       // a different position owns the entry in this batch: evaluate, do not store
+        }
     }
-    miss_idx[atomicAdd(miss_count, 1)] = i;
+    // the miss list: one atomic per warp, lanes take consecutive places
+    const unsigned mm = __ballot_sync(0xFFFFFFFFu, miss);
+    int base = 0;
+    if ((threadIdx.x & 31) == 0 && mm) base = atomicAdd(miss_count, __popc(mm));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (miss) miss_idx[base + __popc(mm & ((1u << (threadIdx.x & 31)) - 1u))] = i;
+    warp_count(stats + 0, looked);
+    warp_count(stats + 1, hit);
+    warp_count(stats + 3, dup);
 }
 
 template <int A>
@@ -79,20 +93,24 @@ __global__ void k_cache_insert(CacheEntry<A> *tab, uint64_t mask, uint32_t epoch
                                const int32_t *__restrict__ miss_idx, const float *__restrict__ pm, const float *__restrict__ wm,
                                const float *__restrict__ am, float *probs, float *wdl, float *aux, unsigned long long *stats) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    const int i = miss_idx[j];
-    for (int a = 0; a < A; ++a) probs[(size_t)i * A + a] = pm[(size_t)j * A + a];
-    wdl[3 * i] = wm[3 * j]; wdl[3 * i + 1] = wm[3 * j + 1]; wdl[3 * i + 2] = wm[3 * j + 2];
-    aux[i] = am[j];
-    const az_leaf L = leaves[i];
-    CacheEntry<A> *e = tab + (leaf_hash(L.bb0, L.bb1, L.turn) & mask);
-    if (cache_claim(&e->lock, epoch, i) != i) return;     // another leaf of this batch owns the entry: skip
-    // lookups run in other launches and every entry has one owner per epoch: plain stores
-    e->bb0 = L.bb0; e->bb1 = L.bb1; e->aux = am[j];
-    e->wdl[0] = wm[3 * j]; e->wdl[1] = wm[3 * j + 1]; e->wdl[2] = wm[3 * j + 2];
-    for (int a = 0; a < A; ++a) e->probs[a] = pm[(size_t)j * A + a];
-    e->turn = L.turn;
-    atomicAdd(stats + 2, 1ULL);
+    bool stored = false;
+    if (j < m) {
+        const int i = miss_idx[j];
+        for (int a = 0; a < A; ++a) probs[(size_t)i * A + a] = pm[(size_t)j * A + a];
+        wdl[3 * i] = wm[3 * j]; wdl[3 * i + 1] = wm[3 * j + 1]; wdl[3 * i + 2] = wm[3 * j + 2];
+        aux[i] = am[j];
+        const az_leaf L = leaves[i];
+        CacheEntry<A> *e = tab + (leaf_hash(L.bb0, L.bb1, L.turn) & mask);
+        if (cache_claim(&e->lock, epoch, i) == i) {        // else another leaf of this batch owns the entry: skip
+            // lookups run in other launches and every entry has one owner per epoch: plain stores
+            e->bb0 = L.bb0; e->bb1 = L.bb1; e->aux = am[j];
+            e->wdl[0] = wm[3 * j]; e->wdl[1] = wm[3 * j + 1]; e->wdl[2] = wm[3 * j + 2];
+            for (int a = 0; a < A; ++a) e->probs[a] = pm[(size_t)j * A + a];
+            e->turn = L.turn;
+            stored = true;
+        }
+    }
+    warp_count(stats + 2, stored);
 }
 
 // Rows that share another row's evaluation (k_cache_lookup<DEDUP>) copy it; runs after k_cache_insert wrote the owners' rows.
