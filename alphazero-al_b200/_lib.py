@@ -75,7 +75,7 @@ def lib() -> C.CDLL:
         "az_mcts_set_env_base": [_vp, C.c_uint64], "az_selfplay_layout_for": [_i, _vp],
         "az_selfplay_ply_dev": [_vp, _vp, _vp, _vp], "az_selfplay_flush_dev": [_vp, _vp],
         "az_mcts_set_lanes": [_vp, _i], "az_mcts_get_lanes": [_vp], "az_mcts_reserve": [_vp, _i],
-        "az_mcts_set_variant": [_vp, _i], "az_mcts_get_variant": [_vp], "az_selftest_div": [_i, C.c_uint64, C.c_uint64, _vp],
+        "az_mcts_set_variant": [_vp, _i], "az_mcts_get_variant": [_vp], "az_mcts_set_wave_max": [_vp, _i], "az_mcts_get_wave_max": [_vp], "az_selftest_div": [_i, C.c_uint64, C.c_uint64, _vp],
         "az_mcts_backprop_dev": [_vp, _i] + [_vp] * 8,
         "az_mcts_search_range_dev": [_vp, _i, _vp, _vp, _i, _i, _i64, _i, _vp],
         "az_mcts_backprop_range_dev": [_vp, _i] + [_vp] * 7 + [_i, _i, _i64, _vp],

@@ -950,6 +950,7 @@ __global__ void __launch_bounds__(CTA, 4) k_backprop_t(Dev d, az_search_config c
 
 }  // namespace az
 #include "az_mcts_fast.cuh"
+#include "az_mcts_wave.cuh"
 namespace az {
 
 // remove_all_vl without backprop (BatchedMCTS.h:209-216)
@@ -1232,7 +1233,7 @@ struct az_mcts {
     // CUDA graphs of whole playout loops (az_mcts_playout_synthetic_dev): the native loop issues ~600 launches per move at
     // ~6.5 us of host time each; a captured graph replays them with one call.  Keyed by everything a launch bakes in.
     struct GraphKey {
-        int mode, n_playout, K, ns, W, variant, hints, kcap; uint32_t cap; const void *ptrs[10]; az_search_config cfg; uint64_t seed, env_base;
+        int mode, n_playout, K, ns, W, variant, wave_max, hints, kcap; uint32_t cap; const void *ptrs[10]; az_search_config cfg; uint64_t seed, env_base;
     };
     struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t epoch0; int launches; uint64_t last_use; };
     std::vector<GraphEntry> graphs;
@@ -1256,6 +1257,7 @@ struct az_mcts {
     float2 *d_ls_lut = nullptr;
     bool last_select_ro = false;      // the last select launch was read-only: its back-prop applies the leaf flags, removes no virtual loss
     int variant = 1;                  // thread-per-tree kernels: 0 = first generation (k_*_t), 1 = lean (k_*_f)
+    int wave_max = 0;                 // batches of at most this many trees run the staggered-descent select (az_mcts_wave.cuh); 0 = off
     // VL bookkeeping
     int kcap = 0;
     int prepared_K = 0;               // vl_paths_.size() (MCTS.h:421-429)
@@ -1474,6 +1476,14 @@ static int auto_lanes(int game, int n) {
         }                                                                                                            \
     } while (0)
 
+// Small batches: one lane per descent, the K descents of a tree staggered by one level (az_mcts_wave.cuh)
+static bool use_wave(const az_mcts *h, bool vl, int K) {
+    return vl && K >= 1 && K <= 8 && K <= h->kcap && h->wave_max > 0 && h->n <= h->wave_max;
+}
+// Does the select launch for K simulations leave the tree untouched (read-only: back-prop applies the leaf flags)?
+static bool select_is_ro(const az_mcts *h, bool vl, int K) {
+    return h->game == GAME_C4 && h->W == 1 && h->variant != 0 && ((vl ? K : 1) <= RS_MAX || use_wave(h, vl, K));
+}
 static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s) {
     const int cnt = h->d.env_cnt;                             // trees of this launch (a whole batch or one shard)
     const int g = grid_groups(cnt, h->W);
@@ -1482,6 +1492,17 @@ static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_l
         const int gf = (cnt + CTA_F - 1) / CTA_F;
         const int kk = vl ? K : 1;
         const bool aux = h->cfg.mlh_slope > 0.0f;            // aux_enabled<C4>
+        if (use_wave(h, vl, K)) {
+            h->last_select_ro = true;
+            const int kl = K <= 4 ? 4 : 8;
+            const int gw = (int)(((size_t)cnt * kl + CTA_W - 1) / CTA_W);
+            if (kl == 4) { if (aux) k_select_w<C4, true, 4><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves);
+                           else k_select_w<C4, false, 4><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves); }
+            else { if (aux) k_select_w<C4, true, 8><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves);
+                   else k_select_w<C4, false, 8><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves); }
+            h->launches++;
+            return;
+        }
         // K <= RS_MAX: read-only select (launch-local virtual loss, leaf flags applied by back-prop); the matching back-prop
         // launch must know (last_select_ro)
         const bool ro = kk <= RS_MAX;
@@ -1719,6 +1740,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     h->A = az_game_action_size(game); h->S = az_game_board_size(game);
     h->W = auto_lanes(game, n_envs);
     { const char *ve = getenv("AZB200_VARIANT"); if (ve) { int v = atoi(ve); if (v >= 0 && v <= 1) h->variant = v; } }
+    { const char *we = getenv("AZB200_WAVE_MAX"); h->wave_max = we ? std::max(0, atoi(we)) : 0; }
     { const char *ge = getenv("AZB200_GRAPHS"); if (ge) h->use_graphs = atoi(ge) != 0; }
     { const char *ce2 = getenv("AZB200_COMPACTION"); if (ce2) { int v = atoi(ce2); if (v >= 0 && v <= 2) h->compaction = v; } }
     h->max_depth = game == GAME_C4 ? C4::MAX_DEPTH : Oth::MAX_DEPTH;
@@ -1801,6 +1823,12 @@ int az_mcts_set_variant(az_mcts *h, int variant) {
     return AZ_OK;
 }
 int az_mcts_get_variant(const az_mcts *h) { return h->variant; }
+int az_mcts_set_wave_max(az_mcts *h, int max_trees) {
+    if (max_trees < 0) AZ_FAIL(h, AZ_ERR_INVALID, "wave_max must be >= 0");
+    h->wave_max = max_trees;
+    return AZ_OK;
+}
+int az_mcts_get_wave_max(const az_mcts *h) { return h->wave_max; }
 int az_selftest_div(int mode, uint64_t count, uint64_t seed, uint64_t *mismatches) {
     unsigned long long *dm = nullptr, hm = 0;
     if (mode < 0 || mode > 2 || !mismatches) return AZ_ERR_INVALID;
@@ -2078,7 +2106,7 @@ int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, in
         rc = ensure_arena(h, n_playout, run); if (rc) return rc;
         az_mcts::GraphKey key;
         memset(&key, 0, sizeof(key));
-        key.mode = mode; key.n_playout = n_playout; key.K = K; key.ns = ns; key.W = h->W; key.variant = h->variant; key.hints = h->d.hints;
+        key.mode = mode; key.n_playout = n_playout; key.K = K; key.ns = ns; key.W = h->W; key.variant = h->variant; key.wave_max = h->wave_max; key.hints = h->d.hints;
         key.kcap = h->kcap; key.cap = h->cap; key.cfg = h->cfg; key.seed = h->d.seed; key.env_base = h->d.env_base;
         const void *pp[10] = {d_roots, d_leaves, pol, d, p1, p2, ml, h->d.pool, h->d.leaf_vl, run};
         memcpy(key.ptrs, pp, sizeof(pp));
@@ -2128,7 +2156,7 @@ int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, in
         // host-side state the issued loop would have left behind
         h->d.epoch += (uint64_t)iters.size();
         if (K > 0) h->prepared_K = iters.back() > 0 ? iters.back() : h->prepared_K;
-        h->last_select_ro = h->game == GAME_C4 && h->W == 1 && h->variant != 0 && std::max(iters.back(), 1) <= RS_MAX;
+        h->last_select_ro = select_is_ro(h, iters.back() > 0, std::max(iters.back(), 1));
         h->launches += (uint64_t)launches;
     }
     h->user_stream = main; h->user_pending = true;

@@ -1,0 +1,203 @@
+// Staggered-descent select for SMALL Connect4 batches (included by az_mcts.cu after az_mcts_fast.cuh).
+//
+// The K virtual-loss descents of a tree are sequentially dependent (descent k sees the virtual loss of descents < k), so the
+// thread-per-tree kernels walk K x depth tree levels one after the other: at 8192 trees or fewer that chain IS the kernel
+// time (a few hundred warps cannot hide a DRAM round trip per level).  But descent k only needs to know which child the
+// earlier descents took AT THE LEVEL IT IS SCORING - not their leaves.  Here every descent gets its own lane and starts one
+// level step after its predecessor: in step s lane k scores level s - k, and the choices of lanes < k at that level were made
+// in earlier steps (they are read from the paths kept in shared memory, exactly like the read-only select of k_select_f).
+// K + depth - 1 dependent level steps instead of K x depth, same arithmetic, same bits.
+//
+// Read-only on the tree (launch-local virtual loss, first-visit flags applied by back-prop): the matching back-prop is
+// k_backprop_f<..., RO = true>.  More warp instructions in total than the thread-per-tree kernel (lanes idle while they wait
+// for their start step): only used when the whole batch is small (launch_select).
+#pragma once
+
+namespace az {
+
+constexpr int CTA_W = 128;
+
+// KL lanes per tree (4 or 8), lane k of a group runs descent k (k < K <= KL)
+template <class G, bool AUX, int KL>
+__global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
+                                                 az_leaf *__restrict__ leaves) {
+    static_assert(G::GAME == GAME_C4, "staggered select is specialised for Connect4 (<= 7 edges)");
+    constexpr int NE = G::MAX_EDGES;       // 7
+    __shared__ uint32_t path_s[CTA_W][PATH8 + 1];          // first 8 path entries of every descent; odd stride
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int k = lane % KL;                               // my descent
+    const int gbase = lane - k;                            // first lane of my tree's group
+    const int tree = (blockIdx.x * CTA_W + threadIdx.x) / KL;
+    const bool valid = tree < d.env_cnt && k < K;
+    const int env = d.env_lo + (tree < d.env_cnt ? tree : d.env_cnt - 1);
+    const Slot *arena = d.pool + (size_t)env * d.cap;
+    const TreeRec *tr = d.trees + env;
+    const int vl = cfg.vl_count;
+    const float ne_eps = cfg.noise_epsilon;
+    uint32_t *mypath = &path_s[threadIdx.x][0];
+    const uint32_t *gpaths = &path_s[threadIdx.x - k][0];  // paths of my group: descent q at gpaths + q * (PATH8 + 1)
+#pragma unroll
+    for (int j = 0; j < PATH8; ++j) mypath[j] = 0;
+
+    // import_board (Connect4.h:100-129): the last mover is inferred from piece-count parity
+    uint64_t b0, b1; int turn, last;
+    { const az_root r = ld32(roots + env); b0 = r.bb0; b1 = r.bb1; turn = r.turn;
+      const int np = popc64(r.bb0 | r.bb1); last = np > 0 ? ((np & 1) ? 0 : 1) : -1; }
+    const Slot root = ld_slot(&tr->root);
+    uint32_t root_meta = root.meta;
+    float nz[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) nz[e] = ne_eps > 0.0f ? d.noise[(size_t)env * d.noise_stride + e] : 0.0f;
+    const uint64_t keep = l2_keep_policy();
+
+    int cur_n = root.n; uint32_t cur_meta = root.meta;
+    float cur_Q = mean_q(root.n, root.wp1, root.wp2, (root.meta & F_TURN_P1) != 0);
+    float cur_M = AUX ? mean_m(root.n, root.msum) : 0.0f;
+    bool is_root = true;
+    uint32_t plen = 0, last_slot = 0;
+    int winner = 0; bool full = false;
+    unsigned st_edges = 0;
+    uint32_t *gpath = d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH;       // entries beyond the first 8
+    // w = (block offset << 6) | num_edges of the node I score next, 0 = my descent has ended
+    uint32_t w = (valid && root.child != NONE && !(root.meta & F_TERM) && (root.child & 63u) != 0) ? root.child : 0u;
+    __syncwarp();
+
+    for (int step = 0; __any_sync(FULL, w != 0u); ++step) {
+        const bool act = w != 0u && step >= k;
+        const uint32_t off = w >> 6;
+        const int ne = (int)(w & 63u);
+        // ---- in-flight counts from the earlier descents of my tree: a path that holds a slot of this block at this depth
+        //      passed through this node (parent + 1) and through that child (child + 1); 4 bits per child ----
+        uint32_t packed = 0u, cntp = 0u;
+#pragma unroll
+        for (int q = 0; q < KL - 1; ++q) {
+            const uint32_t pq = __shfl_sync(FULL, plen, gbase + q);      // descent q is at least one level ahead of me (or done)
+            if (act && q < k && pq > plen) {
+                const uint32_t t = plen < (uint32_t)PATH8 ? gpaths[q * (PATH8 + 1) + plen]
+                                                          : __ldcg(d.path_vl + ((size_t)env * d.kcap + q) * G::MAX_DEPTH + plen);
+                const uint32_t dd = t - off;
+                if (dd < (uint32_t)ne) { packed += 1u << (4 * dd); ++cntp; }
+            }
+        }
+        uint32_t nw = 0u;
+        if (act) {
+            st_edges += (unsigned)ne;
+            Slot s[NE];
+#pragma unroll
+            for (int c = 0; c < NE; ++c) {
+                if (c < ne) s[c] = ld_slot256(arena + off + c);
+                else { s[c].prior = 0.0f; s[c].n = 0; s[c].meta = 0u; s[c].child = NONE; s[c].wd = s[c].wp1 = s[c].wp2 = s[c].msum = 0.0f; }
+            }
+            // ---- compute_fpu (MCTS.h:140-156): seen_policy summed in edge order ----
+            const float parent_q = cur_Q;
+            float seen_policy = 0.0f;
+#pragma unroll
+            for (int c = 0; c < NE; ++c) seen_policy += (c < ne && s[c].n > 0) ? s[c].prior : 0.0f;   // + 0.0f is exact
+            const float fscale = (1.0f + parent_q) / 2.0f;
+            const float eff_fpu = cfg.fpu_reduction * fscale;
+            float fpu = parent_q - eff_fpu * sqrtf(seen_policy);
+            fpu = (-1.0f < fpu) ? fpu : -1.0f;
+            // ---- select_edge (MCTS.h:163-234); a node below the root already carries this descent's own virtual loss
+            //      (MCTS.h:492), the root gets its own after the first selection (:471-475) ----
+            const int pn_i = cur_n + (int)(cntp + (is_root ? 0u : 1u)) * vl;
+            const float parent_n = (float)pn_i;
+            const float parent_M = cur_M;
+            float lg, sqrt_pn;
+            if (pn_i >= 0 && pn_i < d.log_lut_n) { const float2 v = __ldg(d.ls_lut + pn_i); lg = v.x; sqrt_pn = v.y; }
+            else { lg = logf((parent_n + cfg.c_base + 1.0f) / cfg.c_base); sqrt_pn = sqrtf(parent_n); }
+            const float c_puct = cfg.c_init + lg;
+            const bool mix_noise = is_root && ne_eps > 0.0f;
+            float best_s = -INFINITY, best_Q = 0.0f, best_M = 0.0f;
+            int best_e = -1;
+#pragma unroll
+            for (int c = 0; c < NE; ++c) {
+                if (c < ne) {
+                    float eff_prior = s[c].prior;
+                    if (mix_noise) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * nz[c];
+                    float q_value = fpu, m_utility = 0.0f, child_Q = 0.0f, child_M = 0.0f;
+                    if (s[c].n > 0) {
+                        child_Q = mean_q(s[c].n, s[c].wp1, s[c].wp2, (s[c].meta & F_TURN_P1) != 0);
+                        q_value = -child_Q;
+                        if (AUX) { child_M = mean_m(s[c].n, s[c].msum); m_utility = aux_utility<G>(child_M, parent_M, child_Q, cfg); }
+                    }
+                    const int visits = s[c].n + (int)((packed >> (4 * c)) & 15u) * vl;
+                    const float u_score = c_puct * eff_prior * sqrt_pn / (1.0f + (float)visits);
+                    const float score = q_value + u_score + m_utility;
+                    if (score > best_s) { best_s = score; best_e = c; best_Q = child_Q; best_M = child_M; }
+                }
+            }
+            if (best_e >= 0) {
+                Slot ch = s[0];
+#pragma unroll
+                for (int c = 1; c < NE; ++c) if (best_e == c) ch = s[c];
+                {   // Connect4::step (Connect4.h:159-172, no legality check): drop a stone of the side to move
+                    const int col7 = (int)((ch.meta >> 16) & 0xFFu) * 7;
+                    const uint64_t occ = b0 | b1;
+                    const uint64_t bit = 1ULL << (col7 + popc64((occ >> col7) & 0x3FULL));
+                    const bool p1_moves = turn == 1;
+                    b0 |= p1_moves ? bit : 0ULL; b1 |= p1_moves ? 0ULL : bit;
+                    last = p1_moves ? 0 : 1; turn = -turn;
+                }
+                uint32_t nmeta = ch.meta;
+                if (!(nmeta & F_ALLOC)) {      // lazy child allocation (MCTS.h:481-488): remember the child's side to move
+                    nmeta |= F_ALLOC;
+                    nmeta = turn == 1 ? (nmeta | F_TURN_P1) : (nmeta & ~F_TURN_P1);
+                }
+                winner = c4_winner_of(last == 0 ? b0 : b1) ? (last == 0 ? 1 : -1) : 0;       // last mover only (:182-203)
+                full = popc64(b0 | b1) == 42;
+                const bool term_now = winner != 0 || full;
+                if (term_now) nmeta = (nmeta & ~(F_WIN_P1 | F_WIN_P2)) | F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+                last_slot = off + (uint32_t)best_e;
+                if (plen < (uint32_t)PATH8) mypath[plen] = last_slot; else gpath[plen] = last_slot;
+                ++plen;
+                cur_n = ch.n; cur_meta = nmeta; cur_Q = best_Q; cur_M = best_M; is_root = false;
+                if (ch.child != NONE && !(ch.meta & F_TERM) && (ch.child & 63u) != 0 && plen < (uint32_t)G::MAX_DEPTH && !term_now) nw = ch.child;
+            }
+        }
+        if (act) w = nw;
+        __syncwarp();                                  // my path entry is visible to the later descents of my tree
+    }
+
+    if (valid) {
+        bool leaf_term = (cur_meta & F_TERM) != 0;
+        if (plen == 0) leaf_term = (root_meta & F_TERM) != 0;
+        if (!leaf_term) {
+            if (winner == 0 && !full) {
+                winner = (last >= 0 && c4_winner_of(last == 0 ? b0 : b1)) ? (last == 0 ? 1 : -1) : 0;
+                full = popc64(b0 | b1) == 42;
+            }
+            if (winner != 0 || full) {
+                leaf_term = true;
+                const uint32_t tf = F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+                if (plen == 0) { root_meta = (root_meta & ~(F_WIN_P1 | F_WIN_P2)) | tf; cur_meta = root_meta; }
+                else cur_meta = (cur_meta & ~(F_WIN_P1 | F_WIN_P2)) | tf;
+            }
+        }
+        int sym = 0;
+        uint64_t e0 = b0, e1 = b1;
+        if (!leaf_term && cfg.use_symmetry) {
+            const uint64_t h = az_rand(d.seed, d.epoch + (d.epoch_add ? *d.epoch_add : 0ULL), STREAM_SYM, d.env_base + (uint64_t)env, (uint64_t)k);
+            sym = (int)(h & 1);
+            if (sym) { e0 = G::flip_bb(b0); e1 = G::flip_bb(b1); }
+        }
+        const uint8_t tflags = (uint8_t)(leaf_term ? (AZ_LEAF_TERMINAL | ((cur_meta & F_WIN_P1) ? AZ_LEAF_P1_WINS : 0u) |
+                                                      ((cur_meta & F_WIN_P2) ? AZ_LEAF_P2_WINS : 0u)) : 0u);
+        const uint32_t lflags = LF_VALID | (leaf_term ? LF_TERM : 0u) | ((tflags & AZ_LEAF_P1_WINS) ? LF_WIN_P1 : 0u) |
+                                ((tflags & AZ_LEAF_P2_WINS) ? LF_WIN_P2 : 0u);
+        LeafRec *dst = d.leaf_vl + (size_t)env * d.kcap + k;
+        st_words256_keep(&dst->h, (uint32_t)b0, (uint32_t)(b0 >> 32), (uint32_t)b1, (uint32_t)(b1 >> 32), (uint32_t)turn,
+                         (((uint32_t)last & 0xFFu) << 16) | (lflags << 24), plen, (uint32_t)sym, keep);     // passes = 0
+        st_words256_keep(dst->path8, mypath[0], mypath[1], mypath[2], mypath[3], mypath[4], mypath[5], mypath[6], mypath[7], keep);
+        st_words256_keep(leaves + (size_t)env * K + k, (uint32_t)e0, (uint32_t)(e0 >> 32), (uint32_t)e1, (uint32_t)(e1 >> 32),
+                         ((uint32_t)turn & 0xFFu) | ((uint32_t)tflags << 8) | ((uint32_t)sym << 16), 0u, 0u, 0u, keep);
+    }
+    if (d.stats) {                                   // warp-uniform; one atomic per warp and counter
+        const unsigned sims = __reduce_add_sync(FULL, valid ? 1u : 0u);
+        const unsigned dep = __reduce_add_sync(FULL, valid ? (unsigned)plen : 0u);
+        const unsigned edg = __reduce_add_sync(FULL, valid ? st_edges : 0u);
+        if (lane == 0) { atomicAdd(d.stats + 0, (unsigned long long)sims); atomicAdd(d.stats + 1, (unsigned long long)dep); atomicAdd(d.stats + 2, (unsigned long long)edg); }
+    }
+}
+
+}  // namespace az

@@ -342,6 +342,13 @@ class _BatchedMCTS:
     def get_variant(self):
         return self._L.az_mcts_get_variant(self._h)
 
+    def set_wave_max(self, max_trees):
+        """Batches of at most `max_trees` trees use the staggered-descent select (one lane per virtual-loss descent); 0 = off."""
+        self._ck(self._L.az_mcts_set_wave_max(self._h, int(max_trees)))
+
+    def get_wave_max(self):
+        return self._L.az_mcts_get_wave_max(self._h)
+
     def set_env_base(self, base):
         """Global index of env 0 (keeps RNG streams sharding-invariant across GPUs)."""
         self._ck(self._L.az_mcts_set_env_base(self._h, int(base)))

@@ -182,6 +182,11 @@ int az_mcts_get_lanes(const az_mcts *h);
  * bit-identical results; the setting exists for A/B measurements and the parity tests.  Env: AZB200_VARIANT. */
 int az_mcts_set_variant(az_mcts *h, int variant);
 int az_mcts_get_variant(const az_mcts *h);
+/* Staggered-descent select (Connect4, lanes == 1, lean kernels, 1 <= K <= 8): batches of at most `max_trees` trees give every
+ * virtual-loss descent its own lane, descent k starting one tree level after descent k-1 (K + depth - 1 dependent level steps
+ * instead of K x depth; simulate_vl, MCTS.h:443-545, same results bit for bit).  0 = off.  Env: AZB200_WAVE_MAX. */
+int az_mcts_set_wave_max(az_mcts *h, int max_trees);
+int az_mcts_get_wave_max(const az_mcts *h);
 /* Self-test of the branch-free division sequences against the compiler's IEEE division: mode 0 = 1/n for n = 1..count,
  * mode 1 = random a/b over the covered range, mode 2 = small-integer ratios (exact results and ties).  Writes the number
  * of bit mismatches (expected 0). */

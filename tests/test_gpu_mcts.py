@@ -208,6 +208,64 @@ def test_c4_read_only_select_deep_paths_and_terminals(K):
         compare_engines(e2, _ref("Connect4", n), "Connect4", n, 200, K, cfg2, boards=boards, turns=turns, moves=2, compare_leaves=True)
 
 
+@pytest.mark.parametrize("n,K,decay,mlh", [(80, 4, 0.98, 0.1), (131, 3, 1.0, 0.1), (64, 8, 1.0, 0.1), (45, 5, 1.0, 0.0), (40, 1, 1.0, 0.1), (33, 2, 1.0, 0.0)])
+def test_c4_staggered_descent_select_is_bit_exact(n, K, decay, mlh):
+    """set_wave_max: one lane per virtual-loss descent, descent k one tree level behind descent k-1 (az_mcts_wave.cuh).  Same
+    leaves, visit counts and root statistics as the oracle: full and ragged warps, 4- and 8-lane groups, K below the group
+    width, remainder iterations, tree reuse over several moves, MLH on and off."""
+    e = _cuda("Connect4", n)
+    e.set_lanes(1)
+    e.set_wave_max(1 << 20)
+    assert e.get_wave_max() == 1 << 20 and e.get_variant() == 1
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True, value_decay=decay, mlh_slope=mlh)
+    boards, turns = random_positions("Connect4", n, 30, 21 + n)
+    compare_engines(e, _orc("Connect4", n), "Connect4", n, 90, K, cfg, boards=boards, turns=turns, moves=6, seed=5)
+
+
+@pytest.mark.parametrize("K", [8, 4, 3])
+def test_c4_staggered_descent_select_deep_paths_and_terminals(K):
+    """Late-game roots, 400 simulations, a large c_init: paths longer than the 8 entries kept in shared memory, terminal children
+    reached repeatedly, duplicate leaves - against the oracle and the compiled reference."""
+    n = 96
+    e = _cuda("Connect4", n)
+    e.set_lanes(1)
+    e.set_wave_max(4096)
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True, c_init=3.0)
+    boards, turns = random_positions("Connect4", n, 34, 1234 + K)
+    compare_engines(e, _orc("Connect4", n), "Connect4", n, 400, K, cfg, boards=boards, turns=turns, moves=3, seed=77)
+    if oracle.ref_available("parity"):
+        e2 = _cuda("Connect4", n)
+        e2.set_lanes(1)
+        e2.set_wave_max(4096)
+        cfg2 = dict(cfg, use_symmetry=False)
+        compare_engines(e2, _ref("Connect4", n), "Connect4", n, 200, K, cfg2, boards=boards, turns=turns, moves=2, compare_leaves=True)
+
+
+def test_c4_staggered_descent_device_loop_equals_plain_loop():
+    """Device-resident loop (native loop, graph replay on the second move) with and without the staggered select."""
+    import torch
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    n, npl, K, A = 1000, 120, 8, 7
+    boards, turns = random_positions("Connect4", 64, 20, 5)
+    boards, turns = np.tile(boards, (16, 1, 1))[:n].copy(), np.tile(turns, 16)[:n].copy()
+    dev = torch.device("cuda", 0)
+    out = []
+    for wave in (0, 1 << 20):
+        e = _cuda("Connect4", n)
+        e.set_lanes(1)
+        e.set_wave_max(wave)
+        set_config(e, **dict(SERVER_DEFAULTS, use_symmetry=True))
+        e.set_seed(4)
+        buf = ds.LeafBuffers(n, n * K, A, (6, 7), dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        buf.pack_roots(torch.from_numpy(boards).to(dev), torch.from_numpy(turns).to(dev), stream)
+        for mv in range(2):
+            ds.playout_device(e, buf, npl, K, ds.SyntheticEvaluator("Connect4", "equivariant"), stream)
+        torch.cuda.synchronize()
+        out.append((counts(e, n, A), e.get_all_root_stats().tobytes()))
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_c4_lean_kernels_fall_back_to_plain_division_on_tiny_numerators(variant):
     """Priors of 1e-30 and WDL sums of 1e-35 push the PUCT numerators below the range the branch-free division covers:
