@@ -1257,7 +1257,7 @@ struct az_mcts {
     float2 *d_ls_lut = nullptr;
     bool last_select_ro = false;      // the last select launch was read-only: its back-prop applies the leaf flags, removes no virtual loss
     int variant = 1;                  // thread-per-tree kernels: 0 = first generation (k_*_t), 1 = lean (k_*_f)
-    int wave_max = 0;                 // batches of at most this many trees run the staggered-descent select (az_mcts_wave.cuh); 0 = off
+    int wave_max = 65536;             // batches of at most this many descent lanes run the staggered-descent select (az_mcts_wave.cuh); 0 = off
     // VL bookkeeping
     int kcap = 0;
     int prepared_K = 0;               // vl_paths_.size() (MCTS.h:421-429)
@@ -1456,10 +1456,12 @@ static int auto_lanes(int game, int n) {
         return n >= 16384 ? 8 : 16;
     }
     if (e) { int w = atoi(e); if (w == 1 || w == 2 || w == 4 || w == 8) return w; }
-    // measured with the lean thread-per-tree kernels (tools/bench_configs.py, B200): one lane per tree wins from 8192 trees
-    // up (16384 trees: 0.97 vs 0.89 G sims/s with 4 lanes; 32768: 1.58 vs 1.24 with 2 lanes); smaller batches are latency
-    // bound and a little faster with 8 lanes (more warps, shorter per-level chains)
-    return n >= 8192 ? 1 : 8;
+    // measured with the lean thread-per-tree kernels (tools/bench_configs.py, tools/exp_wave.py, B200): one lane per tree wins
+    // from 8192 trees up (16384 trees: 0.97 vs 0.89 G sims/s with 4 lanes; 32768: 1.58 vs 1.24 with 2 lanes) and, since the
+    // lean kernels, below as well (n=200, K=4, ms per move, 8 lanes / 1 lane / 1 lane + staggered descents: 100 trees 2.08 /
+    // 1.96 / 1.78, 1024 trees 2.26 / 2.06 / 1.91, 4096 trees 2.45 / 2.20 / 2.00)
+    (void)n;
+    return 1;
 }
 
 // ---- kernel dispatch over (game, lanes, VL) ----
@@ -1477,8 +1479,11 @@ static int auto_lanes(int game, int n) {
     } while (0)
 
 // Small batches: one lane per descent, the K descents of a tree staggered by one level (az_mcts_wave.cuh)
+// wave_max counts descent lanes = trees x group width (4 lanes per tree for K <= 4, 8 for K <= 8).  Measured (tools/exp_wave.py,
+// ms per move, thread-per-tree / staggered): n=800 K=8: 2048 trees 10.5 / 7.1, 8192 trees 11.0 / 8.2, 16384 trees 12.5 / 12.5,
+// 32768 trees 15.0 / 19.9; n=200 K=4: 8192 trees 2.33 / 2.16, 16384 trees 2.71 / 2.59, 32768 trees 3.33 / 3.42.
 static bool use_wave(const az_mcts *h, bool vl, int K) {
-    return vl && K >= 1 && K <= 8 && K <= h->kcap && h->wave_max > 0 && h->n <= h->wave_max;
+    return vl && K >= 1 && K <= 8 && K <= h->kcap && h->wave_max > 0 && (int64_t)h->n * (K <= 4 ? 4 : 8) <= (int64_t)h->wave_max;
 }
 // Does the select launch for K simulations leave the tree untouched (read-only: back-prop applies the leaf flags)?
 static bool select_is_ro(const az_mcts *h, bool vl, int K) {
@@ -1740,7 +1745,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     h->A = az_game_action_size(game); h->S = az_game_board_size(game);
     h->W = auto_lanes(game, n_envs);
     { const char *ve = getenv("AZB200_VARIANT"); if (ve) { int v = atoi(ve); if (v >= 0 && v <= 1) h->variant = v; } }
-    { const char *we = getenv("AZB200_WAVE_MAX"); h->wave_max = we ? std::max(0, atoi(we)) : 0; }
+    { const char *we = getenv("AZB200_WAVE_MAX"); if (we) h->wave_max = std::max(0, atoi(we)); }
     { const char *ge = getenv("AZB200_GRAPHS"); if (ge) h->use_graphs = atoi(ge) != 0; }
     { const char *ce2 = getenv("AZB200_COMPACTION"); if (ce2) { int v = atoi(ce2); if (v >= 0 && v <= 2) h->compaction = v; } }
     h->max_depth = game == GAME_C4 ? C4::MAX_DEPTH : Oth::MAX_DEPTH;
@@ -1823,9 +1828,9 @@ int az_mcts_set_variant(az_mcts *h, int variant) {
     return AZ_OK;
 }
 int az_mcts_get_variant(const az_mcts *h) { return h->variant; }
-int az_mcts_set_wave_max(az_mcts *h, int max_trees) {
-    if (max_trees < 0) AZ_FAIL(h, AZ_ERR_INVALID, "wave_max must be >= 0");
-    h->wave_max = max_trees;
+int az_mcts_set_wave_max(az_mcts *h, int max_lanes) {
+    if (max_lanes < 0) AZ_FAIL(h, AZ_ERR_INVALID, "wave_max must be >= 0");
+    h->wave_max = max_lanes;
     return AZ_OK;
 }
 int az_mcts_get_wave_max(const az_mcts *h) { return h->wave_max; }

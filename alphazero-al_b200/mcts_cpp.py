@@ -342,9 +342,10 @@ class _BatchedMCTS:
     def get_variant(self):
         return self._L.az_mcts_get_variant(self._h)
 
-    def set_wave_max(self, max_trees):
-        """Batches of at most `max_trees` trees use the staggered-descent select (one lane per virtual-loss descent); 0 = off."""
-        self._ck(self._L.az_mcts_set_wave_max(self._h, int(max_trees)))
+    def set_wave_max(self, max_lanes):
+        """Batches of at most `max_lanes` descent lanes (trees x 4 for K <= 4, x 8 for K <= 8) use the staggered-descent select
+        (one lane per virtual-loss descent); 0 = off, default 65536."""
+        self._ck(self._L.az_mcts_set_wave_max(self._h, int(max_lanes)))
 
     def get_wave_max(self):
         return self._L.az_mcts_get_wave_max(self._h)

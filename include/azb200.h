@@ -173,7 +173,7 @@ int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const az_root *d_roots, i
 int az_mcts_get_counts_dev(az_mcts *h, int32_t *d_out, void *stream);
 int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream);
 
-/* Lanes cooperating on one tree: Connect4 1/2/4/8 (0 = choose from n_envs), Othello 16.  More trees per warp means
+/* Lanes cooperating on one tree: Connect4 1/2/4/8 (0 = automatic: 1), Othello 8/16 (0 = choose from n_envs).  More trees per warp means
  * fewer replicated instructions; fewer means more warps to hide latency when n_envs is small. */
 int az_mcts_set_lanes(az_mcts *h, int lanes);
 int az_mcts_get_lanes(const az_mcts *h);
@@ -182,10 +182,11 @@ int az_mcts_get_lanes(const az_mcts *h);
  * bit-identical results; the setting exists for A/B measurements and the parity tests.  Env: AZB200_VARIANT. */
 int az_mcts_set_variant(az_mcts *h, int variant);
 int az_mcts_get_variant(const az_mcts *h);
-/* Staggered-descent select (Connect4, lanes == 1, lean kernels, 1 <= K <= 8): batches of at most `max_trees` trees give every
- * virtual-loss descent its own lane, descent k starting one tree level after descent k-1 (K + depth - 1 dependent level steps
- * instead of K x depth; simulate_vl, MCTS.h:443-545, same results bit for bit).  0 = off.  Env: AZB200_WAVE_MAX. */
-int az_mcts_set_wave_max(az_mcts *h, int max_trees);
+/* Staggered-descent select (Connect4, lanes == 1, lean kernels, 1 <= K <= 8): small batches give every virtual-loss descent
+ * its own lane, descent k starting one tree level after descent k-1 (K + depth - 1 dependent level steps instead of K x depth;
+ * simulate_vl, MCTS.h:443-545, same results bit for bit).  Used when n_envs x group width (4 lanes per tree for K <= 4, 8 for
+ * K <= 8) <= max_lanes; default 65536 (measured crossover), 0 = off.  Env: AZB200_WAVE_MAX. */
+int az_mcts_set_wave_max(az_mcts *h, int max_lanes);
 int az_mcts_get_wave_max(const az_mcts *h);
 /* Self-test of the branch-free division sequences against the compiler's IEEE division: mode 0 = 1/n for n = 1..count,
  * mode 1 = random a/b over the covered range, mode 2 = small-integer ratios (exact results and ties).  Writes the number

@@ -181,6 +181,7 @@ def test_c4_thread_per_tree_kernel_generations_are_bit_exact(variant, n, K, deca
     oracle bit for bit: full warps, a ragged tail warp (131 = 4 warps + 3 trees), K = 8 (record stride 8) and K = 1."""
     e = _cuda("Connect4", n)
     e.set_lanes(1)
+    e.set_wave_max(0)                      # the thread-per-tree select itself (small batches default to the staggered one)
     e.set_variant(variant)
     assert e.get_variant() == variant
     cfg = dict(SERVER_DEFAULTS, use_symmetry=True, value_decay=decay)
@@ -197,6 +198,7 @@ def test_c4_read_only_select_deep_paths_and_terminals(K):
     n = 96
     e = _cuda("Connect4", n)
     e.set_lanes(1)
+    e.set_wave_max(0)
     assert e.get_variant() == 1
     cfg = dict(SERVER_DEFAULTS, use_symmetry=True, c_init=3.0)         # a large c_init spreads visits: long, varied paths
     boards, turns = random_positions("Connect4", n, 34, 1234 + K)
@@ -204,6 +206,7 @@ def test_c4_read_only_select_deep_paths_and_terminals(K):
     if oracle.ref_available("parity"):
         e2 = _cuda("Connect4", n)
         e2.set_lanes(1)
+        e2.set_wave_max(0)
         cfg2 = dict(cfg, use_symmetry=False)
         compare_engines(e2, _ref("Connect4", n), "Connect4", n, 200, K, cfg2, boards=boards, turns=turns, moves=2, compare_leaves=True)
 
@@ -281,7 +284,7 @@ def test_c4_lean_kernels_fall_back_to_plain_division_on_tiny_numerators(variant)
     cfg = dict(SERVER_DEFAULTS, use_symmetry=False)
     boards, turns = random_positions("Connect4", n, 12, 77)
     a, b = _cuda("Connect4", n), _orc("Connect4", n)
-    a.set_lanes(1); a.set_variant(variant)
+    a.set_lanes(1); a.set_variant(variant); a.set_wave_max(0)
     for e in (a, b):
         set_config(e, **cfg); e.set_seed(3)
     playout(a, Tiny(), boards, turns, 120, K)
