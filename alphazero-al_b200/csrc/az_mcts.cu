@@ -1257,7 +1257,7 @@ struct az_mcts {
     float2 *d_ls_lut = nullptr;
     bool last_select_ro = false;      // the last select launch was read-only: its back-prop applies the leaf flags, removes no virtual loss
     int variant = 1;                  // thread-per-tree kernels: 0 = first generation (k_*_t), 1 = lean (k_*_f)
-    int wave_max = 65536;             // batches of at most this many descent lanes run the staggered-descent select (az_mcts_wave.cuh); 0 = off
+    int wave_max = 131072;             // batches of at most this many descent lanes run the staggered-descent select (az_mcts_wave.cuh); 0 = off
     // VL bookkeeping
     int kcap = 0;
     int prepared_K = 0;               // vl_paths_.size() (MCTS.h:421-429)
@@ -1480,8 +1480,8 @@ static int auto_lanes(int game, int n) {
 
 // Small batches: one lane per descent, the K descents of a tree staggered by one level (az_mcts_wave.cuh)
 // wave_max counts descent lanes = trees x group width (4 lanes per tree for K <= 4, 8 for K <= 8).  Measured (tools/exp_wave.py,
-// ms per move, thread-per-tree / staggered): n=800 K=8: 2048 trees 10.5 / 7.1, 8192 trees 11.0 / 8.2, 16384 trees 12.5 / 12.5,
-// 32768 trees 15.0 / 19.9; n=200 K=4: 8192 trees 2.33 / 2.16, 16384 trees 2.71 / 2.59, 32768 trees 3.33 / 3.42.
+// ms per move, thread-per-tree / staggered): n=800 K=8: 2048 trees 10.5 / 6.4, 8192 trees 11.0 / 7.9, 16384 trees 12.5 / 11.7,
+// 32768 trees 15.0 / 17.6; n=200 K=4: 100 trees 1.96 / 1.48, 8192 trees 2.33 / 2.01, 16384 trees 2.71 / 2.50, 32768 trees 3.33 / 3.36.
 static bool use_wave(const az_mcts *h, bool vl, int K) {
     return vl && K >= 1 && K <= 8 && K <= h->kcap && h->wave_max > 0 && (int64_t)h->n * (K <= 4 ? 4 : 8) <= (int64_t)h->wave_max;
 }

@@ -110,27 +110,58 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
             const bool mix_noise = is_root && ne_eps > 0.0f;
             float best_s = -INFINITY, best_Q = 0.0f, best_M = 0.0f;
             int best_e = -1;
+            // the branch-free correctly rounded divisions of k_select_f (az_mcts_fast.cuh): this kernel is instruction bound
+            // (profiles: 51 % issue slots busy at 10 of 32 lanes active), and an IEEE `/` costs ~15 instructions and a branch
+            SafeAcc safe;
 #pragma unroll
             for (int c = 0; c < NE; ++c) {
-                if (c < ne) {
-                    float eff_prior = s[c].prior;
-                    if (mix_noise) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * nz[c];
+                float eff_prior = s[c].prior;
+                if (mix_noise) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * nz[c];
+                const bool has = s[c].n > 0;
+                const float nf = (float)max(s[c].n, 1);
+                const float rn = rcp_refined(nf);                         // == 1.0f / nf
+                const float p1 = s[c].wp1 * rn, p2 = s[c].wp2 * rn;
+                const float dq = p1 - p2;                                  // p2 - p1 == -(p1 - p2) exactly
+                const float child_Q = (s[c].meta & F_TURN_P1) ? dq : -dq;
+                float child_M = 0.0f, m_utility = 0.0f;
+                if (AUX) {
+                    child_M = div_by_rcp(s[c].msum, nf, rn);
+                    const float m_diff = child_M - parent_M;               // Connect4.h:231-239
+                    const float v = cfg.mlh_slope * m_diff, lo = -cfg.mlh_cap, hi = cfg.mlh_cap;
+                    const float u = v < lo ? lo : (hi < v ? hi : v);
+                    m_utility = has ? u * child_Q : 0.0f;
+                    if (c < ne) safe.add(s[c].msum);
+                }
+                const float q_value = has ? -child_Q : fpu;
+                const int visits = s[c].n + (int)((packed >> (4 * c)) & 15u) * vl;
+                const float den = 1.0f + (float)visits;
+                const float num = c_puct * eff_prior * sqrt_pn;
+                if (c < ne) safe.add(num);
+                const float u_score = div_by_rcp(num, den, rcp_refined(den));
+                const float score = q_value + u_score + m_utility;
+                if (c < ne && score > best_s) { best_s = score; best_e = c; best_Q = child_Q; best_M = child_M; }
+            }
+            if (!safe.ok()) {      // rare: a numerator outside the range the fast division covers - the plain IEEE operators
+                best_s = -INFINITY; best_e = -1; best_Q = 0.0f; best_M = 0.0f;
+#pragma unroll 1
+                for (int c = 0; c < ne; ++c) {
+                    const Slot sc = ld_slot256(arena + off + c);
+                    float eff_prior = sc.prior;
+                    if (mix_noise) eff_prior = (1.0f - ne_eps) * sc.prior + ne_eps * d.noise[(size_t)env * d.noise_stride + c];
                     float q_value = fpu, m_utility = 0.0f, child_Q = 0.0f, child_M = 0.0f;
-                    if (s[c].n > 0) {
-                        child_Q = mean_q(s[c].n, s[c].wp1, s[c].wp2, (s[c].meta & F_TURN_P1) != 0);
+                    if (sc.n > 0) {
+                        child_Q = mean_q(sc.n, sc.wp1, sc.wp2, (sc.meta & F_TURN_P1) != 0);
                         q_value = -child_Q;
-                        if (AUX) { child_M = mean_m(s[c].n, s[c].msum); m_utility = aux_utility<G>(child_M, parent_M, child_Q, cfg); }
+                        if (AUX) { child_M = mean_m(sc.n, sc.msum); m_utility = aux_utility<G>(child_M, parent_M, child_Q, cfg); }
                     }
-                    const int visits = s[c].n + (int)((packed >> (4 * c)) & 15u) * vl;
+                    const int visits = sc.n + (int)((packed >> (4 * c)) & 15u) * vl;
                     const float u_score = c_puct * eff_prior * sqrt_pn / (1.0f + (float)visits);
                     const float score = q_value + u_score + m_utility;
                     if (score > best_s) { best_s = score; best_e = c; best_Q = child_Q; best_M = child_M; }
                 }
             }
             if (best_e >= 0) {
-                Slot ch = s[0];
-#pragma unroll
-                for (int c = 1; c < NE; ++c) if (best_e == c) ch = s[c];
+                const Slot ch = ld_slot256(arena + off + best_e);          // re-read (L1 hit) instead of a 7-way select of 8 registers
                 {   // Connect4::step (Connect4.h:159-172, no legality check): drop a stone of the side to move
                     const int col7 = (int)((ch.meta >> 16) & 0xFFu) * 7;
                     const uint64_t occ = b0 | b1;

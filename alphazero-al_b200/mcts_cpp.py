@@ -344,7 +344,7 @@ class _BatchedMCTS:
 
     def set_wave_max(self, max_lanes):
         """Batches of at most `max_lanes` descent lanes (trees x 4 for K <= 4, x 8 for K <= 8) use the staggered-descent select
-        (one lane per virtual-loss descent); 0 = off, default 65536."""
+        (one lane per virtual-loss descent); 0 = off, default 131072."""
         self._ck(self._L.az_mcts_set_wave_max(self._h, int(max_lanes)))
 
     def get_wave_max(self):
