@@ -1535,6 +1535,12 @@ static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_l
         h->launches++;
         return;
     }
+    if (h->game == GAME_OTH && vl && K >= 2 && K <= 4 && h->wave_max > 0 && (int64_t)h->n * 8 <= (int64_t)h->wave_max) {
+        // small Othello batches: a warp per tree, the K descents in 8-lane groups staggered by one level (az_mcts_wave.cuh)
+        k_select_ws<Oth, 8><<<(int)(((size_t)cnt * 32 + CTA - 1) / CTA), CTA, 0, s>>>(h->d, h->cfg, K, roots, leaves);
+        h->launches++;
+        return;
+    }
     if (vl) AZ_DISPATCH_W(h, k_select, true, g, s, h->d, h->cfg, K, roots, leaves);
     else AZ_DISPATCH_W(h, k_select, false, g, s, h->d, h->cfg, 1, roots, leaves);
     h->launches++;

@@ -231,4 +231,194 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// The same staggering for the lane-group kernels (Othello): a warp per tree, 32 / W descents of W cooperating lanes each,
+// descent k one level behind descent k - 1.  Virtual loss stays in the tree as in k_select (written into the slot when a
+// descent passes, removed by back-prop): at every step each tree level is touched by at most one descent, and descents
+// reach a given level in k order, so every load sees exactly what the sequential loop would have seen.  The level body is
+// k_select's.
+template <class G, int W>
+__global__ void __launch_bounds__(CTA) k_select_ws(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
+                                                   az_leaf *__restrict__ leaves) {
+    constexpr int NCH = (G::MAX_EDGES + W - 1) / W;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int tree = (blockIdx.x * CTA + threadIdx.x) >> 5;          // one warp per tree
+    if (tree >= d.env_cnt) return;
+    const int k = (threadIdx.x & 31) / W;                            // my group's descent
+    const int lane = threadIdx.x & (W - 1);
+    const unsigned gm = group_mask<W>();
+    const int env = d.env_lo + tree;
+    Slot *arena = d.pool + (size_t)env * d.cap;
+    TreeRec *tr = d.trees + env;
+    const float *noise = d.noise + (size_t)env * d.noise_stride;
+    const int vl = cfg.vl_count;
+    const bool use_aux = aux_enabled<G>(cfg);
+    const bool mine = k < K;
+
+    State st;
+    { const az_root r = ld32(roots + env); st.bb[0] = r.bb0; st.bb[1] = r.bb1; G::finish_import(st, r.turn); }
+    const Slot root = ld_slot(&tr->root);
+    // Every descent selects at the root or none does (an unexpanded / terminal / edgeless root ends all of them there), so the
+    // root's in-flight count seen by descent k is what the k earlier descents added (MCTS.h:471-475).
+    Slot cur = root;
+    cur.meta += (uint32_t)(k * vl);
+    bool is_root = true, done = !mine;
+    uint32_t plen = 0, last_slot = 0;
+    uint32_t *path = d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH;
+    int winner = 0; bool full = false;
+    unsigned long long st_edges = 0;
+
+    for (int step = 0; __any_sync(FULL, !done); ++step) {
+        if (!done && step >= k) {
+            const int ne = cur.child != NONE ? (int)(cur.child & 63u) : 0;
+            if (cur.child == NONE || (cur.meta & F_TERM) || ne == 0 || plen >= (uint32_t)G::MAX_DEPTH) done = true;
+            else {
+                const uint32_t off = cur.child >> 6;
+                Slot s[NCH]; bool has[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int e = c * W + lane;
+                    has[c] = e < ne;
+                    if (has[c]) s[c] = ld_slot(arena + off + e);
+                    else { s[c].prior = 0.f; s[c].n = 0; s[c].meta = 0; s[c].child = NONE; s[c].wd = s[c].wp1 = s[c].wp2 = s[c].msum = 0.f; }
+                }
+                st_edges += (unsigned long long)ne;
+                // ---- compute_fpu (MCTS.h:140-156): seen_policy summed sequentially in edge order ----
+                const int cur_infl = (int)(cur.meta & INFL_MASK);
+                const float parent_q = mean_q(cur.n, cur.wp1, cur.wp2, (cur.meta & F_TURN_P1) != 0);
+                float seen_policy = 0.0f;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const float pv = (has[c] && s[c].n > 0) ? s[c].prior : 0.0f;   // + 0.0f is exact
+                    const int lim = min(W, ne - c * W);
+                    for (int l = 0; l < lim; ++l) seen_policy += gshfl<W>(gm, pv, l);
+                }
+                const float fscale = (1.0f + parent_q) / 2.0f;
+                const float eff_fpu = cfg.fpu_reduction * fscale;
+                float fpu = parent_q - eff_fpu * sqrtf(seen_policy);
+                fpu = (-1.0f < fpu) ? fpu : -1.0f;
+                // ---- select_edge (MCTS.h:163-234) ----
+                const int pn_i = cur.n + cur_infl;
+                const float parent_n = (float)pn_i;
+                const float parent_M = use_aux ? mean_m(cur.n, cur.msum) : 0.0f;
+                const float lg = (pn_i >= 0 && pn_i < d.log_lut_n) ? d.log_lut[pn_i] : logf((parent_n + cfg.c_base + 1.0f) / cfg.c_base);
+                const float c_puct = cfg.c_init + lg;
+                const float sqrt_pn = sqrtf(parent_n);
+                const float ne_eps = cfg.noise_epsilon;
+                const bool mix_noise = is_root && ne_eps > 0.0f;
+                float best_s = -INFINITY; int best_e = -1;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    if (!has[c]) continue;
+                    const int e = c * W + lane;
+                    float eff_prior = s[c].prior;
+                    if (mix_noise) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * noise[e];
+                    const int cn = s[c].n, cinf = (int)(s[c].meta & INFL_MASK);
+                    float q_value = fpu, m_utility = 0.0f; int visits = cinf;     // unvisited: FPU, in-flight only
+                    if (cn > 0) {
+                        visits = cn + cinf;
+                        const float child_Q = mean_q(cn, s[c].wp1, s[c].wp2, (s[c].meta & F_TURN_P1) != 0);
+                        q_value = -child_Q;
+                        if (use_aux) {
+                            float child_M = mean_m(cn, s[c].msum);
+                            if (G::AUX_NEGATE) child_M = -child_M;
+                            m_utility = aux_utility<G>(child_M, parent_M, child_Q, cfg);
+                        }
+                    }
+                    const float u_score = c_puct * eff_prior * sqrt_pn / (1.0f + (float)visits);
+                    const float score = q_value + u_score + m_utility;
+                    if (score > best_s) { best_s = score; best_e = e; }
+                }
+                // arg-max over the group; ties -> lowest edge index (the reference scans with a strict `>`)
+#pragma unroll
+                for (int o = W / 2; o > 0; o >>= 1) {
+                    const float os = __shfl_xor_sync(gm, best_s, o, W);
+                    const int oe = __shfl_xor_sync(gm, best_e, o, W);
+                    const bool take = oe >= 0 && (best_e < 0 || os > best_s || (os == best_s && oe < best_e));
+                    if (take) { best_s = os; best_e = oe; }
+                }
+                if (best_e < 0) done = true;
+                else {
+                    // broadcast the chosen child to the whole group
+                    const int bl = best_e & (W - 1), bc = best_e / W;
+                    Slot ch = s[0];
+#pragma unroll
+                    for (int c = 1; c < NCH; ++c) if (bc == c) ch = s[c];
+                    ch.n = gshfl<W>(gm, ch.n, bl);
+                    ch.meta = gshfl<W>(gm, ch.meta, bl);
+                    ch.child = gshfl<W>(gm, ch.child, bl);
+                    ch.wp1 = gshfl<W>(gm, ch.wp1, bl);
+                    ch.wp2 = gshfl<W>(gm, ch.wp2, bl);
+                    ch.msum = gshfl<W>(gm, ch.msum, bl);
+                    step_group<G, W>(st, (int)((ch.meta >> 16) & 0xFFu), lane, gm);
+                    uint32_t nmeta = ch.meta;
+                    if (!(nmeta & F_ALLOC)) {      // lazy child allocation (MCTS.h:481-488): remember the child's side to move
+                        nmeta |= F_ALLOC;
+                        nmeta = st.turn == 1 ? (nmeta | F_TURN_P1) : (nmeta & ~F_TURN_P1);
+                    }
+                    nmeta += (uint32_t)vl;         // child virtual loss (MCTS.h:492)
+                    winner = G::winner(st);
+                    full = G::full(st);
+                    const bool term_now = winner != 0 || full;
+                    if (term_now) nmeta = (nmeta & ~(F_WIN_P1 | F_WIN_P2)) | F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+                    last_slot = off + (uint32_t)best_e;
+                    if (lane == 0) {
+                        if (nmeta != ch.meta) arena[last_slot].meta = nmeta;
+                        path[plen] = last_slot;
+                    }
+                    ++plen;
+                    cur = ch; cur.meta = nmeta; is_root = false;
+                    if (term_now) done = true;
+                }
+            }
+        }
+        __syncwarp();          // this step's in-flight / flag updates are visible to the descents that reach the level next
+    }
+
+    const unsigned sel = __ballot_sync(FULL, mine && lane == 0 && plen > 0);       // descents that added virtual loss to the root
+    uint32_t root_meta = root.meta + (uint32_t)(__popc(sel) * vl);
+    if (mine) {
+        // ---- leaf classification (MCTS.h:512-544) ----
+        bool leaf_term = (cur.meta & F_TERM) != 0;
+        if (plen == 0) leaf_term = (root.meta & F_TERM) != 0;
+        if (!leaf_term) {
+            if (winner == 0 && !full) { winner = G::winner(st); full = G::full(st); }
+            if (winner != 0 || full) {
+                leaf_term = true;
+                const uint32_t tf = F_TERM | (winner == 1 ? F_WIN_P1 : (winner == -1 ? F_WIN_P2 : 0u));
+                if (plen == 0) { root_meta = (root_meta & ~(F_WIN_P1 | F_WIN_P2)) | tf; cur.meta = root_meta; }   // (then every descent ends at the root)
+                else { cur.meta = (cur.meta & ~(F_WIN_P1 | F_WIN_P2)) | tf; if (lane == 0) arena[last_slot].meta = cur.meta; }
+            }
+        }
+        // ---- random symmetry for non-terminal leaves (BatchedMCTS.h:261-271) ----
+        int sym = 0;
+        State ex = st;
+        if (!leaf_term && cfg.use_symmetry) {
+            const uint64_t h = az_rand(d.seed, d.epoch + (d.epoch_add ? *d.epoch_add : 0ULL), STREAM_SYM, d.env_base + (uint64_t)env, (uint64_t)k);
+            sym = G::GAME == GAME_C4 ? (int)(h & 1) : ((0x7620 >> (4 * (int)(h & 3))) & 0xF);   // Othello {0,2,6,7}
+            G::symmetry(ex, sym);
+        }
+        if (lane == 0) {
+            const uint8_t tflags = (uint8_t)(leaf_term ? (AZ_LEAF_TERMINAL | ((cur.meta & F_WIN_P1) ? AZ_LEAF_P1_WINS : 0u) |
+                                                          ((cur.meta & F_WIN_P2) ? AZ_LEAF_P2_WINS : 0u)) : 0u);
+            LeafHead L;    // remembered for backprop
+            L.bb0 = st.bb[0]; L.bb1 = st.bb[1]; L.turn = st.turn; L.passes = (int16_t)st.passes; L.last = (int8_t)st.last;
+            L.flags = (uint8_t)(LF_VALID | (plen > 0 ? LF_VLPENDING : 0) | (leaf_term ? LF_TERM : 0) |
+                                ((tflags & AZ_LEAF_P1_WINS) ? LF_WIN_P1 : 0) | ((tflags & AZ_LEAF_P2_WINS) ? LF_WIN_P2 : 0));
+            L.path_len = plen; L.sym = (uint32_t)sym;
+            st32(&(d.leaf_vl + (size_t)env * d.kcap + k)->h, L);
+            az_leaf P;     // handed to the evaluator
+            P.bb0 = ex.bb[0]; P.bb1 = ex.bb[1]; P.turn = (int8_t)st.turn; P.flags = tflags; P.sym = (uint8_t)sym; P.passes = (uint8_t)st.passes;
+            P.reserved[0] = P.reserved[1] = P.reserved[2] = 0;
+            st32(leaves + (size_t)env * K + k, P);
+        }
+    }
+    if ((threadIdx.x & 31) == 0 && root_meta != root.meta) tr->root.meta = root_meta;
+    if (d.stats) {
+        const unsigned dep = __reduce_add_sync(FULL, (mine && lane == 0) ? (unsigned)plen : 0u);
+        const unsigned edg = __reduce_add_sync(FULL, (mine && lane == 0) ? (unsigned)st_edges : 0u);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(d.stats + 0, (unsigned long long)K); atomicAdd(d.stats + 1, (unsigned long long)dep); atomicAdd(d.stats + 2, (unsigned long long)edg); }
+    }
+}
+
 }  // namespace az

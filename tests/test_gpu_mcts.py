@@ -501,10 +501,30 @@ def test_dirichlet_noise_and_symmetry_ids_are_well_formed():
     assert set(vals) == {0, 2, 6, 7} and (np.abs(cnt / osym.size - 0.25) < 0.04).all()
 
 
+@pytest.mark.parametrize("staggered", [False, True])
 @pytest.mark.parametrize("lanes", [8, 16])
-def test_othello_lane_widths_are_bit_exact(lanes):
+def test_othello_lane_widths_are_bit_exact(lanes, staggered):
+    """Both lane widths of the lane-group kernels, with the sequential select (k_select) and with the staggered one
+    (k_select_ws: a warp per tree, the K descents in 8-lane groups one level apart; back-prop keeps the engine's lane width)."""
     e = _cuda("Othello", 40)
     e.set_lanes(lanes)
+    if not staggered:
+        e.set_wave_max(0)
     cfg = dict(OTH_CFG, use_symmetry=True, value_decay=0.99)
     boards, turns = random_positions("Othello", 40, 50, 61)
     compare_engines(e, _orc("Othello", 40), "Othello", 40, 70, 4, cfg, boards=boards, turns=turns, moves=6, seed=8)
+
+
+@pytest.mark.parametrize("K", [2, 3, 4])
+def test_othello_staggered_select_passes_endgames_and_reference(K):
+    """k_select_ws on late Othello positions (pass chains, game ends inside the tree, terminal leaves revisited), K = 2..4 with
+    remainder iterations, against the oracle and the compiled reference."""
+    n = 48
+    e = _cuda("Othello", n)
+    assert e.get_wave_max() > 0
+    cfg = dict(OTH_CFG, use_symmetry=True)
+    boards, turns = random_positions("Othello", n, 56, 300 + K)
+    compare_engines(e, _orc("Othello", n), "Othello", n, 150, K, cfg, boards=boards, turns=turns, moves=4, seed=31)
+    if oracle.ref_available("parity"):
+        e2 = _cuda("Othello", n)
+        compare_engines(e2, _ref("Othello", n), "Othello", n, 100, K, dict(OTH_CFG), boards=boards, turns=turns, moves=2, compare_leaves=True)
