@@ -1453,7 +1453,7 @@ static int auto_lanes(int game, int n) {
     const char *e = getenv("AZB200_LANES");
     if (game == GAME_OTH) {
         if (e) { int w = atoi(e); if (w == 8 || w == 16) return w; }
-        return n >= 16384 ? 8 : 16;
+        return n >= 8192 ? 8 : 16;      // 8192 trees, n=400 K=4: 13.7 ms per move with 8 lanes, 17.1 with 16 (tools/exp_wave_oth.py)
     }
     if (e) { int w = atoi(e); if (w == 1 || w == 2 || w == 4 || w == 8) return w; }
     // measured with the lean thread-per-tree kernels (tools/bench_configs.py, tools/exp_wave.py, B200): one lane per tree wins
@@ -1535,8 +1535,10 @@ static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_l
         h->launches++;
         return;
     }
-    if (h->game == GAME_OTH && vl && K >= 2 && K <= 4 && h->wave_max > 0 && (int64_t)h->n * 8 <= (int64_t)h->wave_max) {
-        // small Othello batches: a warp per tree, the K descents in 8-lane groups staggered by one level (az_mcts_wave.cuh)
+    if (h->game == GAME_OTH && vl && K >= 2 && K <= 4 && h->wave_max > 0 && (int64_t)h->n * 16 <= (int64_t)h->wave_max) {
+        // small Othello batches: a warp per tree, the K descents in 8-lane groups staggered by one level (az_mcts_wave.cuh).
+        // Measured (tools/exp_wave_oth.py, n=400 K=4, ms per move, sequential / staggered): 256 trees 7.9 / 5.3, 1024 trees
+        // 8.2 / 5.7, 4096 trees 9.8 / 8.6, 8192 trees 13.7 / 13.3, 16384 trees 22.7 / 25.0 - on up to 8192 trees by default
         k_select_ws<Oth, 8><<<(int)(((size_t)cnt * 32 + CTA - 1) / CTA), CTA, 0, s>>>(h->d, h->cfg, K, roots, leaves);
         h->launches++;
         return;
