@@ -416,6 +416,10 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         recs = sp.out[:min(g1, sp.out_capacity)]
+        if world > 1:                             # the first collective of this size pays NCCL's connection set-up and the allocations
+            sp_mod.all_gather_records(recs, recs.shape[0], sp.out_capacity)
+            torch.cuda.synchronize()
+            dist.barrier()
         t1 = time.perf_counter()
         gathered, gcounts = sp_mod.all_gather_records(recs, recs.shape[0], sp.out_capacity)
         torch.cuda.synchronize()
