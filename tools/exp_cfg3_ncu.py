@@ -23,3 +23,20 @@ s = torch.cuda.current_stream().cuda_stream
 eng.prune_roots_dev(reset.data_ptr(), s)
 ds.playout_device(eng, buf, npl, K, ev, s)
 torch.cuda.synchronize()
+# select share of the move in the running pipeline (warm caches): CUDA events around every select launch
+if os.environ.get("AZB200_TIME_SELECT"):
+    for wave in (0, eng.get_wave_max()):
+        eng.set_wave_max(wave)
+        for rep in range(2):
+            eng.prune_roots_dev(reset.data_ptr(), s)
+            torch.cuda.synchronize()
+            if rep == 1:
+                eng.time_select(True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ds.playout_device(eng, buf, npl, K, ev, s)
+            e1.record()
+            torch.cuda.synchronize()
+        ms, nl, rows = eng.get_select_time()
+        eng.time_select(False)
+        print(f"N={n} n={npl} K={K} wave={'on' if wave else 'off'}: move {e0.elapsed_time(e1):.3f} ms (launch by launch), select {ms:.3f} ms in {nl} launches = {1e3 * ms / max(nl, 1):.1f} us each")
