@@ -57,3 +57,38 @@ def test_auto_shards(monkeypatch):
     assert ds.auto_shards(16384) == 2 and ds.auto_shards(32768) == 4 and ds.auto_shards(65536) == 8 and ds.auto_shards(1 << 20) == 8
     monkeypatch.setenv("AZB200_SHARDS", "3")
     assert ds.auto_shards(65536) == 3
+
+
+def test_network_batch_buckets():
+    """CachedNetEvaluator pads the miss list to a few batch sizes ({4,5,6,7} x 2^k >= 256): at most 25 % padding, never
+    beyond the buffer, never below the number of misses."""
+    seen = set()
+    for cap in (400, 16384, 262144):
+        for m in list(range(1, 3000)) + [4095, 4096, 4097, 100000, 262143, 262144]:
+            if m > cap:
+                continue
+            b = ds._bucket(m, cap)
+            assert m <= b <= cap
+            if b < cap and m >= 256:
+                assert b <= 1.25 * m + 1
+                assert (b >> (b.bit_length() - 3)) in (4, 5, 6, 7) and b % (1 << (b.bit_length() - 3)) == 0
+            if m <= 256 <= cap:
+                assert b == 256
+            seen.add(b)
+    assert len(seen) < 60                                    # a few dozen shapes, whatever the miss counts
+
+
+def test_net_evaluator_drops_graphs_when_weights_move():
+    nets = importlib.import_module("alphazero-al_b200.nets")
+    net = nets.C4Net()
+    ev = ds.NetEvaluator(net)
+    ev._check_weights()
+    ev._graphs["captured"] = object()
+    ev._check_weights()
+    assert "captured" in ev._graphs                          # same storage: graphs stay
+    net.load_state_dict(net.state_dict())                    # in-place update: graphs stay
+    ev._check_weights()
+    assert "captured" in ev._graphs
+    net.half()                                               # new parameter storage: graphs must go
+    ev._check_weights()
+    assert not ev._graphs
