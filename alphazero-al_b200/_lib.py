@@ -26,6 +26,12 @@ class AzRoot(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class AzGomoku(C.Structure):
+    """az_gomoku (include/azb200_gomoku.h): one Gomoku position as row bit masks, 288 bytes."""
+    _fields_ = [("rows", (C.c_uint32 * 32) * 2)] + [(n, C.c_int32) for n in (
+        "size", "n_in_row", "turn", "n_pieces", "last_action", "last_player", "winner", "done")]
+
+
 def build(force: bool = False) -> str:
     """Compile every CUDA source for sm_100a (nvcc cross-compiles without a GPU)."""
     cmd = ["make", "-C", CSRC] + (["-B"] if force else [])
@@ -97,6 +103,14 @@ def lib() -> C.CDLL:
         "az_envs_observe_dev": [_i, _i] + [_vp] * 7,
         "az_envs_rollout_dev": [_i, _i, _u64, _u64, _vp, _vp, _i, _i] + [_vp] * 7,
     })
+    sig.update({
+        "az_gomoku_set_params": [_vp, _i, _i], "az_gomoku_import": [_vp, _vp], "az_gomoku_step": [_vp, _i],
+        "az_gomoku_valid_moves": [_vp, _vp], "az_gomoku_apply_symmetry": [_vp, _i],
+        "az_gomoku_inverse_symmetry_action": [_i, _i, _i],
+        "az_gomoku_reset_dev": [_i, _i, _i, _vp, _vp], "az_gomoku_step_dev": [_i] + [_vp] * 6,
+        "az_gomoku_observe_dev": [_i, _i] + [_vp] * 7, "az_gomoku_symmetry_dev": [_i, _vp, _vp, _vp],
+        "az_gomoku_rollout_dev": [_i, _i, _i, _u64, _u64, _vp, _vp, _i] + [_vp] * 7,
+    })
     L.az_evalcache_create.restype = _vp
     L.az_evalcache_create.argtypes = [_i, _i, _i]
     L.az_evalcache_destroy.restype = None
@@ -106,7 +120,8 @@ def lib() -> C.CDLL:
                 "az_evalcache_lookup_dedup_dev": [_vp, _i] + [_vp] * 8, "az_evalcache_resolve_dups_dev": [_vp, _i] + [_vp] * 5,
                 "az_evalcache_dups": [_vp, _vp]})
     for name, argt in (("az_env_reset", [_i, _vp]), ("az_env_import", [_i, _vp, _vp]), ("az_env_export", [_i, _vp, _vp]),
-                       ("az_env_step", [_i, _vp, _i]), ("az_env_apply_symmetry", [_i, _vp, _i])):
+                       ("az_env_step", [_i, _vp, _i]), ("az_env_apply_symmetry", [_i, _vp, _i]),
+                       ("az_gomoku_reset", [_vp]), ("az_gomoku_export", [_vp, _vp])):
         f = getattr(L, name)
         f.restype = None
         f.argtypes = argt

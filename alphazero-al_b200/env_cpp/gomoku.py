@@ -1,18 +1,33 @@
 """``env_cpp.gomoku.Env`` - Env-only API parity with the reference's byte-board Gomoku (src/cpp/Gomoku.h:11-296,
-src/cpp/env_gomoku.h:60-171).  The reference registers no MCTS engine for Gomoku (mcts_bindings.cpp:393-394), so this
-is host-side API glue: runtime board size, validated step, incremental line check, D4 symmetries, pickle."""
+src/cpp/env_gomoku.h:60-171).  The reference registers no MCTS engine for Gomoku (mcts_bindings.cpp:393-394).  The
+state is one 288-byte ``az_gomoku`` record of row bit masks; every game-logic method is one call into the C ABI
+(include/azb200_gomoku.h) - the same code the lockstep device kernels run (``BatchedGomoku``)."""
 from __future__ import annotations
 
+import ctypes as C
 import random
 
 import numpy as np
 
+from .. import _lib
+
+_MSG = {1: "game is already finished", 2: "action out of range", 3: "cell is already occupied",
+        4: "board_size must be positive", 5: "n_in_row must be >= 2", 6: "n_in_row must be <= board size",
+        7: "board values must be -1, 0, or 1", 8: "invalid symmetry id",
+        9: "board_size > 32 is not supported by this implementation (32-bit row masks)"}
+
+
+def _ck(rc):
+    if rc != 0:
+        raise RuntimeError(_MSG.get(abs(rc), f"gomoku error {rc}"))
+
 
 class Env:
     NUM_SYMMETRIES = 8
-    _DIRS = ((1, 0), (0, 1), (1, 1), (1, -1))
+    __slots__ = ("_s",)
 
     def __init__(self, board_size=15, n_in_row=5, board=None):
+        self._s = _lib.AzGomoku()
         if board is None and not isinstance(board_size, (int, np.integer)):
             board, board_size = board_size, None           # Env(board, n_in_row=5) overload (env_gomoku.h:70-73)
         if board is not None:
@@ -24,169 +39,100 @@ class Env:
         else:
             self.set_params(int(board_size), int(n_in_row))
 
+    def _p(self):
+        return C.byref(self._s)
+
     # -- configuration (Gomoku.h:21-28, 214-222) ---------------------------------------------------------------
     def set_params(self, board_size, n_in_row):
-        if board_size <= 0:
-            raise RuntimeError("board_size must be positive")
-        if n_in_row <= 1:
-            raise RuntimeError("n_in_row must be >= 2")
-        if n_in_row > board_size:
-            raise RuntimeError("n_in_row must be <= board size")
-        self._n, self._k = int(board_size), int(n_in_row)
-        self._b = np.zeros(self._n * self._n, np.int8)
-        self.reset()
+        _ck(_lib.lib().az_gomoku_set_params(self._p(), int(board_size), int(n_in_row)))
 
     def reset(self):
-        self._b[:] = 0
-        self._turn, self._pieces, self._last_action, self._last_player, self._winner, self._done = 1, 0, -1, 0, 0, False
+        _lib.lib().az_gomoku_reset(self._p())
 
-    board_size = property(lambda self: self._n)
-    rows = property(lambda self: self._n)
-    cols = property(lambda self: self._n)
-    n_in_row = property(lambda self: self._k)
-    action_size = property(lambda self: self._n * self._n)
+    board_size = property(lambda self: int(self._s.size))
+    rows = property(lambda self: int(self._s.size))
+    cols = property(lambda self: int(self._s.size))
+    n_in_row = property(lambda self: int(self._s.n_in_row))
+    action_size = property(lambda self: int(self._s.size) ** 2)
     num_symmetries = property(lambda self: 8)
 
     @property
     def turn(self):
-        return self._turn
+        return int(self._s.turn)
 
     @turn.setter
     def turn(self, t):
         if t != 1 and t != -1:
             raise RuntimeError("turn must be 1 or -1")
-        self._turn = int(t)
+        self._s.turn = int(t)
 
     @property
     def board(self):
-        return self._b.reshape(self._n, self._n).astype(np.float32)
+        n = self.board_size
+        out = np.empty((n, n), np.int8)
+        _lib.lib().az_gomoku_export(self._p(), out.ctypes.data_as(C.c_void_p))
+        return out.astype(np.float32)            # the reference returns a float32 copy (env_gomoku.h:30-44)
 
     @board.setter
     def board(self, arr):
         a = np.ascontiguousarray(arr, dtype=np.float32)
-        if a.ndim != 2 or a.shape != (self._n, self._n):
+        n = self.board_size
+        if a.ndim != 2 or a.shape != (n, n):
             raise RuntimeError("board shape does not match environment dimensions")
-        self._b = a.astype(np.int8).reshape(-1).copy()
-        self._sync_from_board()
-
-    def _sync_from_board(self):                                # Gomoku.h:160-204
-        b = self._b
-        if np.any((b != 0) & (b != 1) & (b != -1)):
-            raise RuntimeError("board values must be -1, 0, or 1")
-        p1, p2 = int(np.sum(b == 1)), int(np.sum(b == -1))
-        self._pieces = p1 + p2
-        nz = np.nonzero(b)[0]
-        self._last_action = int(nz[-1]) if nz.size else -1
-        self._last_player = int(b[nz[-1]]) if nz.size else 0
-        if p1 == p2:
-            self._turn = 1
-        elif p1 == p2 + 1:
-            self._turn = -1
-        else:
-            self._turn = 1 if self._pieces % 2 == 0 else -1
-        self._winner = 0
-        for i in nz:                                           # find_winner_full_scan (Gomoku.h:265-274)
-            if self._has_line_from(int(i), int(b[i])):
-                self._winner = int(b[i])
-                break
-        self._done = self._winner != 0 or self._pieces == self.action_size
-
-    def _count(self, r, c, dr, dc, player):
-        n, cnt = self._n, 0
-        r, c = r + dr, c + dc
-        while 0 <= r < n and 0 <= c < n and self._b[r * n + c] == player:
-            cnt += 1
-            r, c = r + dr, c + dc
-        return cnt
-
-    def _has_line_from(self, action, player):                  # Gomoku.h:247-263
-        r, c = divmod(action, self._n)
-        return any(1 + self._count(r, c, dr, dc, player) + self._count(r, c, -dr, -dc, player) >= self._k for dr, dc in self._DIRS)
+        b = np.ascontiguousarray(a.astype(np.int8))
+        _ck(_lib.lib().az_gomoku_import(self._p(), b.ctypes.data_as(C.c_void_p)))   # import_board + sync_from_board
 
     def step(self, action):                                    # Gomoku.h:63-92 (validated, unlike Connect4/Othello)
-        action = int(action)
-        if self._done:
-            raise RuntimeError("game is already finished")
-        if action < 0 or action >= self.action_size:
-            raise RuntimeError("action out of range")
-        if self._b[action] != 0:
-            raise RuntimeError("cell is already occupied")
-        self._b[action] = self._turn
-        self._pieces += 1
-        self._last_action, self._last_player = action, self._turn
-        if self._has_line_from(action, self._last_player):
-            self._winner, self._done = self._last_player, True
-        elif self._pieces == self.action_size:
-            self._winner, self._done = 0, True
-        self._turn = -self._turn
+        _ck(_lib.lib().az_gomoku_step(self._p(), int(action)))
 
     def step_xy(self, row, col):
         self.step(self.coord_to_action(row, col))
 
     def coord_to_action(self, row, col):
-        if not (0 <= row < self._n and 0 <= col < self._n):
+        n = self.board_size
+        if not (0 <= row < n and 0 <= col < n):
             raise RuntimeError("row/col out of range")
-        return row * self._n + col
+        return row * n + col
 
     def action_to_coord(self, action):
         if action < 0 or action >= self.action_size:
             raise RuntimeError("action out of range")
-        return (action // self._n, action % self._n)
+        return (action // self.board_size, action % self.board_size)
 
     def winPlayer(self):
-        return self._winner
+        return int(self._s.winner)
 
     check_winner = winPlayer
 
     def check_full(self):
-        return self._pieces == self.action_size
+        return int(self._s.n_pieces) == self.action_size
 
     def done(self):
-        return self._done
+        return bool(self._s.done)
 
     def valid_move(self):
-        return [int(i) for i in np.nonzero(self._b == 0)[0]]
+        m = np.empty(self.action_size, np.int32)
+        k = _lib.lib().az_gomoku_valid_moves(self._p(), m.ctypes.data_as(C.c_void_p))
+        return m[:k].tolist()
 
     def valid_mask(self):
-        return [bool(v) for v in (self._b == 0)]
+        return [bool(v) for v in (self.board.reshape(-1) == 0)]
 
     def current_state(self):
-        b, t = self.board, float(self._turn)
-        st = np.zeros((1, 3, self._n, self._n), np.float32)
+        b, t, n = self.board, float(self.turn), self.board_size
+        st = np.zeros((1, 3, n, n), np.float32)
         st[0, 0], st[0, 1], st[0, 2] = b == t, b == -t, t
         return st
 
     def copy(self):
         e = Env.__new__(Env)
-        e.__dict__.update(self.__dict__)
-        e._b = self._b.copy()
+        e._s = _lib.AzGomoku()
+        C.memmove(C.byref(e._s), self._p(), C.sizeof(_lib.AzGomoku))
         return e
-
-    def _xform(self, sym, r, c):                               # Gomoku.h:276-294
-        n = self._n
-        if sym < 0 or sym >= 8:
-            raise RuntimeError("invalid symmetry id")
-        return ((r, c), (c, n - 1 - r), (n - 1 - r, n - 1 - c), (n - 1 - c, r), (r, n - 1 - c), (n - 1 - r, c), (c, r),
-                (n - 1 - c, n - 1 - r))[sym]
 
     def apply_symmetry(self, sym_id, inplace=False):
         e = self if inplace else self.copy()
-        sym_id = int(sym_id)
-        if sym_id < 0 or sym_id >= 8:
-            raise RuntimeError("invalid symmetry id")
-        if sym_id == 0:
-            return e
-        n = e._n
-        old = e._b.reshape(n, n)
-        new = np.zeros_like(old)
-        rr, cc = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
-        nr, nc = e._xform(sym_id, rr, cc)
-        new[nr, nc] = old[rr, cc]
-        e._b = new.reshape(-1).copy()
-        if e._last_action >= 0:
-            r, c = divmod(e._last_action, n)
-            r2, c2 = e._xform(sym_id, r, c)
-            e._last_action = int(r2 * n + c2)
+        _ck(_lib.lib().az_gomoku_apply_symmetry(e._p(), int(sym_id)))
         return e
 
     def random_symmetry(self):
@@ -194,28 +140,29 @@ class Env:
         return self.apply_symmetry(sym), sym
 
     def inverse_symmetry_action(self, sym_id, action):         # Gomoku.h:115-128 (applies transform_coord(sym_id))
-        if action < 0 or action >= self.action_size:
-            raise RuntimeError("action out of range")
-        r, c = divmod(int(action), self._n)
-        r2, c2 = self._xform(int(sym_id), r, c)
-        return int(r2 * self._n + c2)
+        r = _lib.lib().az_gomoku_inverse_symmetry_action(self.board_size, int(sym_id), int(action))
+        if r < 0:
+            _ck(r)
+        return int(r)
 
     def show(self):
-        n = self._n
+        n = self.board_size
+        b = self.board.reshape(-1)
         lines = ["==============================", "    " + "".join(f"{c % 10} " for c in range(n))]
         for r in range(n):
-            row = "".join(("." if v == 0 else ("X" if v == 1 else "O")) + " " for v in self._b[r * n:(r + 1) * n])
+            row = "".join(("." if v == 0 else ("X" if v == 1 else "O")) + " " for v in b[r * n:(r + 1) * n])
             lines.append((" " if r < 10 else "") + f"{r}  " + row)
         lines.append("==============================")
         print("\n".join(lines))
 
     def __getstate__(self):                                     # pickle = (board, turn, n_in_row) (env_gomoku.h:151-168)
-        return (self.board, self._turn, self._k)
+        return (self.board, self.turn, self.n_in_row)
 
     def __setstate__(self, st):
         if len(st) != 3:
             raise RuntimeError("Invalid pickle state")
         a = np.asarray(st[0], dtype=np.float32)
+        self._s = _lib.AzGomoku()
         self.set_params(int(a.shape[0]), int(st[2]))
         self.board = a
         self.turn = int(st[1])

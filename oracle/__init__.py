@@ -60,7 +60,8 @@ def lib() -> C.CDLL:
         for name in ("orc_destroy", "orc_set_config", "orc_get_config", "orc_set_seed", "orc_reset_env",
                      "orc_prune_roots", "orc_search_batch", "orc_backprop_batch", "orc_remove_all_vl",
                      "orc_search_batch_vl", "orc_backprop_batch_vl", "orc_search", "orc_get_counts",
-                     "orc_get_root_stats", "orc_get_tree_stats"):
+                     "orc_get_root_stats", "orc_get_tree_stats", "orc_gmk_reset", "orc_gmk_symmetry", "orc_gmk_board",
+                     "orc_gmk_fields", "orc_gmk_rollout_digests"):
             getattr(_lib, name).restype = None
     return _lib
 
@@ -248,6 +249,85 @@ def env_rollout_digests(game: str, seed: int, first: int, n: int):
     dig = np.empty(n, np.uint64)
     pl = np.empty(n, np.int32)
     L.orc_env_rollout_digests(GAMES[game], C.c_uint64(seed), C.c_uint64(first), C.c_int(n), _p(dig), _p(pl))
+    return dig, pl
+
+
+class OracleGomoku:
+    """Single Gomoku game over the byte-board C restatement (checker for env_cpp.gomoku.Env and BatchedGomoku)."""
+
+    def __init__(self, size: int = 15, n_in_row: int = 5):
+        self.L = lib()
+        self.state = C.create_string_buffer(self.L.orc_gmk_sizeof())
+        if self.L.orc_gmk_set_params(self.state, C.c_int(size), C.c_int(n_in_row)) != 0:
+            raise RuntimeError("invalid Gomoku parameters")
+        self.size, self.k = size, n_in_row
+
+    def reset(self):
+        self.L.orc_gmk_reset(self.state)
+
+    def import_board(self, board):
+        b = np.ascontiguousarray(board, dtype=np.int8)
+        return self.L.orc_gmk_import(self.state, _p(b))
+
+    def step(self, a):
+        """0, or 1 / 2 / 3 = finished / out of range / occupied (the reference's three exceptions)."""
+        return self.L.orc_gmk_step(self.state, C.c_int(int(a)))
+
+    def valid_moves(self):
+        m = np.empty(self.size * self.size, np.int32)
+        n = self.L.orc_gmk_valid(self.state, _p(m))
+        return m[:n].tolist()
+
+    def apply_symmetry(self, s):
+        self.L.orc_gmk_symmetry(self.state, C.c_int(int(s)))
+
+    @property
+    def board(self):
+        out = np.empty((self.size, self.size), np.int8)
+        self.L.orc_gmk_board(self.state, _p(out))
+        return out
+
+    def _fields(self):
+        f = np.empty(6, np.int32)
+        self.L.orc_gmk_fields(self.state, _p(f))
+        return f
+
+    turn = property(lambda self: int(self._fields()[0]))
+    n_pieces = property(lambda self: int(self._fields()[1]))
+    last_action = property(lambda self: int(self._fields()[2]))
+
+    def winner(self):
+        return int(self._fields()[4])
+
+    def done(self):
+        return bool(self._fields()[5])
+
+
+def gomoku_rollout(size: int, n_in_row: int, seed: int, gidx: int, record: bool = True):
+    """Lockstep random rollout of one Gomoku game on the C restatement (twin of az_gomoku_rollout_dev)."""
+    L = lib()
+    S = size * size
+    digest = C.c_uint64(0)
+    final = np.zeros((size, size), np.int8)
+    if record:
+        boards = np.zeros((S, size, size), np.int8)
+        turns, actions, winners = (np.zeros(S, np.int32) for _ in range(3))
+        dones = np.zeros(S, np.uint8)
+        n = L.orc_gmk_rollout(size, n_in_row, C.c_uint64(seed), C.c_uint64(gidx), _p(boards), _p(turns), _p(actions),
+                              _p(winners), _p(dones), C.byref(digest), _p(final))
+        return dict(plies=n, boards=boards[:n], turns=turns[:n], actions=actions[:n], winners=winners[:n], dones=dones[:n],
+                    digest=digest.value, final=final)
+    n = L.orc_gmk_rollout(size, n_in_row, C.c_uint64(seed), C.c_uint64(gidx), None, None, None, None, None,
+                          C.byref(digest), _p(final))
+    return dict(plies=n, digest=digest.value, final=final)
+
+
+def gomoku_rollout_digests(size: int, n_in_row: int, seed: int, first: int, n: int):
+    """(digests uint64[n], plies int32[n]) of Gomoku rollout games [first, first+n) on the C restatement."""
+    L = lib()
+    dig = np.empty(n, np.uint64)
+    pl = np.empty(n, np.int32)
+    L.orc_gmk_rollout_digests(size, n_in_row, C.c_uint64(seed), C.c_uint64(first), C.c_int(n), _p(dig), _p(pl))
     return dig, pl
 
 

@@ -920,3 +920,156 @@ void orc_env_rollout_digests(int g, uint64_t seed, uint64_t first, int n, uint64
         if (plies) plies[i] = p;
     }
 }
+
+/* ============================================================================================================
+ * Gomoku (Env-only in the reference: src/cpp/Gomoku.h:11-296).  BYTE-BOARD restatement, deliberately in the
+ * reference's own representation - the product keeps row bit masks (alphazero-al_b200/csrc/az_gomoku.cu), so the
+ * two share no code.  Pinned against the compiled reference by tests/test_oracle_vs_ref.py.
+ * ============================================================================================================ */
+#define ORC_GMK_MAX 32
+typedef struct orc_gomoku {
+    int size, k;                                  /* board_size_, n_in_row_ */
+    int8_t board[ORC_GMK_MAX * ORC_GMK_MAX];
+    int turn, n_pieces, last_action, last_player, winner, done;
+} orc_gomoku;
+
+int orc_gmk_sizeof(void) { return (int)sizeof(orc_gomoku); }
+void orc_gmk_reset(orc_gomoku *e) {                           /* Gomoku.h:30-39 */
+    memset(e->board, 0, sizeof(e->board));
+    e->turn = 1; e->n_pieces = 0; e->last_action = -1; e->last_player = 0; e->winner = 0; e->done = 0;
+}
+int orc_gmk_set_params(orc_gomoku *e, int size, int k) {      /* Gomoku.h:21-28, 214-222 */
+    if (size <= 0 || k <= 1 || k > size || size > ORC_GMK_MAX) return -1;
+    e->size = size; e->k = k;
+    orc_gmk_reset(e);
+    return 0;
+}
+static int gmk_in_bounds(const orc_gomoku *e, int r, int c) { return r >= 0 && r < e->size && c >= 0 && c < e->size; }   /* :224-227 */
+static int gmk_count_direction(const orc_gomoku *e, int row, int col, int dr, int dc, int player) {   /* Gomoku.h:232-245 */
+    int count = 0, r = row + dr, c = col + dc;
+    while (gmk_in_bounds(e, r, c) && e->board[r * e->size + c] == player) { count++; r += dr; c += dc; }
+    return count;
+}
+static int gmk_has_line_from(const orc_gomoku *e, int action, int player) {   /* Gomoku.h:247-263 */
+    static const int DR[4] = {1, 0, 1, 1}, DC[4] = {0, 1, 1, -1};
+    const int row = action / e->size, col = action % e->size;
+    for (int i = 0; i < 4; ++i) {
+        int fwd = gmk_count_direction(e, row, col, DR[i], DC[i], player);
+        int bwd = gmk_count_direction(e, row, col, -DR[i], -DC[i], player);
+        if (1 + fwd + bwd >= e->k) return 1;
+    }
+    return 0;
+}
+int orc_gmk_step(orc_gomoku *e, int action) {                 /* Gomoku.h:63-92; 1/2/3 = the three exceptions */
+    const int S = e->size * e->size;
+    if (e->done) return 1;
+    if (action < 0 || action >= S) return 2;
+    if (e->board[action] != 0) return 3;
+    e->board[action] = (int8_t)e->turn;
+    e->n_pieces++;
+    e->last_action = action;
+    e->last_player = e->turn;
+    if (gmk_has_line_from(e, action, e->last_player)) { e->winner = e->last_player; e->done = 1; }
+    else if (e->n_pieces == S) { e->winner = 0; e->done = 1; }
+    e->turn = -e->turn;
+    return 0;
+}
+int orc_gmk_import(orc_gomoku *e, const int8_t *src) {        /* import_board + sync_from_board: Gomoku.h:57-61,160-204 */
+    const int S = e->size * e->size;
+    int p1 = 0, p2 = 0;
+    memcpy(e->board, src, (size_t)S);
+    e->n_pieces = 0; e->last_action = -1; e->last_player = 0; e->winner = 0; e->done = 0;
+    for (int i = 0; i < S; ++i) {
+        int8_t v = e->board[i];
+        if (v == 1) { p1++; e->n_pieces++; e->last_action = i; e->last_player = 1; }
+        else if (v == -1) { p2++; e->n_pieces++; e->last_action = i; e->last_player = -1; }
+        else if (v != 0) return 7;
+    }
+    if (p1 == p2) e->turn = 1;
+    else if (p1 == p2 + 1) e->turn = -1;
+    else e->turn = (e->n_pieces % 2 == 0) ? 1 : -1;
+    for (int i = 0; i < S; ++i) {                             /* find_winner_full_scan: Gomoku.h:265-274 */
+        int8_t v = e->board[i];
+        if (v != 0 && gmk_has_line_from(e, i, v)) { e->winner = v; break; }
+    }
+    e->done = (e->winner != 0) || (e->n_pieces == S);
+    return 0;
+}
+int orc_gmk_valid(const orc_gomoku *e, int32_t *moves) {      /* Gomoku.h:99-107 */
+    int n = 0;
+    for (int i = 0; i < e->size * e->size; ++i) if (e->board[i] == 0) moves[n++] = i;
+    return n;
+}
+static void gmk_transform(int sym, int n, int r, int c, int *nr, int *nc) {   /* Gomoku.h:276-294 */
+    switch (sym) {
+        case 0: *nr = r; *nc = c; break;
+        case 1: *nr = c; *nc = n - 1 - r; break;
+        case 2: *nr = n - 1 - r; *nc = n - 1 - c; break;
+        case 3: *nr = n - 1 - c; *nc = r; break;
+        case 4: *nr = r; *nc = n - 1 - c; break;
+        case 5: *nr = n - 1 - r; *nc = c; break;
+        case 6: *nr = c; *nc = r; break;
+        default: *nr = n - 1 - c; *nc = n - 1 - r; break;
+    }
+}
+void orc_gmk_symmetry(orc_gomoku *e, int sym) {               /* Gomoku.h:130-158 */
+    if (sym <= 0 || sym >= 8) return;
+    const int n = e->size;
+    int8_t nb[ORC_GMK_MAX * ORC_GMK_MAX];
+    memset(nb, 0, sizeof(nb));
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) {
+            int nr, nc; gmk_transform(sym, n, r, c, &nr, &nc);
+            nb[nr * n + nc] = e->board[r * n + c];
+        }
+    memcpy(e->board, nb, (size_t)(n * n));
+    if (e->last_action >= 0) {
+        int nr, nc; gmk_transform(sym, n, e->last_action / n, e->last_action % n, &nr, &nc);
+        e->last_action = nr * n + nc;
+    }
+}
+void orc_gmk_board(const orc_gomoku *e, int8_t *out) { memcpy(out, e->board, (size_t)(e->size * e->size)); }
+void orc_gmk_fields(const orc_gomoku *e, int32_t *out) {      /* turn, n_pieces, last_action, last_player, winner, done */
+    out[0] = e->turn; out[1] = e->n_pieces; out[2] = e->last_action; out[3] = e->last_player; out[4] = e->winner; out[5] = e->done;
+}
+static uint64_t gmk_digest(const orc_gomoku *e, int plies) {
+    uint64_t d = 0x9E3779B97F4A7C15ULL;
+    for (int r = 0; r < e->size; ++r) {
+        uint64_t lo = 0, hi = 0;
+        for (int c = 0; c < e->size; ++c) {
+            if (e->board[r * e->size + c] == 1) lo |= 1ULL << c;
+            else if (e->board[r * e->size + c] == -1) hi |= 1ULL << c;
+        }
+        d = splitmix64(d ^ ((hi << 32) | lo));
+    }
+    return splitmix64(d ^ (uint64_t)(uint32_t)(e->winner + 1) ^ ((uint64_t)plies << 8) ^ ((uint64_t)(uint32_t)(e->turn + 1) << 20));
+}
+/* lockstep random rollout of game gidx: the (hash mod #legal)-th legal move in ascending order until the game is over;
+ * boards [plies, S*S] / turns / actions recorded BEFORE each move, winners / dones AFTER it (any may be NULL together) */
+int orc_gmk_rollout(int size, int k, uint64_t seed, uint64_t gidx, int8_t *boards, int32_t *turns, int32_t *actions,
+                    int32_t *winners, uint8_t *dones, uint64_t *digest, int8_t *final_board) {
+    orc_gomoku e;
+    if (orc_gmk_set_params(&e, size, k)) return -1;
+    const int S = size * size;
+    int32_t moves[ORC_GMK_MAX * ORC_GMK_MAX];
+    int ply = 0;
+    while (!e.done) {
+        int n = orc_gmk_valid(&e, moves);
+        int a = moves[orc_rollout_hash(seed, gidx, (uint64_t)ply) % (uint64_t)n];
+        if (boards) { memcpy(boards + (size_t)ply * S, e.board, (size_t)S); turns[ply] = e.turn; actions[ply] = a; }
+        orc_gmk_step(&e, a);
+        if (boards) { winners[ply] = e.winner; dones[ply] = (uint8_t)e.done; }
+        ply++;
+    }
+    if (digest) *digest = gmk_digest(&e, ply);
+    if (final_board) memcpy(final_board, e.board, (size_t)S);
+    return ply;
+}
+void orc_gmk_rollout_digests(int size, int k, uint64_t seed, uint64_t first, int n, uint64_t *digests, int32_t *plies) {
+    for (int i = 0; i < n; ++i) {
+        uint64_t d = 0;
+        int p = orc_gmk_rollout(size, k, seed, first + (uint64_t)i, NULL, NULL, NULL, NULL, NULL, &d, NULL);
+        digests[i] = d;
+        if (plies) plies[i] = p;
+    }
+}

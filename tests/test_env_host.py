@@ -73,8 +73,8 @@ def test_env_differential_vs_reference_objects(game):
 def test_gomoku_differential_vs_reference():
     _, ref_env = oracle.load_ref("parity")
     rng = np.random.default_rng(5)
-    for size, k in ((15, 5), (9, 5), (6, 4), (3, 3)):
-        for g in range(8):
+    for size, k, games in ((15, 5, 8), (9, 5, 8), (6, 4, 8), (3, 3, 8), (19, 6, 2), (32, 5, 1), (2, 2, 2)):
+        for g in range(games):
             r, m = ref_env.gomoku.Env(size, k), env_cpp.gomoku.Env(size, k)
             assert (r.board_size, r.rows, r.cols, r.n_in_row, r.action_size, r.num_symmetries) == \
                    (m.board_size, m.rows, m.cols, m.n_in_row, m.action_size, m.num_symmetries)
@@ -105,6 +105,28 @@ def test_gomoku_differential_vs_reference():
     assert tuple(ref_env.gomoku.Env(9, 5).action_to_coord(21)) == env_cpp.gomoku.Env(9, 5).action_to_coord(21)
     with pytest.raises(RuntimeError):
         env_cpp.gomoku.Env(4, 5)
+    # imported boards nobody could have played: unequal stone counts, several lines of both colours (turn inference
+    # Gomoku.h:194-199, first line in scan order wins :265-274), and cell values outside {-1, 0, 1}
+    for size, k in ((8, 4), (15, 5), (5, 3)):
+        for g in range(40):
+            b = rng.choice(np.array([-1, 0, 1], np.float32), size=(size, size), p=(0.3 + 0.1 * (g % 3), 0.3, 0.4 - 0.1 * (g % 3)))
+            r, m = ref_env.gomoku.Env(b, k), env_cpp.gomoku.Env(b, k)
+            assert (r.turn, r.done(), r.winPlayer(), r.check_full()) == (m.turn, m.done(), m.winPlayer(), m.check_full())
+            assert np.array_equal(np.asarray(r.board), m.board) and r.valid_move() == m.valid_move()
+            for s in (1, 6):
+                rs, ms = r.apply_symmetry(s), m.apply_symmetry(s)
+                assert np.array_equal(np.asarray(rs.board), ms.board) and rs.winPlayer() == ms.winPlayer()
+    bad = np.zeros((6, 6), np.float32)
+    bad[2, 3] = 2
+    for mod in (ref_env.gomoku, env_cpp.gomoku):
+        with pytest.raises(RuntimeError):
+            mod.Env(bad, 4)
+        with pytest.raises(RuntimeError):
+            mod.Env(6, 4).apply_symmetry(8)
+        with pytest.raises(RuntimeError):
+            mod.Env(6, 4).inverse_symmetry_action(-1, 0)
+    with pytest.raises(RuntimeError):
+        env_cpp.gomoku.Env(33, 5)                     # this implementation's limit (32-bit row masks)
 
 
 def test_gomoku_basics_without_reference():
@@ -116,6 +138,29 @@ def test_gomoku_basics_without_reference():
         e.step(20)
     e2 = pickle.loads(pickle.dumps(e))
     assert e2.done() and e2.winPlayer() == 1 and np.array_equal(e2.board, e.board)
+
+
+@pytest.mark.parametrize("size,k", [(15, 5), (8, 4), (32, 5), (4, 4)])
+def test_gomoku_env_matches_restatement_on_rollouts(size, k):
+    """env_cpp.gomoku.Env (row bit masks, C ABI host functions - the code the device kernels share) vs the byte-board
+    restatement; runs without the compiled reference."""
+    for g in range(6):
+        o = oracle.gomoku_rollout(size, k, 9, g)
+        m = env_cpp.gomoku.Env(size, k)
+        for ply in range(o["plies"]):
+            assert np.array_equal(m.board.astype(np.int8), o["boards"][ply]) and m.turn == o["turns"][ply]
+            m.step(int(o["actions"][ply]))
+            assert m.winPlayer() == o["winners"][ply] and m.done() == bool(o["dones"][ply])
+        assert m.done() and np.array_equal(m.board.astype(np.int8), o["final"])
+        for s in range(8):
+            e = oracle.OracleGomoku(size, k)
+            e.import_board(o["final"])
+            e.apply_symmetry(s)
+            ms = m.apply_symmetry(s)
+            assert np.array_equal(ms.board.astype(np.int8), e.board)
+            m2 = env_cpp.gomoku.Env(ms.board, k)               # fresh import of the transformed final board
+            assert e.import_board(e.board) == 0
+            assert (m2.turn, m2.done(), m2.winPlayer()) == (e.turn, e.done(), e.winner())
 
 
 @pytest.mark.parametrize("game", ["Connect4", "Othello"])

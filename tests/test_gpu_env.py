@@ -93,3 +93,81 @@ def test_env_states_feed_the_search_directly():
     ds.playout_device(b, buf, 60, 4, ds.SyntheticEvaluator("Connect4", "hash"))
     torch.cuda.synchronize()
     assert np.array_equal(counts(a, n, 7), counts(b, n, 7))
+
+
+# ---- Gomoku (Env-only in the reference, src/cpp/Gomoku.h): lockstep device kernels vs the byte-board restatement ----
+@pytest.mark.parametrize("size,k,n_rec", [(15, 5, 192), (9, 4, 256), (32, 5, 8), (3, 3, 64), (6, 6, 64)])
+def test_gomoku_recorded_rollouts_match_restatement_per_ply(size, k, n_rec):
+    import torch
+    be = env_cpp.BatchedGomoku(n_rec + 37, size, k)              # ragged tail: 37 unrecorded games
+    digest, plies, rec = be.random_rollouts(seed=3, first_game=5, n_record=n_rec)
+    torch.cuda.synchronize()
+    rec = {kk: v.cpu().numpy() for kk, v in rec.items()}
+    plies, digest = plies.cpu().numpy(), digest.cpu().numpy().view(np.uint64)
+    obs = {kk: v.cpu().numpy() for kk, v in be.observe().items()}
+    for g in range(n_rec + 37):
+        o = oracle.gomoku_rollout(size, k, 3, 5 + g, record=g < n_rec)
+        n = o["plies"]
+        assert plies[g] == n and digest[g] == o["digest"]
+        assert np.array_equal(obs["boards"][g], o["final"]) and obs["dones"][g] == 1
+        assert np.array_equal(obs["masks"][g], (o["final"].reshape(-1) == 0).astype(np.uint8))
+        if g < n_rec:
+            assert np.array_equal(rec["boards"][g, :n], o["boards"]) and np.array_equal(rec["turns"][g, :n], o["turns"])
+            assert np.array_equal(rec["actions"][g, :n], o["actions"]) and np.array_equal(rec["winners"][g, :n], o["winners"])
+            assert np.array_equal(rec["dones"][g, :n], o["dones"]) and obs["winners"][g] == o["winners"][-1]
+
+
+def test_gomoku_256k_games_checksum():
+    import torch
+    n = 262_144
+    be = env_cpp.BatchedGomoku(n, 15, 5)
+    digest, plies, _ = be.random_rollouts(seed=1, first_game=0, keep_final=False)
+    torch.cuda.synchronize()
+    d, p = digest.cpu().numpy().view(np.uint64), plies.cpu().numpy()
+    od, op = oracle.gomoku_rollout_digests(15, 5, 1, 0, n)
+    assert np.array_equal(p, op) and np.array_equal(d, od)
+    assert int(np.bitwise_xor.reduce(d)) == int(np.bitwise_xor.reduce(od))
+    assert 9 <= p.min() and p.max() <= 225
+
+
+@pytest.mark.parametrize("size,k", [(15, 5), (7, 4), (32, 6)])
+def test_gomoku_lockstep_step_observe_symmetry(size, k):
+    import torch
+    n = 200
+    be = env_cpp.BatchedGomoku(n, size, k)
+    envs = [oracle.OracleGomoku(size, k) for _ in range(n)]
+    rng = np.random.default_rng(4)
+    status = torch.zeros(n, dtype=torch.uint8, device=be.device)
+    winners = torch.zeros(n, dtype=torch.int32, device=be.device)
+    dones = torch.zeros(n, dtype=torch.uint8, device=be.device)
+    for ply in range(size * size + 2):
+        obs = {kk: v.cpu().numpy() for kk, v in be.observe().items()}
+        acts = np.full(n, -1, np.int32)
+        want = np.zeros(n, np.uint8)
+        for i, e in enumerate(envs):
+            assert np.array_equal(obs["boards"][i], e.board) and obs["turns"][i] == e.turn
+            assert bool(obs["dones"][i]) == e.done() and obs["winners"][i] == e.winner()
+            if e.done():
+                acts[i] = 0 if i % 2 else -1                     # finished games are skipped whatever the action
+                continue
+            mv = e.valid_moves()
+            roll = rng.random()
+            if roll < 0.05 and e.n_pieces:                        # occupied cell: reported, game untouched
+                acts[i], want[i] = e.last_action, 3
+            elif roll < 0.08:                                     # out of range
+                acts[i], want[i] = size * size + int(rng.integers(0, 5)), 2
+            else:
+                acts[i] = mv[int(rng.integers(0, len(mv)))]
+                assert e.step(int(acts[i])) == 0
+        if all(e.done() for e in envs):
+            break
+        be.step(torch.from_numpy(acts).to(be.device), status, winners, dones)
+        assert np.array_equal(status.cpu().numpy(), want)
+        assert np.array_equal(winners.cpu().numpy(), [e.winner() for e in envs])
+        assert np.array_equal(dones.cpu().numpy(), [int(e.done()) for e in envs])
+        if ply % 16 == 5:                                         # D4 symmetries on the device (ids outside 1..7 = no-op)
+            syms = rng.integers(-1, 9, n).astype(np.int32)
+            be.apply_symmetry(torch.from_numpy(syms).to(be.device))
+            for e, s in zip(envs, syms):
+                e.apply_symmetry(int(s))
+    assert all(e.done() for e in envs)

@@ -118,3 +118,42 @@ def test_env_random_games_match_reference_env():
                 os_.import_board(o.board, o.turn)
                 os_.apply_symmetry(s)
                 assert np.array_equal(np.asarray(rs.board).astype(np.int8), os_.board)
+
+
+def test_gomoku_restatement_vs_reference_env():
+    """Byte-board Gomoku restatement vs the compiled reference Env (src/cpp/Gomoku.h): recorded rollouts replayed move by
+    move, imports of unplayable boards (turn inference, full-scan winner), the D4 symmetries, and the three step errors."""
+    _, ref_env = oracle.load_ref("parity")
+    for size, k, games in ((15, 5, 12), (9, 4, 12), (6, 6, 6), (19, 5, 3), (32, 5, 1), (3, 3, 12)):
+        for g in range(games):
+            o = oracle.gomoku_rollout(size, k, 7, g)
+            r = ref_env.gomoku.Env(size, k)
+            e = oracle.OracleGomoku(size, k)
+            for ply in range(o["plies"]):
+                assert np.array_equal(np.asarray(r.board).astype(np.int8), o["boards"][ply]) and r.turn == o["turns"][ply]
+                a = int(o["actions"][ply])
+                mv = r.valid_move()
+                assert mv == e.valid_moves() and a == mv[oracle.lib().orc_rollout_hash(7, g, ply) % len(mv)]
+                r.step(a)
+                assert e.step(a) == 0
+                assert r.winPlayer() == o["winners"][ply] == e.winner() and r.done() == bool(o["dones"][ply]) == e.done()
+            assert r.done() and np.array_equal(np.asarray(r.board).astype(np.int8), o["final"])
+            assert e.step(0) == 1
+            for s in range(8):
+                e2 = oracle.OracleGomoku(size, k)
+                e2.import_board(o["final"])
+                e2.apply_symmetry(s)
+                assert np.array_equal(np.asarray(r.apply_symmetry(s).board).astype(np.int8), e2.board)
+    rng = np.random.default_rng(11)
+    for size, k in ((8, 4), (15, 5), (5, 3)):
+        for g in range(60):
+            b = rng.choice(np.array([-1, 0, 1], np.int8), size=(size, size), p=(0.3 + 0.1 * (g % 3), 0.3, 0.4 - 0.1 * (g % 3)))
+            r = ref_env.gomoku.Env(b.astype(np.float32), k)
+            e = oracle.OracleGomoku(size, k)
+            assert e.import_board(b) == 0
+            assert (r.turn, r.done(), r.winPlayer()) == (e.turn, e.done(), e.winner())
+    e = oracle.OracleGomoku(5, 3)
+    assert e.step(-1) == 2 and e.step(25) == 2 and e.step(3) == 0 and e.step(3) == 3
+    bad = np.zeros((5, 5), np.int8)
+    bad[1, 1] = 3
+    assert e.import_board(bad) == 7
