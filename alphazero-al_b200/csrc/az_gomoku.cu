@@ -174,22 +174,48 @@ __global__ void k_gmk_step(int n, az_gomoku *st, const int32_t *__restrict__ act
     if (winners) winners[i] = m.winner;
     if (dones) dones[i] = (uint8_t)m.done;
 }
-// one thread per (game, cell): coalesced byte-board / mask stores
+// one thread per 16 consecutive cells of the flat [n, S*S] outputs (a chunk may straddle two games): 128-bit stores for
+// boards and masks, each row mask loaded once per row; thread t < n also writes the per-game scalars
 __global__ void k_gmk_observe(int n, int size, const az_gomoku *__restrict__ st, int8_t *boards, uint8_t *masks, int32_t *turns,
                               int32_t *winners, uint8_t *dones) {
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const int S = size * size;
-    if (t >= (size_t)n * S) return;
-    const size_t g = t / S; const int j = (int)(t - g * S);
-    const az_gomoku *s = st + g;
-    const int r = j / size, c = j % size;
-    const int v = (int)((s->rows[0][r] >> c) & 1u) - (int)((s->rows[1][r] >> c) & 1u);
-    if (boards) boards[t] = (int8_t)v;
-    if (masks) masks[t] = v == 0 ? 1 : 0;
-    if (j == 0) {
-        if (turns) turns[g] = s->turn;
-        if (winners) winners[g] = s->winner;
-        if (dones) dones[g] = (uint8_t)s->done;
+    const size_t total = (size_t)n * S;
+    if (t < (size_t)n) {
+        const az_gomoku *s = st + t;
+        if (turns) turns[t] = s->turn;
+        if (winners) winners[t] = s->winner;
+        if (dones) dones[t] = (uint8_t)s->done;
+    }
+    const size_t idx = t * 16;
+    if (idx >= total || (!boards && !masks)) return;
+    size_t g = idx / S;
+    const int j = (int)(idx - g * S);
+    int r = j / size, c = j % size;
+    uint32_t w0 = st[g].rows[0][r], w1 = st[g].rows[1][r];
+    const int cnt = total - idx < 16 ? (int)(total - idx) : 16;
+    uint32_t bw[4] = {0, 0, 0, 0}, mw[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        if (q < cnt) {
+            const int v = (int)((w0 >> c) & 1u) - (int)((w1 >> c) & 1u);
+            bw[q >> 2] |= ((uint32_t)v & 0xFFu) << ((q & 3) * 8);
+            mw[q >> 2] |= (v == 0 ? 1u : 0u) << ((q & 3) * 8);
+            if (++c == size) {
+                c = 0;
+                if (++r == size) { r = 0; ++g; }
+                if (q + 1 < cnt) { w0 = st[g].rows[0][r]; w1 = st[g].rows[1][r]; }
+            }
+        }
+    }
+    if (cnt == 16) {
+        if (boards) *reinterpret_cast<uint4 *>(boards + idx) = make_uint4(bw[0], bw[1], bw[2], bw[3]);
+        if (masks) *reinterpret_cast<uint4 *>(masks + idx) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+    } else {
+        for (int q = 0; q < cnt; ++q) {
+            if (boards) boards[idx + q] = (int8_t)((bw[q >> 2] >> ((q & 3) * 8)) & 0xFFu);
+            if (masks) masks[idx + q] = (uint8_t)((mw[q >> 2] >> ((q & 3) * 8)) & 0xFFu);
+        }
     }
 }
 __global__ void k_gmk_symmetry(int n, az_gomoku *st, const int32_t *__restrict__ syms) {
@@ -331,8 +357,10 @@ int az_gomoku_observe_dev(int n, int size, const az_gomoku *st, int8_t *boards, 
                           uint8_t *dones, void *stream) {
     if (size <= 0 || size > AZ_GOMOKU_MAX_SIZE) return AZ_ERR_INVALID;
     if (n <= 0) return AZ_OK;
-    const size_t cells = (size_t)n * size * size;
-    k_gmk_observe<<<(unsigned)((cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, size, st, boards, masks, turns, winners, dones);
+    if ((((uintptr_t)boards) | ((uintptr_t)masks)) & 15u) return AZ_ERR_INVALID;      /* 128-bit stores */
+    const size_t chunks = ((size_t)n * size * size + 15) / 16;
+    const size_t threads = chunks > (size_t)n ? chunks : (size_t)n;
+    k_gmk_observe<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, size, st, boards, masks, turns, winners, dones);
     AZ_GMK_DONE();
 }
 int az_gomoku_symmetry_dev(int n, az_gomoku *st, const int32_t *syms, void *stream) {

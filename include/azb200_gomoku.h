@@ -61,8 +61,8 @@ int az_gomoku_reset_dev(int n, int board_size, int n_in_row, az_gomoku *d_states
 int az_gomoku_step_dev(int n, az_gomoku *d_states, const int32_t *d_actions, uint8_t *d_status, int32_t *d_winners,
                        uint8_t *d_dones, void *stream);
 /* byte boards int8[n,S*S], legal masks u8[n,S*S] (= empty cells, also after the game is over, like valid_mask of
- * env_gomoku.h:118-125), turns i32[n], winners i32[n], dones u8[n]; any pointer may be NULL.  board_size = the size all n
- * games were reset with. */
+ * env_gomoku.h:118-125), turns i32[n], winners i32[n], dones u8[n]; any pointer may be NULL; d_boards / d_masks must be
+ * 16-byte aligned (128-bit stores).  board_size = the size all n games were reset with. */
 int az_gomoku_observe_dev(int n, int board_size, const az_gomoku *d_states, int8_t *d_boards, uint8_t *d_masks, int32_t *d_turns,
                           int32_t *d_winners, uint8_t *d_dones, void *stream);
 /* D4 symmetry sym_ids[i] applied to game i (apply_symmetry, Gomoku.h:130-158); an invalid id leaves the game untouched */

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 env_cpp = importlib.import_module("alphazero-al_b200.env_cpp")
 
 
-@pytest.mark.parametrize("game,n_rec", [("Connect4", 4096), ("Othello", 1024)])
+@pytest.mark.parametrize("game,n_rec", [("Connect4", 10240), ("Othello", 1024)])
 def test_recorded_rollouts_match_restatement_per_ply(game, n_rec):
     import torch
     be = env_cpp.BatchedEnv(game, n_rec)
@@ -117,9 +117,9 @@ def test_gomoku_recorded_rollouts_match_restatement_per_ply(size, k, n_rec):
             assert np.array_equal(rec["dones"][g, :n], o["dones"]) and obs["winners"][g] == o["winners"][-1]
 
 
-def test_gomoku_256k_games_checksum():
+def test_gomoku_128k_games_checksum():
     import torch
-    n = 262_144
+    n = 131_072
     be = env_cpp.BatchedGomoku(n, 15, 5)
     digest, plies, _ = be.random_rollouts(seed=1, first_game=0, keep_final=False)
     torch.cuda.synchronize()
