@@ -55,8 +55,8 @@ template <class R> AZ_HD int gmk_count_dir(const R &b, int size, int row, int co
     return count;
 }
 // has_line_from: Gomoku.h:247-263 (directions in the reference's order: vertical, horizontal, diagonal, anti-diagonal)
-template <class R> AZ_HD bool gmk_has_line_from(const R &b, int size, int k, int action, int player) {
-    const int row = action / size, col = action % size, p = gmk_pidx(player);
+template <class R> AZ_HD bool gmk_has_line_rc(const R &b, int size, int k, int row, int col, int player) {
+    const int p = gmk_pidx(player);
     const int DR[4] = {1, 0, 1, 1}, DC[4] = {0, 1, 1, -1};
     for (int i = 0; i < 4; ++i) {
         const int f = gmk_count_dir(b, size, row, col, DR[i], DC[i], p);
@@ -65,36 +65,48 @@ template <class R> AZ_HD bool gmk_has_line_from(const R &b, int size, int k, int
     }
     return false;
 }
+template <class R> AZ_HD bool gmk_has_line_from(const R &b, int size, int k, int action, int player) {
+    return gmk_has_line_rc(b, size, k, action / size, action % size, player);
+}
 // step: Gomoku.h:63-92 (validated, unlike Connect4 / Othello); returns 0 or the status of the exception the reference throws
-template <class R> AZ_HD int gmk_step(R &b, GmkMeta &m, int action) {
+// (row, col) = action / size, action % size, passed in by callers that know them (runtime divisions are ~30 instructions each)
+template <class R> AZ_HD int gmk_step_rc(R &b, GmkMeta &m, int action, int row, int col) {
     if (m.done) return AZ_GOMOKU_FINISHED;
     if (action < 0 || action >= m.size * m.size) return AZ_GOMOKU_OUT_OF_RANGE;
-    const int row = action / m.size, col = action % m.size;
     if (((b.get(0, row) | b.get(1, row)) >> col) & 1u) return AZ_GOMOKU_OCCUPIED;
     const int p = gmk_pidx(m.turn);
     b.set(p, row, b.get(p, row) | (1u << col));
     m.n_pieces++;
     m.last_action = action;
     m.last_player = m.turn;
-    if (gmk_has_line_from(b, m.size, m.k, action, m.last_player)) { m.winner = m.last_player; m.done = 1; }
+    if (gmk_has_line_rc(b, m.size, m.k, row, col, m.last_player)) { m.winner = m.last_player; m.done = 1; }
     else if (m.n_pieces == m.size * m.size) { m.winner = 0; m.done = 1; }
     m.turn = -m.turn;
     return 0;
 }
+template <class R> AZ_HD int gmk_step(R &b, GmkMeta &m, int action) {
+    if (action < 0 || action >= m.size * m.size) return m.done ? AZ_GOMOKU_FINISHED : AZ_GOMOKU_OUT_OF_RANGE;
+    return gmk_step_rc(b, m, action, action / m.size, action % m.size);
+}
 // the idx-th empty cell in ascending action order (get_valid_moves()[idx], Gomoku.h:99-107) without building the list
-template <class R> AZ_HD int gmk_nth_empty(const R &b, int size, int idx) {
+template <class R> AZ_HD int gmk_nth_empty(const R &b, int size, int idx, int &row, int &col) {
     const uint32_t full = size == 32 ? 0xFFFFFFFFu : ((1u << size) - 1u);
     for (int r = 0; r < size; ++r) {
         uint32_t e = ~(b.get(0, r) | b.get(1, r)) & full;
         const int c = popc32(e);
         if (idx < c) {
             for (int i = 0; i < idx; ++i) e &= e - 1;
-            return r * size + ctz32(e);
+            row = r; col = ctz32(e);
+            return r * size + col;
         }
         idx -= c;
     }
+    row = col = -1;
     return -1;
 }
+// rollout policy: index of the move among the n legal ones = high half of the 64-bit hash scaled to [0, n) (one wide
+// multiply; a 64-bit modulo by a runtime value costs ~150 instructions on the device).  Twin: orc_gmk_pick.
+AZ_HD int gmk_pick(uint64_t h, int n) { return (int)(((h >> 32) * (uint64_t)(uint32_t)n) >> 32); }
 // transform_coord: Gomoku.h:276-294 (full D4 group of the square board)
 AZ_HD void gmk_xform(int sym, int n, int r, int c, int &nr, int &nc) {
     switch (sym) {
@@ -225,27 +237,30 @@ __global__ void k_gmk_symmetry(int n, az_gomoku *st, const int32_t *__restrict__
     if (sym <= 0 || sym >= 8) return;
     gmk_symmetry(st + i, sym);
 }
-// one thread per game; the row masks live in shared memory for the whole game (2*size words per thread, bank = thread)
+// one thread per game; the row masks live in shared memory for the whole game (2*size words per thread, bank = thread).
+// (Tried: a block-local queue from which a lane whose game is over takes the next one, 2..8 games per lane - 4.69..5.2 ms
+// against 4.72 ms for 1 M games: the warp instructions go to the divergent row / ray walks inside a ply, not to idle tails.)
 __global__ void k_gmk_rollout(int n, int size, int k, uint64_t seed, uint64_t first, uint64_t *digest, int32_t *plies, int nrec,
                               int8_t *rb, int32_t *rt, int32_t *ra, int32_t *rw, uint8_t *rd, az_gomoku *fin) {
     extern __shared__ uint32_t sh_rows[];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
     RowsShared b{sh_rows + threadIdx.x, size, (int)blockDim.x};
     for (int w = 0; w < 2 * size; ++w) sh_rows[w * blockDim.x + threadIdx.x] = 0;
-    if (i >= n) return;
     const uint64_t g = first + (uint64_t)i;
     const int S = size * size;
     GmkMeta m; m.size = size; m.k = k; gmk_reset_meta(m);
     const bool rec = i < nrec;
     int ply = 0;
     while (!m.done) {
-        const int a = gmk_nth_empty(b, size, (int)(rollout_hash(seed, g, (uint64_t)ply) % (uint64_t)(S - m.n_pieces)));
+        int row, col;
+        const int a = gmk_nth_empty(b, size, gmk_pick(rollout_hash(seed, g, (uint64_t)ply), S - m.n_pieces), row, col);
         const size_t o = (size_t)i * S + ply;
         if (rec) {
             for (int j = 0; j < S; ++j) rb[o * S + j] = (int8_t)gmk_cell(b, j / size, j % size);
             rt[o] = m.turn; ra[o] = a;
         }
-        gmk_step(b, m, a);
+        gmk_step_rc(b, m, a, row, col);
         if (rec) { rw[o] = m.winner; rd[o] = (uint8_t)m.done; }
         ++ply;
     }

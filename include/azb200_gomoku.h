@@ -68,7 +68,7 @@ int az_gomoku_observe_dev(int n, int board_size, const az_gomoku *d_states, int8
 /* D4 symmetry sym_ids[i] applied to game i (apply_symmetry, Gomoku.h:130-158); an invalid id leaves the game untouched */
 int az_gomoku_symmetry_dev(int n, az_gomoku *d_states, const int32_t *d_sym_ids, void *stream);
 /* Lockstep random rollouts (the Gomoku twin of az_envs_rollout_dev): game g = first_game + i plays the
- * (hash(seed, g, ply) mod #empty)-th empty cell in ascending action order from the empty board until it is over.
+ * ((hash(seed, g, ply) >> 32) * #empty >> 32)-th empty cell in ascending action order from the empty board until it is over.
  * d_digest[i] = checksum of the final state, d_plies[i] = game length.  When n_record > 0 the first n_record games also
  * record, per ply, the byte board and turn BEFORE the move, the action, and winner / done AFTER it, into arrays shaped
  * [n_record, S*S, ...] (S*S = the longest possible game).  d_final (optional) receives the final az_gomoku records. */

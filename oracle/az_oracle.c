@@ -1044,7 +1044,8 @@ static uint64_t gmk_digest(const orc_gomoku *e, int plies) {
     }
     return splitmix64(d ^ (uint64_t)(uint32_t)(e->winner + 1) ^ ((uint64_t)plies << 8) ^ ((uint64_t)(uint32_t)(e->turn + 1) << 20));
 }
-/* lockstep random rollout of game gidx: the (hash mod #legal)-th legal move in ascending order until the game is over;
+int orc_gmk_pick(uint64_t h, int n) { return (int)(((h >> 32) * (uint64_t)(uint32_t)n) >> 32); }   /* high half scaled to [0, n) */
+/* lockstep random rollout of game gidx: the orc_gmk_pick(hash, #legal)-th legal move in ascending order until the game is over;
  * boards [plies, S*S] / turns / actions recorded BEFORE each move, winners / dones AFTER it (any may be NULL together) */
 int orc_gmk_rollout(int size, int k, uint64_t seed, uint64_t gidx, int8_t *boards, int32_t *turns, int32_t *actions,
                     int32_t *winners, uint8_t *dones, uint64_t *digest, int8_t *final_board) {
@@ -1055,7 +1056,7 @@ int orc_gmk_rollout(int size, int k, uint64_t seed, uint64_t gidx, int8_t *board
     int ply = 0;
     while (!e.done) {
         int n = orc_gmk_valid(&e, moves);
-        int a = moves[orc_rollout_hash(seed, gidx, (uint64_t)ply) % (uint64_t)n];
+        int a = moves[orc_gmk_pick(orc_rollout_hash(seed, gidx, (uint64_t)ply), n)];
         if (boards) { memcpy(boards + (size_t)ply * S, e.board, (size_t)S); turns[ply] = e.turn; actions[ply] = a; }
         orc_gmk_step(&e, a);
         if (boards) { winners[ply] = e.winner; dones[ply] = (uint8_t)e.done; }

@@ -133,7 +133,7 @@ def test_gomoku_restatement_vs_reference_env():
                 assert np.array_equal(np.asarray(r.board).astype(np.int8), o["boards"][ply]) and r.turn == o["turns"][ply]
                 a = int(o["actions"][ply])
                 mv = r.valid_move()
-                assert mv == e.valid_moves() and a == mv[oracle.lib().orc_rollout_hash(7, g, ply) % len(mv)]
+                assert mv == e.valid_moves() and a == mv[(oracle.lib().orc_rollout_hash(7, g, ply) >> 32) * len(mv) >> 32]
                 r.step(a)
                 assert e.step(a) == 0
                 assert r.winPlayer() == o["winners"][ply] == e.winner() and r.done() == bool(o["dones"][ply]) == e.done()
