@@ -54,7 +54,9 @@ template <class R> AZ_HD int gmk_count_dir(const R &b, int size, int row, int co
     while (r >= 0 && r < size && c >= 0 && c < size && ((b.get(p, r) >> c) & 1u)) { ++count; r += dr; c += dc; }
     return count;
 }
-// has_line_from: Gomoku.h:247-263 (directions in the reference's order: vertical, horizontal, diagonal, anti-diagonal)
+// has_line_from: Gomoku.h:247-263 (directions in the reference's order: vertical, horizontal, diagonal, anti-diagonal).
+// (Tried: the 2k-1 cells of each line gathered into bit vectors and a shift-AND run test, no data-dependent loops - bit-exact,
+// but 5.42 vs 4.68 ms per 1 M games of 15 x 15: most rays stop at their first probe, the fixed 2k-1 row gathers cost more.)
 template <class R> AZ_HD bool gmk_has_line_rc(const R &b, int size, int k, int row, int col, int player) {
     const int p = gmk_pidx(player);
     const int DR[4] = {1, 0, 1, 1}, DC[4] = {0, 1, 1, -1};
