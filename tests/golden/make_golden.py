@@ -95,5 +95,46 @@ def main():
         print("env", game, len(games))
 
 
+GOMOKU_CASES = ((15, 5, 10), (9, 4, 10), (6, 3, 10), (19, 6, 2))
+
+
+def gomoku_main():
+    """tests/golden/env_gomoku_games.npz from the reference's env_cpp.gomoku.Env: random games (per-ply boards, turns, winner /
+    done after each move, final board) and unplayable imported boards with the turn / done / winner the reference infers."""
+    _, env_cpp = oracle.load_ref("parity")
+    rng = np.random.default_rng(17)
+    out, gi = {}, 0
+    for size, k, games in GOMOKU_CASES:
+        for _ in range(games):
+            e = env_cpp.gomoku.Env(size, k)
+            acts, boards_, winners, dones, turns_ = [], [], [], [], []
+            while not e.done():
+                mv = e.valid_move()
+                a = mv[int(rng.integers(0, len(mv)))]
+                boards_.append(np.asarray(e.board).astype(np.int8))
+                turns_.append(e.turn)
+                e.step(a)
+                acts.append(a); winners.append(e.winPlayer()); dones.append(e.done())
+            d = dict(params=np.array([size, k], np.int32), actions=np.array(acts, np.int32), boards=np.stack(boards_),
+                     winners=np.array(winners, np.int32), dones=np.array(dones, np.uint8), turns=np.array(turns_, np.int32),
+                     final=np.asarray(e.board).astype(np.int8),
+                     sym=np.stack([np.asarray(e.apply_symmetry(s).board).astype(np.int8) for s in range(8)]))
+            out.update({f"g{gi}_{kk}": v for kk, v in d.items()})
+            gi += 1
+    imp_boards, imp_res = [], []
+    for j in range(120):
+        b = rng.choice(np.array([-1, 0, 1], np.int8), size=(8, 8), p=(0.3 + 0.1 * (j % 3), 0.3, 0.4 - 0.1 * (j % 3)))
+        e = env_cpp.gomoku.Env(b.astype(np.float32), 4)
+        imp_boards.append(b)
+        imp_res.append((e.turn, int(e.done()), e.winPlayer()))
+    out["import_boards"], out["import_results"] = np.stack(imp_boards), np.array(imp_res, np.int32)
+    np.savez_compressed(os.path.join(HERE, "env_gomoku_games.npz"), **out)
+    print("env Gomoku", gi, "games,", len(imp_boards), "imported boards")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "gomoku":
+        gomoku_main()
+    else:
+        main()
+        gomoku_main()
