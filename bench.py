@@ -184,8 +184,37 @@ def run_reference(n, n_playout, K, steps, warmup, seed=0):
     dt = time.perf_counter() - t0
     # The numpy stand-in evaluator between search and back-prop is not the reference engine's work (this repo's arm evaluates on
     # the device): `value` counts the time inside the reference's own entry points only; the whole loop is reported beside it.
-    return dict(value=n * n_playout * steps / max(dt - t_ev, 1e-9), ms_per_step=1e3 * (dt - t_ev) / steps, kind=kind, cores=cores,
-                value_with_numpy_evaluator=n * n_playout * steps / dt, ms_per_step_with_numpy_evaluator=1e3 * dt / steps)
+    out = dict(value=n * n_playout * steps / max(dt - t_ev, 1e-9), ms_per_step=1e3 * (dt - t_ev) / steps, kind=kind, cores=cores,
+               value_with_numpy_evaluator=n * n_playout * steps / dt, ms_per_step_with_numpy_evaluator=1e3 * dt / steps)
+    native = run_reference_native(boards, turns, n, n_playout, K, steps, warmup)
+    if native:
+        out["native_harness"] = native
+    return out
+
+
+def run_reference_native(boards, turns, n, n_playout, K, steps, warmup):
+    """The same loop over the reference's BatchedMCTS.h with no Python in between (oracle/_ref/timing/ref_native_bench, built from
+    oracle/ref_native_bench.cpp against the reference headers).  Reported beside the pybind figure; None when the
+    binary did not travel."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "timing", "ref_native_bench")
+    if not os.path.exists(exe):
+        return None
+    try:
+        with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+            f.write(np.ascontiguousarray(boards, np.int8).tobytes())
+            f.write(np.ascontiguousarray(turns, np.int32).tobytes())
+            f.flush()
+            env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count()))
+            r = subprocess.run([exe, f.name, str(n), str(n_playout), str(K), str(steps), str(warmup)], capture_output=True, text=True,
+                               env=env, timeout=600, check=True)
+        j = json.loads(r.stdout)
+        sims = n * n_playout * steps
+        return dict(value=sims / j["engine_s"], value_whole_loop=sims / j["total_s"], threads=j["threads"],
+                    note="reference BatchedMCTS<Connect4> driven from C++ (no pybind / numpy); value = time inside its entry points")
+    except Exception as e:   # pragma: no cover
+        return dict(error=repr(e)[:200])
 
 
 def main():
@@ -240,6 +269,7 @@ def main():
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "value_with_numpy_evaluator": r["value_with_numpy_evaluator"],
                 "ms_per_step_with_numpy_evaluator": r["ms_per_step_with_numpy_evaluator"],
+                "native_harness": r.get("native_harness"),
                 "note": "value / ms_per_step count the time inside the reference engine's own entry points (search_batch[_vl], "
                         "backprop_batch[_vl], prune_roots: all host threads); the numpy stand-in evaluator that runs between them on "
                         "one thread is excluded (this repo's arm evaluates on the device) and reported in the *_with_numpy_evaluator keys"}
@@ -557,6 +587,7 @@ def main():
             cpu["sample"] = (f"{args.cpu_baseline_games} games x {n_playout} sims x 3 steps (same workload, fewer games); time inside the "
                              "reference engine's entry points only, the numpy stand-in evaluator excluded")
             cpu["value_with_numpy_evaluator"] = r.get("value_with_numpy_evaluator")
+            cpu["native_harness"] = r.get("native_harness")
         except Exception as e:   # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
