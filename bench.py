@@ -252,8 +252,6 @@ def main():
               "search_params": "server defaults (c_init 1.4, c_base 1000, fpu 0.2, alpha 0.3, eps 0.25, mlh 0.1/0.2, symmetry on)",
               "evaluator": "constant (uniform prior, fixed WDL/aux; stands in for the random-init CNN)",
               "parallelism": f"{world} x independent game shards, no data-path collective"}
-    
-    
 
     if args.impl == "reference":
         if rank != 0:
