@@ -338,7 +338,9 @@ typedef struct {
     vlent_t **paths; int *plen, *pcap;
     orc_env *vl_envs; int *vl_leaf; int *vl_turn; int vl_alloc;
     /* statistics for the roofline model (not in the reference) */
-    uint64_t stat_depth, stat_edges, stat_expanded, stat_sims;
+    uint64_t stat_depth, stat_edges, stat_expanded, stat_sims, stat_alloc, stat_seen, stat_expansions;
+    uint64_t stat_lvl_nodes[8], stat_lvl_edges[8], stat_lvl_alloc[8];   /* per level of the descent (7 = deeper) */
+    int stat_level;
 } tree_t;
 
 typedef struct {
@@ -503,6 +505,10 @@ static int select_edge(const engine_t *E, tree_t *t, int node_idx, float fpu_val
         float score = q_value + u_score + m_utility;
         if (score > best_score) { best_score = score; best_edge = i; }
         t->stat_edges++;
+        t->stat_alloc += (uint64_t)(e->child != -1);
+        t->stat_seen += (uint64_t)seen;
+        t->stat_lvl_edges[t->stat_level]++;
+        t->stat_lvl_alloc[t->stat_level] += (uint64_t)(e->child != -1);
     }
     return best_edge;
 }
@@ -523,12 +529,15 @@ static sim_result simulate_common(engine_t *E, tree_t *t, const orc_env *start, 
     if (use_vl) t->plen[k] = 0;
     t->sim_env = *start;
     int curr = t->root, winner = 0, full = 0, root_vl_applied = 0;
+    t->stat_level = 0;
     while (t->nodes[curr].is_expanded) {
         node_t *node = &t->nodes[curr];
         if (node->is_terminal) break;
         if (node->num_edges == 0) break;
         float fpu = compute_fpu(E, t, curr);
+        t->stat_lvl_nodes[t->stat_level]++;
         int best = select_edge(E, t, curr, fpu);
+        if (t->stat_level < 7) t->stat_level++;
         if (best < 0) break;
         if (use_vl && !root_vl_applied) { t->nodes[t->root].n_inflight += E->cfg.vl_count; root_vl_applied = 1; }
         edge_t *e = &t->edges[node->edge_offset + best];
@@ -589,6 +598,7 @@ static void expand_leaf(engine_t *E, int env, tree_t *t, const float *policy) { 
         if (has_noise) e->noise = noise[i];
     }
     t->stat_expanded += (uint64_t)nv;
+    t->stat_expansions++;
 }
 static void propagate(engine_t *E, tree_t *t, wdl_t w, float moves_left) {   /* MCTS.h:381-402 */
     int idx = t->cur_leaf;
@@ -838,14 +848,18 @@ void orc_get_root_stats(void *h, float *out) {              /* MCTS.h:637-673, B
         }
     }
 }
-/* tree statistics for the roofline model: [sims, depth(edges traversed), edges scanned, edges created, nodes, edges] summed */
+/* tree statistics for the roofline model: [sims, depth(edges traversed), edges scanned, edges created, nodes, edges, scanned
+ * edges whose child is allocated, scanned edges whose child has visits, expansions, then per descent level 0..7: nodes scanned[8],
+ * edges scanned[8], allocated among them[8]] summed */
 void orc_get_tree_stats(void *h, uint64_t *out) {
     engine_t *E = (engine_t *)h;
-    memset(out, 0, sizeof(uint64_t) * 6);
+    memset(out, 0, sizeof(uint64_t) * 33);
     for (int i = 0; i < E->n_envs; ++i) {
         tree_t *t = &E->trees[i];
         out[0] += t->stat_sims; out[1] += t->stat_depth; out[2] += t->stat_edges; out[3] += t->stat_expanded;
         out[4] += (uint64_t)t->ncount; out[5] += (uint64_t)t->ecount;
+        out[6] += t->stat_alloc; out[7] += t->stat_seen; out[8] += t->stat_expansions;
+        for (int l = 0; l < 8; ++l) { out[9 + l] += t->stat_lvl_nodes[l]; out[17 + l] += t->stat_lvl_edges[l]; out[25 + l] += t->stat_lvl_alloc[l]; }
     }
 }
 
