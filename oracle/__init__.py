@@ -168,11 +168,12 @@ class OracleMCTS:
         return out
 
     def tree_stats(self):
-        out = np.zeros(33, np.uint64)
+        out = np.zeros(36, np.uint64)
         self.L.orc_get_tree_stats(self.h, _p(out))
         d = dict(zip(("sims", "depth", "edges_scanned", "edges_created", "nodes", "edges", "scanned_allocated", "scanned_visited",
                       "expansions"), out[:9].tolist()))
-        d.update(level_nodes=out[9:17].tolist(), level_edges=out[17:25].tolist(), level_allocated=out[25:33].tolist())
+        d.update(level_nodes=out[9:17].tolist(), level_edges=out[17:25].tolist(), level_allocated=out[25:33].tolist(),
+                 expanded_nodes=int(out[33]), expanded_revisited=int(out[34]), expanded_revisited_edges=int(out[35]))
         return d
 
 

@@ -850,16 +850,21 @@ void orc_get_root_stats(void *h, float *out) {              /* MCTS.h:637-673, B
 }
 /* tree statistics for the roofline model: [sims, depth(edges traversed), edges scanned, edges created, nodes, edges, scanned
  * edges whose child is allocated, scanned edges whose child has visits, expansions, then per descent level 0..7: nodes scanned[8],
- * edges scanned[8], allocated among them[8]] summed */
+ * edges scanned[8], allocated among them[8], then: expanded nodes, expanded nodes with >= 2 visits, edges of the latter] summed */
 void orc_get_tree_stats(void *h, uint64_t *out) {
     engine_t *E = (engine_t *)h;
-    memset(out, 0, sizeof(uint64_t) * 33);
+    memset(out, 0, sizeof(uint64_t) * 36);
     for (int i = 0; i < E->n_envs; ++i) {
         tree_t *t = &E->trees[i];
         out[0] += t->stat_sims; out[1] += t->stat_depth; out[2] += t->stat_edges; out[3] += t->stat_expanded;
         out[4] += (uint64_t)t->ncount; out[5] += (uint64_t)t->ecount;
         out[6] += t->stat_alloc; out[7] += t->stat_seen; out[8] += t->stat_expansions;
         for (int l = 0; l < 8; ++l) { out[9 + l] += t->stat_lvl_nodes[l]; out[17 + l] += t->stat_lvl_edges[l]; out[25 + l] += t->stat_lvl_alloc[l]; }
+        for (int j = 0; j < t->ncount; ++j) {            /* expanded nodes now, and those among them visited more than once */
+            if (!t->nodes[j].is_expanded) continue;
+            out[33]++;
+            if (t->nodes[j].n_visits >= 2) { out[34]++; out[35] += (uint64_t)t->nodes[j].num_edges; }
+        }
     }
 }
 

@@ -8,7 +8,7 @@ roots).  Test-infrastructure only (runs oracle/): it sizes next round's layout c
                    already has a record (allocated at its first visit)              child is allocated)
                    an expansion writes the header only; a first visit appends    -> 32 B x (expansions + first visits)
                    one record
-python tools/model_visited_prefix.py [trees]"""
+python tools/model_visited_prefix.py [trees] [n_playout] [K]"""
 import os
 import sys
 
@@ -23,11 +23,14 @@ import oracle  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-    n_playout, K, A = 200, 4, 7
+    n_playout = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+    K = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    A = 7
     boards, turns = bench.c4_random_roots(n, 1000)
     eng = oracle.OracleMCTS("Connect4", n)
     for k, v in bench.SERVER_DEFAULTS.items():
         setattr(eng.config, k, v)
+    eng.config.c_base = 5.0 * n_playout                                  # server.py: c_base = 5 n (1000 at n = 200)
     eng.set_seed(0)
     bench.host_step(eng, boards, turns, n_playout, K, A, np.full(n, -1, np.int32))
     s = eng.tree_stats()
@@ -46,6 +49,10 @@ def main():
         ln, le, la = s["level_nodes"][l], s["level_edges"][l], s["level_allocated"][l]
         if ln:
             print(f"  level {l}{'+' if l == 7 else ' '}: {ln / sims:5.2f}  {le / ln:4.2f}  {la / ln:4.2f}   {32 * le / sims:6.1f} -> {32 * (ln + la) / sims:6.1f} B")
+    xn, xr, xe = s["expanded_nodes"], s["expanded_revisited"], s["expanded_revisited_edges"]
+    lazy = 32 * (x + xe / sims)                                   # header at expansion, the full block only on the second visit
+    print(f"expanded nodes {xn / n:.1f} per tree, visited again {xr / n:.1f} ({100 * xr / xn:.0f} %): lazy full blocks (header at expansion, "
+          f"block on the second visit) write {lazy:.1f} B per simulation ({lazy / cur_exp:.2f}x), select unchanged")
     print(f"select + expand : current {cur_sel + cur_exp:7.1f} B   visited-prefix {new_sel + new_exp:7.1f} B   "
           f"({(new_sel + new_exp) / (cur_sel + cur_exp):.2f}x)")
 
