@@ -66,6 +66,11 @@ def test_no_cpu_fallback():
     m = importlib.import_module("alphazero-al_b200.mcts_cpp")
     with pytest.raises(RuntimeError, match="no CUDA device"):
         m.BatchedMCTS_Connect4(8)
+    env_cpp = importlib.import_module("alphazero-al_b200.env_cpp")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        env_cpp.BatchedEnv("Connect4", 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        env_cpp.BatchedGomoku(8, 15, 5)
 
 
 def test_hash_evaluator_is_flip_equivariant_and_deterministic():
