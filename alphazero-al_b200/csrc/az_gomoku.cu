@@ -56,7 +56,7 @@ template <class R> AZ_HD int gmk_count_dir(const R &b, int size, int row, int co
 }
 // has_line_from: Gomoku.h:247-263 (directions in the reference's order: vertical, horizontal, diagonal, anti-diagonal).
 // (Tried: the 2k-1 cells of each line gathered into bit vectors and a shift-AND run test, no data-dependent loops - bit-exact,
-// but 5.42 vs 4.68 ms per 1 M games of 15 x 15: most rays stop at their first probe, the fixed 2k-1 row gathers cost more.)
+// but 5.42 vs 4.03 ms per 1 M games of 15 x 15: most rays stop at their first probe, the fixed 2k-1 row gathers cost more.)
 template <class R> AZ_HD bool gmk_has_line_rc(const R &b, int size, int k, int row, int col, int player) {
     const int p = gmk_pidx(player);
     const int DR[4] = {1, 0, 1, 1}, DC[4] = {0, 1, 1, -1};
@@ -240,8 +240,8 @@ __global__ void k_gmk_symmetry(int n, az_gomoku *st, const int32_t *__restrict__
     gmk_symmetry(st + i, sym);
 }
 // one thread per game; the row masks live in shared memory for the whole game (2*size words per thread, bank = thread).
-// (Tried: a block-local queue from which a lane whose game is over takes the next one, 2..8 games per lane - 4.69..5.2 ms
-// against 4.72 ms for 1 M games: the warp instructions go to the divergent row / ray walks inside a ply, not to idle tails.)
+// (Tried: a block-local queue from which a lane whose game is over takes the next one, 1..8 games per lane - 4.69..5.2 ms
+// against 4.03 ms for 1 M games: the warp instructions go to the divergent row / ray walks inside a ply, not to idle tails.)
 __global__ void k_gmk_rollout(int n, int size, int k, uint64_t seed, uint64_t first, uint64_t *digest, int32_t *plies, int nrec,
                               int8_t *rb, int32_t *rt, int32_t *ra, int32_t *rw, uint8_t *rd, az_gomoku *fin) {
     extern __shared__ uint32_t sh_rows[];
