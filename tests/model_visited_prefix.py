@@ -1,6 +1,7 @@
 """CPU model of the select / expansion traffic of the visited-prefix node layout against the current one, from the
 C restatement's tree statistics on bench.py's workload (Connect4, n=200, K=4, server defaults, constant evaluator, fresh mid-game
-roots).  Test-infrastructure only (runs oracle/): it sizes next round's layout change before any kernel is written.
+roots).  Test infrastructure (it runs oracle/, so it lives under tests/, not tools/): it sizes next round's layout change
+before any kernel is written.
 
   current layout : select gathers every edge slot of every node on the path      -> 32 B x edges scanned
                    an expansion writes one slot per legal move                   -> 32 B x edges created
@@ -8,7 +9,7 @@ roots).  Test-infrastructure only (runs oracle/): it sizes next round's layout c
                    already has a record (allocated at its first visit)              child is allocated)
                    an expansion writes the header only; a first visit appends    -> 32 B x (expansions + first visits)
                    one record
-python tools/model_visited_prefix.py [trees] [n_playout] [K]"""
+python tests/model_visited_prefix.py [trees] [n_playout] [K]"""
 import os
 import sys
 
@@ -16,7 +17,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench  # noqa: E402
 import oracle  # noqa: E402
 
