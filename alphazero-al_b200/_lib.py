@@ -34,7 +34,7 @@ class AzGomoku(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile every CUDA source for sm_100a (nvcc cross-compiles without a GPU)."""
-    cmd = ["make", "-C", CSRC] + (["-B"] if force else [])
+    cmd = ["make", "-j8", "-C", CSRC] + (["-B"] if force else [])
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("building libazb200.so failed:\n" + r.stdout + r.stderr)
@@ -74,7 +74,7 @@ def lib() -> C.CDLL:
         "az_mcts_backprop_batch_vl": [_vp, _i] + [_vp] * 7,
         "az_mcts_search": [_vp, _i, _vp, _vp, _i],
         "az_mcts_get_counts": [_vp, _vp], "az_mcts_get_counts64": [_vp, _vp], "az_mcts_get_root_stats": [_vp, _vp],
-        "az_mcts_prune_roots_dev": [_vp, _vp, _vp],
+        "az_mcts_prune_roots_dev": [_vp, _vp, _vp], "az_mcts_reset_all_dev": [_vp, _vp],
         "az_mcts_search_dev": [_vp, _i, _vp, _vp, _vp],
         "az_pack_roots_dev": [_i, _i, _vp, _vp, _vp, _vp],
         "az_unpack_leaves_dev": [_i, _i] + [_vp] * 11,

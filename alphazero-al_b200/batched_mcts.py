@@ -76,6 +76,7 @@ class BatchedMCTS:
         self.n_playout, self.batch_size = n_playout, batch_size
         self.action_size, self.board_shape = backend_cls.action_size, backend_cls.board_shape
         self._convert_board = board_converter or _default_convert_board
+        self._custom_converter = board_converter is not None      # the device path encodes leaves itself (default planes only)
         self.cache = _LRU(cache_size) if cache_size > 0 else None      # host LRU, used by the numpy `predict` path only
         self._cache_size, self._dev_cache = cache_size, None
         self._evaluators = {}
@@ -200,14 +201,14 @@ class BatchedMCTS:
         if hasattr(pv_func, "score_scale"):
             pv_func.score_scale = self.mcts.config.score_scale
         from . import device_search as ds
-        if not use_time and ds.ReferenceNetAdapter.accepts(pv_func):
+        if not use_time and not self._custom_converter and ds.ReferenceNetAdapter.accepts(pv_func):
             # an unmodified network of the reference on a CUDA device: same numbers as its predict(), but nothing leaves the device
             ad = self._adapters.get(id(pv_func))
             if ad is None or ad.net is not pv_func:
                 ad = ds.ReferenceNetAdapter(pv_func, self._game_name)
                 self._adapters = {id(pv_func): ad}
             pv_func = ad
-        if not use_time and (isinstance(pv_func, ds.SyntheticEvaluator) or hasattr(pv_func, "predict_device")):
+        if not use_time and not self._custom_converter and (isinstance(pv_func, ds.SyntheticEvaluator) or hasattr(pv_func, "predict_device")):
             self._playout_device(pv_func, np.asarray(current_boards), np.asarray(turns), max_n, vl_batch)
             return self
         current_boards = np.asarray(current_boards).astype(np.int8)

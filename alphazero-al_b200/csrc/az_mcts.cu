@@ -1256,6 +1256,10 @@ struct az_mcts {
     float *d_log_lut = nullptr, *d_atan_lut = nullptr;
     float2 *d_ls_lut = nullptr;
     bool last_select_ro = false;      // the last select launch was read-only: its back-prop applies the leaf flags, removes no virtual loss
+    // ... remembered per tree range: shards of one batch run ahead of each other on their own streams and may interleave launches of
+    // different K in host order; a back-prop looks up the select of ITS range and is refused when none matches
+    struct SelRec { int lo, hi, K; bool vl, ro; };
+    std::vector<SelRec> sel_recs;
     int variant = 1;                  // thread-per-tree kernels: 0 = first generation (k_*_t), 1 = lean (k_*_f)
     int wave_max = 131072;             // batches of at most this many descent lanes run the staggered-descent select (az_mcts_wave.cuh); 0 = off
     // VL bookkeeping
@@ -1489,7 +1493,18 @@ static bool use_wave(const az_mcts *h, bool vl, int K) {
 static bool select_is_ro(const az_mcts *h, bool vl, int K) {
     return h->game == GAME_C4 && h->W == 1 && h->variant != 0 && ((vl ? K : 1) <= RS_MAX || use_wave(h, vl, K));
 }
+static void note_select(az_mcts *h, bool vl, int K) {
+    const int lo = h->d.env_lo, hi = lo + h->d.env_cnt;
+    auto &v = h->sel_recs;
+    v.erase(std::remove_if(v.begin(), v.end(), [&](const az_mcts::SelRec &r) { return r.lo < hi && lo < r.hi; }), v.end());
+    v.push_back({lo, hi, K, vl, h->last_select_ro});
+}
+static void launch_select_impl(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s);
 static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s) {
+    launch_select_impl(h, vl, K, roots, leaves, s);
+    note_select(h, vl, K);
+}
+static void launch_select_impl(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s) {
     const int cnt = h->d.env_cnt;                             // trees of this launch (a whole batch or one shard)
     const int g = grid_groups(cnt, h->W);
     if (h->game == GAME_C4 && h->W == 1 && h->variant != 0 && (uint64_t)(h->n + 32) * h->cap < (1ull << 31) &&
@@ -1554,6 +1569,18 @@ static int launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym,
                             const float *p2, const float *ml, const uint8_t *it, const int32_t *sym, cudaStream_t s) {
     const int cnt = h->d.env_cnt;
     const int g = grid_groups(cnt, h->W);
+    {   // which select produced the leaves of this range?  (read-only selects leave work to the back-prop, the others do not)
+        const int lo = h->d.env_lo, hi = lo + cnt;
+        bool found = false, ro = false, mixed = false;
+        for (const auto &r : h->sel_recs) {
+            if (!(r.lo < hi && lo < r.hi)) continue;
+            if (r.lo > lo || r.hi < hi) { mixed = true; continue; }        // covers only a part of the range
+            found = true; ro = r.ro;
+            if (r.vl != vl || (vl && K > r.K)) AZ_FAIL(h, AZ_ERR_INVALID, "back-prop of trees [%d, %d) with K=%d does not match their last select (K=%d)", lo, hi, vl ? K : 0, r.vl ? r.K : 0);
+        }
+        if (mixed && !found) AZ_FAIL(h, AZ_ERR_INVALID, "back-prop of trees [%d, %d): the range was searched in pieces; back-propagate the same pieces", lo, hi);
+        if (found) h->last_select_ro = ro;
+    }
     if (h->game == GAME_C4 && h->W == 1 && h->variant != 0 && ((uintptr_t)pol & 15) == 0) {
         // staged back-prop: leaf records + policy rows of a warp in shared memory (dynamic, sized by K and the record stride)
         const int kk = vl ? K : 1;
@@ -1911,6 +1938,19 @@ int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream) 
     }
     return AZ_OK;
 }
+// Every tree back to a fresh root (prune_roots with all actions < 0, MCTS.h:107 -> reset()), stream-ordered, and - unlike
+// az_mcts_prune_roots_dev, which cannot see the device array - with the host's arena bookkeeping reset too: the arenas are empty,
+// so the next playout needs no bound refresh (no device synchronisation between a reset and a search).
+int az_mcts_reset_all_dev(az_mcts *h, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = enter_dev(h, s); if (rc) return rc;
+    k_reset<<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, -1);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    h->bump_bound = 0; h->bounds.clear(); h->base_after_prune = 0; h->bound_stale = false; h->base_pending = false; h->growth_est = 0;
+    h->sel_recs.clear();
+    return AZ_OK;
+}
 int az_mcts_set_compaction(az_mcts *h, int mode) {
     if (mode < 0 || mode > 2) AZ_FAIL(h, AZ_ERR_INVALID, "compaction mode must be 0 (never), 1 (auto) or 2 (every re-root)");
     h->compaction = mode;
@@ -2087,8 +2127,9 @@ int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, in
     if (n_playout < 0 || K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "playout: n_playout and K must be >= 0");
     cudaStream_t main = (cudaStream_t)stream;
     int rc = enter_dev(h, main); if (rc) return rc;
-    const int per = (((h->n + std::max(shards, 1) - 1) / std::max(shards, 1)) + 31) / 32 * 32;
-    const int ns = std::min(16, std::max(1, (h->n + per - 1) / per));
+    shards = std::min(std::max(shards, 1), 16);             // side[] / lanes[] hold 16 streams: more shards than that are merged
+    const int per = (((h->n + shards - 1) / shards) + 31) / 32 * 32;
+    const int ns = std::max(1, (h->n + per - 1) / per);
     std::vector<int> iters;
     if (K <= 1) iters.assign((size_t)n_playout, 0);
     else if (n_playout > 0) {
@@ -2170,6 +2211,11 @@ int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, in
         h->d.epoch += (uint64_t)iters.size();
         if (K > 0) h->prepared_K = iters.back() > 0 ? iters.back() : h->prepared_K;
         h->last_select_ro = select_is_ro(h, iters.back() > 0, std::max(iters.back(), 1));
+        for (int j = 0; j < ns; ++j) {                       // what the issued loop's last select of every shard would have noted
+            h->d.env_lo = j * per; h->d.env_cnt = std::min(per, h->n - j * per);
+            note_select(h, iters.back() > 0, iters.back());
+        }
+        h->d.env_lo = 0; h->d.env_cnt = h->n;
         h->launches += (uint64_t)launches;
     }
     h->user_stream = main; h->user_pending = true;

@@ -90,21 +90,41 @@ class NetEvaluator:
         self._wdl = self._aux = None
         self.graph_rows = int(graph_rows)
         self._graphs = {}
-        self._fp, self._fp_params, self._fp_calls = None, None, 0
+        self._fp, self._fp_params, self._fp_calls, self._fp_gen = None, None, 0, 0
         self.graph_replays = 0
 
     def _check_weights(self):
         """Captured graphs read the parameter tensors that existed at capture time: in-place updates (load_state_dict) are seen,
-        re-created parameters (net.to(dtype), net.half(), a swapped module) are not - drop the graphs when the storage moved."""
+        re-created parameters (net.to(dtype), net.half(), a swapped module) are not - drop the graphs when any storage moved.
+        The fingerprint covers every parameter and buffer (data pointer + dtype); modules that re-create tensors do it through
+        ``_apply``, which is hooked once so the walk (~90 us) only happens after such a call or every 64th evaluation."""
         self._fp_calls += 1
-        if self._fp_params is None or self._fp_calls % 256 == 0:      # walking the module tree costs ~90 us: not on every call
-            params = getattr(self.net, "parameters", None)
-            ps = list(params()) if callable(params) else []
-            self._fp_params = (ps[0], ps[-1], len(ps)) if ps else ()
-        fp = tuple((p.data_ptr(), p.dtype) if hasattr(p, "data_ptr") else p for p in self._fp_params)
-        if fp != self._fp:
-            self._graphs.clear()
-            self._fp = fp
+        net = self.net
+        inner = getattr(net, "net", net)                     # ReferenceNetAdapter wraps the module
+        if self._fp_params is None and isinstance(inner, torch.nn.Module) and not getattr(inner, "_azb200_apply_hooked", False):
+            orig_apply = inner._apply
+
+            def hooked(fn, *a, _orig=orig_apply, _mod=inner, **k):
+                _mod._azb200_generation = getattr(_mod, "_azb200_generation", 0) + 1
+                return _orig(fn, *a, **k)
+            try:
+                inner._apply = hooked
+                inner._azb200_apply_hooked = True
+            except Exception:
+                pass
+        gen = getattr(inner, "_azb200_generation", 0)
+        if self._fp_params is None or gen != self._fp_gen or self._fp_calls % 64 == 0:
+            self._fp_gen = gen
+            ps = []
+            for name in ("parameters", "buffers"):
+                it = getattr(net, name, None)
+                if callable(it):
+                    ps.extend(it())
+            self._fp_params = ps
+            fp = tuple((p.data_ptr(), p.dtype) for p in ps if hasattr(p, "data_ptr"))
+            if fp != self._fp:
+                self._graphs.clear()
+                self._fp = fp
 
     def _forward(self, buf, r, rows):
         probs, wdl_rel, aux = self.net.predict_device(buf.planes[r], buf.mask[r])
@@ -180,6 +200,9 @@ class ReferenceNetAdapter:
     def parameters(self):
         return self.net.parameters()
 
+    def buffers(self):
+        return self.net.buffers()
+
     @property
     def score_scale(self):
         return getattr(self.net, "score_scale", 8.0)
@@ -193,12 +216,14 @@ class ReferenceNetAdapter:
         kind = planes.device.type
         with torch.autocast(kind, dtype=torch.bfloat16, enabled=kind != "cpu"):
             log_prob, value_log_prob, aux = self.net(planes, action_mask=action_mask.bool())
-        probs, wdl = log_prob.float().exp(), value_log_prob.float().exp()
-        aux = aux.float().reshape(-1) * float(self.net.aux_target_offset)
+        # the dtype flow of the reference's predict(): policy .float().exp(); WDL exp() in the head's dtype then .float(); the aux
+        # scaling (and Othello's atan) in the head's dtype - bf16 under autocast - and .float() last
+        probs, wdl = log_prob.float().exp(), value_log_prob.exp().float()
+        aux = aux * float(self.net.aux_target_offset)
         if self.game == "Othello":
             import math
             aux = torch.atan(aux / self.score_scale) * (2.0 / math.pi)
-        return probs, wdl, aux
+        return probs, wdl, aux.float().reshape(-1)
 
 
 class EvalCache:
@@ -386,6 +411,8 @@ def playout_device(engine, buf: LeafBuffers, n_playout: int, K: int, evaluator, 
     if shards > 1:
         return _playout_sharded(engine, buf, iters, evaluator, stream, shards, on_select)
     launches = 0
+    # torch evaluators launch on torch's current stream: make that the stream the engine kernels run on
+    ext = torch.cuda.ExternalStream(stream, device=buf.leaves.device) if stream else torch.cuda.default_stream(buf.leaves.device)
     for k in iters:
         rows = n * max(k, 1)
         assert rows <= buf.rows
@@ -393,7 +420,8 @@ def playout_device(engine, buf: LeafBuffers, n_playout: int, K: int, evaluator, 
             on_select(rows, lambda: engine.search_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), stream))
         else:
             engine.search_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), stream)
-        evaluator(buf, rows, stream)
+        with torch.cuda.stream(ext):
+            evaluator(buf, rows, stream)
         # is_term / sym ids: the engine uses what it remembered from the matching search
         engine.backprop_dev(k, buf.policy.data_ptr(), buf.d.data_ptr(), buf.p1w.data_ptr(), buf.p2w.data_ptr(),
                             buf.ml.data_ptr(), 0, 0, stream)

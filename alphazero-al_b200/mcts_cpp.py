@@ -318,6 +318,10 @@ class _BatchedMCTS:
         self._push_cfg()
         self._ck(self._L.az_mcts_prune_roots_dev(self._h, actions_ptr, stream or None))
 
+    def reset_all_dev(self, stream=0):
+        """Every tree back to a fresh root, stream-ordered, host arena bookkeeping included (include/azb200.h)."""
+        self._ck(self._L.az_mcts_reset_all_dev(self._h, stream or None))
+
     def search_eval_dev(self, evaluator_kind, roots_ptr, n_playout, stream=0):
         self._push_cfg()
         self._ck(self._L.az_mcts_search_eval_dev(self._h, int(evaluator_kind), roots_ptr, int(n_playout), stream or None))

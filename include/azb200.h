@@ -138,6 +138,10 @@ int az_unpack_leaves_dev(int game, int rows, const az_leaf *d_leaves, int8_t *d_
                          float *d_planes, void *stream);
 
 int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream);
+/* prune_roots with every action < 0 (each tree back to a fresh root, MCTS.h:101-109), stream-ordered.  Unlike the call above -
+ * which cannot see the device array - the host-side arena bookkeeping is reset too, so the next search starts from empty arenas
+ * with no device synchronisation in between. */
+int az_mcts_reset_all_dev(az_mcts *h, void *stream);
 /* K == 0 selects the non-VL search_batch (1 leaf per tree, d_leaves[n]); K >= 1 the virtual-loss search (d_leaves[n*K]). */
 int az_mcts_search_dev(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leaves, void *stream);
 /* d_is_term / d_sym_ids may be NULL: the engine then uses the flags / ids it remembered from the matching search. */

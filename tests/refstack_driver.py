@@ -11,6 +11,11 @@ tasks
             fed like server.py:295-304) and out.pkl (the upload payload of client.py:367-373)
   playout   src.MCTS_cpp.BatchedMCTS.batch_playout over several moves with the LRU cache on -> counts / root stats per move, the
             cache's key order and values at the end
+  cnn       the reference's own CNN (bf16 autocast on CUDA) in the loop: (a) its predict() drives the compiled reference engine through
+            the reference-style host loop while every leaf batch and evaluator output is recorded, (b) the CUDA engine is fed the
+            recorded outputs (same evaluator outputs to both -> leaves and visit counts must be identical), (c) the
+            device-resident path (ReferenceNetAdapter, no host copy) is compared with (a) in L1, (d) the adapter's outputs are
+            compared with predict() on one batch -> out.json
   actor     wall-clock of one batch_self_play call with the reference's own CNN (config 1 of BASELINE.json) -> out.json
 """
 import json
@@ -177,6 +182,96 @@ def task_playout(out, p):
     print("playout", p["game"], "moves", p["moves"], "cache entries", len(keys), "predict rows", pv.rows)
 
 
+def task_cnn(out, p):
+    import importlib
+    import torch
+    import oracle
+    from harness import SERVER_DEFAULTS, counts, playout, random_positions, set_config
+    from src.environments import load
+    from src import mcts_cpp as ref_cpp                          # overlay "reference": the compiled reference engine
+    ours_cpp = importlib.import_module("alphazero-al_b200.mcts_cpp")
+    bm = importlib.import_module("alphazero-al_b200.batched_mcts")
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    game, n, npl, K = p["game"], p["n"], p["n_playout"], p["K"]
+    A = oracle.ACTION_SIZE[game]
+    mod = load(game)
+    torch.manual_seed(p.get("seed", 0))
+    net = mod.CNN(lr=0.0, device="cuda")
+    net.eval()
+    with torch.no_grad():                                        # random-init heads are nearly uniform: give them some signal
+        for q in net.parameters():
+            q.add_(p.get("perturb", 0.05) * torch.randn_like(q))
+    boards, turns = random_positions(game, n, p.get("max_plies", 14), p.get("pos_seed", 41))
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=False)
+    if game == "Othello":
+        cfg = dict(c_init=1.4, c_base=500.0, fpu_reduction=0.2, dirichlet_alpha=0.0, use_symmetry=False, score_utility_factor=0.15, score_scale=8.0)
+    log = []
+
+    def host_eval(lb, lt, it, td, tp1, tp2):                     # src/MCTS_cpp.py:275-297 with the network's own predict()
+        t = it.astype(bool)
+        probs = np.zeros((lb.shape[0], A), np.float32)
+        d, p1w, p2w, ml = td.copy(), tp1.copy(), tp2.copy(), np.zeros(lb.shape[0], np.float32)
+        if (~t).any():
+            planes = bm._default_convert_board(lb[~t], lt[~t])
+            mask = None
+            pr, w, a = net.predict(planes, mask)
+            probs[~t] = pr
+            d[~t] = w[:, 0]
+            p1w[~t] = np.where(lt[~t] == 1, w[:, 1], w[:, 2])
+            p2w[~t] = np.where(lt[~t] == 1, w[:, 2], w[:, 1])
+            ml[~t] = a.reshape(-1)
+        log.append((lb.copy(), lt.copy(), it.copy(), probs, d, p1w, p2w, ml))
+        return probs, d, p1w, p2w, ml
+
+    ref = getattr(ref_cpp, f"BatchedMCTS_{game}")(n)
+    set_config(ref, **cfg)
+    playout(ref, host_eval, boards, turns, npl, K)
+    theirs = counts(ref, n, A)
+    # (b) oracle-fed: same evaluator outputs to the CUDA engine; its leaves must be the recorded ones at every iteration
+    it_no = [0]
+
+    def replay_eval(lb, lt, it, td, tp1, tp2):
+        rec = log[it_no[0]]
+        it_no[0] += 1
+        assert np.array_equal(lb, rec[0]) and np.array_equal(lt, rec[1]) and np.array_equal(it, rec[2]), f"leaves differ at iteration {it_no[0] - 1}"
+        return rec[3:]
+
+    mine = getattr(ours_cpp, f"BatchedMCTS_{game}")(n)
+    set_config(mine, **cfg)
+    playout(mine, replay_eval, boards, turns, npl, K)
+    fed = counts(mine, n, A)
+    fed_equal = bool(np.array_equal(fed, theirs)) and mine.get_all_root_stats().tobytes() == ref.get_all_root_stats().tobytes()
+
+    def l1(a, b):
+        a, b = a.astype(np.float64), b.astype(np.float64)
+        return np.abs(a / a.sum(1, keepdims=True) - b / b.sum(1, keepdims=True)).sum(1)
+
+    # (c) the device-resident path: batch_playout wraps the CUDA reference network by itself (ReferenceNetAdapter)
+    kw = dict(game_name=game, noise_epsilon=0.25, fpu_reduction=cfg["fpu_reduction"], use_symmetry=False, mlh_slope=cfg.get("mlh_slope", 0.0),
+              mlh_cap=cfg.get("mlh_cap", 0.2), score_utility_factor=cfg.get("score_utility_factor", 0.0), score_scale=cfg.get("score_scale", 8.0))
+    dev_eng = bm.BatchedMCTS(n, cfg["c_init"], cfg["c_base"], 0.0, npl, **kw)
+    dev_eng.batch_playout(net, boards, turns, vl_batch=K)
+    adapter_used = isinstance(dev_eng._last_evaluator.net, ds.ReferenceNetAdapter)
+    l1_dev = l1(dev_eng.get_visits_count(), theirs)
+    # (d) adapter vs predict() on the first recorded non-terminal leaf batch
+    lb, lt, it = log[1][0], log[1][1], log[1][2].astype(bool)
+    planes = bm._default_convert_board(lb[~it], lt[~it])
+    masks = np.ones((planes.shape[0], A), bool)
+    net.score_scale = cfg.get("score_scale", 8.0)
+    pr, w, a = net.predict(planes, masks)
+    ad = ds.ReferenceNetAdapter(net, game)
+    pd_, wd_, ad_ = ad.predict_device(torch.from_numpy(planes).cuda(), torch.from_numpy(masks.astype(np.uint8)).cuda())
+    adapter_equal = bool(np.array_equal(pd_.cpu().numpy(), pr) and np.array_equal(wd_.cpu().numpy(), w) and np.array_equal(ad_.cpu().numpy(), a.reshape(-1)))
+    adapter_maxdiff = float(max(np.abs(pd_.cpu().numpy() - pr).max(), np.abs(wd_.cpu().numpy() - w).max(), np.abs(ad_.cpu().numpy() - a.reshape(-1)).max()))
+    res = dict(game=game, iterations=len(log), fed_counts_and_stats_identical=fed_equal, fed_l1_max=float(l1(fed, theirs).max()),
+               device_path_l1_max=float(l1_dev.max()), device_path_l1_mean=float(l1_dev.mean()), device_path_identical_trees=float(np.mean(l1_dev == 0)),
+               adapter_used=adapter_used, adapter_equals_predict=adapter_equal, adapter_maxdiff=adapter_maxdiff, net=type(net).__module__,
+               policy_spread=float(pr.max() - pr.min()))
+    with open(out, "w") as f:
+        json.dump(res, f)
+    print("cnn", json.dumps(res))
+
+
 def task_actor(out, p):
     import torch
     from src.environments import load
@@ -213,4 +308,4 @@ def task_actor(out, p):
 
 if __name__ == "__main__":
     task, out, params = sys.argv[1], sys.argv[2], json.loads(sys.argv[3])
-    {"selfplay": task_selfplay, "playout": task_playout, "actor": task_actor}[task](out, params)
+    {"selfplay": task_selfplay, "playout": task_playout, "actor": task_actor, "cnn": task_cnn}[task](out, params)
