@@ -78,7 +78,8 @@ def lib() -> C.CDLL:
         "az_mcts_search_dev": [_vp, _i, _vp, _vp, _vp],
         "az_pack_roots_dev": [_i, _i, _vp, _vp, _vp, _vp],
         "az_unpack_leaves_dev": [_i, _i] + [_vp] * 11,
-        "az_mcts_set_env_base": [_vp, C.c_uint64], "az_selfplay_layout_for": [_i, _vp],
+        "az_mcts_set_env_base": [_vp, C.c_uint64], "az_selfplay_pos_bytes": [_i], "az_selfplay_max_plies": [_i],
+        "az_selfplay_expand_dev": [_i, _i, _vp, _vp, _i] + [_vp] * 9,
         "az_selfplay_ply_dev": [_vp, _vp, _vp, _vp], "az_selfplay_flush_dev": [_vp, _vp],
         "az_mcts_set_lanes": [_vp, _i], "az_mcts_get_lanes": [_vp], "az_mcts_reserve": [_vp, _i],
         "az_mcts_set_variant": [_vp, _i], "az_mcts_get_variant": [_vp], "az_mcts_set_wave_max": [_vp, _i], "az_mcts_get_wave_max": [_vp], "az_selftest_div": [_i, C.c_uint64, C.c_uint64, _vp],
@@ -89,7 +90,7 @@ def lib() -> C.CDLL:
         "az_mcts_playout_synthetic_dev": [_vp, _i, _i, _i, _i] + [_vp] * 9,
         "az_mcts_search_eval_dev": [_vp, _i, _vp, _i, _vp],
         "az_mcts_get_counts_dev": [_vp, _vp, _vp], "az_mcts_get_root_stats_dev": [_vp, _vp, _vp],
-        "az_mcts_enable_stats": [_vp, _i], "az_mcts_get_stats": [_vp, _vp], "az_mcts_get_warp_times": [_vp, _vp, _i], "az_mcts_time_select": [_vp, _i], "az_mcts_set_compaction": [_vp, _i], "az_mcts_get_select_time": [_vp, _vp, _vp, _vp],
+        "az_mcts_enable_stats": [_vp, _i], "az_mcts_get_stats": [_vp, _vp], "az_mcts_get_warp_times": [_vp, _vp, _i], "az_mcts_time_select": [_vp, _i], "az_mcts_set_compaction": [_vp, _i], "az_mcts_get_select_time": [_vp, _vp, _vp, _vp], "az_mcts_get_backprop_time": [_vp, _vp, _vp, _vp],
         "az_eval_synthetic_dev": [_i, _i, _i] + [_vp] * 7,
         "az_eval_finalize_dev": [_i] + [_vp] * 8,
         "az_game_action_size": [_i], "az_game_board_size": [_i], "az_game_board_rows": [_i], "az_game_board_cols": [_i],

@@ -1248,6 +1248,7 @@ struct az_mcts {
     uint64_t base_after_prune = 0, growth_est = 0; bool base_pending = false;   // arena-use bookkeeping between re-roots
     bool time_select = false;         // az_mcts_time_select: CUDA events around every select launch
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sel_ev; size_t sel_used = 0; uint64_t sel_rows = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> bp_ev; size_t bp_used = 0; uint64_t bp_rows = 0;   // the same around every back-prop launch
     cudaEvent_t side_ev[16] = {};
     unsigned int *d_scratch_u32 = nullptr;
     // LUT state
@@ -1691,8 +1692,19 @@ static int do_backprop(az_mcts *h, int K, const float *pol, const float *d, cons
     rc = ensure_arena(h, vl ? K : 1, s); if (rc) return rc;
     h->d.stats = h->stats_on ? h->d_stats : nullptr;
     const int removeK = vl ? std::min(K, h->prepared_K) : 0;
+    if (h->time_select) {
+        if (h->bp_used == h->bp_ev.size()) {
+            cudaEvent_t a, b; CU(h, cudaEventCreate(&a)); CU(h, cudaEventCreate(&b));
+            h->bp_ev.push_back({a, b});
+        }
+        CU(h, cudaEventRecord(h->bp_ev[h->bp_used].first, s));
+    }
     // non-VL: the symmetry id is the one search_batch remembered (pending_sym_ids_, BatchedMCTS.h:45,194)
     rc = launch_backprop(h, vl, K, removeK, 1, pol, d, p1, p2, ml, it, vl ? sym : nullptr, s); if (rc) return rc;
+    if (h->time_select) {
+        CU(h, cudaEventRecord(h->bp_ev[h->bp_used].second, s));
+        h->bp_used++; h->bp_rows += (uint64_t)h->d.env_cnt * (uint64_t)std::max(K, 1);
+    }
     CU(h, cudaGetLastError());
     return AZ_OK;
 }
@@ -1835,6 +1847,7 @@ void az_mcts_destroy(az_mcts *h) {
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->ev) cudaEventDestroy(h->ev);
     for (auto &pr : h->sel_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto &pr : h->bp_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
     if (h->d_epoch_add) cudaFree(h->d_epoch_add);
     for (int j = 0; j < 16; ++j) { if (h->side_ev[j]) cudaEventDestroy(h->side_ev[j]); if (h->side[j]) cudaStreamDestroy(h->side[j]); }
@@ -2328,7 +2341,18 @@ int az_mcts_enable_stats(az_mcts *h, int on) {
     CU(h, cudaMemset(h->d_stats, 0, 8 * sizeof(unsigned long long)));
     return AZ_OK;
 }
-int az_mcts_time_select(az_mcts *h, int on) { h->time_select = on != 0; h->sel_used = 0; h->sel_rows = 0; return AZ_OK; }
+int az_mcts_time_select(az_mcts *h, int on) { h->time_select = on != 0; h->sel_used = 0; h->sel_rows = 0; h->bp_used = 0; h->bp_rows = 0; return AZ_OK; }
+int az_mcts_get_backprop_time(az_mcts *h, float *ms_out, int *launches_out, uint64_t *rows_out) {
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());
+    float tot = 0.0f;
+    for (size_t i = 0; i < h->bp_used; ++i) { float ms = 0.0f; CU(h, cudaEventElapsedTime(&ms, h->bp_ev[i].first, h->bp_ev[i].second)); tot += ms; }
+    if (ms_out) *ms_out = tot;
+    if (launches_out) *launches_out = (int)h->bp_used;
+    if (rows_out) *rows_out = h->bp_rows;
+    h->bp_used = 0; h->bp_rows = 0;
+    return AZ_OK;
+}
 int az_mcts_get_select_time(az_mcts *h, float *ms_out, int *launches_out, uint64_t *rows_out) {
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaDeviceSynchronize());

@@ -311,6 +311,12 @@ class _BatchedMCTS:
         self._ck(self._L.az_mcts_get_select_time(self._h, C.byref(ms), C.byref(n), C.byref(rows)))
         return ms.value, n.value, rows.value
 
+    def get_backprop_time(self):
+        """(summed back-prop ms, launches, leaf rows) since the last call; synchronises the device."""
+        ms, n, rows = C.c_float(0), C.c_int(0), C.c_uint64(0)
+        self._ck(self._L.az_mcts_get_backprop_time(self._h, C.byref(ms), C.byref(n), C.byref(rows)))
+        return ms.value, n.value, rows.value
+
     def stream_handover_dev(self, stream=0):
         self._ck(self._L.az_mcts_stream_handover_dev(self._h, stream or None))
 

@@ -11,12 +11,17 @@ schedules them (src/MCTS_cpp.py:217-357: 1 non-VL warm-up simulation + 50 virtua
 server-default search parameters (server.py:44-72) and a deterministic constant evaluator standing in for the
 random-init CNN (the CNN is outside the path: SURVEY.md 8d).  Simulations/s = G*n/step time, whole job over all GPUs.
 
-  value : device-resident loop (inputs in HBM, CUDA-event timed, max over ranks)
+  value : device-resident loop (inputs in HBM, CUDA-event timed, max over ranks; no host synchronisation inside the region)
   e2e   : the same search through the wrapper API with HOST buffers (BatchedMCTS.prune_roots + batch_playout(numpy boards)
           + get_visits_count(), the calls src/player.py makes; H2D/D2H inside the timed region); e2e_split_api: the split
           plugin API (mcts_cpp.search_batch[_vl] / backprop_batch[_vl]) with numpy leaf buffers every iteration
-  roofline     : k_select (dominant kernel) algorithmic bytes / its CUDA-event time vs measured HBM peak
-  cpu_baseline : the reference engine (oracle/_ref/timing) on this box's host cores, bounded sample
+  roofline     : the two tree kernels (select, back-prop): algorithmic bytes / CUDA-event time of their launches vs the measured
+                 HBM peak; `traffic` = measured DRAM bytes per launch from the committed ncu summary of THESE kernel sources
+  selfplay     : the on-device self-play driver, games/s from finished-game counts, with the trajectory all-gather (the one
+                 collective of the path) INSIDE the timed loop at N > 1, overlapped with the next batch's search; plus the
+                 strong-scaling form of BASELINE config 5 (65 536 games in total over the N GPUs)
+  cpu_baseline : the reference engine (oracle/_ref/timing) on this box's host cores, bounded sample; and the reference ACTOR
+                 (its unmodified Game.batch_self_play + its CNN's GPU predict, BASELINE config 1) on this box
 """
 from __future__ import annotations
 
@@ -217,31 +222,81 @@ def run_reference_native(boards, turns, n, n_playout, K, steps, warmup):
         return dict(error=repr(e)[:200])
 
 
+def kernel_src_sha():
+    """sha256 over the kernel sources: keys the committed ncu DRAM-traffic summary to the code it was captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "alphazero-al_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_traffic():
+    """profiles/dram_traffic.json: {"kernel_src_sha", "captured_from", "kernels": {name: {"dram_read_bytes", "dram_write_bytes", "launches"}}}
+    written by tools/ncu_summary.py from an `ncu --set full` capture of this very command.  Stale (other kernel sources) -> flagged."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+    except Exception:
+        return None
+    t["stale"] = t.get("kernel_src_sha") != kernel_src_sha()
+    return t
+
+
+def reference_actor(timeout=900):
+    """BASELINE config 1 on this box with the reference's own actor: unmodified Game.batch_self_play + AlphaZeroPlayer + its CNN's GPU
+    predict (bf16 autocast) on its compiled engine (oracle/_ref: pysrc + timing build).  None when the byte-compiled layer is absent."""
+    try:
+        from oracle import refstack
+        if not refstack.available("timing"):
+            return None
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            ov = refstack.make_overlay(os.path.join(d, "ref"), "reference", "timing")
+            out = os.path.join(d, "actor.json")
+            env = {"OMP_NUM_THREADS": str(os.cpu_count())}
+            refstack.run_driver(ov, "actor", out, dict(game="Connect4", n_games=100, n_playout=200, K=4, reps=1, warm_games=100), timeout=timeout,
+                                env_extra=env)
+            r = json.load(open(out))
+        r["what"] = ("reference actor, BASELINE config 1: Game.batch_self_play(100 games, n=200, vl_batch=4, temp 1 for 20 plies, td_steps 10), "
+                     "random-init reference CNN on the GPU through its own predict(), reference engine on all host cores")
+        return r
+    except Exception as e:   # pragma: no cover
+        return {"error": repr(e)[:300]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 300 = about 1.2 s; reference arm: 5)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games-per-gpu", type=int, default=65536)
     ap.add_argument("--n-playout", type=int, default=200)
     ap.add_argument("--vl-batch", type=int, default=4)
     ap.add_argument("--cpu-baseline-games", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-actor-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-split", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true")
     ap.add_argument("--no-cnn", action="store_true")
     ap.add_argument("--cnn-slots", type=int, default=4096)
     ap.add_argument("--cnn-plies", type=int, default=3)
-    ap.add_argument("--cnn-plies-100", type=int, default=8)
+    ap.add_argument("--cnn-plies-100", type=int, default=30)
     ap.add_argument("--cnn-cached-plies", type=int, default=8)
     ap.add_argument("--cnn-cached-warm-plies", type=int, default=22)
     ap.add_argument("--selfplay-slots", type=int, default=65536)
-    ap.add_argument("--selfplay-plies", type=int, default=30)
+    ap.add_argument("--selfplay-plies", type=int, default=40)
+    ap.add_argument("--exchange-every", type=int, default=10, help="self-play plies per trajectory all-gather")
+    ap.add_argument("--strong-total", type=int, default=65536, help="games in total for the strong-scaling self-play leg (BASELINE config 5)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (Connect4: 1/2/4/8, 0 = auto)")
     ap.add_argument("--shards", type=int, default=0, help="independent tree shards on their own streams (0 = auto)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 300 if args.impl == "b200" else 5
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,7 +306,8 @@ def main():
     config = {"workload": workload, "game": "Connect4", "games_per_gpu": G, "n_playout": n_playout, "vl_batch": K,
               "search_params": "server defaults (c_init 1.4, c_base 1000, fpu 0.2, alpha 0.3, eps 0.25, mlh 0.1/0.2, symmetry on)",
               "evaluator": "constant (uniform prior, fixed WDL/aux; stands in for the random-init CNN)",
-              "parallelism": f"{world} x independent game shards, no data-path collective"}
+              "parallelism": "independent game shards per GPU, no collective in the search path (trajectory all-gather in the self-play leg)",
+              "l2": "inputs larger than L2: the tree arenas touched per step exceed the 126 MB L2, no flush between steps"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -290,7 +346,6 @@ def main():
     boards = torch.from_numpy(boards_np).to(dev)
     turns = torch.from_numpy(turns_np).to(dev)
     reset_np = np.full(G, -1, np.int32)
-    reset_actions = torch.from_numpy(reset_np).to(dev)
     eng = mcts_cpp.BatchedMCTS_Connect4(G, device=local_rank)
     for k, v in SERVER_DEFAULTS.items():
         setattr(eng.config, k, v)
@@ -304,7 +359,7 @@ def main():
     shards = args.shards if args.shards > 0 else ds.auto_shards(G)
 
     def dev_step(n_shards=None):
-        eng.prune_roots_dev(reset_actions.data_ptr(), stream)
+        eng.reset_all_dev(stream)        # every tree back to a fresh root: stream-ordered, host arena bookkeeping included (no sync)
         buf.pack_roots(boards, turns, stream)
         return 2 + ds.playout_device(eng, buf, n_playout, K, ev, stream, shards=n_shards or shards)
 
@@ -318,6 +373,7 @@ def main():
     d_bar, E_bar, b_bar, x_bar = st["depth"] / sims, st["edges_scanned"] / sims, st["edges_created"] / sims, st["expansions"] / sims
     bytes_select_sim = 36 * d_bar + 40 * E_bar + 8 * (d_bar + 1) + 68 * x_bar + (S + A + 21)
     bytes_total_sim = 36 * d_bar + 40 * E_bar + 60 * (d_bar + 1) + 16 * b_bar + S + 5 * A + 118     # SURVEY.md 8(d) B_sim
+    bytes_backprop_sim = bytes_total_sim - bytes_select_sim
 
     for _ in range(args.warmup):
         dev_step()
@@ -328,7 +384,6 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    l0 = eng.get_stats()["launches"]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     launches = 0
@@ -340,14 +395,11 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     ms = t_start.elapsed_time(t_end)
-    # the dominant kernel with CUDA events around every select launch (az_mcts_time_select; the loop is then issued launch by
-    # launch instead of replayed from its graph): one more sharded step, then ...
+    clk = clocks.stop() if rank == 0 else None
+    # the tree kernels with CUDA events around every select and back-prop launch (az_mcts_time_select; the loop is then issued
+    # launch by launch instead of replayed from its graph), timed ALONE: two more steps with the whole batch per launch on one
+    # stream, so a launch's elapsed time is the kernel's own (in the sharded step it shares the SMs with other shards' kernels)
     eng.time_select(True)
-    dev_step()
-    torch.cuda.synchronize()
-    sel_ms, sel_launches, sel_rows = eng.get_select_time()
-    # ... the dominant kernel timed ALONE: two more steps with the whole batch per launch on one stream (no overlap with other
-    # shards' kernels)
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a0.record()
     for _ in range(2):
@@ -355,7 +407,8 @@ def main():
     a1.record()
     torch.cuda.synchronize()
     alone_step_ms = a0.elapsed_time(a1) / 2
-    alone_sel_ms, alone_sel_launches, alone_sel_rows = eng.get_select_time()
+    sel_ms, sel_launches, sel_rows = eng.get_select_time()
+    bp_ms, bp_launches, bp_rows = eng.get_backprop_time()
     eng.time_select(False)
     if world > 1:
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -389,8 +442,9 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        e2e_steps = min(args.steps, 60)
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             wrap_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -398,8 +452,8 @@ def main():
             tt = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        e2e = {"value": total_sims / dt, "unit": UNIT, "h2d_bytes_per_step": G * (S + 4 + 4), "d2h_bytes_per_step": G * A * 4,
-               "ms_per_step": 1e3 * dt / args.steps,
+        e2e = {"value": world * G * n_playout * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": G * (S + 4 + 4), "d2h_bytes_per_step": G * A * 4,
+               "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
                "api": "BatchedMCTS.prune_roots + batch_playout(numpy boards, numpy turns) + get_visits_count() (wrapper mirror of "
                       "src/MCTS_cpp.py; evaluator runs on the device)"}
         del wrap
@@ -412,63 +466,95 @@ def main():
             bs_np, ts_np, rs_np = boards_np[:Gs], turns_np[:Gs], reset_np[:Gs]
             host_step(engs, bs_np, ts_np, n_playout, K, A, rs_np)
             t0, t_ev = time.perf_counter(), 0.0
-            for _ in range(2):
+            for _ in range(3):
                 t_ev += host_step(engs, bs_np, ts_np, n_playout, K, A, rs_np)
-            dts, t_ev = (time.perf_counter() - t0) / 2, t_ev / 2
+            dts, t_ev = (time.perf_counter() - t0) / 3, t_ev / 3
             h2d, d2h = step_io_bytes(Gs, n_playout, K, S, A)
             e2e_split = {"value": Gs * n_playout / dts, "unit": UNIT, "games": Gs, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                          "ms_per_step": 1e3 * dts, "ms_in_engine_calls": 1e3 * (dts - t_ev), "ms_in_numpy_evaluator": 1e3 * t_ev,
                          "value_engine_calls_only": Gs * n_playout / max(dts - t_ev, 1e-9),
-                         "api": "mcts_cpp.search_batch[_vl]/backprop_batch[_vl] with numpy leaf buffers + numpy evaluator on the host"}
+                         "api": "mcts_cpp.search_batch[_vl]/backprop_batch[_vl] with numpy leaf buffers + numpy evaluator on the host "
+                                "(what the unmodified src/MCTS_cpp.py drives)"}
             del engs
-    # ---- self-play games/s: the on-device driver (search + sample + record + env step + re-root + training tuples) ----
-    selfplay = None
-    if not args.no_selfplay:
-        sp_mod = importlib.import_module("alphazero-al_b200.selfplay")
-        n_slots = min(G, args.selfplay_slots)
+    del eng, buf
+    torch.cuda.empty_cache()
+
+    # ---- self-play games/s: the on-device driver (search + sample + record + env step + re-root + finished trajectories), with the
+    # trajectory all-gather - the one collective of the path - inside the timed loop, issued on a side stream behind the next batch ----
+    sp_mod = importlib.import_module("alphazero-al_b200.selfplay")
+
+    def selfplay_leg(n_slots, plies, every):
         lo, _ = sp_mod.shard_range(world * n_slots, rank, world)
         sp = sp_mod.SelfPlay("Connect4", n_slots, n_playout, K, ds.SyntheticEvaluator("Connect4", "constant"), search_cfg=SERVER_DEFAULTS,
                              temperature=1.0, temp_decay_moves=20, temp_endgame=0.0, td_steps=10, seed=0, uid_base=lo,
-                             uid_stride=world * n_slots, device=local_rank, out_capacity=4 * n_slots)
+                             uid_stride=world * n_slots, device=local_rank, out_capacity=2 * n_slots)
         sp.engine.reserve(16384)                  # arena compaction at re-roots keeps every game inside 16384 slots (2 pools x 512 KB)
+        exch = sp_mod.TrajectoryExchange("Connect4", sp.out_capacity, dev)
         for _ in range(12):                       # reach the steady state of continuously restarting games
             sp.ply()
+        exch.gather(sp.hand_over())               # warm-up exchange: NCCL connection set-up, buffer registration
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        g0, p0 = int(sp.out_count.item()), sp.plies
+        torch.cuda.synchronize()
+        p0, l0 = sp.plies, sp.launches
         t0 = time.perf_counter()
-        for _ in range(args.selfplay_plies):
-            sp.ply()
-        g1 = int(sp.out_count.item())
+        pending, gathered_games, gathered_pos, replay_rows = None, 0, 0, 0
+        done_plies = 0
+        while done_plies < plies:
+            for _ in range(min(every, plies - done_plies)):
+                sp.ply()
+            done_plies += min(every, plies - done_plies)
+            ring = sp.hand_over()                 # batch closed on the main stream; the other ring takes over
+            if pending is not None:               # the previous batch's gather is issued behind this batch's (already enqueued) search
+                exch.submit(pending)
+            pending = ring
+        e_main = torch.cuda.Event()
+        e_main.record()
+        exch.submit(pending)
+        e_main.synchronize()
+        t_main = time.perf_counter() - t0
+        while exch.pending:
+            rec = exch.collect()
+            gathered_games += len(rec)
+            gathered_pos += rec.positions
+            if len(rec):
+                replay_rows += int(rec.to_replay_tensors(10)["state"].shape[0])      # the receiving side's expansion into training tuples
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        recs = sp.out[:min(g1, sp.out_capacity)]
-        if world > 1:                             # the first collective of this size pays NCCL's connection set-up and the allocations
-            sp_mod.all_gather_records(recs, recs.shape[0], sp.out_capacity)
-            torch.cuda.synchronize()
-            dist.barrier()
-        t1 = time.perf_counter()
-        gathered, gcounts = sp_mod.all_gather_records(recs, recs.shape[0], sp.out_capacity)
-        torch.cuda.synchronize()
-        t_gather = time.perf_counter() - t1
-        tot = torch.tensor([g1 - g0, dt], device=dev, dtype=torch.float64)
+        tot = torch.tensor([dt, t_main], device=dev, dtype=torch.float64)
         if world > 1:
-            mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-            tot[1] = mx[1]
-        games, dt = float(tot[0].item()), float(tot[1].item())
-        selfplay = {"games_per_sec": games / dt, "sims_per_sec": world * n_slots * n_playout * (sp.plies - p0) / dt,
-                    "slots_per_gpu": n_slots, "plies_timed": sp.plies - p0, "games_finished": games,
-                    "record_bytes": sp.layout.record_bytes, "allgather_ms": 1e3 * t_gather, "gathered_records": int(gathered.shape[0]),
-                    "note": "continuous self-play with tree reuse, temp 1 for 20 plies then 0, td_steps 10, constant evaluator; "
-                            "every finished game becomes one packed training record, all-gathered over NCCL when world > 1"}
-        del sp
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        dt, t_main = float(tot[0].item()), float(tot[1].item())
+        out = {"games_per_sec": gathered_games / dt, "sims_per_sec": world * n_slots * n_playout * (sp.plies - p0) / dt,
+               "slots_per_gpu": n_slots, "plies_timed": sp.plies - p0, "games_finished_all_ranks": gathered_games,
+               "positions_gathered": gathered_pos, "replay_rows_expanded": replay_rows, "seconds": dt,
+               "exchange_every_plies": every, "exchanges": len(exch.ms) - 1,
+               "allgather_ms_mean": float(np.mean(exch.ms[1:])) if len(exch.ms) > 1 else None,
+               "allgather_ms_max": float(np.max(exch.ms[1:])) if len(exch.ms) > 1 else None,
+               "collective_exposed_ms": 1e3 * (dt - t_main),
+               "bytes_received_per_rank": exch.bytes_gathered, "position_record_bytes": sp.pb, "game_header_bytes": sp_mod.GAME_BYTES,
+               "gpu_launches": sp.launches - l0}
+        del sp, exch
+        torch.cuda.empty_cache()
+        return out
+
+    selfplay = None
+    if not args.no_selfplay:
+        selfplay = selfplay_leg(min(G, args.selfplay_slots), args.selfplay_plies, args.exchange_every)
+        selfplay["note"] = ("continuous self-play with tree reuse, temp 1 for 20 plies then 0, constant evaluator; games counted from the "
+                            "gathered records of all ranks (finished games, no estimate); every `exchange_every_plies` plies the finished "
+                            "trajectories (compact records: 32-byte header + 64 bytes per position) are all-gathered over NCCL on a side "
+                            "stream while the next batch is searched, then expanded into replay tensors on every rank; "
+                            "collective_exposed_ms = time after the last ply until the last gather + expansion completed")
+        if world > 1 and args.strong_total >= world * 1024:
+            selfplay["strong_scaling"] = dict(selfplay_leg(args.strong_total // world, args.selfplay_plies, args.exchange_every),
+                                              total_games_in_flight=args.strong_total,
+                                              note="BASELINE config 5 as stated: 65 536 concurrent games in total, split over the GPUs")
     # ---- the same self-play with a random-init CNN of the reference's Connect4 architecture in the loop (bf16 autocast) ----
     selfplay_cnn = None
     if not args.no_cnn and world == 1:
         nets = importlib.import_module("alphazero-al_b200.nets")
-        sp_mod = importlib.import_module("alphazero-al_b200.selfplay")
         torch.manual_seed(0)
         net = nets.C4Net(device=f"cuda:{local_rank}")
         n_slots = args.cnn_slots
@@ -477,36 +563,37 @@ def main():
         sp.engine.reserve(16384)
         sp.ply()
         torch.cuda.synchronize()
-        g0, p0 = int(sp.out_count.item()), sp.plies
+        p0 = sp.plies
         t0 = time.perf_counter()
         for _ in range(args.cnn_plies):
             sp.ply()
-        g1 = int(sp.out_count.item())
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         selfplay_cnn = {"sims_per_sec": n_slots * n_playout * (sp.plies - p0) / dt, "positions_per_sec": n_slots * (sp.plies - p0) / dt,
-                        "games_per_sec_est": n_slots * (sp.plies - p0) / dt / 21.0, "slots": n_slots, "plies_timed": sp.plies - p0,
+                        "slots": n_slots, "plies_timed": sp.plies - p0,
                         "evaluator": "C4Net (160358 params, reference Connect4 CNN shape), random init, bf16 autocast, device contract "
-                                     "(leaves -> planes -> net -> finalize, no host copy)",
-                        "note": "games_per_sec_est = positions/s / 21 plies (mean length of random-init self-play games, SURVEY.md App. C.4)"}
+                                     "(leaves -> planes -> net -> finalize, no host copy)"}
         del sp
         # BASELINE config 1 itself: 100 games, n=200, K=4, random-init CNN - 100..400 leaves per evaluation, bound by the launches
-        # of the forward pass; NetEvaluator replays it from a CUDA graph (eager timed beside it)
+        # of the forward pass; NetEvaluator replays it from a CUDA graph (eager timed beside it).  games/s = finished games / time
+        # over the timed plies at the steady state of continuously restarting slots.
         c0 = {}
         for name, graph_rows, csize in (("eager", 0, 0), ("graph", 8192, 0), ("graph+cache", 8192, 1 << 20)):
             sp = sp_mod.SelfPlay("Connect4", 100, n_playout, K, net, search_cfg=SERVER_DEFAULTS, temperature=1.0, temp_decay_moves=20,
                                  temp_endgame=0.0, td_steps=10, seed=0, device=local_rank, out_capacity=1024, cache_size=csize)
             sp.evaluator.graph_rows = graph_rows
-            for _ in range(12 if csize else 2):     # the cache is timed past the opening (every game starts from the same position)
+            for _ in range(14):                   # past the opening: slots at mixed plies (and the cache past the shared first moves)
                 sp.ply()
+            sp.drain()
             torch.cuda.synchronize()
             p0, t0 = sp.plies, time.perf_counter()
-            for _ in range(args.cnn_plies_100):
+            for _ in range(args.cnn_plies_100 if name != "eager" else max(4, args.cnn_plies_100 // 4)):
                 sp.ply()
+            fin = sp.drain()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             c0[name] = {"sims_per_sec": 100 * n_playout * (sp.plies - p0) / dt, "ms_per_ply": 1e3 * dt / (sp.plies - p0),
-                        "games_per_sec_est": 100 * (sp.plies - p0) / dt / 21.0, "graph_replays": sp.evaluator.graph_replays}
+                        "games_finished": len(fin), "games_per_sec": len(fin) / dt, "graph_replays": sp.evaluator.graph_replays}
             del sp
         selfplay_cnn["config1_100_games"] = c0
         # the same with the device evaluation cache + in-batch de-duplication: only distinct unseen positions
@@ -517,24 +604,25 @@ def main():
             sp.engine.reserve(16384)
             for _ in range(args.cnn_cached_warm_plies):
                 sp.ply()
+            sp.drain()
             torch.cuda.synchronize()
             st0, r0, p0 = sp.eval_cache.stats(), sp.evaluator.net_rows, sp.plies
             t0 = time.perf_counter()
             for _ in range(args.cnn_cached_plies):
                 sp.ply()
+            fin = sp.drain()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             st1 = sp.eval_cache.stats()
             look = max(st1["lookups"] - st0["lookups"], 1)
             selfplay_cnn["cached"] = {
                 "sims_per_sec": n_slots * n_playout * (sp.plies - p0) / dt, "positions_per_sec": n_slots * (sp.plies - p0) / dt,
-                "games_per_sec_est": n_slots * (sp.plies - p0) / dt / 21.0, "plies_timed": sp.plies - p0, "plies_before": p0,
+                "games_finished": len(fin), "games_per_sec": len(fin) / dt, "plies_timed": sp.plies - p0, "plies_before": p0,
                 "cache_entries": st1["capacity"], "hit_frac": (st1["hits"] - st0["hits"]) / look, "dup_frac": (st1["dups"] - st0["dups"]) / look,
                 "net_rows_frac": (sp.evaluator.net_rows - r0) / look,
                 "note": "device evaluation cache + in-batch de-duplication; timed after the warm plies, slots at mixed game plies"}
             del sp
         del net
-    clk = clocks.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -546,33 +634,39 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = (sel_rows * bytes_select_sim) / (sel_ms * 1e-3) / 1e9 if sel_ms > 0 else 0.0
-    achieved_alone = (alone_sel_rows * bytes_select_sim) / (alone_sel_ms * 1e-3) / 1e9 if alone_sel_ms > 0 else 0.0
-    # DRAM bytes per select launch from the committed `ncu --set full` capture of the same workload (profiles/)
-    traffic, traffic_src = None, None
-    if G == 65536 and K == 4 and eng.get_lanes() == 1 and eng.get_variant() == 1:
-        traffic = 99.600e6 + 24.502e6
-        traffic_src = ("profiles/r1m_per_kernel_traffic_warm_l2_n65536.csv: dram__bytes_read.sum + dram__bytes_write.sum per k_select_f launch, mean "
-                       "over the 50 launches of one step, ncu --cache-control none (warm L2 as in a real run; the writes are mostly dirty sectors "
-                       "of the previous back-prop being evicted; cold-L2 capture: 101.2 + 16.9 MB, profiles/r1g_*); algorithmic bytes of one "
-                       "launch (262144 simulations) = %.1f MB" % (G * K * bytes_select_sim / 1e6))
-    kname = ("az::k_select_f<C4,VL,AUX>" if eng.get_variant() == 1 else "az::k_select_t<C4,VL>") if eng.get_lanes() == 1 else f"az::k_select<C4,{eng.get_lanes()},VL>"
-    roofline = {"bound": "hbm", "kernel": kname, "lanes_per_tree": eng.get_lanes(), "achieved": achieved_alone, "peak": peak, "unit": "GB/s",
-                "frac": achieved_alone / peak, "shards": shards,
-                "note": ("achieved = algorithmic select bytes / CUDA-event time of the select launches (events on the launching stream, "
-                         "az_mcts_time_select), taken in 2 extra steps right after the timed region with the whole batch per launch on ONE "
-                         "stream.  The timed region itself replays the step from a CUDA graph with `shards` tree ranges on their own "
-                         "streams: there a select launch shares the SMs with other shards' evaluate / back-prop kernels and its elapsed "
-                         "time is not the kernel's own - one extra sharded step with events is reported under sharded_step"),
-                "sharded_step": {"achieved": achieved, "frac": achieved / peak, "select_launches": sel_launches,
-                                    "select_us_per_launch": 1e3 * sel_ms / max(sel_launches, 1), "trees_per_launch": G // max(shards, 1)},
-                "select_us_per_launch": 1e3 * alone_sel_ms / max(alone_sel_launches, 1), "ms_per_step_one_stream": alone_step_ms,
-                "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "bytes_per_sim_select": bytes_select_sim, "bytes_per_sim_whole_path": bytes_total_sim,
-                "tree_stats": {"depth": d_bar, "edges_scanned": E_bar, "edges_created": b_bar, "expansions": x_bar},
-                "select_share_of_step": alone_sel_ms / (2 * alone_step_ms) if alone_step_ms > 0 else None,
-                "whole_path_frac": value / world * bytes_total_sim / 1e9 / peak}
+    traffic_all = load_traffic()
+
+    def kernel_roofline(kname, key, ms_sum, n_launch, rows, bytes_sim):
+        ach = (rows * bytes_sim) / (ms_sum * 1e-3) / 1e9 if ms_sum > 0 else 0.0
+        tr = src = None
+        if traffic_all and not traffic_all["stale"] and key in traffic_all.get("kernels", {}):
+            k = traffic_all["kernels"][key]
+            tr = (k["dram_read_bytes"] + k["dram_write_bytes"]) / max(k["launches"], 1)
+            src = f"profiles/dram_traffic.json ({traffic_all.get('captured_from')}; kernel_src_sha {traffic_all.get('kernel_src_sha')})"
+        elif traffic_all and traffic_all["stale"]:
+            src = "profiles/dram_traffic.json is stale (captured from other kernel sources): not reported"
+        return {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": tr,
+                "traffic_source": src, "us_per_launch": 1e3 * ms_sum / max(n_launch, 1), "launches_timed": n_launch,
+                "algorithmic_bytes_per_sim": bytes_sim, "algorithmic_bytes_per_launch": bytes_sim * rows / max(n_launch, 1),
+                "share_of_one_stream_step": ms_sum / (2 * alone_step_ms) if alone_step_ms > 0 else None}
+
+    lanes, variant = 1, 1
+    sel = kernel_roofline("az::k_select_f<C4,VL,AUX,RO>", "k_select_f", sel_ms, sel_launches, sel_rows, bytes_select_sim)
+    bp = kernel_roofline("az::k_backprop_f<C4,VL,RO>", "k_backprop_f", bp_ms, bp_launches, bp_rows, bytes_backprop_sim)
+    dominant = sel if sel_ms >= bp_ms else bp
+    roofline = dict(dominant)
+    roofline.update({
+        "kernels": {"select": sel, "backprop": bp},
+        "note": ("per kernel: achieved = algorithmic bytes (SURVEY.md 8d model x on-device tree statistics of an untimed pass) / CUDA-event "
+                 "time of its launches, events on the launching stream (az_mcts_time_select), taken in 2 extra steps right after the timed "
+                 "region with the whole batch per launch on ONE stream so that a launch's elapsed time is the kernel's own (the timed region "
+                 "replays the step from a CUDA graph with tree shards on several streams, where kernels of different shards share the SMs).  "
+                 "The top-level keys repeat the kernel with the larger share of the step"),
+        "ms_per_step_one_stream": alone_step_ms, "shards_in_timed_region": shards,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+        "bytes_per_sim_whole_path": bytes_total_sim,
+        "tree_stats": {"depth": d_bar, "edges_scanned": E_bar, "edges_created": b_bar, "expansions": x_bar},
+        "whole_path_frac": value / world * bytes_total_sim / 1e9 / peak})
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
@@ -588,9 +682,11 @@ def main():
             cpu["native_harness"] = r.get("native_harness")
         except Exception as e:   # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+        if not args.no_actor_baseline:
+            cpu["reference_actor_config1"] = reference_actor()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(config, l2="working set (tree arenas touched per step) > 126 MB L2, no flush"),
+            "data": "synthetic", "config": config,
             "clocks": clk, "e2e": e2e, "e2e_split_api": e2e_split, "selfplay": selfplay, "selfplay_cnn": selfplay_cnn, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:

@@ -221,6 +221,8 @@ int az_mcts_get_stats(az_mcts *h, uint64_t *out8);
  * the leaf rows (trees x simulations) they produced since the last call (bench.py: roofline of the dominant kernel). */
 int az_mcts_time_select(az_mcts *h, int on);
 int az_mcts_get_select_time(az_mcts *h, float *ms_out, int *launches_out, uint64_t *rows_out);
+/* the same for the back-prop launches (timed whenever az_mcts_time_select is on) */
+int az_mcts_get_backprop_time(az_mcts *h, float *ms_out, int *launches_out, uint64_t *rows_out);
 /* Diagnostics (stats mode, thread-per-tree Connect4 select): out[2w], out[2w+1] = %globaltimer (ns) at the start / end of
  * warp w of the most recent select launch.  Returns the number of warps written (<= max_warps) or a negative error. */
 int az_mcts_get_warp_times(az_mcts *h, uint64_t *out, int max_warps);

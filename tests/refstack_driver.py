@@ -11,6 +11,7 @@ tasks
             fed like server.py:295-304) and out.pkl (the upload payload of client.py:367-373)
   playout   src.MCTS_cpp.BatchedMCTS.batch_playout over several moves with the LRU cache on -> counts / root stats per move, the
             cache's key order and values at the end
+  load_pt   the reference's ReplayBuffer.load on a .pt file -> what it holds afterwards
   cnn       the reference's own CNN (bf16 autocast on CUDA) in the loop: (a) its predict() drives the compiled reference engine through
             the reference-style host loop while every leaf batch and evaluator output is recorded, (b) the CUDA engine is fed the
             recorded outputs (same evaluator outputs to both -> leaves and visit counts must be identical), (c) the
@@ -182,6 +183,17 @@ def task_playout(out, p):
     print("playout", p["game"], "moves", p["moves"], "cache entries", len(keys), "predict rows", pv.rows)
 
 
+def task_load_pt(out, p):
+    """The reference's ReplayBuffer.load on a file (src/ReplayBuffer.py:40-62)."""
+    from src.ReplayBuffer import ReplayBuffer
+    buf = ReplayBuffer(3, p["rows"], p["A"], p["R"], p["C"])
+    buf.load(p["path"])
+    np.savez_compressed(out, ptr=np.array(buf._ptr), len=np.array(len(buf)), state=buf.state.numpy(), prob=buf.prob.numpy(),
+                        winner=buf.winner.numpy(), steps_to_end=buf.steps_to_end.numpy(), aux_target=buf.aux_target.numpy(),
+                        root_wdl=buf.root_wdl.numpy(), valid_mask=buf.valid_mask.numpy(), future_root_wdl=buf.future_root_wdl.numpy())
+    print("load_pt", len(buf))
+
+
 def task_cnn(out, p):
     import importlib
     import torch
@@ -308,4 +320,4 @@ def task_actor(out, p):
 
 if __name__ == "__main__":
     task, out, params = sys.argv[1], sys.argv[2], json.loads(sys.argv[3])
-    {"selfplay": task_selfplay, "playout": task_playout, "actor": task_actor, "cnn": task_cnn}[task](out, params)
+    {"selfplay": task_selfplay, "playout": task_playout, "actor": task_actor, "cnn": task_cnn, "load_pt": task_load_pt}[task](out, params)

@@ -110,17 +110,17 @@ def test_selfplay_32768_slots_record_invariants():
     for _ in range(46):
         sp.ply()
     torch.cuda.synchronize()
-    m = min(int(sp.out_count.item()), sp.out_capacity)
+    rec = sp.drain()
+    m = len(rec)
     assert m >= n, "every slot finishes at least one game in 46 plies"
     assert sp.engine.compactions() > 0
-    recs = sp.out[:m]
-    L = sp.layout
-    length = recs[:, L.off_header:L.off_header + 4].contiguous().view(torch.int32).reshape(m)
-    winner = recs[:, L.off_header + 4:L.off_header + 8].contiguous().view(torch.int32).reshape(m)
-    uid = recs[:, L.off_header + 8:L.off_header + 16].contiguous().view(torch.int64).reshape(m)
+    recs = rec.games
+    length, winner, uid = rec.length, rec.winner, rec.uid
     assert int(length.min()) >= 8 and int(length.max()) <= 43 and bool(((winner >= -1) & (winner <= 1)).all())
     assert uid.unique().numel() == m, "game uids are unique"
-    t = sp_mod.to_replay_tensors(recs, "Connect4")
+    rec = rec.sorted_by_uid()
+    length, winner, uid = rec.length, rec.winner, rec.uid
+    t = rec.to_replay_tensors(5)
     st, prob, mask = t["state"].to(torch.int32), t["prob"], t["valid_mask"]
     P = st.shape[0]
     assert P == int(length.sum())

@@ -335,6 +335,79 @@ def test_sharded_device_loop_equals_unsharded_loop(game, n, lanes, shards):
     assert res[0][1].tobytes() == res[1][1].tobytes()
 
 
+def test_more_shards_than_streams_still_searches_every_tree():
+    """az_mcts_playout_synthetic_dev drives at most 16 streams: a larger shard count is merged, every tree still gets its
+    simulations (root N = n_playout; visit counts sum to n_playout - 1 below a fresh root)."""
+    import torch
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    n, K, npl = 4096, 4, 41
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    boards, turns = np.zeros((n, 6, 7), np.int8), np.ones(n, np.int32)
+    res = []
+    for sh in (1, 32):
+        e = _cuda("Connect4", n)
+        set_config(e, **dict(SERVER_DEFAULTS, use_symmetry=True))
+        e.set_seed(5)
+        buf = ds.LeafBuffers(n, n * K, 7, (6, 7), dev)
+        buf.pack_roots(torch.from_numpy(boards).to(dev), torch.from_numpy(turns).to(dev), stream)
+        ds.playout_device(e, buf, npl, K, ds.SyntheticEvaluator("Connect4", "hash"), stream, shards=sh)
+        st = e.get_all_root_stats()
+        assert (st[:, 0] == npl).all(), f"shards={sh}: {int((st[:, 0] != npl).sum())} trees were not searched"
+        res.append(counts(e, n, 7))
+    assert np.array_equal(res[0], res[1]) and (res[0].sum(1) == npl - 1).all()
+
+
+def test_interleaved_shard_launches_keep_their_own_select_mode():
+    """Shards run ahead of each other: search(shard 0, K=4), search(shard 1, non-VL), back-prop(shard 0), back-prop(shard 1) in host
+    order.  Every back-prop must pair with the select of ITS tree range (a read-only select leaves the leaf flags and the virtual
+    loss to its back-prop, the others do not); a back-prop that matches no select of its range is refused."""
+    import torch
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    n, K = 8192 * 2, 4
+    dev = torch.device("cuda", 0)
+    s = torch.cuda.current_stream().cuda_stream
+    boards, turns = random_positions("Connect4", 64, 10, 3)
+    boards, turns = np.tile(boards, (n // 64, 1, 1)), np.tile(turns, n // 64)
+    ev = ds.SyntheticEvaluator("Connect4", "hash")
+    half = n // 2
+
+    def engine():
+        e = _cuda("Connect4", n)
+        set_config(e, **dict(SERVER_DEFAULTS, use_symmetry=False))
+        e.set_wave_max(0)
+        buf = ds.LeafBuffers(n, n * K, 7, (6, 7), dev)
+        buf.pack_roots(torch.from_numpy(boards).to(dev), torch.from_numpy(turns).to(dev), s)
+        return e, buf
+
+    def step(e, buf, k, lo, cnt, do_search=True, do_back=True):
+        row0 = lo * K
+        if do_search:
+            e.search_range_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), lo, cnt, row0, True, s)
+            ev(buf, cnt * max(k, 1), s, row0)
+        if do_back:
+            e.backprop_range_dev(k, buf.policy.data_ptr(), buf.d.data_ptr(), buf.p1w.data_ptr(), buf.p2w.data_ptr(), buf.ml.data_ptr(), lo, cnt, row0, 0, 0, s)
+
+    a, ba = engine()                                          # shard by shard, each search followed by its back-prop
+    for lo in (0, half):
+        step(a, ba, 0, lo, half)
+        step(a, ba, K, lo, half)
+    step(a, ba, 0, half, half)
+    b, bb = engine()                                          # interleaved host order
+    step(b, bb, 0, 0, half); step(b, bb, 0, half, half)
+    step(b, bb, K, 0, half, do_back=False)                    # shard 0: VL select (read-only variant) ...
+    step(b, bb, K, half, half)                                # ... shard 1 runs a whole VL iteration and then a non-VL select ...
+    step(b, bb, 0, half, half, do_back=False)
+    step(b, bb, K, 0, half, do_search=False)                  # ... before shard 0's back-prop
+    step(b, bb, 0, half, half, do_search=False)
+    assert np.array_equal(counts(a, n, 7), counts(b, n, 7))
+    assert a.get_all_root_stats().tobytes() == b.get_all_root_stats().tobytes()
+    step(b, bb, K, 0, half, do_back=False)
+    with pytest.raises(RuntimeError, match="does not match"):
+        step(b, bb, 0, 0, half, do_search=False)              # non-VL back-prop after a VL select of the same range
+    b.remove_all_vl(K)
+
+
 @pytest.mark.parametrize("game,mode,K", [("Connect4", "hash", 4), ("Connect4", "equivariant", 8), ("Othello", "hash", 4)])
 def test_device_resident_loop_equals_host_buffer_loop(game, mode, K):
     """search_dev -> az_eval_synthetic_dev -> backprop_dev (no host round trip, flags/sym ids remembered inside the

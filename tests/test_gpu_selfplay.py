@@ -91,8 +91,8 @@ def test_selfplay_records_equal_reference_style_loop(game, n, npl, K, cfg):
     want = reference_style_self_play(orc, ev_mod.HashEvaluator(game, "hash"), game, n, npl, K, td)
     sp = sp_mod.SelfPlay(game, n, npl, K, ds.SyntheticEvaluator(game, "hash"), search_cfg=cfg, temperature=0.0, temp_decay_moves=0,
                          temp_endgame=0.0, td_steps=td, seed=11, out_capacity=8 * n)
-    recs, m = sp.run(target_games=8 * n, max_plies=max(w["length"] for w in want) + 1)
-    got = {g["uid"]: g for g in sp_mod.unpack_records(recs, game, td) if g["uid"] < n}
+    recs = sp.run(target_games=8 * n, max_plies=max(w["length"] for w in want) + 1)
+    got = {g["uid"]: g for g in recs.unpack(td) if g["uid"] < n}
     assert sorted(got) == list(range(n)), "every first-generation game must have been flushed"
     for i in range(n):
         g, w = got[i], want[i]
@@ -101,6 +101,63 @@ def test_selfplay_records_equal_reference_style_loop(game, n, npl, K, cfg):
             assert np.array_equal(np.asarray(g[k]), w[k]), f"game {i} field {k}"
     w0, tup = got[0]["tuples"]
     assert w0 == want[0]["winner"] and len(tup) == want[0]["length"] and len(tup[0]) == 8 and tup[0][0].dtype == np.int8
+
+
+@pytest.mark.parametrize("name", ["py_c4_selfplay_k4_sym", "py_c4_selfplay_k1_td0", "py_oth_selfplay_k4"])
+def test_selfplay_driver_reproduces_reference_batch_self_play(name):
+    """Pinned to the reference: tests/golden/py_*_selfplay_* hold what the UNMODIFIED Game.batch_self_play + get_batch_action
+    returned on the compiled reference engine (temperature 1 on the opening plies, sampled from numpy's generator).  The on-device
+    driver replays the recorded moves (opening script; the sampling RNG itself is unpinned by nature) and must produce the same
+    compact records bit for bit - policy targets from its own visit counts, root WDL from its own root statistics, winner, length,
+    positions - hence, through the expansion kernel, every training tuple of the fixture."""
+    import json
+    import os
+    import torch
+    from fixture_records import GOLD, fixture_records, forced_actions, load_fixture
+    from test_record_formats import _assert_tensors_match_fixture
+    sp_mod = importlib.import_module("alphazero-al_b200.selfplay")
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    case = json.load(open(os.path.join(GOLD, "py_cases.json")))["selfplay"][name]
+    z = load_fixture(name)
+    game, n, td = case["game"], case["n_games"], case["td_steps"]
+    cfg = dict(case["cfg"], dirichlet_alpha=0.0, use_symmetry=case["use_symmetry"])
+    cfg.setdefault("mlh_slope", 0.0)
+    sp = sp_mod.SelfPlay(game, n, case["n_playout"], case["K"], ds.SyntheticEvaluator(game, case["mode"]), search_cfg=cfg,
+                         temperature=case["temperature"], temp_decay_moves=case["temp_decay_moves"], temp_endgame=0.0, td_steps=td,
+                         seed=case["seed"], out_capacity=8 * n, forced_actions=forced_actions(z, game), forced_uid0=0)
+    recs = sp.run(target_games=8 * n, max_plies=int(z["length"].max()))
+    first = recs.uid < n
+    mine = sp_mod.Records.cat([sp_mod.Records(game, recs.games[i:i + 1], recs.pos) for i in torch.nonzero(first).flatten().tolist()]).sorted_by_uid()
+    want = fixture_records(z, game)
+    assert mine.uid.tolist() == list(range(n)) and mine.length.tolist() == want.length.tolist() and mine.winner.tolist() == want.winner.tolist()
+    assert torch.equal(mine.games.cpu(), want.games), "game headers differ from the reference's games"
+    assert torch.equal(mine.pos.cpu(), want.pos), "position records differ (bitboards / side to move / root WDL / policy target)"
+    _assert_tensors_match_fixture(mine.to_replay_tensors(td), z, td)
+
+
+def test_self_play_records_do_not_depend_on_the_sharding():
+    """game i must give the same record whichever rank / slot range owns it.  One engine with G slots against
+    two engines with G/2 slots each (`set_env_base`, `uid_base`, `uid_stride` = G, as rank 0 / rank 1 of a 2-GPU run would be set up),
+    everything RNG-dependent switched on (Dirichlet noise, random leaf symmetries, temperature sampling): identical records per uid."""
+    import torch
+    sp_mod = importlib.import_module("alphazero-al_b200.selfplay")
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    G, npl, K, plies = 256, 40, 4, 30
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True, dirichlet_alpha=0.3)
+
+    def play(n, base):
+        sp = sp_mod.SelfPlay("Connect4", n, npl, K, ds.SyntheticEvaluator("Connect4", "hash"), search_cfg=cfg, temperature=1.0, temp_decay_moves=8,
+                             td_steps=4, seed=21, uid_base=base, uid_stride=G, out_capacity=6 * n)
+        for _ in range(plies):
+            sp.ply()
+        return sp.drain()
+
+    whole = play(G, 0).sorted_by_uid()
+    halves = sp_mod.Records.cat([play(G // 2, 0), play(G // 2, G // 2)]).sorted_by_uid()
+    assert len(whole) > G and whole.uid.unique().numel() == len(whole)
+    assert torch.equal(whole.games, halves.games) and torch.equal(whole.pos, halves.pos)
+    t = whole.to_replay_tensors(4)
+    assert float(t["prob"].sum()) > 0
 
 
 def test_temperature_sampling_follows_visit_distribution():
@@ -113,7 +170,7 @@ def test_temperature_sampling_follows_visit_distribution():
     sp.ply()
     import torch
     torch.cuda.synchronize()
-    probs = sp.st_prob[:, 0].cpu().numpy()                   # identical trees: same visit distribution in every slot
+    probs = sp.st_pos[:, 0, 32:60].contiguous().view(torch.float32).cpu().numpy()      # identical trees: same visit distribution in every slot
     acts = sp.actions.cpu().numpy()
     assert np.allclose(probs, probs[0])
     freq = np.bincount(acts, minlength=7) / n

@@ -1,10 +1,9 @@
-"""world_size-2 CPU (gloo) tests of the N>1 host logic: contiguous game sharding, sharding-invariant uids, and the
-single all-gather of fixed-size packed trajectory records."""
+"""world_size-2 CPU (gloo) tests of the N>1 host logic: contiguous game sharding, sharding-invariant uids, and the single
+all-gather of compact trajectory records: counts first, then max(count) rows per rank, ragged ranks, rank order."""
 import importlib
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -19,21 +18,22 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, total, out):
+def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fixture_records import fixture_records, load_fixture
     sp_mod = importlib.import_module("alphazero-al_b200.selfplay")
-    lo, hi = sp_mod.shard_range(total, rank, world)
-    rb = sp_mod.record_layout("Connect4").record_bytes
-    cap = 8
-    count = 3 + 2 * rank                                           # ragged: ranks finish different numbers of games
-    local = torch.zeros((cap, rb), dtype=torch.uint8)
-    for j in range(count):
-        local[j, :] = (lo + j) % 251                               # recognisable payload
-        local[j, 8:16] = torch.from_numpy(np.array([lo + j], np.uint64).view(np.uint8))
-    gathered, counts = sp_mod.all_gather_records(local, count, cap)
+    full = fixture_records(load_fixture("py_c4_selfplay_k4_sym"), "Connect4")
+    m = len(full)
+    lo, hi = (0, 7) if rank == 0 else (7, m)                        # ragged: ranks finished different numbers of games
+    mine = sp_mod.Records.cat([sp_mod.Records("Connect4", full.games[i:i + 1], full.pos) for i in range(lo, hi)])
+    got = sp_mod.all_gather_records(mine)
+    empty = sp_mod.Records("Connect4", full.games[:0], full.pos[:0])
+    got2 = sp_mod.all_gather_records(mine if rank == 1 else empty)  # a rank with nothing to contribute
     if rank == 0:
-        out.put((lo, hi, counts, gathered.numpy()))
+        out.put((torch.equal(got.games, full.games), torch.equal(got.pos, full.pos), len(got2), got2.uid.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -42,17 +42,15 @@ def test_all_gather_records_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    total = 10
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    lo, hi, counts, g = q.get(timeout=120)
+    same_games, same_pos, n2, uids2 = q.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert (lo, hi) == (0, 5) and counts == [3, 5] and g.shape[0] == 8
-    uids = [int(r[8:16].view(np.uint64)[0]) for r in g]
-    assert uids == [0, 1, 2, 5, 6, 7, 8, 9]                        # rank 0's games then rank 1's, in order
+    assert same_games and same_pos, "rank 0's games then rank 1's, positions re-based: the unsharded record set"
+    assert n2 == 24 - 7 and uids2 == list(range(7, 24))
 
 
 def test_shard_ranges_cover_everything():

@@ -1,69 +1,89 @@
-"""Packed trajectory records -> the reference's replay-buffer tensors, .pt file and upload pickle (CPU only)."""
+"""Compact trajectory records <-> the reference's formats, on fixtures the UNMODIFIED reference produced
+(tests/golden/py_*_selfplay_*: Game.batch_self_play tuples, the ReplayBuffer.save file, the actor's upload pickle).
+
+CPU: record container logic (header views, sort, concatenation).  GPU: the expansion kernel reproduces every training tuple of the
+fixture, `save_replay_pt` writes the file the reference's ReplayBuffer wrote, `to_upload_payload` the pickle its actor uploads; in
+the build container the reference's own `ReplayBuffer.load` additionally reads our file."""
 import importlib
+import json
 import os
 import pickle
-import tempfile
 
 import numpy as np
+import pytest
 import torch
 
+from fixture_records import GOLD, fixture_records, load_fixture
+
 sp_mod = importlib.import_module("alphazero-al_b200.selfplay")
+CASES = json.load(open(os.path.join(GOLD, "py_cases.json")))["selfplay"]
+NAMES = list(CASES)
 
 
-def _fake_records(game, lengths, seed=0):
-    """Builds packed records on the host with the layout az_selfplay_layout_for reports."""
-    rng = np.random.default_rng(seed)
-    L = sp_mod.record_layout(game)
-    gid, R, Cc, A, T = sp_mod._G[game]
-    S = R * Cc
-    out = np.zeros((len(lengths), L.record_bytes), np.uint8)
-    truth = []
-    for i, n in enumerate(lengths):
-        rec = out[i]
-        rec[L.off_header:L.off_header + 8].view(np.int32)[:] = (n, 1 - 2 * (i % 2))
-        rec[L.off_header + 8:L.off_header + 16].view(np.uint64)[:] = 1000 + i
-        st = rng.integers(-1, 2, size=(n, 3, R, Cc)).astype(np.int8)
-        pr = rng.random((n, A)).astype(np.float32)
-        rw, fw = rng.random((n, 3)).astype(np.float32), rng.random((n, 3)).astype(np.float32)
-        wz = np.full(n, 1 - 2 * (i % 2), np.int8)
-        ste = np.arange(n - 1, -1, -1).astype(np.int16)
-        aux = rng.integers(-60, 60, size=n).astype(np.int16)
-        mk = rng.integers(0, 2, size=(n, A)).astype(np.uint8)
-        rec[L.off_state:L.off_state + n * 3 * S] = st.reshape(-1).view(np.uint8)
-        rec[L.off_prob:L.off_prob + n * A * 4] = pr.reshape(-1).view(np.uint8)
-        rec[L.off_root_wdl:L.off_root_wdl + n * 12] = rw.reshape(-1).view(np.uint8)
-        rec[L.off_future:L.off_future + n * 12] = fw.reshape(-1).view(np.uint8)
-        rec[L.off_winner:L.off_winner + n] = wz.view(np.uint8)
-        rec[L.off_steps:L.off_steps + n * 2] = ste.view(np.uint8)
-        rec[L.off_aux:L.off_aux + n * 2] = aux.view(np.uint8)
-        rec[L.off_mask:L.off_mask + n * A] = mk.reshape(-1)
-        truth.append(dict(state=st, prob=pr, root_wdl=rw, future_root_wdl=fw, winner=wz, steps_to_end=ste, aux=aux, mask=mk.astype(bool)))
-    return out, truth
+def test_record_container_sort_and_cat():
+    z = load_fixture("py_c4_selfplay_k4_sym")
+    rec = fixture_records(z, "Connect4", uid0=100)
+    m = len(rec)
+    assert m == len(z["length"]) and rec.positions == int(z["length"].sum())
+    assert rec.uid.tolist() == list(range(100, 100 + m)) and rec.length.tolist() == z["length"].tolist() and rec.winner.tolist() == z["winner"].tolist()
+    perm = torch.randperm(m, generator=torch.Generator().manual_seed(1))
+    parts = [sp_mod.Records("Connect4", rec.games[i:i + 1], rec.pos) for i in perm.tolist()]     # each part drags the whole position array along
+    shuffled = sp_mod.Records.cat(parts)
+    assert shuffled.positions == rec.positions and shuffled.uid.tolist() == (perm + 100).tolist()
+    back = shuffled.sorted_by_uid()
+    assert torch.equal(back.games, rec.games) and torch.equal(back.pos, rec.pos)
 
 
-def test_replay_tensors_pt_and_upload_payload():
-    for game, lengths in (("Connect4", [8, 43, 1, 22]), ("Othello", [61, 5])):
-        packed, truth = _fake_records(game, lengths)
-        t = sp_mod.to_replay_tensors(torch.from_numpy(packed), game)
-        n = sum(lengths)
-        gid, R, Cc, A, T = sp_mod._G[game]
-        assert t["state"].shape == (n, 3, R, Cc) and t["state"].dtype == torch.int8
-        assert t["prob"].shape == (n, A) and t["winner"].shape == (n, 1) and t["winner"].dtype == torch.int8
-        assert t["steps_to_end"].dtype == torch.int16 and t["aux_target"].dtype == torch.int16
-        assert t["valid_mask"].dtype == torch.bool and t["future_root_wdl"].shape == (n, 3)
-        cat = lambda k: np.concatenate([x[k] for x in truth])
-        assert np.array_equal(t["state"].numpy(), cat("state")) and np.array_equal(t["prob"].numpy(), cat("prob"))
-        assert np.array_equal(t["root_wdl"].numpy(), cat("root_wdl")) and np.array_equal(t["future_root_wdl"].numpy(), cat("future_root_wdl"))
-        assert np.array_equal(t["winner"].numpy()[:, 0], cat("winner")) and np.array_equal(t["steps_to_end"].numpy()[:, 0], cat("steps_to_end"))
-        assert np.array_equal(t["aux_target"].numpy()[:, 0], cat("aux")) and np.array_equal(t["valid_mask"].numpy(), cat("mask"))
-        games = sp_mod.unpack_records(packed, game, td_steps=3)
-        assert [g["uid"] for g in games] == [1000 + i for i in range(len(lengths))]
-        assert [len(g["tuples"][1]) for g in games] == lengths and len(games[0]["tuples"][1][0]) == 8
-        payload = pickle.loads(sp_mod.to_upload_payload(games))
-        assert payload["__az__"] is True and len(payload["data"]) == len(lengths) and len(payload["data"][1]) == lengths[1]
-        with tempfile.TemporaryDirectory() as d:
-            p = os.path.join(d, "buffer.pt")
-            sp_mod.save_replay_pt(p, t)
-            sd = torch.load(p, weights_only=True)
-            assert sd["_ptr"] == n and sd["current_capacity"] == n and set(sd) >= {"state", "prob", "winner", "steps_to_end", "aux_target",
-                                                                                 "root_wdl", "valid_mask", "future_root_wdl"}
+def _assert_tensors_match_fixture(t, z, td):
+    n = lambda k: t[k].cpu().numpy()
+    assert np.array_equal(n("state"), z["state"]) and n("state").dtype == np.int8
+    assert n("prob").tobytes() == z["prob"].tobytes() and n("root_wdl").tobytes() == z["root_wdl"].tobytes()
+    assert np.array_equal(n("winner")[:, 0], z["winner_z"]) and np.array_equal(n("steps_to_end")[:, 0], z["steps_to_end"])
+    assert np.array_equal(n("aux_target")[:, 0], z["aux"]) and np.array_equal(n("valid_mask"), z["valid_mask"])
+    if td > 0:
+        assert n("future_root_wdl").tobytes() == z["future_root_wdl"].tobytes()
+    else:
+        assert not n("future_root_wdl").any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_expand_reproduces_reference_tuples_pt_and_pickle(name, tmp_path):
+    from test_gpu_dropin_python_layer import assert_pt_equal, assert_same_structure
+    case = CASES[name]
+    game, td = case["game"], case["td_steps"]
+    z = load_fixture(name)
+    rec = fixture_records(z, game).to("cuda")
+    t = rec.to_replay_tensors(td)
+    _assert_tensors_match_fixture(t, z, td)
+    games = rec.unpack(td)
+    assert [g["winner"] for g in games] == z["winner"].tolist() and [g["length"] for g in games] == z["length"].tolist()
+    assert len(games[0]["tuples"][1][0]) == int(z["tuple_width"])
+    if case.get("formats"):
+        p = str(tmp_path / "buffer.pt")
+        sp_mod.save_replay_pt(p, t)
+        assert_pt_equal(p, os.path.join(GOLD, name + ".pt"))
+        with open(os.path.join(GOLD, name + ".pkl"), "rb") as f:
+            assert_same_structure(pickle.loads(sp_mod.to_upload_payload(games)), pickle.load(f))
+
+
+@pytest.mark.gpu
+def test_reference_replay_buffer_loads_our_file(tmp_path):
+    """Build container / GPU box with oracle/_ref/pysrc: the reference's own ReplayBuffer.load (src/ReplayBuffer.py:40-62) reads
+    the file save_replay_pt wrote and ends up with the fixture's contents."""
+    from oracle import refstack
+    if not refstack.available("parity"):
+        pytest.skip("oracle/_ref/pysrc not present")
+    name = "py_c4_selfplay_k4_sym"
+    z = load_fixture(name)
+    t = fixture_records(z, "Connect4").to("cuda").to_replay_tensors(CASES[name]["td_steps"])
+    p = str(tmp_path / "ours.pt")
+    sp_mod.save_replay_pt(p, t)
+    ov = refstack.make_overlay(str(tmp_path / "ref"), "reference")
+    out = str(tmp_path / "loaded.npz")
+    refstack.run_driver(ov, "load_pt", out, dict(path=p, rows=int(z["length"].sum()), A=7, R=6, C=7))
+    got = np.load(out)
+    assert int(got["ptr"]) == int(z["length"].sum()) and int(got["len"]) == int(z["length"].sum())
+    assert np.array_equal(got["state"], z["state"]) and got["prob"].tobytes() == z["prob"].tobytes()
+    assert np.array_equal(got["winner"][:, 0], z["winner_z"]) and np.array_equal(got["valid_mask"], z["valid_mask"])
+    assert got["future_root_wdl"].tobytes() == z["future_root_wdl"].tobytes()

@@ -19,7 +19,7 @@ for ply in range(48):
     sp.ply()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    g = int(sp.out_count.item())
+    g = sp.finished()
     st = sp.engine.get_stats()
     if ply % 4 == 3 or dt > 0.05:
         print(f"ply {ply:2d}: {dt*1e3:7.2f} ms  games done {g:6d} (+{g-g_prev})  arena cap {st['arena_cap']} max used {st['max_arena_slots']} lanes {sp.engine.get_lanes()}")

@@ -31,7 +31,7 @@ for mode in ("cache+dedup", "cache", "plain"):
             print(f"  {mode} ply {p:2d}: {1e3 * (time.perf_counter() - t1):8.1f} ms  lookups {st['lookups']} hits {st['hits']} dups {st['dups']} "
                   f"net rows {sp.evaluator.net_rows}", flush=True)
     dt = time.perf_counter() - t0
-    g = int(sp.out_count.item())
+    g = sp.finished()
     print(f"{mode:12s}: {n_slots} slots, {n_pl} plies in {dt:.2f} s -> {n_slots * n_pl / dt:9.0f} positions/s  {n_slots * n_pl * 200 / dt / 1e6:8.2f} M sims/s  "
           f"games finished {g}", flush=True)
     del sp, net
