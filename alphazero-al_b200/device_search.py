@@ -412,7 +412,10 @@ def playout_device(engine, buf: LeafBuffers, n_playout: int, K: int, evaluator, 
         return _playout_sharded(engine, buf, iters, evaluator, stream, shards, on_select)
     launches = 0
     # torch evaluators launch on torch's current stream: make that the stream the engine kernels run on
-    ext = torch.cuda.ExternalStream(stream, device=buf.leaves.device) if stream else torch.cuda.default_stream(buf.leaves.device)
+    import contextlib
+    ext = None
+    if buf.leaves.is_cuda:
+        ext = torch.cuda.ExternalStream(stream, device=buf.leaves.device) if stream else torch.cuda.default_stream(buf.leaves.device)
     for k in iters:
         rows = n * max(k, 1)
         assert rows <= buf.rows
@@ -420,7 +423,7 @@ def playout_device(engine, buf: LeafBuffers, n_playout: int, K: int, evaluator, 
             on_select(rows, lambda: engine.search_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), stream))
         else:
             engine.search_dev(k, buf.roots.data_ptr(), buf.leaves.data_ptr(), stream)
-        with torch.cuda.stream(ext):
+        with (torch.cuda.stream(ext) if ext is not None else contextlib.nullcontext()):
             evaluator(buf, rows, stream)
         # is_term / sym ids: the engine uses what it remembered from the matching search
         engine.backprop_dev(k, buf.policy.data_ptr(), buf.d.data_ptr(), buf.p1w.data_ptr(), buf.p2w.data_ptr(),
