@@ -1,8 +1,9 @@
 """Byte-compiles the reference's Python layer (src/*.py, src/environments/**) into oracle/_ref/pysrc/src/**/*.pyc.
 
 TEST INFRASTRUCTURE ONLY (part of `make -C oracle ref`).  Nothing is copied: every module is compiled from where it lies under
-/root/reference with ``py_compile`` and only the resulting code object is written (legacy sourceless layout ``<module>.pyc``,
-unchecked-hash invalidation so no source file is ever looked for).  The build container and the GPU box run the same CPython,
+/root/reference with ``py_compile`` and only the resulting code object is written (a ``.pyc`` image with unchecked-hash
+invalidation so no source file is ever looked for, stored as ``<module>.pycode``: the GPU-box snapshot skips ``*.pyc``;
+oracle/refstack.py copies the images to ``<module>.pyc`` names in a scratch overlay, the legacy sourceless layout).  The build container and the GPU box run the same CPython,
 so the files import there like the compiled ``.so`` modules do.
 
 usage: compile_pysrc.py <reference/src> <out dir>"""
@@ -20,7 +21,7 @@ def main(src: str, out: str) -> int:
         for f in files:
             if not f.endswith(".py"):
                 continue
-            dst = os.path.join(out, rel, f + "c")
+            dst = os.path.join(out, rel, f[:-3] + ".pycode")
             s = os.path.join(root, f)
             if os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(s):
                 continue

@@ -3,7 +3,7 @@ run UNMODIFIED on either engine - TEST INFRASTRUCTURE ONLY (tests/, and bench.py
 
 ``make -C oracle ref`` byte-compiles that layer into ``oracle/_ref/pysrc/src`` (oracle/compile_pysrc.py; no source is copied, the
 ``.pyc`` files are git-ignored like the compiled ``.so`` modules and travel to the GPU box with them).  ``make_overlay`` builds a
-directory whose ``src`` package is made of symlinks to those files plus what the reference's build step would have put there:
+directory whose ``src`` package is made of copies of those byte-code images (named ``<module>.pyc``) plus what the reference's build step would have put there:
 
 * engine "reference": ``src/mcts_cpp*.so`` / ``src/env_cpp*.so`` -> oracle/_ref/<kind>/ (what setup.py:62-65 does), or
 * engine "ours": the three shims of INTEGRATION.md section 1 (``src/azb200`` -> the package, ``src/mcts_cpp.py``, ``src/env_cpp/``).
@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import json
 import os
+import shutil
 import subprocess
 import sys
 
@@ -24,7 +25,7 @@ PYSRC = os.path.join(_HERE, "_ref", "pysrc", "src")
 
 def available(kind: str = "parity") -> bool:
     d = os.path.join(_HERE, "_ref", kind)
-    return os.path.isfile(os.path.join(PYSRC, "MCTS_cpp.pyc")) and os.path.isdir(d) and any(f.startswith("mcts_cpp") for f in os.listdir(d))
+    return os.path.isfile(os.path.join(PYSRC, "MCTS_cpp.pycode")) and os.path.isdir(d) and any(f.startswith("mcts_cpp") for f in os.listdir(d))
 
 
 def make_overlay(dst: str, engine: str, kind: str = "parity") -> str:
@@ -35,8 +36,8 @@ def make_overlay(dst: str, engine: str, kind: str = "parity") -> str:
         rel = os.path.relpath(root, PYSRC)
         os.makedirs(os.path.join(src, rel), exist_ok=True)
         for f in files:
-            if f.endswith(".pyc") and f != "pipeline.pyc":
-                os.symlink(os.path.join(root, f), os.path.join(src, rel, f))
+            if f.endswith(".pycode") and f != "pipeline.pycode":       # byte-code images -> sourceless modules of the scratch overlay
+                shutil.copyfile(os.path.join(root, f), os.path.join(src, rel, f[:-7] + ".pyc"))
     if engine == "reference":
         d = os.path.join(_HERE, "_ref", kind)
         for f in os.listdir(d):
