@@ -56,6 +56,16 @@ constexpr uint32_t F_TERM = 1u << 25;     // child is_terminal
 constexpr uint32_t F_WIN_P1 = 1u << 26;   // cached terminal result: neither bit = draw
 constexpr uint32_t F_WIN_P2 = 1u << 27;
 constexpr uint32_t F_TURN_P1 = 1u << 28;  // child node.turn == +1
+// LAZY BLOCKS (Connect4, thread-per-tree lean kernels).  Only a quarter of the expanded nodes are ever visited again (measured:
+// 137.6 expanded nodes per tree after a 200-simulation move, 35.0 with a second visit), yet an expansion wrote the node's whole edge
+// block, num_edges x 32 bytes - most of back-prop's DRAM write traffic.  With F_LAZY set in the slot that owns the `child` pointer, the
+// block's slots are RESERVED (the pointer, num_edges and the bump allocation are what they would be) but only a 32-byte HEADER
+// {prior[0..6] in edge order, legal-move mask} is stored in the block's first slot.  The read-only selects score such a node from
+// the header (every child is unvisited: N = 0, no sums, child = NONE, action = the e-th legal move); the back-prop of the node's
+// second visit MATERIALISES the block - header -> num_edges slots - and clears the flag.  The root is never lazy (root expansions
+// write the block; k_prune materialises a promoted lazy child), arena compaction materialises what it copies, and before a kernel
+// that does not know about headers runs on such trees the host materialises everything (materialise_all) and stops creating them.
+constexpr uint32_t F_LAZY = 1u << 29;
 constexpr uint32_t INFL_MASK = 0xFFFFu;
 
 struct __align__(64) TreeRec {   // per tree: the root's own statistics + allocator state
@@ -98,7 +108,7 @@ struct Dev {   // kernel-visible view of an engine
     int *err;                            // sticky device error flag (arena overflow)
     int n_envs;
     int env_lo, env_cnt;                 // trees [env_lo, env_lo + env_cnt) are processed by the select / back-prop launch
-    int hints;                           // bit 0: streaming (.cs) stores for new edge blocks (on; AZB200_HINTS=0 turns it off for A/B runs)
+    int hints;                           // bit 0: streaming (.cs) stores for new edge blocks; bit 1: expansions below the root write lazy blocks (F_LAZY).  AZB200_HINTS overrides (A/B runs)
     uint64_t seed, epoch;
     const unsigned long long *epoch_add;   // graph replays: added to `epoch` (kernel parameters are frozen in a captured graph)
     uint64_t env_base;                   // global index of env 0 (RNG keys are sharding-invariant)
@@ -131,6 +141,16 @@ __device__ __forceinline__ void st_slot(Slot *p, const Slot &s) {
     uint4 *q = reinterpret_cast<uint4 *>(p);
     q[0] = make_uint4(__float_as_uint(s.prior), (uint32_t)s.n, s.meta, s.child);
     q[1] = make_uint4(__float_as_uint(s.wd), __float_as_uint(s.wp1), __float_as_uint(s.wp2), __float_as_uint(s.msum));
+}
+// edge e of a lazy block, rebuilt from its header (stored in the block's first slot): {prior[e], N = 0, action = e-th legal move}
+__device__ __forceinline__ Slot lazy_edge(const Slot &hdr, int e) {
+    const float pr[7] = {hdr.prior, __int_as_float(hdr.n), __uint_as_float(hdr.meta), __uint_as_float(hdr.child), hdr.wd, hdr.wp1, hdr.wp2};
+    uint32_t m = __float_as_uint(hdr.msum);
+    float p = pr[0];
+#pragma unroll
+    for (int q = 1; q < 7; ++q) { if (q <= e) m &= m - 1; if (q == e) p = pr[q]; }
+    Slot s; s.prior = p; s.n = 0; s.meta = (uint32_t)(__ffs((int)m) - 1) << 16; s.child = NONE; s.wd = s.wp1 = s.wp2 = s.msum = 0.0f;
+    return s;
 }
 template <class T> __device__ __forceinline__ T ld32(const T *p) {      // 32-byte record as two 16-byte loads
     T v;
@@ -991,8 +1011,14 @@ __global__ void k_prune(Dev d, az_search_config cfg, const int32_t *__restrict__
             Slot s = ld_slot(arena + off + e);
             if ((int)((s.meta >> 16) & 0xFFu) == action && (s.meta & F_ALLOC)) {
                 s.prior = 0.f;
-                st_slot(&tr->root, s);                      // promoted child becomes the root (parent = -1)
                 const int cne = s.child == NONE ? 0 : (int)(s.child & 63u);
+                if (s.meta & F_LAZY) {                      // the root's block is always a real one
+                    Slot *blk = arena + (s.child >> 6);
+                    const Slot hdr = ld_slot(blk);
+                    for (int q = 0; q < cne; ++q) st_slot(blk + q, lazy_edge(hdr, q));
+                    s.meta &= ~F_LAZY;
+                }
+                st_slot(&tr->root, s);                      // promoted child becomes the root (parent = -1)
                 if (cfg.dirichlet_alpha > 0.0f && cne > 0) {  // apply_root_noise (MCTS.h:113-132)
                     uint32_t ctr = tr->noise_ctr;
                     draw_root_noise(d.seed, d.env_base + (uint64_t)env, ctr, cfg.dirichlet_alpha, cne, nrow);
@@ -1042,12 +1068,13 @@ __global__ void __launch_bounds__(CTA) k_compact(Dev d, Slot *__restrict__ dst_p
         uint32_t i = 0;
         while (i < nb) {
             const uint32_t lim = min(i + (uint32_t)(J * W), nb);
-            uint32_t c[J], my_off[J];
+            uint32_t c[J], my_off[J], lz[J];
             uint32_t run = nb;                                   // next free slot of the new arena
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const uint32_t idx = i + (uint32_t)(j * W + lane);
                 c[j] = idx < lim ? dst[idx].child : NONE;
+                lz[j] = (G::GAME == GAME_C4 && idx < lim && c[j] != NONE) ? (dst[idx].meta & F_LAZY) : 0u;   // header-only block
             }
 #pragma unroll
             for (int j = 0; j < J; ++j) {                        // queue order: window j, then lane
@@ -1069,10 +1096,11 @@ __global__ void __launch_bounds__(CTA) k_compact(Dev d, Slot *__restrict__ dst_p
                         if (!todo) continue;
                         const int l = __ffs((int)todo) - 1; todo &= todo - 1;
                         const uint32_t cl = gshfl<W>(gm, c[j], l), ol = gshfl<W>(gm, my_off[j], l);
+                        const uint32_t lzl = gshfl<W>(gm, lz[j], l);
                         const uint32_t nl = cl & 63u, sl = cl >> 6;
                         if (G::MAX_EDGES <= W) {                 // one slot per lane
                             mine[q] = (uint32_t)lane < nl; to[q] = ol + (uint32_t)lane;
-                            if (mine[q]) tmp[q] = ld_slot(src + sl + lane);
+                            if (mine[q]) tmp[q] = lzl ? lazy_edge(ld_slot(src + sl), lane) : ld_slot(src + sl + lane);   // lazy blocks are materialised
                         } else {
                             for (uint32_t e = lane; e < nl; e += W) st_slot(dst + ol + e, ld_slot(src + sl + e));
                         }
@@ -1081,6 +1109,7 @@ __global__ void __launch_bounds__(CTA) k_compact(Dev d, Slot *__restrict__ dst_p
                     for (int q = 0; q < 4; ++q) if (mine[q]) st_slot(dst + to[q], tmp[q]);
                 }
                 if (c[j] != NONE) dst[i + (uint32_t)(j * W + lane)].child = (my_off[j] << 6) | (c[j] & 63u);
+                if (lz[j]) dst[i + (uint32_t)(j * W + lane)].meta &= ~F_LAZY;
             }
             nb = run;
             i = lim;
@@ -1261,6 +1290,7 @@ struct az_mcts {
     // different K in host order; a back-prop looks up the select of ITS range and is refused when none matches
     struct SelRec { int lo, hi, K; bool vl, ro; };
     std::vector<SelRec> sel_recs;
+    bool lazy_live = false;           // the trees may hold lazy blocks (F_LAZY): only the read-only selects and k_backprop_f know them
     int variant = 1;                  // thread-per-tree kernels: 0 = first generation (k_*_t), 1 = lean (k_*_f)
     int wave_max = 131072;             // batches of at most this many descent lanes run the staggered-descent select (az_mcts_wave.cuh); 0 = off
     // VL bookkeeping
@@ -1494,16 +1524,57 @@ static bool use_wave(const az_mcts *h, bool vl, int K) {
 static bool select_is_ro(const az_mcts *h, bool vl, int K) {
     return h->game == GAME_C4 && h->W == 1 && h->variant != 0 && ((vl ? K : 1) <= RS_MAX || use_wave(h, vl, K));
 }
+// Copies the live tree of every env into the second pool (k_compact: breadth-first, child pointers rewritten, lazy blocks
+// materialised) and swaps the pools.  must = the caller cannot go on without it (materialise_all).
+static int run_compaction(az_mcts *h, cudaStream_t s, bool must) {
+    if (!h->pool_alt) {
+        cudaError_t e = cudaMalloc((void **)&h->pool_alt, sizeof(Slot) * (size_t)h->n * h->cap);
+        if (e != cudaSuccess) {
+            h->pool_alt = nullptr; cudaGetLastError();
+            if (must) AZ_FAIL(h, AZ_ERR_NOMEM, "no memory for the second arena pool (needed to materialise lazy blocks)");
+            return AZ_OK;                                  // no room for a second pool: keep growing instead
+        }
+    }
+    CU(h, cudaMemsetAsync(h->d_scratch_u32 + 1, 0, sizeof(unsigned int), s));
+    const int g = grid_groups(h->n, 8);
+    if (h->game == GAME_C4) k_compact<C4, 8><<<g, CTA, 0, s>>>(h->d, h->pool_alt, h->d_scratch_u32 + 1);
+    else k_compact<Oth, 8><<<g, CTA, 0, s>>>(h->d, h->pool_alt, h->d_scratch_u32 + 1);
+    std::swap(h->d.pool, h->pool_alt);
+    h->bound_stale = true; h->base_pending = true; h->compactions++; h->launches++;
+    h->lazy_live = false;                                  // whatever was copied is a real block now
+    h->sel_recs.clear();                                   // pending leaf records were invalidated
+    CU(h, cudaGetLastError());
+    return AZ_OK;
+}
+// A kernel that does not know lazy blocks is about to run on trees that may hold some: materialise them all (one compaction
+// pass) and stop creating them for this engine (the configuration - lanes, kernel generation, K beyond the read-only select - is
+// unlikely to change back).
+static int materialise_all(az_mcts *h, cudaStream_t s) {
+    if (!h->lazy_live) return AZ_OK;
+    if (h->capturing) AZ_FAIL(h, AZ_ERR_INVALID, "internal: lazy blocks must be materialised before a graph capture");
+    CU(h, cudaDeviceSynchronize());                        // other shards' streams may still be working on the old pool
+    int rc = run_compaction(h, s, true); if (rc) return rc;
+    h->d.hints &= ~2;
+    return AZ_OK;
+}
 static void note_select(az_mcts *h, bool vl, int K) {
     const int lo = h->d.env_lo, hi = lo + h->d.env_cnt;
     auto &v = h->sel_recs;
     v.erase(std::remove_if(v.begin(), v.end(), [&](const az_mcts::SelRec &r) { return r.lo < hi && lo < r.hi; }), v.end());
     v.push_back({lo, hi, K, vl, h->last_select_ro});
 }
+static bool use_wave(const az_mcts *h, bool vl, int K);
+// Will the select launch for these arguments be one that understands lazy blocks (the read-only lean kernels)?
+static bool select_lazy_aware(const az_mcts *h, bool vl, int K, const az_leaf *leaves) {
+    const bool lean = h->game == GAME_C4 && h->W == 1 && h->variant != 0 && (uint64_t)(h->n + 32) * h->cap < (1ull << 31) && ((uintptr_t)leaves & 31) == 0;
+    return lean && (use_wave(h, vl, K) || (vl ? K : 1) <= 4 /* RS_MAX */);
+}
 static void launch_select_impl(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s);
-static void launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s) {
+static int launch_select(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s) {
+    if (h->lazy_live && !select_lazy_aware(h, vl, K, leaves)) { int rc = materialise_all(h, s); if (rc) return rc; }
     launch_select_impl(h, vl, K, roots, leaves, s);
     note_select(h, vl, K);
+    return AZ_OK;
 }
 static void launch_select_impl(az_mcts *h, bool vl, int K, const az_root *roots, az_leaf *leaves, cudaStream_t s) {
     const int cnt = h->d.env_cnt;                             // trees of this launch (a whole batch or one shard)
@@ -1600,6 +1671,7 @@ static int launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym,
                 h->bp_smem_set = smem;
             }
             const bool ro = h->last_select_ro, wide = gf > 6 * 148;
+            if (ro && (h->d.hints & 2)) h->lazy_live = true;   // expansions below the root write headers only (F_LAZY)
 #define AZ_BP_F(KERNEL, VLF, ROF, KARG, RARG) KERNEL<C4, VLF, ROF><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, KARG, RARG, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym)
             if (vl) {
                 if (ro) { if (wide) AZ_BP_F(k_backprop_f, true, true, kk, removeK); else AZ_BP_F(k_backprop_f_r, true, true, kk, removeK); }
@@ -1668,7 +1740,7 @@ static int do_search(az_mcts *h, int K, const az_root *d_roots, az_leaf *d_leave
         }
         CU(h, cudaEventRecord(h->sel_ev[h->sel_used].first, s));
     }
-    launch_select(h, vl, K, d_roots, d_leaves, s);
+    rc = launch_select(h, vl, K, d_roots, d_leaves, s); if (rc) return rc;
     if (h->time_select) {
         CU(h, cudaEventRecord(h->sel_ev[h->sel_used].second, s));
         h->sel_used++; h->sel_rows += (uint64_t)h->d.env_cnt * (uint64_t)std::max(K, 1);
@@ -1809,7 +1881,8 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     const char *ce = getenv("AZB200_ARENA_SLOTS");
     h->cap = ce ? (uint32_t)std::max(256, atoi(ce)) : (game == GAME_C4 ? 2048u : 4096u);
     h->d.n_envs = n_envs; h->d.env_lo = 0; h->d.env_cnt = n_envs; h->d.cap = h->cap; h->d.noise_stride = h->max_edges;
-    { const char *he = getenv("AZB200_HINTS"); h->d.hints = he ? atoi(he) : 1; }
+    { const char *he = getenv("AZB200_HINTS"); h->d.hints = he ? atoi(he) : 3; }
+    { const char *le = getenv("AZB200_LAZY"); if (le && atoi(le) == 0) h->d.hints &= ~2; }
     h->d.seed = 0x243F6A8885A308D3ULL; h->d.epoch = 0; h->d.epoch_add = nullptr;
     int rc = 0;
     rc |= dev_alloc(h, &h->d.pool, (size_t)n_envs * h->cap);
@@ -1826,6 +1899,9 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     h->d.err = h->d_err;
     cudaMemsetAsync(h->d_stats, 0, (8 + 2 * AZ_DBG_WARPS) * sizeof(unsigned long long), h->stream);
     cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
+    // TreeRec.noise_ctr (the per-tree Dirichlet draw counter) is not touched by a reset: it must start from 0, not from whatever
+    // cudaMalloc handed out, or two engines with the same seed draw different noise (found by the sharding-invariance test)
+    cudaMemsetAsync(h->d.trees, 0, sizeof(TreeRec) * (size_t)n_envs, h->stream);
     k_reset<<<grid_threads((size_t)n_envs), 128, 0, h->stream>>>(h->d, -1);
     k_init_leaf<<<grid_threads((size_t)n_envs), 128, 0, h->stream>>>(h->d.leaf_nv, (size_t)n_envs);
     if (ensure_io(h, n_envs) != AZ_OK) return fail("io allocation");
@@ -1936,19 +2012,7 @@ int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream) 
     h->growth_est = std::max(h->growth_est - h->growth_est / 4, growth);
     const bool due = h->compaction == 2 || (h->compaction == 1 && bound + h->growth_est + h->growth_est / 4 > h->cap && bound > 0);
     h->base_after_prune = bound;
-    if (due) {
-        if (!h->pool_alt) {
-            cudaError_t e = cudaMalloc((void **)&h->pool_alt, sizeof(Slot) * (size_t)h->n * h->cap);
-            if (e != cudaSuccess) { h->pool_alt = nullptr; cudaGetLastError(); return AZ_OK; }   // no room for a second pool: keep growing instead
-        }
-        CU(h, cudaMemsetAsync(h->d_scratch_u32 + 1, 0, sizeof(unsigned int), s));
-        const int g = grid_groups(h->n, 8);
-        if (h->game == GAME_C4) k_compact<C4, 8><<<g, CTA, 0, s>>>(h->d, h->pool_alt, h->d_scratch_u32 + 1);
-        else k_compact<Oth, 8><<<g, CTA, 0, s>>>(h->d, h->pool_alt, h->d_scratch_u32 + 1);
-        std::swap(h->d.pool, h->pool_alt);
-        h->bound_stale = true; h->base_pending = true; h->compactions++; h->launches++;
-        CU(h, cudaGetLastError());
-    }
+    if (due) { rc = run_compaction(h, s, false); if (rc) return rc; }
     return AZ_OK;
 }
 // Every tree back to a fresh root (prune_roots with all actions < 0, MCTS.h:107 -> reset()), stream-ordered, and - unlike
@@ -1961,7 +2025,7 @@ int az_mcts_reset_all_dev(az_mcts *h, void *stream) {
     h->launches++;
     CU(h, cudaGetLastError());
     h->bump_bound = 0; h->bounds.clear(); h->base_after_prune = 0; h->bound_stale = false; h->base_pending = false; h->growth_est = 0;
-    h->sel_recs.clear();
+    h->sel_recs.clear(); h->lazy_live = false;
     return AZ_OK;
 }
 int az_mcts_set_compaction(az_mcts *h, int mode) {
@@ -2171,6 +2235,11 @@ int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, in
         // reserve the growth of the whole loop up front (may synchronise / grow the arenas: before any capture)
         h->d.env_lo = 0; h->d.env_cnt = h->n;
         rc = ensure_arena(h, n_playout, run); if (rc) return rc;
+        if (h->lazy_live) {                                  // (cannot happen inside the capture)
+            bool all_aware = true;
+            for (int k : iters) all_aware = all_aware && select_lazy_aware(h, k > 0, std::max(k, 1), d_leaves);
+            if (!all_aware) { rc = materialise_all(h, run); if (rc) return rc; }
+        }
         az_mcts::GraphKey key;
         memset(&key, 0, sizeof(key));
         key.mode = mode; key.n_playout = n_playout; key.K = K; key.ns = ns; key.W = h->W; key.variant = h->variant; key.wave_max = h->wave_max; key.hints = h->d.hints;
@@ -2252,7 +2321,7 @@ int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const az_root *d_roots, i
     h->d.stats = h->stats_on ? h->d_stats : nullptr;
     for (int p = 0; p < n_playout; ++p) {
         rc = ensure_arena(h, 1, s); if (rc) { h->cfg = saved; return rc; }
-        launch_select(h, false, 1, d_roots, h->io_leaves, s);
+        rc = launch_select(h, false, 1, d_roots, h->io_leaves, s); if (rc) { h->cfg = saved; return rc; }
         if (h->game == GAME_C4) k_eval_builtin<C4><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, evaluator, p, pol, dv, p1, p2, ml);
         else k_eval_builtin<Oth><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, evaluator, p, pol, dv, p1, p2, ml);
         rc = launch_backprop(h, false, 1, 0, 0, pol, dv, p1, p2, ml, nullptr, nullptr, s); if (rc) { h->cfg = saved; return rc; }

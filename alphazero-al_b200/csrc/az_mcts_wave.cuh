@@ -60,13 +60,16 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
     unsigned st_edges = 0;
     uint32_t *gpath = d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH;       // entries beyond the first 8
     // w = (block offset << 6) | num_edges of the node I score next, 0 = my descent has ended
+    // (bit 5 of w: the node is a lazy block - only its 32-byte header exists, see F_LAZY; the root never is)
+    constexpr uint32_t W_LAZY = 32u;
     uint32_t w = (valid && root.child != NONE && !(root.meta & F_TERM) && (root.child & 63u) != 0) ? root.child : 0u;
     __syncwarp();
 
     for (int step = 0; __any_sync(FULL, w != 0u); ++step) {
         const bool act = w != 0u && step >= k;
         const uint32_t off = w >> 6;
-        const int ne = (int)(w & 63u);
+        const int ne = (int)(w & 7u);
+        const bool lazy = (w & W_LAZY) != 0u;
         // ---- in-flight counts from the earlier descents of my tree: a path that holds a slot of this block at this depth
         //      passed through this node (parent + 1) and through that child (child + 1); 4 bits per child ----
         uint32_t packed = 0u, cntp = 0u;
@@ -84,9 +87,11 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
         if (act) {
             st_edges += (unsigned)ne;
             Slot s[NE];
+            Slot hdr;
+            if (lazy) hdr = ld_slot256(arena + off);
 #pragma unroll
             for (int c = 0; c < NE; ++c) {
-                if (c < ne) s[c] = ld_slot256(arena + off + c);
+                if (c < ne) s[c] = lazy ? lazy_edge(hdr, c) : ld_slot256(arena + off + c);
                 else { s[c].prior = 0.0f; s[c].n = 0; s[c].meta = 0u; s[c].child = NONE; s[c].wd = s[c].wp1 = s[c].wp2 = s[c].msum = 0.0f; }
             }
             // ---- compute_fpu (MCTS.h:140-156): seen_policy summed in edge order ----
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
                 best_s = -INFINITY; best_e = -1; best_Q = 0.0f; best_M = 0.0f;
 #pragma unroll 1
                 for (int c = 0; c < ne; ++c) {
-                    const Slot sc = ld_slot256(arena + off + c);
+                    const Slot sc = lazy ? lazy_edge(hdr, c) : ld_slot256(arena + off + c);
                     float eff_prior = sc.prior;
                     if (mix_noise) eff_prior = (1.0f - ne_eps) * sc.prior + ne_eps * d.noise[(size_t)env * d.noise_stride + c];
                     float q_value = fpu, m_utility = 0.0f, child_Q = 0.0f, child_M = 0.0f;
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
                 }
             }
             if (best_e >= 0) {
-                const Slot ch = ld_slot256(arena + off + best_e);          // re-read (L1 hit) instead of a 7-way select of 8 registers
+                const Slot ch = lazy ? lazy_edge(hdr, best_e) : ld_slot256(arena + off + best_e);   // re-read (L1 hit) instead of a 7-way select of 8 registers
                 {   // Connect4::step (Connect4.h:159-172, no legality check): drop a stone of the side to move
                     const int col7 = (int)((ch.meta >> 16) & 0xFFu) * 7;
                     const uint64_t occ = b0 | b1;
@@ -183,7 +188,8 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
                 if (plen < (uint32_t)PATH8) mypath[plen] = last_slot; else gpath[plen] = last_slot;
                 ++plen;
                 cur_n = ch.n; cur_meta = nmeta; cur_Q = best_Q; cur_M = best_M; is_root = false;
-                if (ch.child != NONE && !(ch.meta & F_TERM) && (ch.child & 63u) != 0 && plen < (uint32_t)G::MAX_DEPTH && !term_now) nw = ch.child;
+                if (ch.child != NONE && !(ch.meta & F_TERM) && (ch.child & 63u) != 0 && plen < (uint32_t)G::MAX_DEPTH && !term_now)
+                    nw = (ch.child & ~63u) | (ch.child & 7u) | ((ch.meta & F_LAZY) ? W_LAZY : 0u);
             }
         }
         if (act) w = nw;

@@ -5,9 +5,30 @@ import numpy as np
 
 
 def playout(engine, evaluator, boards, turns, n_playout, K, record=None):
-    """Run n_playout simulations per tree.  `record` (a list) receives every leaf tuple for comparison."""
+    """Run n_playout simulations per tree.  `record` (a list) receives every leaf tuple for comparison.  An evaluator with a true
+    `wants_mask` attribute also receives the leaves' legal masks (what the reference wrapper hands to predict())."""
     boards = np.ascontiguousarray(boards, dtype=np.int8)
     turns = np.ascontiguousarray(turns, dtype=np.int32)
+    if getattr(evaluator, "wants_mask", False):
+        inner = evaluator
+
+        class _WithMask:
+            def __call__(self, lb, lt, it, td, tp1, tp2):
+                return inner(lb, lt, it, td, tp1, tp2, self.vm)
+        evaluator = _WithMask()
+        base_engine = engine
+
+        class _Tap:
+            def __getattr__(self, name):
+                f = getattr(base_engine, name)
+                if name in ("search_batch", "search_batch_vl"):
+                    def g(*a):
+                        out = f(*a)
+                        evaluator.vm = out[-1]
+                        return out
+                    return g
+                return f
+        engine = _Tap()
     if K <= 1:
         for _ in range(n_playout):
             lb, td, tp1, tp2, it, lt, vm = engine.search_batch(boards, turns)

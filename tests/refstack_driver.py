@@ -219,22 +219,23 @@ def task_cnn(out, p):
         cfg = dict(c_init=1.4, c_base=500.0, fpu_reduction=0.2, dirichlet_alpha=0.0, use_symmetry=False, score_utility_factor=0.15, score_scale=8.0)
     log = []
 
-    def host_eval(lb, lt, it, td, tp1, tp2):                     # src/MCTS_cpp.py:275-297 with the network's own predict()
+    def host_eval(lb, lt, it, td, tp1, tp2, vm):                 # src/MCTS_cpp.py:275-297 with the network's own predict()
         t = it.astype(bool)
         probs = np.zeros((lb.shape[0], A), np.float32)
         d, p1w, p2w, ml = td.copy(), tp1.copy(), tp2.copy(), np.zeros(lb.shape[0], np.float32)
         if (~t).any():
             planes = bm._default_convert_board(lb[~t], lt[~t])
-            mask = None
+            mask = vm[~t].astype(bool, copy=False)
             pr, w, a = net.predict(planes, mask)
             probs[~t] = pr
             d[~t] = w[:, 0]
             p1w[~t] = np.where(lt[~t] == 1, w[:, 1], w[:, 2])
             p2w[~t] = np.where(lt[~t] == 1, w[:, 2], w[:, 1])
             ml[~t] = a.reshape(-1)
-        log.append((lb.copy(), lt.copy(), it.copy(), probs, d, p1w, p2w, ml))
+        log.append((lb.copy(), lt.copy(), it.copy(), probs, d, p1w, p2w, ml, vm.copy()))
         return probs, d, p1w, p2w, ml
 
+    host_eval.wants_mask = True
     ref = getattr(ref_cpp, f"BatchedMCTS_{game}")(n)
     set_config(ref, **cfg)
     playout(ref, host_eval, boards, turns, npl, K)
@@ -246,7 +247,7 @@ def task_cnn(out, p):
         rec = log[it_no[0]]
         it_no[0] += 1
         assert np.array_equal(lb, rec[0]) and np.array_equal(lt, rec[1]) and np.array_equal(it, rec[2]), f"leaves differ at iteration {it_no[0] - 1}"
-        return rec[3:]
+        return rec[3:8]
 
     mine = getattr(ours_cpp, f"BatchedMCTS_{game}")(n)
     set_config(mine, **cfg)
@@ -268,7 +269,7 @@ def task_cnn(out, p):
     # (d) adapter vs predict() on the first recorded non-terminal leaf batch
     lb, lt, it = log[1][0], log[1][1], log[1][2].astype(bool)
     planes = bm._default_convert_board(lb[~it], lt[~it])
-    masks = np.ones((planes.shape[0], A), bool)
+    masks = log[1][8][~it].astype(bool)
     net.score_scale = cfg.get("score_scale", 8.0)
     pr, w, a = net.predict(planes, masks)
     ad = ds.ReferenceNetAdapter(net, game)

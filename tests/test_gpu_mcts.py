@@ -335,6 +335,31 @@ def test_sharded_device_loop_equals_unsharded_loop(game, n, lanes, shards):
     assert res[0][1].tobytes() == res[1][1].tobytes()
 
 
+@pytest.mark.parametrize("switch", ["variant0", "lanes8", "k8_read_write_select", "stay"])
+def test_c4_lazy_blocks_survive_kernel_switches(switch):
+    """Expansions below the root store a 32-byte header instead of the edge block (F_LAZY, az_mcts.cu); the block is materialised on the
+    node's second visit, by a re-root that promotes it, by arena compaction - and all at once before a kernel that does not know
+    headers runs (first-generation kernels, lane-group kernels, the read-write select of K > 4 on large batches).  Trees built with
+    lazy blocks, then searched on by such kernels, must stay bit-exact with the restatement through tree reuse."""
+    n = 96
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True)
+    boards, turns = random_positions("Connect4", n, 8, 71)
+    e, o = _cuda("Connect4", n), _orc("Connect4", n)
+    e.set_lanes(1)
+    compare_engines(e, o, "Connect4", n, 60, 4, cfg, boards=boards, turns=turns, moves=4, seed=31)
+    K = 4
+    if switch == "variant0":
+        e.set_variant(0)
+    elif switch == "lanes8":
+        e.set_lanes(8)
+    elif switch == "k8_read_write_select":
+        e.set_wave_max(0)
+        K = 8
+    compare_engines(e, o, "Connect4", n, 60, K, cfg, boards=boards, turns=turns, moves=4, seed=None)
+    e.set_variant(1); e.set_lanes(1); e.set_wave_max(131072)
+    compare_engines(e, o, "Connect4", n, 60, 4, cfg, boards=boards, turns=turns, moves=3, seed=None)
+
+
 def test_more_shards_than_streams_still_searches_every_tree():
     """az_mcts_playout_synthetic_dev drives at most 16 streams: a larger shard count is merged, every tree still gets its
     simulations (root N = n_playout; visit counts sum to n_playout - 1 below a fresh root)."""
