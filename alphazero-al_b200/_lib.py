@@ -20,6 +20,12 @@ class AzSearchConfig(C.Structure):
         "score_utility_factor", "score_scale", "value_decay")] + [("use_symmetry", C.c_int32), ("vl_count", C.c_int32)]
 
 
+class AzHostLeaves(C.Structure):
+    """az_host_leaves (include/azb200.h): leaf arrays of a host search inside a pinned block the caller owns."""
+    _fields_ = [("block", C.c_int32), ("rows", C.c_int32), ("boards", C.c_void_p), ("term_d", C.c_void_p), ("term_p1w", C.c_void_p),
+                ("term_p2w", C.c_void_p), ("is_term", C.c_void_p), ("turns", C.c_void_p), ("sym_ids", C.c_void_p), ("valid_mask", C.c_void_p)]
+
+
 class AzRoot(C.Structure):
     """az_root (include/azb200.h): one position as bitboards, 32 bytes."""
     _fields_ = [("bb0", C.c_uint64), ("bb1", C.c_uint64), ("turn", C.c_int32), ("passes", C.c_int32), ("last", C.c_int32),
@@ -49,9 +55,10 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("AZB200_LIB") or LIB_PATH          # AZB200_LIB: another build of the same sources (A/B measurements)
+    if not os.path.exists(path):
         build()
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     L.az_version.restype = C.c_char_p
     L.az_global_last_error.restype = C.c_char_p
     L.az_mcts_last_error.restype = C.c_char_p
@@ -69,7 +76,7 @@ def lib() -> C.CDLL:
         "az_mcts_set_seed": [_vp, _i64], "az_mcts_reset_env": [_vp, _i], "az_mcts_prune_roots": [_vp, _vp],
         "az_mcts_search_batch": [_vp] + [_vp] * 9,
         "az_mcts_backprop_batch": [_vp] + [_vp] * 6,
-        "az_mcts_remove_all_vl": [_vp, _i],
+        "az_mcts_remove_all_vl": [_vp, _i], "az_mcts_search_batch_pinned": [_vp, _i, _vp, _vp, _vp], "az_pinned_release": [_i],
         "az_mcts_search_batch_vl": [_vp, _i] + [_vp] * 10,
         "az_mcts_backprop_batch_vl": [_vp, _i] + [_vp] * 7,
         "az_mcts_search": [_vp, _i, _vp, _vp, _i],
@@ -82,7 +89,7 @@ def lib() -> C.CDLL:
         "az_selfplay_expand_dev": [_i, _i, _vp, _vp, _i] + [_vp] * 9,
         "az_selfplay_ply_dev": [_vp, _vp, _vp, _vp], "az_selfplay_flush_dev": [_vp, _vp],
         "az_mcts_set_lanes": [_vp, _i], "az_mcts_get_lanes": [_vp], "az_mcts_reserve": [_vp, _i],
-        "az_mcts_set_variant": [_vp, _i], "az_mcts_get_variant": [_vp], "az_mcts_set_wave_max": [_vp, _i], "az_mcts_get_wave_max": [_vp], "az_selftest_div": [_i, C.c_uint64, C.c_uint64, _vp],
+        "az_mcts_set_lazy": [_vp, _i], "az_mcts_get_lazy": [_vp], "az_mcts_set_variant": [_vp, _i], "az_mcts_get_variant": [_vp], "az_mcts_set_wave_max": [_vp, _i], "az_mcts_get_wave_max": [_vp], "az_selftest_div": [_i, C.c_uint64, C.c_uint64, _vp],
         "az_mcts_backprop_dev": [_vp, _i] + [_vp] * 8,
         "az_mcts_search_range_dev": [_vp, _i, _vp, _vp, _i, _i, _i64, _i, _vp],
         "az_mcts_backprop_range_dev": [_vp, _i] + [_vp] * 7 + [_i, _i, _i64, _vp],
@@ -127,6 +134,9 @@ def lib() -> C.CDLL:
         f.restype = None
         f.argtypes = argt
     for name, argt in sig.items():
+        f = getattr(L, name, None)
+        if f is None and os.environ.get("AZB200_LIB"):        # an older build in an A/B run may lack the newest entry points
+            continue
         f = getattr(L, name)
         f.restype = _i
         f.argtypes = argt

@@ -27,6 +27,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 #if defined(__x86_64__)
@@ -108,7 +109,7 @@ struct Dev {   // kernel-visible view of an engine
     int *err;                            // sticky device error flag (arena overflow)
     int n_envs;
     int env_lo, env_cnt;                 // trees [env_lo, env_lo + env_cnt) are processed by the select / back-prop launch
-    int hints;                           // bit 0: streaming (.cs) stores for new edge blocks; bit 1: expansions below the root write lazy blocks (F_LAZY).  AZB200_HINTS overrides (A/B runs)
+    int hints;                           // bit 0: streaming (.cs) stores for new edge blocks; bit 1: expansions below the root write lazy blocks (F_LAZY; off by default, AZB200_LAZY=1 / az_mcts_set_lazy).  AZB200_HINTS overrides (A/B runs)
     uint64_t seed, epoch;
     const unsigned long long *epoch_add;   // graph replays: added to `epoch` (kernel parameters are frozen in a captured graph)
     uint64_t env_base;                   // global index of env 0 (RNG keys are sharding-invariant)
@@ -1245,6 +1246,32 @@ using namespace az;
 
 static thread_local std::string g_global_err;
 
+// Pinned host blocks handed out to callers of the *_pinned host entry points (zero-copy leaf arrays: the one device-to-host copy
+// of a search lands in the memory the caller's arrays live in).  Process-wide so that a block outlives the engine it came from.
+namespace {
+struct PinnedBlock { void *ptr; size_t bytes; bool in_use; };
+std::mutex g_pin_mu;
+std::vector<PinnedBlock> g_pin;
+int pinned_acquire(size_t bytes, void **out) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    int best = -1;
+    for (size_t i = 0; i < g_pin.size(); ++i)
+        if (g_pin[i].ptr && !g_pin[i].in_use && g_pin[i].bytes >= bytes && (best < 0 || g_pin[i].bytes < g_pin[(size_t)best].bytes)) best = (int)i;
+    if (best < 0) {
+        size_t slot = g_pin.size();
+        for (size_t i = 0; i < g_pin.size(); ++i) if (!g_pin[i].in_use) { if (g_pin[i].ptr) cudaFreeHost(g_pin[i].ptr); g_pin[i].ptr = nullptr; slot = i; break; }
+        void *p = nullptr;
+        const size_t cap = bytes + bytes / 4;                 // a little slack: remainder iterations and K changes reuse the block
+        if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); return -1; }
+        if (slot == g_pin.size()) g_pin.push_back({p, cap, false}); else g_pin[slot] = {p, cap, false};
+        best = (int)slot;
+    }
+    g_pin[(size_t)best].in_use = true;
+    *out = g_pin[(size_t)best].ptr;
+    return best;
+}
+}  // namespace
+
 struct az_mcts {
     int game = 0, n = 0, device = 0;
     int A = 0, S = 0, W = 0, max_depth = 0, max_edges = 0;
@@ -1303,6 +1330,8 @@ struct az_mcts {
     uint8_t *io_in = nullptr;         // packed eval arrays: policy | d | p1 | p2 | ml | sym | is_term
     int32_t *io_actions = nullptr; int32_t *io_counts = nullptr; float *io_stats = nullptr;
     uint8_t *h_out = nullptr, *h_in = nullptr;   // pinned mirrors of io_out / io_in
+    uint8_t *h_in2 = nullptr; cudaEvent_t h_in_ev[2] = {nullptr, nullptr}; int h_in_sel = 0;   // back-prop inputs are double-buffered: the host call returns once the copy is queued
+    bool err_check_pending = false;              // a back-prop was queued without reading the device error flag back
     int32_t *h_counts = nullptr;                 // pinned staging of the visit counts
     unsigned long long *d_stats = nullptr; int *d_err = nullptr;
     uint64_t launches = 0;
@@ -1421,8 +1450,11 @@ static int ensure_io(az_mcts *h, int rows) {
     if (rc) return AZ_ERR_CUDA;
     if (h->h_out) { cudaFreeHost(h->h_out); h->h_out = nullptr; }
     if (h->h_in) { cudaFreeHost(h->h_in); h->h_in = nullptr; }
+    if (h->h_in2) { cudaFreeHost(h->h_in2); h->h_in2 = nullptr; }
     CU(h, cudaMallocHost((void **)&h->h_out, ol.total));
     CU(h, cudaMallocHost((void **)&h->h_in, il.total));
+    CU(h, cudaMallocHost((void **)&h->h_in2, il.total));
+    for (int j = 0; j < 2; ++j) if (!h->h_in_ev[j]) CU(h, cudaEventCreateWithFlags(&h->h_in_ev[j], cudaEventDisableTiming));
     h->io_rows = r;
     return AZ_OK;
 }
@@ -1584,14 +1616,19 @@ static void launch_select_impl(az_mcts *h, bool vl, int K, const az_root *roots,
         const int gf = (cnt + CTA_F - 1) / CTA_F;
         const int kk = vl ? K : 1;
         const bool aux = h->cfg.mlh_slope > 0.0f;            // aux_enabled<C4>
+        const bool lz = (h->d.hints & 2) != 0;               // lazy blocks on: the variants that understand headers
         if (use_wave(h, vl, K)) {
             h->last_select_ro = true;
             const int kl = K <= 4 ? 4 : 8;
             const int gw = (int)(((size_t)cnt * kl + CTA_W - 1) / CTA_W);
-            if (kl == 4) { if (aux) k_select_w<C4, true, 4><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves);
-                           else k_select_w<C4, false, 4><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves); }
-            else { if (aux) k_select_w<C4, true, 8><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves);
-                   else k_select_w<C4, false, 8><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves); }
+#define AZ_SELECT_W(AX, KLV)                                                                                              \
+    do {                                                                                                                  \
+        if (lz) k_select_w<C4, AX, KLV, true><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves);                        \
+        else k_select_w<C4, AX, KLV, false><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves);                          \
+    } while (0)
+            if (kl == 4) { if (aux) AZ_SELECT_W(true, 4); else AZ_SELECT_W(false, 4); }
+            else { if (aux) AZ_SELECT_W(true, 8); else AZ_SELECT_W(false, 8); }
+#undef AZ_SELECT_W
             h->launches++;
             return;
         }
@@ -1602,16 +1639,20 @@ static void launch_select_impl(az_mcts *h, bool vl, int K, const az_root *roots,
         // launches that fill the machine on their own (more CTAs than 6 per SM) run the 128-register build, shard-sized
         // launches the spill-free 144-register build (see az_mcts_fast.cuh)
         const bool wide = gf > 6 * 148;
-#define AZ_SELECT_F(VLF, AX)                                                                                             \
-    do {                                                                                                                 \
-        if (ro) { if (wide) k_select_f<C4, VLF, AX, true><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);           \
-                  else k_select_f_r<C4, VLF, AX, true><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves); }           \
-        else { if (wide) k_select_f<C4, VLF, AX, false><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);            \
-               else k_select_f_r<C4, VLF, AX, false><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves); }            \
+#define AZ_SELECT_F2(VLF, AX, ROF, LZF)                                                                                   \
+    do {                                                                                                                  \
+        if (wide) k_select_f<C4, VLF, AX, ROF, LZF><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);                 \
+        else k_select_f_r<C4, VLF, AX, ROF, LZF><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);                    \
+    } while (0)
+#define AZ_SELECT_F(VLF, AX)                                                                                              \
+    do {                                                                                                                  \
+        if (ro) { if (lz) AZ_SELECT_F2(VLF, AX, true, true); else AZ_SELECT_F2(VLF, AX, true, false); }                   \
+        else AZ_SELECT_F2(VLF, AX, false, false);      /* the read-write select never sees lazy blocks (materialise_all) */  \
     } while (0)
         if (vl) { if (aux) AZ_SELECT_F(true, true); else AZ_SELECT_F(true, false); }
         else { if (aux) AZ_SELECT_F(false, true); else AZ_SELECT_F(false, false); }
 #undef AZ_SELECT_F
+#undef AZ_SELECT_F2
         h->launches++;
         return;
     }
@@ -1667,19 +1708,26 @@ static int launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym,
                 AZ_BP_ATTR((k_backprop_f<C4, false, true>)); AZ_BP_ATTR((k_backprop_f<C4, false, false>));
                 AZ_BP_ATTR((k_backprop_f_r<C4, true, true>)); AZ_BP_ATTR((k_backprop_f_r<C4, true, false>));
                 AZ_BP_ATTR((k_backprop_f_r<C4, false, true>)); AZ_BP_ATTR((k_backprop_f_r<C4, false, false>));
+                AZ_BP_ATTR((k_backprop_f<C4, true, true, true>)); AZ_BP_ATTR((k_backprop_f<C4, false, true, true>));
+                AZ_BP_ATTR((k_backprop_f_r<C4, true, true, true>)); AZ_BP_ATTR((k_backprop_f_r<C4, false, true, true>));
 #undef AZ_BP_ATTR
                 h->bp_smem_set = smem;
             }
             const bool ro = h->last_select_ro, wide = gf > 6 * 148;
-            if (ro && (h->d.hints & 2)) h->lazy_live = true;   // expansions below the root write headers only (F_LAZY)
-#define AZ_BP_F(KERNEL, VLF, ROF, KARG, RARG) KERNEL<C4, VLF, ROF><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, KARG, RARG, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym)
-            if (vl) {
-                if (ro) { if (wide) AZ_BP_F(k_backprop_f, true, true, kk, removeK); else AZ_BP_F(k_backprop_f_r, true, true, kk, removeK); }
-                else { if (wide) AZ_BP_F(k_backprop_f, true, false, kk, removeK); else AZ_BP_F(k_backprop_f_r, true, false, kk, removeK); }
-            } else {
-                if (ro) { if (wide) AZ_BP_F(k_backprop_f, false, true, 1, 0); else AZ_BP_F(k_backprop_f_r, false, true, 1, 0); }
-                else { if (wide) AZ_BP_F(k_backprop_f, false, false, 1, 0); else AZ_BP_F(k_backprop_f_r, false, false, 1, 0); }
-            }
+            const bool lz = ro && (h->d.hints & 2) != 0;
+            if (lz) h->lazy_live = true;                     // expansions below the root write headers only (F_LAZY)
+#define AZ_BP_F2(VLF, ROF, LZF, KARG, RARG)                                                                               \
+    do {                                                                                                                  \
+        if (wide) k_backprop_f<C4, VLF, ROF, LZF><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, KARG, RARG, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);    \
+        else k_backprop_f_r<C4, VLF, ROF, LZF><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, KARG, RARG, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);      \
+    } while (0)
+#define AZ_BP_F(VLF, KARG, RARG)                                                                                          \
+    do {                                                                                                                  \
+        if (ro) { if (lz) AZ_BP_F2(VLF, true, true, KARG, RARG); else AZ_BP_F2(VLF, true, false, KARG, RARG); }           \
+        else AZ_BP_F2(VLF, false, false, KARG, RARG);                                                                     \
+    } while (0)
+            if (vl) AZ_BP_F(true, kk, removeK); else AZ_BP_F(false, 1, 0);
+#undef AZ_BP_F2
 #undef AZ_BP_F
             h->launches++;
             return AZ_OK;
@@ -1710,6 +1758,8 @@ static void bp_prepare(az_mcts *h, bool vl, int K) {
         AZ_BP_ATTR((k_backprop_f<C4, false, true>)); AZ_BP_ATTR((k_backprop_f<C4, false, false>));
         AZ_BP_ATTR((k_backprop_f_r<C4, true, true>)); AZ_BP_ATTR((k_backprop_f_r<C4, true, false>));
         AZ_BP_ATTR((k_backprop_f_r<C4, false, true>)); AZ_BP_ATTR((k_backprop_f_r<C4, false, false>));
+        AZ_BP_ATTR((k_backprop_f<C4, true, true, true>)); AZ_BP_ATTR((k_backprop_f<C4, false, true, true>));
+        AZ_BP_ATTR((k_backprop_f_r<C4, true, true, true>)); AZ_BP_ATTR((k_backprop_f_r<C4, false, true, true>));
 #undef AZ_BP_ATTR
         h->bp_smem_set = smem;
     }
@@ -1881,8 +1931,8 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     const char *ce = getenv("AZB200_ARENA_SLOTS");
     h->cap = ce ? (uint32_t)std::max(256, atoi(ce)) : (game == GAME_C4 ? 2048u : 4096u);
     h->d.n_envs = n_envs; h->d.env_lo = 0; h->d.env_cnt = n_envs; h->d.cap = h->cap; h->d.noise_stride = h->max_edges;
-    { const char *he = getenv("AZB200_HINTS"); h->d.hints = he ? atoi(he) : 3; }
-    { const char *le = getenv("AZB200_LAZY"); if (le && atoi(le) == 0) h->d.hints &= ~2; }
+    { const char *he = getenv("AZB200_HINTS"); h->d.hints = he ? atoi(he) : 1; }
+    { const char *le = getenv("AZB200_LAZY"); if (le) h->d.hints = atoi(le) ? (h->d.hints | 2) : (h->d.hints & ~2); }   // lazy blocks: off by default (measured slower)
     h->d.seed = 0x243F6A8885A308D3ULL; h->d.epoch = 0; h->d.epoch_add = nullptr;
     int rc = 0;
     rc |= dev_alloc(h, &h->d.pool, (size_t)n_envs * h->cap);
@@ -1920,6 +1970,8 @@ void az_mcts_destroy(az_mcts *h) {
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_in2) cudaFreeHost(h->h_in2);
+    for (int j = 0; j < 2; ++j) if (h->h_in_ev[j]) cudaEventDestroy(h->h_in_ev[j]);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->ev) cudaEventDestroy(h->ev);
     for (auto &pr : h->sel_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -2028,6 +2080,13 @@ int az_mcts_reset_all_dev(az_mcts *h, void *stream) {
     h->sel_recs.clear(); h->lazy_live = false;
     return AZ_OK;
 }
+int az_mcts_set_lazy(az_mcts *h, int on) {
+    if (on) { h->d.hints |= 2; return AZ_OK; }
+    if (h->lazy_live) { CU(h, cudaSetDevice(h->device)); int rc = materialise_all(h, h->stream); if (rc) return rc; CU(h, cudaStreamSynchronize(h->stream)); }
+    h->d.hints &= ~2;
+    return AZ_OK;
+}
+int az_mcts_get_lazy(const az_mcts *h) { return (h->d.hints & 2) ? 1 : 0; }
 int az_mcts_set_compaction(az_mcts *h, int mode) {
     if (mode < 0 || mode > 2) AZ_FAIL(h, AZ_ERR_INVALID, "compaction mode must be 0 (never), 1 (auto) or 2 (every re-root)");
     h->compaction = mode;
@@ -2051,9 +2110,13 @@ int az_mcts_prune_roots(az_mcts *h, const int32_t *actions) {
     return AZ_OK;
 }
 
-// host entry points: pack -> search -> unpack into one packed staging buffer -> ONE D2H copy into pinned memory
+int az_pinned_release(int block);
+// host entry points: pack -> search -> unpack into one packed staging buffer -> ONE D2H copy into pinned memory.
+// `pinned` != NULL: the copy lands in a pinned block of the process-wide pool that the caller owns until az_pinned_release - its
+// arrays ARE the copy's destination (no second pass over 2.3 MB per K = 4 iteration at 8192 games).  Otherwise the arrays the caller
+// passed are filled from the engine's own pinned mirror.
 static int host_search(az_mcts *h, int K, const int8_t *boards, const int32_t *turns, int8_t *ob, float *td, float *tp1, float *tp2,
-                       uint8_t *it, int32_t *ot, int32_t *sym, uint8_t *vm) {
+                       uint8_t *it, int32_t *ot, int32_t *sym, uint8_t *vm, az_host_leaves *pinned = nullptr) {
     { int rc0 = enter_host(h); if (rc0) return rc0; }
     const int rowsK = K > 0 ? K : 1;
     const size_t rows = (size_t)h->n * rowsK;
@@ -2069,14 +2132,41 @@ static int host_search(az_mcts *h, int K, const int8_t *boards, const int32_t *t
                               (float *)(o + L.tp2), o + L.term, (int32_t *)(o + L.turns), (int32_t *)(o + L.sym), o + L.mask, nullptr, s);
     if (rc) AZ_FAIL(h, rc, "unpack_leaves launch failed");
     h->launches += 2;
-    CU(h, cudaMemcpyAsync(h->h_out, o, L.total, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaStreamSynchronize(s));
-    const uint8_t *p = h->h_out;
+    uint8_t *dst = h->h_out;
+    int block = -1;
+    if (pinned) {
+        void *bp = nullptr;
+        block = pinned_acquire(L.total, &bp);
+        if (block < 0) AZ_FAIL(h, AZ_ERR_NOMEM, "cannot allocate %zu bytes of pinned host memory for the leaf arrays", L.total);
+        dst = (uint8_t *)bp;
+    }
+    int dev_err = 0;
+    CU(h, cudaMemcpyAsync(dst, o, L.total, cudaMemcpyDeviceToHost, s));
+    if (h->err_check_pending) CU(h, cudaMemcpyAsync(&dev_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    cudaError_t se = cudaStreamSynchronize(s);
+    if (se != cudaSuccess || dev_err) {
+        if (block >= 0) az_pinned_release(block);
+        if (se != cudaSuccess) AZ_FAIL(h, AZ_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(se));
+        AZ_FAIL(h, AZ_ERR_NOMEM, "device tree arena overflow (internal sizing error)");
+    }
+    h->err_check_pending = false;
+    const uint8_t *p = dst;
+    if (pinned) {
+        pinned->block = block; pinned->rows = (int32_t)rows;
+        pinned->boards = (int8_t *)(dst + L.boards); pinned->term_d = (float *)(dst + L.td); pinned->term_p1w = (float *)(dst + L.tp1);
+        pinned->term_p2w = (float *)(dst + L.tp2); pinned->is_term = dst + L.term; pinned->turns = (int32_t *)(dst + L.turns);
+        pinned->sym_ids = (int32_t *)(dst + L.sym); pinned->valid_mask = dst + L.mask;
+        return AZ_OK;
+    }
     memcpy(ob, p + L.boards, rows * h->S); memcpy(td, p + L.td, rows * 4); memcpy(tp1, p + L.tp1, rows * 4); memcpy(tp2, p + L.tp2, rows * 4);
     memcpy(it, p + L.term, rows); memcpy(ot, p + L.turns, rows * 4); memcpy(vm, p + L.mask, rows * h->A);
     if (sym) memcpy(sym, p + L.sym, rows * 4);
     return AZ_OK;
 }
+// The evaluation tuple is packed into one of two pinned buffers, copied with ONE host-to-device copy, and the back-prop kernel is
+// queued behind it: the call returns without waiting for either (the next host entry point is stream-ordered after them; the
+// device error flag is read back by the next search).  The reference's call is synchronous, but nothing a caller can observe
+// through the API happens before the next entry point anyway.
 static int host_backprop(az_mcts *h, int K, const float *pol, const float *d, const float *p1, const float *p2, const float *ml,
                          const uint8_t *it, const int32_t *sym) {
     { int rc0 = enter_host(h); if (rc0) return rc0; }
@@ -2085,16 +2175,20 @@ static int host_backprop(az_mcts *h, int K, const float *pol, const float *d, co
     int rc = ensure_io(h, (int)rows); if (rc) return rc;
     cudaStream_t s = h->stream;
     const InLayout L = in_layout(rows, h->A);
-    uint8_t *p = h->h_in;
+    const int sel = h->h_in_sel; h->h_in_sel ^= 1;
+    uint8_t *p = sel ? h->h_in2 : h->h_in;
+    CU(h, cudaEventSynchronize(h->h_in_ev[sel]));          // the copy that last read this buffer has completed
     memcpy(p + L.policy, pol, rows * h->A * 4); memcpy(p + L.d, d, rows * 4); memcpy(p + L.p1, p1, rows * 4); memcpy(p + L.p2, p2, rows * 4);
     memcpy(p + L.ml, ml, rows * 4); memcpy(p + L.term, it, rows);
     if (sym) memcpy(p + L.sym, sym, rows * 4);
     CU(h, cudaMemcpyAsync(h->io_in, p, L.total, cudaMemcpyHostToDevice, s));
+    CU(h, cudaEventRecord(h->h_in_ev[sel], s));
     uint8_t *q = h->io_in;
     rc = do_backprop(h, K, (const float *)(q + L.policy), (const float *)(q + L.d), (const float *)(q + L.p1), (const float *)(q + L.p2),
                      (const float *)(q + L.ml), q + L.term, sym ? (const int32_t *)(q + L.sym) : nullptr, s);
     if (rc) return rc;
-    return check_device_error(h);
+    h->err_check_pending = true; h->internal_pending = true;
+    return AZ_OK;
 }
 
 int az_mcts_search_batch(az_mcts *h, const int8_t *b, const int32_t *t, int8_t *ob, float *td, float *tp1, float *tp2, uint8_t *it,
@@ -2113,6 +2207,19 @@ int az_mcts_backprop_batch_vl(az_mcts *h, int K, const float *pol, const float *
                               const uint8_t *it, const int32_t *sym) {
     if (K < 1) AZ_FAIL(h, AZ_ERR_INVALID, "backprop_batch_vl: K must be >= 1");
     return host_backprop(h, K, pol, d, p1, p2, ml, it, sym);
+}
+int az_mcts_search_batch_pinned(az_mcts *h, int K, const int8_t *b, const int32_t *t, az_host_leaves *out) {
+    if (K < 0 || !out) AZ_FAIL(h, AZ_ERR_INVALID, "search_batch_pinned: K must be >= 0 and out non-NULL");
+    return host_search(h, K, b, t, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out);
+}
+int az_pinned_release(int block) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (block < 0 || (size_t)block >= g_pin.size() || !g_pin[(size_t)block].in_use) return AZ_ERR_INVALID;
+    g_pin[(size_t)block].in_use = false;
+    size_t idle = 0;                                         // keep a few idle blocks for reuse, give the rest back
+    for (auto &b : g_pin) if (b.ptr && !b.in_use) ++idle;
+    if (idle > 6) { cudaFreeHost(g_pin[(size_t)block].ptr); g_pin[(size_t)block].ptr = nullptr; g_pin[(size_t)block].bytes = 0; }
+    return AZ_OK;
 }
 int az_mcts_remove_all_vl(az_mcts *h, int K) {
     int rc = check_cfg(h, 1); if (rc) return rc;

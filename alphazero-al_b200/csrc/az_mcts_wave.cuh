@@ -18,7 +18,7 @@ namespace az {
 constexpr int CTA_W = 128;
 
 // KL lanes per tree (4 or 8), lane k of a group runs descent k (k < K <= KL)
-template <class G, bool AUX, int KL>
+template <class G, bool AUX, int KL, bool LAZY = false>
 __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
                                                  az_leaf *__restrict__ leaves) {
     static_assert(G::GAME == GAME_C4, "staggered select is specialised for Connect4 (<= 7 edges)");
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
         const bool act = w != 0u && step >= k;
         const uint32_t off = w >> 6;
         const int ne = (int)(w & 7u);
-        const bool lazy = (w & W_LAZY) != 0u;
+        const bool lazy = LAZY && (w & W_LAZY) != 0u;
         // ---- in-flight counts from the earlier descents of my tree: a path that holds a slot of this block at this depth
         //      passed through this node (parent + 1) and through that child (child + 1); 4 bits per child ----
         uint32_t packed = 0u, cntp = 0u;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
                 ++plen;
                 cur_n = ch.n; cur_meta = nmeta; cur_Q = best_Q; cur_M = best_M; is_root = false;
                 if (ch.child != NONE && !(ch.meta & F_TERM) && (ch.child & 63u) != 0 && plen < (uint32_t)G::MAX_DEPTH && !term_now)
-                    nw = (ch.child & ~63u) | (ch.child & 7u) | ((ch.meta & F_LAZY) ? W_LAZY : 0u);
+                    nw = LAZY ? ((ch.child & ~63u) | (ch.child & 7u) | ((ch.meta & F_LAZY) ? W_LAZY : 0u)) : ch.child;
             }
         }
         if (act) w = nw;

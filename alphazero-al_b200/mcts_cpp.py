@@ -13,11 +13,12 @@ and a stream, never synchronise, and can encode leaves straight into the CNN inp
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
 from . import _lib
-from ._lib import AzSearchConfig
+from ._lib import AzHostLeaves, AzSearchConfig
 
 GAME_IDS = {"Connect4": 0, "Othello": 1}
 EVAL_UNIFORM, EVAL_ROLLOUT = 0, 1
@@ -147,6 +148,30 @@ class _BatchedMCTS:
                 np.empty(total, np.float32), np.empty(total, np.uint8), np.empty(total, np.int32),
                 np.empty((total, self._A), np.uint8))
 
+    def _search_pinned(self, K, b, t):
+        """One call, one device-to-host copy, no second pass: the returned arrays are views of a pinned block that goes back to the
+        library's pool when the last of them is garbage collected (fresh arrays owned by Python, as mcts_bindings.cpp returns)."""
+        out = AzHostLeaves()
+        self._push_cfg()
+        self._ck(self._L.az_mcts_search_batch_pinned(self._h, K, _ptr(b), _ptr(t), C.byref(out)))
+        rows, A, S = out.rows, self._A, self._S
+        base = out.boards                                         # lowest address of the block's arrays
+        end = max(out.valid_mask + rows * A, out.sym_ids + rows * 4, out.turns + rows * 4, out.is_term + rows)
+        buf = (C.c_uint8 * (end - base)).from_address(base)
+        weakref.finalize(buf, self._L.az_pinned_release, out.block)
+        raw = np.frombuffer(buf, dtype=np.uint8)
+
+        def arr(ptr, dtype, count, shape):
+            o = ptr - base
+            return raw[o:o + count * np.dtype(dtype).itemsize].view(dtype).reshape(shape)
+        ob = arr(out.boards, np.int8, rows * S, (rows, *self.board_shape))
+        td, tp1, tp2 = (arr(p, np.float32, rows, (rows,)) for p in (out.term_d, out.term_p1w, out.term_p2w))
+        it = arr(out.is_term, np.uint8, rows, (rows,))
+        ot = arr(out.turns, np.int32, rows, (rows,))
+        sym = arr(out.sym_ids, np.int32, rows, (rows,))
+        vm = arr(out.valid_mask, np.uint8, rows * A, (rows, A))
+        return ob, td, tp1, tp2, it, ot, sym, vm
+
     def search_batch(self, input_boards, turns):
         b, t = _carr(input_boards, np.int8), _carr(turns, np.int32)
         batch = b.shape[0] if b.ndim else 0
@@ -156,10 +181,7 @@ class _BatchedMCTS:
             raise RuntimeError("Turns size must match batch size")
         if b.size != batch * self._S:
             raise RuntimeError(f"search_batch: input_boards must have {self._S} cells per board")
-        ob, td, tp1, tp2, it, ot, vm = self._leaf_arrays(batch)
-        self._push_cfg()
-        self._ck(self._L.az_mcts_search_batch(self._h, _ptr(b), _ptr(t), _ptr(ob), _ptr(td), _ptr(tp1), _ptr(tp2),
-                                              _ptr(it), _ptr(ot), _ptr(vm)))
+        ob, td, tp1, tp2, it, ot, _, vm = self._search_pinned(0, b, t)
         return ob, td, tp1, tp2, it, ot, vm
 
     def backprop_batch(self, policy_logits, d_vals, p1w_vals, p2w_vals, moves_left, is_term):
@@ -198,12 +220,7 @@ class _BatchedMCTS:
             raise RuntimeError("search_batch_vl: K must be >= 1")
         if b.size != batch * self._S:
             raise RuntimeError(f"search_batch_vl: input_boards must have {self._S} cells per board")
-        ob, td, tp1, tp2, it, ot, vm = self._leaf_arrays(n * K)
-        sym = np.empty(n * K, np.int32)
-        self._push_cfg()
-        self._ck(self._L.az_mcts_search_batch_vl(self._h, K, _ptr(b), _ptr(t), _ptr(ob), _ptr(td), _ptr(tp1), _ptr(tp2),
-                                                 _ptr(it), _ptr(ot), _ptr(sym), _ptr(vm)))
-        return ob, td, tp1, tp2, it, ot, sym, vm
+        return self._search_pinned(K, b, t)
 
     def backprop_batch_vl(self, K, policy_logits, d_vals, p1w_vals, p2w_vals, moves_left, is_term, sym_ids):
         K = int(K)
@@ -344,6 +361,13 @@ class _BatchedMCTS:
 
     def get_lanes(self):
         return self._L.az_mcts_get_lanes(self._h)
+
+    def set_lazy(self, on=True):
+        """Lazy edge blocks (include/azb200.h): header-only expansions, materialised on the second visit.  Off by default."""
+        self._ck(self._L.az_mcts_set_lazy(self._h, 1 if on else 0))
+
+    def get_lazy(self):
+        return bool(self._L.az_mcts_get_lazy(self._h))
 
     def set_variant(self, variant):
         """Generation of the thread-per-tree Connect4 kernels (0 first, 1 lean); bit-identical results."""

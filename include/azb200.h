@@ -88,6 +88,20 @@ int az_mcts_backprop_batch(az_mcts *h, const float *policy, const float *d_vals,
                            const float *p2w_vals, const float *moves_left, const uint8_t *is_term);
 /* remove_all_vl - BatchedMCTS.h:209-216 (idempotent clean-up) */
 int az_mcts_remove_all_vl(az_mcts *h, int K);
+/* Zero-copy form of search_batch (K == 0) / search_batch_vl (K >= 1): the leaf arrays are delivered in a pinned host block that
+ * the CALLER owns until az_pinned_release(out->block) - the single device-to-host copy of the call lands there, so a binding can
+ * hand out numpy arrays over it without a second pass (mcts_bindings.cpp:89-134,197-252 return fresh arrays owned by Python: the
+ * binding releases the block when the last of them is collected).  Blocks come from a process-wide pool and outlive the engine. */
+typedef struct az_host_leaves {
+    int32_t block, rows;             /* pool block id; rows = n_envs * max(K, 1) */
+    int8_t *boards;                  /* [rows, R, C] */
+    float *term_d, *term_p1w, *term_p2w;
+    uint8_t *is_term;
+    int32_t *turns, *sym_ids;        /* sym_ids: the ids applied (all 0 when K == 0: the non-VL search keeps them internally) */
+    uint8_t *valid_mask;             /* [rows, A] */
+} az_host_leaves;
+int az_mcts_search_batch_pinned(az_mcts *h, int K, const int8_t *boards, const int32_t *turns, az_host_leaves *out);
+int az_pinned_release(int block);
 /* search_batch_vl - BatchedMCTS.h:227-286 / mcts_bindings.cpp:197-252.  K virtual-loss simulations per tree,
  * sequential inside a tree; outputs have n*K rows plus sym_ids i32[n*K]. */
 int az_mcts_search_batch_vl(az_mcts *h, int K, const int8_t *boards, const int32_t *turns, int8_t *out_boards,
@@ -209,6 +223,12 @@ int az_mcts_set_env_base(az_mcts *h, uint64_t base);
  * Env: AZB200_COMPACTION.  az_mcts_compactions = compactions performed so far. */
 int az_mcts_set_compaction(az_mcts *h, int mode);
 uint64_t az_mcts_compactions(const az_mcts *h);
+/* Lazy edge blocks (Connect4, lean thread-per-tree kernels, read-only selects): an expansion below the root stores a 32-byte header
+ * {priors, legal mask} instead of num_edges x 32 bytes; the block is materialised on the node's second visit.  Fewer DRAM bytes
+ * (most expanded nodes are never visited again), but one more dependent load per back-propagated path: measured slower on B200
+ * (DESIGN.md), hence OFF by default.  Results are identical either way.  Env: AZB200_LAZY=1. */
+int az_mcts_set_lazy(az_mcts *h, int on);
+int az_mcts_get_lazy(const az_mcts *h);
 /* Pre-size every tree arena (slots of 32 bytes per tree) so no reallocation happens later (e.g. under graph capture). */
 int az_mcts_reserve(az_mcts *h, int slots_per_tree);
 

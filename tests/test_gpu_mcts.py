@@ -346,6 +346,10 @@ def test_c4_lazy_blocks_survive_kernel_switches(switch):
     boards, turns = random_positions("Connect4", n, 8, 71)
     e, o = _cuda("Connect4", n), _orc("Connect4", n)
     e.set_lanes(1)
+    e.set_lazy(True)                                        # off by default (measured slower on B200)
+    assert e.get_lazy()
+    if switch == "stay":
+        e.set_compaction(2)                                 # ... and a compaction (which materialises what it copies) at every re-root
     compare_engines(e, o, "Connect4", n, 60, 4, cfg, boards=boards, turns=turns, moves=4, seed=31)
     K = 4
     if switch == "variant0":
@@ -356,8 +360,38 @@ def test_c4_lazy_blocks_survive_kernel_switches(switch):
         e.set_wave_max(0)
         K = 8
     compare_engines(e, o, "Connect4", n, 60, K, cfg, boards=boards, turns=turns, moves=4, seed=None)
-    e.set_variant(1); e.set_lanes(1); e.set_wave_max(131072)
+    e.set_variant(1); e.set_lanes(1); e.set_wave_max(131072); e.set_lazy(True)
     compare_engines(e, o, "Connect4", n, 60, 4, cfg, boards=boards, turns=turns, moves=3, seed=None)
+    e.set_lazy(False)                                       # materialises whatever is still a header
+    compare_engines(e, o, "Connect4", n, 60, 4, cfg, boards=boards, turns=turns, moves=2, seed=None)
+
+
+def test_c4_lazy_blocks_thread_per_tree_kernel_and_shards():
+    """The same with the thread-per-tree select (k_select_f, the large-batch kernel: staggered descents off) and the device-resident
+    sharded loop: lazy blocks on / off build identical trees."""
+    import torch
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    n, K, npl = 2048, 4, 81
+    boards, turns = random_positions("Connect4", 64, 10, 5)
+    boards, turns = np.tile(boards, (n // 64, 1, 1)), np.tile(turns, n // 64)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    res = []
+    for lazy in (False, True):
+        e = _cuda("Connect4", n)
+        set_config(e, **dict(SERVER_DEFAULTS, use_symmetry=True))
+        e.set_seed(5)
+        e.set_wave_max(0)
+        e.set_lazy(lazy)
+        buf = ds.LeafBuffers(n, n * K, 7, (6, 7), dev)
+        buf.pack_roots(torch.from_numpy(boards).to(dev), torch.from_numpy(turns).to(dev), stream)
+        for mv in range(3):                                   # tree reuse: re-root on the most visited move
+            ds.playout_device(e, buf, npl, K, ds.SyntheticEvaluator("Connect4", "hash"), stream, shards=2 if mv else 1)
+            c = counts(e, n, 7)
+            res.append((c, e.get_all_root_stats()))
+            e.prune_roots(c.argmax(1).astype(np.int32))
+    for a, b in zip(res[:3], res[3:]):
+        assert np.array_equal(a[0], b[0]) and a[1].tobytes() == b[1].tobytes()
 
 
 def test_more_shards_than_streams_still_searches_every_tree():
