@@ -273,7 +273,7 @@ def task_cnn(out, p):
     net.score_scale = cfg.get("score_scale", 8.0)
     pr, w, a = net.predict(planes, masks)
     ad = ds.ReferenceNetAdapter(net, game)
-    pd_, wd_, ad_ = ad.predict_device(torch.from_numpy(planes).cuda(), torch.from_numpy(masks.astype(np.uint8)).cuda())
+    pd_, wd_, ad_ = ad.predict_device(torch.from_numpy(planes.astype(np.float32)).cuda(), torch.from_numpy(masks.astype(np.uint8)).cuda())
     adapter_equal = bool(np.array_equal(pd_.cpu().numpy(), pr) and np.array_equal(wd_.cpu().numpy(), w) and np.array_equal(ad_.cpu().numpy(), a.reshape(-1)))
     adapter_maxdiff = float(max(np.abs(pd_.cpu().numpy() - pr).max(), np.abs(wd_.cpu().numpy() - w).max(), np.abs(ad_.cpu().numpy() - a.reshape(-1)).max()))
     res = dict(game=game, iterations=len(log), fed_counts_and_stats_identical=fed_equal, fed_l1_max=float(l1(fed, theirs).max()),
