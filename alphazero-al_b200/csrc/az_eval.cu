@@ -7,6 +7,7 @@
 // bit for bit.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/azb200.h"
 #include "az_games.cuh"
@@ -23,6 +24,7 @@ template <class G>
 __global__ void k_eval_synth(int mode, int n, const az_leaf *__restrict__ leaves, float *__restrict__ policy, float *__restrict__ dv,
                              float *__restrict__ p1v, float *__restrict__ p2v, float *__restrict__ mlv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();                                      // the leaves are the previous kernel's output
     if (i >= n) return;
     constexpr int A = G::A;
     const uint64_t keep = l2_keep_policy();          // leaves / policy / value rows live in L2 (az_rng.cuh)
@@ -109,8 +111,9 @@ extern "C" int az_eval_synthetic_dev(int game, int mode, int n, const az_leaf *l
     if (mode < 0 || mode > 2 || (mode == 1 && game != AZ_GAME_CONNECT4)) return AZ_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     const int bs = 128, g = (n + bs - 1) / bs;
-    if (game == AZ_GAME_CONNECT4) az::k_eval_synth<az::C4><<<g, bs, 0, s>>>(mode, n, leaves, pol, d, p1, p2, ml);
-    else if (game == AZ_GAME_OTHELLO) az::k_eval_synth<az::Oth><<<g, bs, 0, s>>>(mode, n, leaves, pol, d, p1, p2, ml);
+    static const bool pdl = !(getenv("AZB200_PDL") && atoi(getenv("AZB200_PDL")) == 0);
+    if (game == AZ_GAME_CONNECT4) az::launch_pdl(az::k_eval_synth<az::C4>, g, bs, 0, s, pdl, mode, n, leaves, pol, d, p1, p2, ml);
+    else if (game == AZ_GAME_OTHELLO) az::launch_pdl(az::k_eval_synth<az::Oth>, g, bs, 0, s, pdl, mode, n, leaves, pol, d, p1, p2, ml);
     else return AZ_ERR_INVALID;
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_ERR_CUDA;
 }

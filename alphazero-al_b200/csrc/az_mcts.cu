@@ -1317,6 +1317,7 @@ struct az_mcts {
     // different K in host order; a back-prop looks up the select of ITS range and is refused when none matches
     struct SelRec { int lo, hi, K; bool vl, ro; };
     std::vector<SelRec> sel_recs;
+    bool pdl = true;                  // programmatic dependent launch for the lean kernels of the playout loop (AZB200_PDL=0 turns it off)
     bool lazy_live = false;           // the trees may hold lazy blocks (F_LAZY): only the read-only selects and k_backprop_f know them
     int variant = 1;                  // thread-per-tree kernels: 0 = first generation (k_*_t), 1 = lean (k_*_f)
     int wave_max = 131072;             // batches of at most this many descent lanes run the staggered-descent select (az_mcts_wave.cuh); 0 = off
@@ -1623,8 +1624,8 @@ static void launch_select_impl(az_mcts *h, bool vl, int K, const az_root *roots,
             const int gw = (int)(((size_t)cnt * kl + CTA_W - 1) / CTA_W);
 #define AZ_SELECT_W(AX, KLV)                                                                                              \
     do {                                                                                                                  \
-        if (lz) k_select_w<C4, AX, KLV, true><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves);                        \
-        else k_select_w<C4, AX, KLV, false><<<gw, CTA_W, 0, s>>>(h->d, h->cfg, K, roots, leaves);                          \
+        if (lz) launch_pdl(k_select_w<C4, AX, KLV, true>, gw, CTA_W, 0, s, h->pdl, h->d, h->cfg, K, roots, leaves);       \
+        else launch_pdl(k_select_w<C4, AX, KLV, false>, gw, CTA_W, 0, s, h->pdl, h->d, h->cfg, K, roots, leaves);         \
     } while (0)
             if (kl == 4) { if (aux) AZ_SELECT_W(true, 4); else AZ_SELECT_W(false, 4); }
             else { if (aux) AZ_SELECT_W(true, 8); else AZ_SELECT_W(false, 8); }
@@ -1641,8 +1642,8 @@ static void launch_select_impl(az_mcts *h, bool vl, int K, const az_root *roots,
         const bool wide = gf > 6 * 148;
 #define AZ_SELECT_F2(VLF, AX, ROF, LZF)                                                                                   \
     do {                                                                                                                  \
-        if (wide) k_select_f<C4, VLF, AX, ROF, LZF><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);                 \
-        else k_select_f_r<C4, VLF, AX, ROF, LZF><<<gf, CTA_F, 0, s>>>(h->d, h->cfg, kk, roots, leaves);                    \
+        if (wide) launch_pdl(k_select_f<C4, VLF, AX, ROF, LZF>, gf, CTA_F, 0, s, h->pdl, h->d, h->cfg, kk, roots, leaves);  \
+        else launch_pdl(k_select_f_r<C4, VLF, AX, ROF, LZF>, gf, CTA_F, 0, s, h->pdl, h->d, h->cfg, kk, roots, leaves);     \
     } while (0)
 #define AZ_SELECT_F(VLF, AX)                                                                                              \
     do {                                                                                                                  \
@@ -1718,8 +1719,8 @@ static int launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym,
             if (lz) h->lazy_live = true;                     // expansions below the root write headers only (F_LAZY)
 #define AZ_BP_F2(VLF, ROF, LZF, KARG, RARG)                                                                               \
     do {                                                                                                                  \
-        if (wide) k_backprop_f<C4, VLF, ROF, LZF><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, KARG, RARG, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);    \
-        else k_backprop_f_r<C4, VLF, ROF, LZF><<<gf, CTA_F, smem, s>>>(h->d, h->cfg, KARG, RARG, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);      \
+        if (wide) launch_pdl(k_backprop_f<C4, VLF, ROF, LZF>, gf, CTA_F, smem, s, h->pdl, h->d, h->cfg, KARG, RARG, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);    \
+        else launch_pdl(k_backprop_f_r<C4, VLF, ROF, LZF>, gf, CTA_F, smem, s, h->pdl, h->d, h->cfg, KARG, RARG, use_sym, rec_shift, pol, d, p1, p2, ml, it, sym);      \
     } while (0)
 #define AZ_BP_F(VLF, KARG, RARG)                                                                                          \
     do {                                                                                                                  \
@@ -1916,6 +1917,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     { const char *ve = getenv("AZB200_VARIANT"); if (ve) { int v = atoi(ve); if (v >= 0 && v <= 1) h->variant = v; } }
     { const char *we = getenv("AZB200_WAVE_MAX"); if (we) h->wave_max = std::max(0, atoi(we)); }
     { const char *ge = getenv("AZB200_GRAPHS"); if (ge) h->use_graphs = atoi(ge) != 0; }
+    { const char *pe = getenv("AZB200_PDL"); if (pe) h->pdl = atoi(pe) != 0; }
     { const char *ce2 = getenv("AZB200_COMPACTION"); if (ce2) { int v = atoi(ce2); if (v >= 0 && v <= 2) h->compaction = v; } }
     h->max_depth = game == GAME_C4 ? C4::MAX_DEPTH : Oth::MAX_DEPTH;
     h->max_edges = game == GAME_C4 ? 8 : 48;

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
 #pragma unroll
     for (int j = 0; j < PATH8; ++j) mypath[j] = 0;
 
+    pdl_wait();                                            // the tree is the previous kernel's output
     // import_board (Connect4.h:100-129): the last mover is inferred from piece-count parity
     uint64_t b0, b1; int turn, last;
     { const az_root r = ld32(roots + env); b0 = r.bb0; b1 = r.bb1; turn = r.turn;

@@ -29,6 +29,24 @@ AZ_HD uint64_t rollout_hash(uint64_t seed, uint64_t gidx, uint64_t ply) {
 }
 
 #if defined(__CUDACC__)
+// ---- programmatic dependent launch (sm_90+) ------------------------------------------------------------------------
+// The playout loop is a chain of dependent kernels (select -> evaluate -> back-prop, 51 times per move and shard): with the
+// programmatic-stream-serialization launch attribute a kernel's CTAs may become resident while the tail of its predecessor is
+// still running; it executes whatever does not depend on the predecessor (index arithmetic, staging the {log, sqrt} table) and
+// then blocks in pdl_wait() until the predecessor grid has completed and its writes are visible.  Without the attribute (or
+// without a kernel predecessor) both calls are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 // ---- L2 residency hints --------------------------------------------------------------------------------------------
 // The leaf records, az_leaf rows, policy rows and value rows are producer -> consumer buffers rewritten in place every
 // iteration (select -> evaluator -> back-prop), ~37 MB at 65 536 trees x K = 4.  Accessed with the evict_last policy they
