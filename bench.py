@@ -500,6 +500,16 @@ def main():
         p0, l0 = sp.plies, sp.launches
         t0 = time.perf_counter()
         pending, gathered_games, gathered_pos, replay_rows = None, 0, 0, 0
+
+        def consume():                            # the receiving side: oldest finished gather -> training tuples, on the exchange's stream
+            nonlocal gathered_games, gathered_pos, replay_rows
+            rec = exch.collect()
+            gathered_games += len(rec)
+            gathered_pos += rec.positions
+            if len(rec):
+                with torch.cuda.stream(exch.stream):
+                    replay_rows += int(rec.to_replay_tensors(10, stream=exch.stream.cuda_stream)["state"].shape[0])
+
         done_plies = 0
         while done_plies < plies:
             for _ in range(min(every, plies - done_plies)):
@@ -508,6 +518,8 @@ def main():
             ring = sp.hand_over()                 # batch closed on the main stream; the other ring takes over
             if pending is not None:               # the previous batch's gather is issued behind this batch's (already enqueued) search
                 exch.submit(pending)
+                while len(exch.pending) > 1:
+                    consume()
             pending = ring
         e_main = torch.cuda.Event()
         e_main.record()
@@ -515,11 +527,7 @@ def main():
         e_main.synchronize()
         t_main = time.perf_counter() - t0
         while exch.pending:
-            rec = exch.collect()
-            gathered_games += len(rec)
-            gathered_pos += rec.positions
-            if len(rec):
-                replay_rows += int(rec.to_replay_tensors(10)["state"].shape[0])      # the receiving side's expansion into training tuples
+            consume()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tot = torch.tensor([dt, t_main], device=dev, dtype=torch.float64)
