@@ -1333,6 +1333,8 @@ struct az_mcts {
     uint8_t *h_out = nullptr, *h_in = nullptr;   // pinned mirrors of io_out / io_in
     uint8_t *h_in2 = nullptr; cudaEvent_t h_in_ev[2] = {nullptr, nullptr}; int h_in_sel = 0;   // back-prop inputs are double-buffered: the host call returns once the copy is queued
     bool err_check_pending = false;              // a back-prop was queued without reading the device error flag back
+    int host_direct = 0;                         // AZB200_HOST_DIRECT=1: back-prop inputs copied straight from the caller's (pageable) arrays
+    std::vector<int8_t> last_boards; std::vector<int32_t> last_turns; bool roots_valid = false;   // host searches: roots already packed on the device
     int32_t *h_counts = nullptr;                 // pinned staging of the visit counts
     unsigned long long *d_stats = nullptr; int *d_err = nullptr;
     uint64_t launches = 0;
@@ -1918,6 +1920,7 @@ az_mcts *az_mcts_create(int game, int n_envs, int device) {
     { const char *we = getenv("AZB200_WAVE_MAX"); if (we) h->wave_max = std::max(0, atoi(we)); }
     { const char *ge = getenv("AZB200_GRAPHS"); if (ge) h->use_graphs = atoi(ge) != 0; }
     { const char *pe = getenv("AZB200_PDL"); if (pe) h->pdl = atoi(pe) != 0; }
+    { const char *de = getenv("AZB200_HOST_DIRECT"); if (de) h->host_direct = atoi(de); }
     { const char *ce2 = getenv("AZB200_COMPACTION"); if (ce2) { int v = atoi(ce2); if (v >= 0 && v <= 2) h->compaction = v; } }
     h->max_depth = game == GAME_C4 ? C4::MAX_DEPTH : Oth::MAX_DEPTH;
     h->max_edges = game == GAME_C4 ? 8 : 48;
@@ -2124,9 +2127,18 @@ static int host_search(az_mcts *h, int K, const int8_t *boards, const int32_t *t
     const size_t rows = (size_t)h->n * rowsK;
     int rc = ensure_io(h, (int)rows); if (rc) return rc;
     cudaStream_t s = h->stream;
-    CU(h, cudaMemcpyAsync(h->io_boards_in, boards, (size_t)h->n * h->S, cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->io_turns_in, turns, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, s));
-    rc = az_pack_roots_dev(h->game, h->n, h->io_boards_in, h->io_turns_in, h->io_roots, s); if (rc) AZ_FAIL(h, rc, "pack_roots launch failed");
+    // the wrapper hands the same boards to every iteration of a move (src/MCTS_cpp.py:217-357: 51 calls at n = 200, K = 4): the
+    // packed roots of the previous call are still on the device when the bytes are unchanged (a 344 KB compare instead of a
+    // pageable host-to-device copy + pack kernel)
+    const size_t bbytes = (size_t)h->n * h->S, tbytes = sizeof(int32_t) * (size_t)h->n;
+    const bool same = h->roots_valid && h->last_boards.size() == bbytes && memcmp(h->last_boards.data(), boards, bbytes) == 0 &&
+                      memcmp(h->last_turns.data(), turns, tbytes) == 0;
+    if (!same) {
+        CU(h, cudaMemcpyAsync(h->io_boards_in, boards, bbytes, cudaMemcpyHostToDevice, s));
+        CU(h, cudaMemcpyAsync(h->io_turns_in, turns, tbytes, cudaMemcpyHostToDevice, s));
+        rc = az_pack_roots_dev(h->game, h->n, h->io_boards_in, h->io_turns_in, h->io_roots, s); if (rc) AZ_FAIL(h, rc, "pack_roots launch failed");
+        h->last_boards.assign(boards, boards + bbytes); h->last_turns.assign(turns, turns + h->n); h->roots_valid = true;
+    }
     rc = do_search(h, K, h->io_roots, h->io_leaves, s); if (rc) return rc;
     const OutLayout L = out_layout(rows, h->S, h->A);
     uint8_t *o = h->io_out;
@@ -2177,15 +2189,23 @@ static int host_backprop(az_mcts *h, int K, const float *pol, const float *d, co
     int rc = ensure_io(h, (int)rows); if (rc) return rc;
     cudaStream_t s = h->stream;
     const InLayout L = in_layout(rows, h->A);
-    const int sel = h->h_in_sel; h->h_in_sel ^= 1;
-    uint8_t *p = sel ? h->h_in2 : h->h_in;
-    CU(h, cudaEventSynchronize(h->h_in_ev[sel]));          // the copy that last read this buffer has completed
-    memcpy(p + L.policy, pol, rows * h->A * 4); memcpy(p + L.d, d, rows * 4); memcpy(p + L.p1, p1, rows * 4); memcpy(p + L.p2, p2, rows * 4);
-    memcpy(p + L.ml, ml, rows * 4); memcpy(p + L.term, it, rows);
-    if (sym) memcpy(p + L.sym, sym, rows * 4);
-    CU(h, cudaMemcpyAsync(h->io_in, p, L.total, cudaMemcpyHostToDevice, s));
-    CU(h, cudaEventRecord(h->h_in_ev[sel], s));
     uint8_t *q = h->io_in;
+    if (h->host_direct) {      // (A/B) the driver stages pageable memory itself: no pass through our pinned buffer, but one copy per array
+        CU(h, cudaMemcpyAsync(q + L.policy, pol, rows * h->A * 4, cudaMemcpyHostToDevice, s));
+        CU(h, cudaMemcpyAsync(q + L.d, d, rows * 4, cudaMemcpyHostToDevice, s)); CU(h, cudaMemcpyAsync(q + L.p1, p1, rows * 4, cudaMemcpyHostToDevice, s));
+        CU(h, cudaMemcpyAsync(q + L.p2, p2, rows * 4, cudaMemcpyHostToDevice, s)); CU(h, cudaMemcpyAsync(q + L.ml, ml, rows * 4, cudaMemcpyHostToDevice, s));
+        CU(h, cudaMemcpyAsync(q + L.term, it, rows, cudaMemcpyHostToDevice, s));
+        if (sym) CU(h, cudaMemcpyAsync(q + L.sym, sym, rows * 4, cudaMemcpyHostToDevice, s));
+    } else {
+        const int sel = h->h_in_sel; h->h_in_sel ^= 1;
+        uint8_t *p = sel ? h->h_in2 : h->h_in;
+        CU(h, cudaEventSynchronize(h->h_in_ev[sel]));          // the copy that last read this buffer has completed
+        memcpy(p + L.policy, pol, rows * h->A * 4); memcpy(p + L.d, d, rows * 4); memcpy(p + L.p1, p1, rows * 4); memcpy(p + L.p2, p2, rows * 4);
+        memcpy(p + L.ml, ml, rows * 4); memcpy(p + L.term, it, rows);
+        if (sym) memcpy(p + L.sym, sym, rows * 4);
+        CU(h, cudaMemcpyAsync(h->io_in, p, L.total, cudaMemcpyHostToDevice, s));
+        CU(h, cudaEventRecord(h->h_in_ev[sel], s));
+    }
     rc = do_backprop(h, K, (const float *)(q + L.policy), (const float *)(q + L.d), (const float *)(q + L.p1), (const float *)(q + L.p2),
                      (const float *)(q + L.ml), q + L.term, sym ? (const int32_t *)(q + L.sym) : nullptr, s);
     if (rc) return rc;
@@ -2444,6 +2464,7 @@ int az_mcts_search(az_mcts *h, int evaluator, const int8_t *boards, const int32_
     { int rc0 = enter_host(h); if (rc0) return rc0; }
     CU(h, cudaMemcpyAsync(h->io_boards_in, boards, (size_t)h->n * h->S, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->io_turns_in, turns, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    h->roots_valid = false;                               // io_roots no longer holds what host_search packed last
     int rc = az_pack_roots_dev(h->game, h->n, h->io_boards_in, h->io_turns_in, h->io_roots, h->stream); if (rc) AZ_FAIL(h, rc, "pack_roots launch failed");
     rc = az_mcts_search_eval_dev(h, evaluator, h->io_roots, n_playout, h->stream); if (rc) return rc;
     return check_device_error(h);

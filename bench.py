@@ -247,22 +247,29 @@ def load_traffic():
 
 def reference_actor(timeout=900):
     """BASELINE config 1 on this box with the reference's own actor: unmodified Game.batch_self_play + AlphaZeroPlayer + its CNN's GPU
-    predict (bf16 autocast) on its compiled engine (oracle/_ref: pysrc + timing build).  None when the byte-compiled layer is absent."""
+    predict (bf16 autocast) on its compiled engine (oracle/_ref: pysrc + timing build) - and the SAME unmodified actor code on this
+    repository's modules (the four shims of INTEGRATION.md: device-resident search, the reference CNN evaluated through
+    ReferenceNetAdapter with no host copy).  None when the byte-compiled layer is absent."""
     try:
         from oracle import refstack
         if not refstack.available("timing"):
             return None
         import tempfile
+        res = {}
         with tempfile.TemporaryDirectory() as d:
-            ov = refstack.make_overlay(os.path.join(d, "ref"), "reference", "timing")
-            out = os.path.join(d, "actor.json")
-            env = {"OMP_NUM_THREADS": str(os.cpu_count())}
-            refstack.run_driver(ov, "actor", out, dict(game="Connect4", n_games=100, n_playout=200, K=4, reps=1, warm_games=100), timeout=timeout,
-                                env_extra=env)
-            r = json.load(open(out))
-        r["what"] = ("reference actor, BASELINE config 1: Game.batch_self_play(100 games, n=200, vl_batch=4, temp 1 for 20 plies, td_steps 10), "
-                     "random-init reference CNN on the GPU through its own predict(), reference engine on all host cores")
-        return r
+            for key, engine in (("reference", "reference"), ("drop_in", "ours+wrapper")):
+                ov = refstack.make_overlay(os.path.join(d, key), engine, "timing")
+                out = os.path.join(d, key + ".json")
+                env = {"OMP_NUM_THREADS": str(os.cpu_count())}
+                refstack.run_driver(ov, "actor", out, dict(game="Connect4", n_games=100, n_playout=200, K=4, reps=1, warm_games=100), timeout=timeout,
+                                    env_extra=env)
+                res[key] = json.load(open(out))
+        res["what"] = ("BASELINE config 1 through the reference's unmodified actor code: Game.batch_self_play(100 games, n=200, vl_batch=4, temp 1 "
+                       "for 20 plies, td_steps 10), random-init reference CNN on the GPU.  reference = its compiled engine on all host cores + its "
+                       "predict(); drop_in = the same code on this repository's modules (src/mcts_cpp, src/env_cpp, src/MCTS_cpp shims)")
+        if res["reference"].get("games_per_sec") and res["drop_in"].get("games_per_sec"):
+            res["drop_in_over_reference"] = res["drop_in"]["games_per_sec"] / res["reference"]["games_per_sec"]
+        return res
     except Exception as e:   # pragma: no cover
         return {"error": repr(e)[:300]}
 

@@ -6,7 +6,9 @@ run UNMODIFIED on either engine - TEST INFRASTRUCTURE ONLY (tests/, and bench.py
 directory whose ``src`` package is made of copies of those byte-code images (named ``<module>.pyc``) plus what the reference's build step would have put there:
 
 * engine "reference": ``src/mcts_cpp*.so`` / ``src/env_cpp*.so`` -> oracle/_ref/<kind>/ (what setup.py:62-65 does), or
-* engine "ours": the three shims of INTEGRATION.md section 1 (``src/azb200`` -> the package, ``src/mcts_cpp.py``, ``src/env_cpp/``).
+* engine "ours": the three shims of INTEGRATION.md section 1 (``src/azb200`` -> the package, ``src/mcts_cpp.py``, ``src/env_cpp/``);
+* engine "ours+wrapper": those plus the fourth shim, ``src/MCTS_cpp.py`` -> ``batched_mcts.BatchedMCTS`` (the mirror of the search wrapper
+  whose device-resident path keeps the whole per-move loop on the GPU), replacing the reference's own wrapper module.
 
 ``run_driver`` executes tests/refstack_driver.py in a subprocess with that overlay first on PYTHONPATH (two overlays cannot share a
 process: both define the package ``src``)."""
@@ -37,13 +39,18 @@ def make_overlay(dst: str, engine: str, kind: str = "parity") -> str:
         os.makedirs(os.path.join(src, rel), exist_ok=True)
         for f in files:
             if f.endswith(".pycode") and f != "pipeline.pycode":       # byte-code images -> sourceless modules of the scratch overlay
+                if engine == "ours+wrapper" and rel == "." and f == "MCTS_cpp.pycode":
+                    continue                                        # replaced by the shim below
                 shutil.copyfile(os.path.join(root, f), os.path.join(src, rel, f[:-7] + ".pyc"))
     if engine == "reference":
         d = os.path.join(_HERE, "_ref", kind)
         for f in os.listdir(d):
             if f.endswith(".so"):
                 os.symlink(os.path.join(d, f), os.path.join(src, f))
-    elif engine == "ours":
+    elif engine in ("ours", "ours+wrapper"):
+        if engine == "ours+wrapper":
+            with open(os.path.join(src, "MCTS_cpp.py"), "w") as f:
+                f.write("from src.azb200.batched_mcts import BatchedMCTS, _default_convert_board, _relative_wdl_to_absolute\n")
         os.symlink(os.path.join(ROOT, "alphazero-al_b200"), os.path.join(src, "azb200"))
         with open(os.path.join(src, "mcts_cpp.py"), "w") as f:
             f.write("from src.azb200.mcts_cpp import *\n")
