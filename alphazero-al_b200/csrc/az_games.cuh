@@ -205,7 +205,46 @@ struct Oth {
         }
     }
     AZ_HD static int xform_idx(int sym, int i) { int nr, nc; xform(sym, i >> 3, i & 7, nr, nc); return nr * 8 + nc; }
-    AZ_HD static uint64_t xform_bb(uint64_t b, int sym) {               // :329-341
+    // transform_bb (:329-341) moves every stone with transform_coord; here the eight D4 maps are composed from three word-parallel
+    // primitives on the 8x8 bit matrix (bit 8r + c): rows reversed (byte swap), all bits reversed (= rotate by 180 degrees) and the
+    // transpose (three delta swaps) - ~20 instructions instead of ~15 per stone (the leaf symmetry was 19 % of the Othello select).
+    AZ_HD static uint64_t bb_flip_rows(uint64_t x) {                    // (r, c) -> (7 - r, c)
+#if defined(__CUDA_ARCH__)
+        return ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(x >> 32), 0, 0x0123);
+#else
+        return __builtin_bswap64(x);
+#endif
+    }
+    AZ_HD static uint64_t bb_rot180(uint64_t x) {                       // (r, c) -> (7 - r, 7 - c): bit i -> bit 63 - i
+#if defined(__CUDA_ARCH__)
+        return __brevll(x);
+#else
+        x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+        x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+        x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+        return __builtin_bswap64(x);
+#endif
+    }
+    AZ_HD static uint64_t bb_transpose(uint64_t x) {                    // (r, c) -> (c, r)
+        uint64_t t;
+        t = 0x0F0F0F0F00000000ULL & (x ^ (x << 28)); x ^= t ^ (t >> 28);
+        t = 0x3333000033330000ULL & (x ^ (x << 14)); x ^= t ^ (t >> 14);
+        t = 0x5500550055005500ULL & (x ^ (x << 7));  x ^= t ^ (t >> 7);
+        return x;
+    }
+    AZ_HD static uint64_t xform_bb(uint64_t b, int sym) {               // == the stone-by-stone transform_bb with xform() above
+        switch (sym) {
+        case 1: return bb_flip_rows(bb_rot180(bb_transpose(b)));        // (c, 7 - r): transpose, then columns reversed
+        case 2: return bb_rot180(b);                                    // (7 - r, 7 - c)
+        case 3: return bb_flip_rows(bb_transpose(b));                   // (7 - c, r)
+        case 4: return bb_flip_rows(bb_rot180(b));                      // (r, 7 - c): columns reversed
+        case 5: return bb_flip_rows(b);                                 // (7 - r, c)
+        case 6: return bb_transpose(b);                                 // (c, r)
+        case 7: return bb_rot180(bb_transpose(b));                      // (7 - c, 7 - r)
+        default: return b;
+        }
+    }
+    AZ_HD static uint64_t xform_bb_by_stone(uint64_t b, int sym) {      // the definition, kept for the self-check (tests)
         if (sym == 0) return b;
         uint64_t r = 0;
         for (; b; b &= b - 1) r |= 1ULL << xform_idx(sym, ctz64(b));

@@ -342,8 +342,9 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
 #pragma unroll
                     for (int l = 0; l < W; ++l) if (c * W + l < G::MAX_EDGES) seen_policy += gshfl<W>(gm, pv, l);
                 } else {
-                    const int lim = min(W, ne - c * W);
-                    for (int l = 0; l < lim; ++l) seen_policy += gshfl<W>(gm, pv, l);
+                    // only the visited children contribute (+ 0.0f is exact): walk the lanes that hold one, in edge order
+                    unsigned vmask = (__ballot_sync(gm, pv != 0.0f) >> ((threadIdx.x & 31) & ~(W - 1))) & ((W == 32) ? 0xFFFFFFFFu : ((1u << W) - 1u));
+                    while (vmask) { const int l = __ffs((int)vmask) - 1; vmask &= vmask - 1; seen_policy += gshfl<W>(gm, pv, l); }
                 }
             }
             const float fscale = (1.0f + parent_q) / 2.0f;
