@@ -27,7 +27,12 @@ for (_, base), m in per.items():
     a["dram_read_bytes"] += m.get("dram__bytes_read.sum", 0.0)
     a["dram_write_bytes"] += m.get("dram__bytes_write.sum", 0.0)
     a["gpu_time_ns"] += m.get("gpu__time_duration.sum", 0.0)
-out = {"kernel_src_sha": bench.kernel_src_sha(), "captured_from": sys.argv[2] if len(sys.argv) > 2 else os.path.basename(sys.argv[1]),
+sha_here = bench.kernel_src_sha()
+sha_file = os.path.join(os.path.dirname(os.path.abspath(sys.argv[1])), "r2p_kernel_src_sha.txt")
+sha_box = open(sha_file).read().strip() if os.path.exists(sha_file) else None
+if sha_box and sha_box != sha_here:
+    raise SystemExit(f"the capture was taken from kernel sources {sha_box}, the tree now holds {sha_here}: re-capture")
+out = {"kernel_src_sha": sha_box or sha_here, "captured_from": sys.argv[2] if len(sys.argv) > 2 else os.path.basename(sys.argv[1]),
        "note": "sums over the launches of ONE search step (51 iterations, whole batch of 65 536 trees per launch); bench.py divides by `launches`",
        "kernels": agg}
 json.dump(out, open(os.path.join(ROOT, "profiles", "dram_traffic.json"), "w"), indent=1)

@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round-2 profile captures on the GPU box (one GPU).  Outputs under gpurun_out/r2p_*.
 P="python tools/traffic_probe.py"
+python -c "import bench; print(bench.kernel_src_sha())" > gpurun_out/r2p_kernel_src_sha.txt
 $P > gpurun_out/r2p_plain.log 2>&1 || { echo "probe failed"; tail -5 gpurun_out/r2p_plain.log; exit 1; }
 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --cache-control none --clock-control none \
     --csv --log-file gpurun_out/r2p_traffic.csv $P > gpurun_out/r2p_traffic.log 2>&1; echo "traffic rc=$?"
