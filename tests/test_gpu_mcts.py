@@ -660,3 +660,34 @@ def test_othello_staggered_select_passes_endgames_and_reference(K):
     if oracle.ref_available("parity"):
         e2 = _cuda("Othello", n)
         compare_engines(e2, _ref("Othello", n), "Othello", n, 100, K, dict(OTH_CFG), boards=boards, turns=turns, moves=2, compare_leaves=True)
+
+
+def test_reset_all_dev_and_pinned_leaf_arrays():
+    """az_mcts_reset_all_dev == prune_roots with every action < 0 (stream-ordered, host bookkeeping included); the leaf arrays of the
+    host split API are views of pinned blocks that stay valid after later calls and after the engine is gone."""
+    import gc
+    import torch
+    n = 128
+    boards, turns = random_positions("Connect4", n, 10, 13)
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=False)
+    a, b = _cuda("Connect4", n), _cuda("Connect4", n)
+    for e in (a, b):
+        set_config(e, **cfg)
+    ev = importlib.import_module("alphazero-al_b200.evaluators").HashEvaluator("Connect4", "hash")
+    playout(a, ev, boards, turns, 40, 4)
+    playout(b, ev, boards, turns, 40, 4)
+    a.prune_roots(np.full(n, -1, np.int32))
+    b.reset_all_dev(torch.cuda.current_stream().cuda_stream)
+    playout(a, ev, boards, turns, 40, 4)
+    playout(b, ev, boards, turns, 40, 4)
+    assert np.array_equal(counts(a, n, 7), counts(b, n, 7)) and a.get_all_root_stats().tobytes() == b.get_all_root_stats().tobytes()
+    first = a.search_batch_vl(4, boards, turns)
+    keep = [x.copy() for x in first]
+    a.backprop_batch_vl(4, *ev(first[0], first[5], first[4], first[1], first[2], first[3]), first[4], first[6])
+    for _ in range(4):                                        # later calls get other blocks: the first arrays are untouched
+        out = a.search_batch_vl(4, boards, turns)
+        a.backprop_batch_vl(4, *ev(out[0], out[5], out[4], out[1], out[2], out[3]), out[4], out[6])
+    del a, out
+    gc.collect()
+    assert all(np.array_equal(x, y) for x, y in zip(first, keep)) and first[0].flags.writeable
+    first[0][:] = 0                                           # still Python-owned memory

@@ -371,3 +371,31 @@ def test_reference_style_network_takes_the_device_path():
     ca, cb = a.get_visits_count(), b.get_visits_count()
     pa, pb = ca / ca.sum(1, keepdims=True), cb / cb.sum(1, keepdims=True)
     assert np.abs(pa - pb).sum(1).max() <= 1e-3
+
+
+def test_output_ring_overflow_is_reported_not_silent():
+    """games finished after the ring filled up used to vanish.  Now every finished game is either in the ring or counted as
+    dropped, and drain() raises instead of returning a truncated set; draining in time loses nothing."""
+    sp_mod = importlib.import_module("alphazero-al_b200.selfplay")
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    n = 256
+    kw = dict(search_cfg=dict(SERVER_DEFAULTS), temperature=1.0, temp_decay_moves=50, td_steps=0, seed=2)
+    sp = sp_mod.SelfPlay("Connect4", n, 16, 4, ds.SyntheticEvaluator("Connect4", "constant"), out_capacity=64, **kw)
+    for _ in range(43):                                       # every slot finishes at least one game: 256 > 64
+        sp.ply()
+    with pytest.raises(RuntimeError, match="overflowed"):
+        sp.drain()
+    sp2 = sp_mod.SelfPlay("Connect4", n, 16, 4, ds.SyntheticEvaluator("Connect4", "constant"), out_capacity=64, **kw)
+    total, uids = 0, set()
+    for _ in range(43):
+        sp2.ply()
+        if sp2.finished() > 16:
+            rec = sp2.drain()
+            total += len(rec)
+            uids.update(rec.uid.tolist())
+    rec = sp2.drain()
+    total += len(rec)
+    uids.update(rec.uid.tolist())
+    assert total >= n and len(uids) == total and set(range(n)) <= uids
+    again = sp2.run(target_games=10)                          # run() after a drain continues with new games (no stale records)
+    assert len(again) >= 10 and not (set(again.uid.tolist()) & uids)
