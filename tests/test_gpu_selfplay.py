@@ -385,7 +385,7 @@ def test_output_ring_overflow_is_reported_not_silent():
         sp.ply()
     with pytest.raises(RuntimeError, match="overflowed"):
         sp.drain()
-    sp2 = sp_mod.SelfPlay("Connect4", n, 16, 4, ds.SyntheticEvaluator("Connect4", "constant"), out_capacity=64, **kw)
+    sp2 = sp_mod.SelfPlay("Connect4", n, 16, 4, ds.SyntheticEvaluator("Connect4", "constant"), out_capacity=n, **kw)   # >= one ply's worth
     total, uids = 0, set()
     for _ in range(43):
         sp2.ply()
