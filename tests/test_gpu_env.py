@@ -28,6 +28,33 @@ def test_recorded_rollouts_match_restatement_per_ply(game, n_rec):
         assert np.array_equal(rec["winners"][g, :n], o["winners"]) and np.array_equal(rec["dones"][g, :n], o["dones"])
 
 
+@pytest.mark.parametrize("game,n_rec", [("Connect4", 10240), ("Othello", 512)])
+def test_recorded_rollouts_match_the_compiled_reference_env_per_ply(game, n_rec):
+    """The same recorded slice against the UNMODIFIED reference itself: every game is replayed, action by action, on an
+    `env_cpp.<game>.Env` object of the compiled reference (oracle/_ref/parity travels to the GPU box) and its board, legal mask, side
+    to move, winner and done flag are compared with what the device kernels recorded at every ply (BASELINE config 2's check)."""
+    import torch
+    if not oracle.ref_available("parity"):
+        pytest.skip("oracle/_ref/parity not present")
+    _, ref_env = oracle.load_ref("parity")
+    sub = getattr(ref_env, game.lower())
+    be = env_cpp.BatchedEnv(game, n_rec)
+    digest, plies, rec = be.random_rollouts(seed=0, first_game=0, n_record=n_rec)
+    torch.cuda.synchronize()
+    rec = {k: v.cpu().numpy() for k, v in rec.items()}
+    plies = plies.cpu().numpy()
+    A = be.A
+    for g in range(n_rec):
+        e = sub.Env()
+        n = int(plies[g])
+        for t in range(n):
+            assert np.array_equal(np.asarray(e.board).astype(np.int8), rec["boards"][g, t]), (g, t)
+            assert np.array_equal(np.asarray(e.valid_mask(), dtype=np.uint8), rec["masks"][g, t][:A]) and e.turn == rec["turns"][g, t]
+            e.step(int(rec["actions"][g, t]))
+            assert e.winPlayer() == rec["winners"][g, t] and bool(e.done()) == bool(rec["dones"][g, t]), (g, t)
+        assert e.done()
+
+
 def test_one_million_connect4_games_checksum():
     import torch
     n = 1_000_000
