@@ -110,7 +110,7 @@ class BatchedMCTS:
             self._dev["h_turns_np"] = self._dev["h_turns"].numpy()
         return self._dev
 
-    def _playout_device(self, pv_func, current_boards, turns, max_n, K):
+    def _playout_device(self, pv_func, current_boards, turns, max_n, K, time_budget=None):
         import torch
         from . import device_search as ds
         st = self._device_state(K)
@@ -138,7 +138,25 @@ class BatchedMCTS:
             elif self._cache_size > 0:
                 evaluator.net_rows = 0
         self._last_evaluator = evaluator
-        ds.playout_device(self.mcts, buf, max_n, K, evaluator, stream)
+        if time_budget is None:
+            ds.playout_device(self.mcts, buf, max_n, K, evaluator, stream)
+            return
+        # time-budgeted search (src/MCTS_cpp.py:112-128, 250-262: n_playout is the cap): the schedule is issued in chunks of a few
+        # iterations with a stream synchronisation in between to read the clock (and, like the reference, stop early once the runner-up
+        # can no longer catch up); the granularity of the budget is one chunk instead of one iteration
+        sched = ds.iteration_schedule(max_n, K)
+        t0, done, pos, chunk = time.perf_counter(), 0, 0, 4
+        while pos < len(sched):
+            part = sched[pos:pos + chunk]
+            ds.playout_device(self.mcts, buf, 0, K, evaluator, stream, iters=part, shards=1)
+            torch.cuda.current_stream().synchronize()
+            pos += len(part)
+            done += sum(max(k, 1) for k in part)
+            elapsed = time.perf_counter() - t0
+            if elapsed >= time_budget:
+                break
+            if self._should_early_exit(done, (time_budget - elapsed) / (elapsed / done)):
+                break
 
     # ------------------------------------------------------------------------------------------------------
     # reference API
@@ -201,15 +219,15 @@ class BatchedMCTS:
         if hasattr(pv_func, "score_scale"):
             pv_func.score_scale = self.mcts.config.score_scale
         from . import device_search as ds
-        if not use_time and not self._custom_converter and ds.ReferenceNetAdapter.accepts(pv_func):
+        if not self._custom_converter and ds.ReferenceNetAdapter.accepts(pv_func):
             # an unmodified network of the reference on a CUDA device: same numbers as its predict(), but nothing leaves the device
             ad = self._adapters.get(id(pv_func))
             if ad is None or ad.net is not pv_func:
                 ad = ds.ReferenceNetAdapter(pv_func, self._game_name)
                 self._adapters = {id(pv_func): ad}
             pv_func = ad
-        if not use_time and not self._custom_converter and (isinstance(pv_func, ds.SyntheticEvaluator) or hasattr(pv_func, "predict_device")):
-            self._playout_device(pv_func, np.asarray(current_boards), np.asarray(turns), max_n, vl_batch)
+        if not self._custom_converter and (isinstance(pv_func, ds.SyntheticEvaluator) or hasattr(pv_func, "predict_device")):
+            self._playout_device(pv_func, np.asarray(current_boards), np.asarray(turns), max_n, vl_batch, time_budget if use_time else None)
             return self
         current_boards = np.asarray(current_boards).astype(np.int8)
         turns = np.asarray(turns).astype(np.int32)

@@ -379,11 +379,24 @@ def auto_shards(n: int) -> int:
     return max(1, min(8, n // 8192))
 
 
+def iteration_schedule(n_playout: int, K: int):
+    """K of every iteration of the wrapper's loop (src/MCTS_cpp.py:217-357): 0 = the non-VL warm-up simulation, then virtual-loss
+    batches of K (the last one smaller); K <= 1: n_playout non-VL simulations."""
+    if K <= 1:
+        return [0] * n_playout
+    if n_playout <= 0:
+        return []
+    rem = n_playout - 1
+    return [0] + [K] * (rem // K) + ([rem % K] if rem % K else [])
+
+
 def playout_device(engine, buf: LeafBuffers, n_playout: int, K: int, evaluator, stream: int | None = None,
-                   on_select=None, shards: int | None = None):
+                   on_select=None, shards: int | None = None, iters=None):
     """Run `n_playout` simulations per tree entirely on the device from the roots in `buf.roots` (see
     LeafBuffers.pack_roots).  `on_select(rows, fn)` (optional) wraps each select launch (bench.py times the dominant
     kernel with CUDA events through it).  Returns the number of kernels launched.
+
+    `iters` (optional) = an explicit list of per-iteration K values instead of the whole schedule of (n_playout, K).
 
     `shards` > 1 splits the batch into that many independent tree ranges, each running its own
     select -> evaluate -> backprop chain on its own stream, so that the latency-bound tree kernels of one shard overlap
@@ -396,13 +409,10 @@ def playout_device(engine, buf: LeafBuffers, n_playout: int, K: int, evaluator, 
         shards = auto_shards(n)
     if not getattr(evaluator, "shardable", True) or n < 64 * shards:
         shards = 1
-    iters = []                              # K of every iteration: warm-up (non-VL), then virtual-loss batches
-    if K <= 1:
-        iters = [0] * n_playout
-    elif n_playout > 0:
-        rem = n_playout - 1
-        iters = [0] + [K] * (rem // K) + ([rem % K] if rem % K else [])
-    if isinstance(evaluator, SyntheticEvaluator) and on_select is None:
+    explicit = iters is not None            # a slice of the schedule (time-budgeted searches issue it in chunks)
+    if not explicit:
+        iters = iteration_schedule(n_playout, K)
+    if isinstance(evaluator, SyntheticEvaluator) and on_select is None and not explicit:
         # everything is inside the library: let it drive the loop (no per-launch Python / ctypes cost)
         assert n * max(K, 1) <= buf.rows
         return engine.playout_synthetic_dev(evaluator.mode, n_playout, K, shards, buf.roots.data_ptr(), buf.leaves.data_ptr(),

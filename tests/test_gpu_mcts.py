@@ -691,3 +691,28 @@ def test_reset_all_dev_and_pinned_leaf_arrays():
     gc.collect()
     assert all(np.array_equal(x, y) for x, y in zip(first, keep)) and first[0].flags.writeable
     first[0][:] = 0                                           # still Python-owned memory
+
+
+def test_time_budgeted_search_runs_on_the_device_path():
+    """batch_playout(time_budget=...) (src/MCTS_cpp.py:112-128; used by the GUI worker) with a device evaluator: the schedule is issued in
+    chunks until the budget is spent - n_playout is only the cap - and the trees are the prefix of the full search's."""
+    import time
+    bm = importlib.import_module("alphazero-al_b200.batched_mcts")
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    n = 512
+    boards, turns = random_positions("Connect4", n, 10, 17)
+    kw = dict(game_name="Connect4", noise_epsilon=0.0, fpu_reduction=0.2, use_symmetry=False, mlh_slope=0.1)
+    ev = ds.SyntheticEvaluator("Connect4", "hash")
+    timed = bm.BatchedMCTS(n, 1.4, 1000.0, 0.0, 1_000_000, **kw)
+    timed.batch_playout(ev, boards, turns, vl_batch=4, time_budget=0.02)          # warm-up (kernel load)
+    timed.prune_roots(np.full(n, -1, np.int32))
+    t0 = time.perf_counter()
+    timed.batch_playout(ev, boards, turns, vl_batch=4, time_budget=0.05)
+    dt = time.perf_counter() - t0
+    c = timed.get_visits_count()
+    sims = int(c[0].sum()) + 1
+    assert 0.05 <= dt < 0.5 and 50 < sims < 1_000_000 and (c.sum(1) == sims - 1).all()
+    full = bm.BatchedMCTS(n, 1.4, 1000.0, 0.0, sims, **kw)
+    full.batch_playout(ev, boards, turns, vl_batch=4)
+    if (sims - 1) % 4 == 0:                                   # the timed run stopped on a full K = 4 batch: same schedule, same trees
+        assert np.array_equal(full.get_visits_count(), c)
