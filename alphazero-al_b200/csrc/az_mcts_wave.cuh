@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
 // reach a given level in k order, so every load sees exactly what the sequential loop would have seen.  The level body is
 // k_select's.
 template <class G, int W>
-__global__ void __launch_bounds__(CTA) k_select_ws(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
+__global__ void __launch_bounds__(CTA, 8) k_select_ws(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
                                                    az_leaf *__restrict__ leaves) {
     constexpr int NCH = (G::MAX_EDGES + W - 1) / W;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -281,24 +281,21 @@ __global__ void __launch_bounds__(CTA) k_select_ws(Dev d, az_search_config cfg, 
             if (cur.child == NONE || (cur.meta & F_TERM) || ne == 0 || plen >= (uint32_t)G::MAX_DEPTH) done = true;
             else {
                 const uint32_t off = cur.child >> 6;
-                Slot s[NCH]; bool has[NCH];
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    const int e = c * W + lane;
-                    has[c] = e < ne;
-                    if (has[c]) s[c] = ld_slot(arena + off + e);
-                    else { s[c].prior = 0.f; s[c].n = 0; s[c].meta = 0; s[c].child = NONE; s[c].wd = s[c].wp1 = s[c].wp2 = s[c].msum = 0.f; }
-                }
+                // The edges are walked in chunks of W (lane l owns edges l, l + W, ...) with nothing but the running best kept in
+                // registers: an array of all ceil(48 / W) chunks cost 96 registers per thread, 20 resident warps per SM, and 4096
+                // trees (one warp each) then need 1.4 waves; at 64 registers they are all resident (config 4: 8.8 -> 8.0 ms per move
+                // already with a forced cap and its spills).  Second reads of a slot hit L1.
                 st_edges += (unsigned long long)ne;
-                // ---- compute_fpu (MCTS.h:140-156): seen_policy summed sequentially in edge order ----
+                // ---- compute_fpu (MCTS.h:140-156): seen_policy summed sequentially in edge order over the visited children ----
                 const int cur_infl = (int)(cur.meta & INFL_MASK);
                 const float parent_q = mean_q(cur.n, cur.wp1, cur.wp2, (cur.meta & F_TURN_P1) != 0);
                 float seen_policy = 0.0f;
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    const float pv = (has[c] && s[c].n > 0) ? s[c].prior : 0.0f;   // + 0.0f is exact
-                    // only the visited children contribute (+ 0.0f is exact): walk the lanes that hold one, in edge order
-                    unsigned vmask = (__ballot_sync(gm, pv != 0.0f) >> ((threadIdx.x & 31) & ~(W - 1))) & ((W == 32) ? 0xFFFFFFFFu : ((1u << W) - 1u));
+#pragma unroll 1
+                for (int c0 = 0; c0 < ne; c0 += W) {
+                    const int e = c0 + lane;
+                    float pv = 0.0f;                                              // + 0.0f is exact: only visited children matter
+                    if (e < ne) { const uint2 pn = *reinterpret_cast<const uint2 *>(arena + off + e); if ((int)pn.y > 0) pv = __uint_as_float(pn.x); }
+                    unsigned vmask = (__ballot_sync(gm, pv != 0.0f) >> ((threadIdx.x & 31) & ~(W - 1))) & ((1u << W) - 1u);
                     while (vmask) { const int l = __ffs((int)vmask) - 1; vmask &= vmask - 1; seen_policy += gshfl<W>(gm, pv, l); }
                 }
                 const float fscale = (1.0f + parent_q) / 2.0f;
@@ -315,27 +312,29 @@ __global__ void __launch_bounds__(CTA) k_select_ws(Dev d, az_search_config cfg, 
                 const float ne_eps = cfg.noise_epsilon;
                 const bool mix_noise = is_root && ne_eps > 0.0f;
                 float best_s = -INFINITY; int best_e = -1;
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    if (!has[c]) continue;
-                    const int e = c * W + lane;
-                    float eff_prior = s[c].prior;
-                    if (mix_noise) eff_prior = (1.0f - ne_eps) * s[c].prior + ne_eps * noise[e];
-                    const int cn = s[c].n, cinf = (int)(s[c].meta & INFL_MASK);
+                Slot bs; bs.prior = 0.f; bs.n = 0; bs.meta = 0; bs.child = NONE; bs.wd = bs.wp1 = bs.wp2 = bs.msum = 0.f;   // my best edge's slot
+#pragma unroll 1
+                for (int c0 = 0; c0 < ne; c0 += W) {
+                    const int e = c0 + lane;
+                    if (e >= ne) continue;
+                    const Slot sl = ld_slot(arena + off + e);
+                    float eff_prior = sl.prior;
+                    if (mix_noise) eff_prior = (1.0f - ne_eps) * sl.prior + ne_eps * noise[e];
+                    const int cn = sl.n, cinf = (int)(sl.meta & INFL_MASK);
                     float q_value = fpu, m_utility = 0.0f; int visits = cinf;     // unvisited: FPU, in-flight only
                     if (cn > 0) {
                         visits = cn + cinf;
-                        const float child_Q = mean_q(cn, s[c].wp1, s[c].wp2, (s[c].meta & F_TURN_P1) != 0);
+                        const float child_Q = mean_q(cn, sl.wp1, sl.wp2, (sl.meta & F_TURN_P1) != 0);
                         q_value = -child_Q;
                         if (use_aux) {
-                            float child_M = mean_m(cn, s[c].msum);
+                            float child_M = mean_m(cn, sl.msum);
                             if (G::AUX_NEGATE) child_M = -child_M;
                             m_utility = aux_utility<G>(child_M, parent_M, child_Q, cfg);
                         }
                     }
                     const float u_score = c_puct * eff_prior * sqrt_pn / (1.0f + (float)visits);
                     const float score = q_value + u_score + m_utility;
-                    if (score > best_s) { best_s = score; best_e = e; }
+                    if (score > best_s) { best_s = score; best_e = e; bs = sl; }   // ascending e per lane: strict > keeps the lowest index
                 }
                 // arg-max over the group; ties -> lowest edge index (the reference scans with a strict `>`)
 #pragma unroll
@@ -347,17 +346,16 @@ __global__ void __launch_bounds__(CTA) k_select_ws(Dev d, az_search_config cfg, 
                 }
                 if (best_e < 0) done = true;
                 else {
-                    // broadcast the chosen child to the whole group
-                    const int bl = best_e & (W - 1), bc = best_e / W;
-                    Slot ch = s[0];
-#pragma unroll
-                    for (int c = 1; c < NCH; ++c) if (bc == c) ch = s[c];
-                    ch.n = gshfl<W>(gm, ch.n, bl);
-                    ch.meta = gshfl<W>(gm, ch.meta, bl);
-                    ch.child = gshfl<W>(gm, ch.child, bl);
-                    ch.wp1 = gshfl<W>(gm, ch.wp1, bl);
-                    ch.wp2 = gshfl<W>(gm, ch.wp2, bl);
-                    ch.msum = gshfl<W>(gm, ch.msum, bl);
+                    // broadcast the chosen child (held by the lane that owns the edge) to the whole group
+                    const int bl = best_e & (W - 1);
+                    Slot ch;
+                    ch.n = gshfl<W>(gm, bs.n, bl);
+                    ch.meta = gshfl<W>(gm, bs.meta, bl);
+                    ch.child = gshfl<W>(gm, bs.child, bl);
+                    ch.wp1 = gshfl<W>(gm, bs.wp1, bl);
+                    ch.wp2 = gshfl<W>(gm, bs.wp2, bl);
+                    ch.msum = gshfl<W>(gm, bs.msum, bl);
+                    ch.prior = 0.f; ch.wd = 0.f;
                     step_group<G, W>(st, (int)((ch.meta >> 16) & 0xFFu), lane, gm);
                     uint32_t nmeta = ch.meta;
                     if (!(nmeta & F_ALLOC)) {      // lazy child allocation (MCTS.h:481-488): remember the child's side to move
