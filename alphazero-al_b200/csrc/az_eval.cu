@@ -79,6 +79,59 @@ __global__ void k_eval_synth(int mode, int n, const az_leaf *__restrict__ leaves
     st_f32_keep(mlv + i, aux, keep);
 }
 
+// The same evaluator with LPL lanes per leaf (Othello: 65 policy entries of one splitmix64 each are the bulk of the work; one
+// thread per leaf made this stand-in for the network 10 us of every 68 us iteration at 4096 trees).  Lane l fills actions l, l + LPL, ...;
+// lane 0 also writes the value tuple.  Same bits as k_eval_synth.
+template <class G, int LPL>
+__global__ void k_eval_synth_wide(int mode, int n, const az_leaf *__restrict__ leaves, float *__restrict__ policy, float *__restrict__ dv,
+                                  float *__restrict__ p1v, float *__restrict__ p2v, float *__restrict__ mlv) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t / LPL, lane = t % LPL;
+    pdl_wait();
+    if (i >= n) return;
+    constexpr int A = G::A;
+    const uint64_t keep = l2_keep_policy();
+    az_leaf L;
+    *reinterpret_cast<uint4 *>(&L) = ld_u4_keep(leaves + i, keep);
+    *(reinterpret_cast<uint4 *>(&L) + 1) = ld_u4_keep(reinterpret_cast<const uint4 *>(leaves + i) + 1, keep);
+    float *prow = policy + (size_t)i * A;
+    if (L.flags & AZ_LEAF_TERMINAL) {
+        for (int a = lane; a < A; a += LPL) st_f32_keep(prow + a, 0.0f, keep);
+        if (lane == 0) {
+            const bool w1 = (L.flags & AZ_LEAF_P1_WINS) != 0, w2 = (L.flags & AZ_LEAF_P2_WINS) != 0;
+            st_f32_keep(dv + i, (!w1 && !w2) ? 1.0f : 0.0f, keep); st_f32_keep(p1v + i, w1 ? 1.0f : 0.0f, keep);
+            st_f32_keep(p2v + i, w2 ? 1.0f : 0.0f, keep); st_f32_keep(mlv + i, 0.0f, keep);
+        }
+        return;
+    }
+    const int turn = L.turn;
+    float wdl0, wdl1, wdl2, aux;
+    if (mode == 2) {   // constant
+        for (int a = lane; a < A; a += LPL) st_f32_keep(prow + a, 1.0f, keep);
+        wdl0 = 0.25f; wdl1 = 0.5f; wdl2 = 0.25f;
+        aux = G::GAME == GAME_C4 ? 10.0f : 0.125f;
+    } else {           // hash (mode 1, the flip-equivariant variant, is Connect4 only and stays on the one-thread kernel)
+        const uint64_t h = board_key(L.bb0, L.bb1, turn);
+        for (int a = lane; a < A; a += LPL) {
+            const uint64_t ph = splitmix64(h + (uint64_t)a + 1ULL);
+            st_f32_keep(prow + a, ((float)((ph >> 40) & 0xFFFFULL) + 1.0f) * (1.0f / 65536.0f), keep);
+        }
+        if (lane != 0) return;
+        const float w0 = (float)((splitmix64(h ^ 0x1111ULL) >> 40) & 0xFFULL) + 1.0f;
+        const float w1 = (float)((splitmix64(h ^ 0x2222ULL) >> 40) & 0xFFULL) + 1.0f;
+        const float w2 = (float)((splitmix64(h ^ 0x3333ULL) >> 40) & 0xFFULL) + 1.0f;
+        const float s = (w0 + w1) + w2;
+        wdl0 = w0 / s; wdl1 = w1 / s; wdl2 = w2 / s;
+        if (G::GAME == GAME_C4) aux = (float)((h >> 20) & 31ULL);
+        else aux = (float)((h >> 20) & 63ULL) * (1.0f / 32.0f) - 1.0f;
+    }
+    if (lane != 0) return;
+    st_f32_keep(dv + i, wdl0, keep);
+    st_f32_keep(p1v + i, turn == 1 ? wdl1 : wdl2, keep);
+    st_f32_keep(p2v + i, turn == 1 ? wdl2 : wdl1, keep);
+    st_f32_keep(mlv + i, aux, keep);
+}
+
 // CNN.predict outputs -> backprop tuple: relative WDL [draw, win(to move), loss(to move)] to absolute [draw, p1w, p2w]
 // (src/MCTS_cpp.py:23-30) with terminal leaves overridden by their cached result (src/MCTS_cpp.py:276-297).
 __global__ void k_eval_finalize(int n, const az_leaf *__restrict__ leaves, const float *__restrict__ wdl_rel, const float *__restrict__ aux,
@@ -113,7 +166,10 @@ extern "C" int az_eval_synthetic_dev(int game, int mode, int n, const az_leaf *l
     const int bs = 128, g = (n + bs - 1) / bs;
     static const bool pdl = !(getenv("AZB200_PDL") && atoi(getenv("AZB200_PDL")) == 0);
     if (game == AZ_GAME_CONNECT4) az::launch_pdl(az::k_eval_synth<az::C4>, g, bs, 0, s, pdl, mode, n, leaves, pol, d, p1, p2, ml);
-    else if (game == AZ_GAME_OTHELLO) az::launch_pdl(az::k_eval_synth<az::Oth>, g, bs, 0, s, pdl, mode, n, leaves, pol, d, p1, p2, ml);
+    else if (game == AZ_GAME_OTHELLO) {
+        const int gw = (int)(((size_t)n * 16 + bs - 1) / bs);
+        az::launch_pdl(az::k_eval_synth_wide<az::Oth, 16>, gw, bs, 0, s, pdl, mode, n, leaves, pol, d, p1, p2, ml);
+    }
     else return AZ_ERR_INVALID;
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_ERR_CUDA;
 }

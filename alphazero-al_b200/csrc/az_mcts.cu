@@ -504,6 +504,26 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
 
     const int vl = cfg.vl_count;
 
+    // The K simulations of a tree are applied one after the other (sums are order dependent), each a chain of dependent loads
+    // (record -> path -> slots).  Start all of them now: the records' path lengths are read together, then every path slot of every
+    // simulation is prefetched, so the chains below run on L1 / L2 hits.
+    {
+        const LeafRec *recs0 = VL ? d.leaf_vl + (size_t)env * d.kcap : d.leaf_nv + env;
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            uint32_t pl[4]; uint32_t fl[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { pl[q] = 0; fl[q] = 0; if (k0 + q < K) { pl[q] = recs0[k0 + q].h.path_len; fl[q] = recs0[k0 + q].h.flags; } }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k0 + q;
+                if (k < K && (fl[q] & LF_VALID)) {
+                    const uint32_t *pth = VL ? d.path_vl + ((size_t)env * d.kcap + k) * G::MAX_DEPTH : d.path_nv + (size_t)env * G::MAX_DEPTH;
+                    for (uint32_t t = lane; t < pl[q]; t += W) asm volatile("prefetch.global.L1 [%0];" ::"l"(arena + pth[t]));
+                }
+            }
+        }
+    }
+
     for (int k = 0; k < K; ++k) {
         LeafRec *rp = VL ? d.leaf_vl + (size_t)env * d.kcap + k : d.leaf_nv + env;
         const LeafHead L = ld32(&rp->h);
