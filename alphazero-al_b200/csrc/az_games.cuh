@@ -253,7 +253,17 @@ struct Oth {
     AZ_HD static void symmetry(State &s, int sym) { if (sym) { s.bb[0] = xform_bb(s.bb[0], sym); s.bb[1] = xform_bb(s.bb[1], sym); } }
     AZ_HD static int inverse_sym(int sym) { return (sym == 1) ? 3 : (sym == 3 ? 1 : sym); }   // :356-361
     // inverse_symmetry_policy (:373-387): restored[T_inv(i)] = given[i]  <=>  restored[a] = given[T_sym(a)]
-    AZ_HD static int sym_action(int sym, int a) { return (a == PASS || sym == 0) ? a : xform_idx(sym, a); }
+    // every D4 map is "transpose?, then rows reversed?, then columns reversed?" (bits 0 / 1 / 2 of the table entry below; xform()
+    // above is the definition, tests/test_env_host.py and the leaf-symmetry parity tests cover both forms)
+    AZ_HD static int sym_action(int sym, int a) {
+        if (a == PASS || sym == 0) return a;
+        const int f = (0x71243650 >> (4 * sym)) & 7;       // sym 1: T+C (5), 2: R+C (6), 3: T+R (3), 4: C (4), 5: R (2), 6: T (1), 7: T+R+C (7)
+        int r = a >> 3, c = a & 7;
+        if (f & 1) { const int t = r; r = c; c = t; }
+        if (f & 2) r = 7 - r;
+        if (f & 4) c = 7 - c;
+        return r * 8 + c;
+    }
     AZ_HD static int cell(const State &s, int j) { return (int)((s.bb[0] >> j) & 1ULL) - (int)((s.bb[1] >> j) & 1ULL); }
     AZ_HD static int cell_bit(int j) { return j; }
 };

@@ -572,12 +572,12 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
             } else if (pass_only) {
                 psum += gshfl<W>(gm, pmine[NJ - 1], 0);   // action 64 lives in lane 0, last register
             } else {
-                for (uint64_t v = legal; v; v &= v - 1) {
-                    const int a = ctz64(v), j = a / W;
-                    float x = pmine[0];
+                // ascending legal actions = register j (actions j * W ...), then lane: no 64-bit bit scan, no dynamic register select
 #pragma unroll
-                    for (int jj = 1; jj < NJ; ++jj) if (j == jj) x = pmine[jj];
-                    psum += gshfl<W>(gm, x, a & (W - 1));
+                for (int j = 0; j < NJ; ++j) {
+                    uint32_t m = (uint32_t)(legal >> ((j * W) & 63)) & ((W >= 32) ? 0xFFFFFFFFu : ((1u << W) - 1u));
+                    if (j * W >= 64) m = 0u;
+                    while (m) { const int l = __ffs((int)m) - 1; m &= m - 1; psum += gshfl<W>(gm, pmine[j], l); }
                 }
             }
             const float denom = psum + 1e-8f;
