@@ -14,5 +14,6 @@ O="python tools/exp_othello.py 4096"
 $O > gpurun_out/r2p_oth_plain.log 2>&1 && cat gpurun_out/r2p_oth_plain.log | tail -1
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --cache-control none --clock-control none -s 1400 -c 600 --csv \
     --log-file gpurun_out/r2p_oth_launches.csv $O > gpurun_out/r2p_oth_launches.log 2>&1; echo "oth launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'k_select_ws|k_backprop<' -s 300 -c 2 -o gpurun_out/r2p_full_oth -f $O > gpurun_out/r2p_oth_full.log 2>&1; echo "oth full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:k_select_ws -s 150 -c 1 -o gpurun_out/r2p_full_oth -f $O > gpurun_out/r2p_oth_full.log 2>&1; echo "oth full select rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:k_backprop -s 150 -c 1 -o gpurun_out/r2p_full_oth_bp -f $O >> gpurun_out/r2p_oth_full.log 2>&1; echo "oth full backprop rc=$?"
 ls -la gpurun_out/ | grep r2p
