@@ -95,6 +95,7 @@ def lib() -> C.CDLL:
         "az_mcts_backprop_range_dev": [_vp, _i] + [_vp] * 7 + [_i, _i, _i64, _vp],
         "az_mcts_stream_handover_dev": [_vp, _vp],
         "az_mcts_playout_synthetic_dev": [_vp, _i, _i, _i, _i] + [_vp] * 9,
+        "az_mcts_playout_synthetic_host": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp], "az_mcts_get_counts64_pinned": [_vp, _vp, _vp],
         "az_mcts_search_eval_dev": [_vp, _i, _vp, _i, _vp],
         "az_mcts_get_counts_dev": [_vp, _vp, _vp], "az_mcts_get_root_stats_dev": [_vp, _vp, _vp],
         "az_mcts_enable_stats": [_vp, _i], "az_mcts_get_stats": [_vp, _vp], "az_mcts_get_warp_times": [_vp, _vp, _i], "az_mcts_time_select": [_vp, _i], "az_mcts_set_compaction": [_vp, _i], "az_mcts_get_select_time": [_vp, _vp, _vp, _vp], "az_mcts_get_backprop_time": [_vp, _vp, _vp, _vp],

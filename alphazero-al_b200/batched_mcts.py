@@ -113,6 +113,12 @@ class BatchedMCTS:
     def _playout_device(self, pv_func, current_boards, turns, max_n, K, time_budget=None):
         import torch
         from . import device_search as ds
+        if isinstance(pv_func, ds.SyntheticEvaluator) and time_budget is None:
+            # everything is inside the library: host arrays in, the loop pipelined shard by shard, visit counts left in pinned memory
+            # for the get_visits_count() that follows (src/player.py:333-343)
+            self._last_evaluator = pv_func
+            self.mcts.playout_synthetic_host(pv_func.mode, max_n, K, ds.auto_shards(self.batch_size), current_boards, turns)
+            return
         st = self._device_state(K)
         buf = st["buf"]
         stream = torch.cuda.current_stream().cuda_stream

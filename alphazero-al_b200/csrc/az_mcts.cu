@@ -30,6 +30,10 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <thread>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -1175,6 +1179,26 @@ __global__ void k_counts(Dev d, int32_t *__restrict__ out) {
         if (s.meta & F_ALLOC) o[(s.meta >> 16) & 0xFFu] = s.n;
     }
 }
+// the same for trees [lo, lo + cnt), widened to int64 on the device (the dtype callers of the reference hold: np.array(get_all_counts()))
+template <class G>
+__global__ void k_counts64_range(Dev d, int lo, int cnt, int64_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const int env = lo + i;
+    int64_t *o = out + (size_t)env * G::A;
+    int32_t c[G::A];
+    for (int a = 0; a < G::A; ++a) c[a] = 0;
+    const Slot root = ld_slot(&d.trees[env].root);
+    if (root.child != NONE) {
+        const Slot *blk = d.pool + (size_t)env * d.cap + (root.child >> 6);
+        const int ne = (int)(root.child & 63u);
+        for (int e = 0; e < ne; ++e) {
+            const Slot s = ld_slot(blk + e);
+            if (s.meta & F_ALLOC) c[(s.meta >> 16) & 0xFFu] = s.n;
+        }
+    }
+    for (int a = 0; a < G::A; ++a) o[a] = (int64_t)c[a];
+}
 template <class G>
 __global__ void k_root_stats(Dev d, float *__restrict__ out) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1284,6 +1308,83 @@ int pinned_acquire(size_t bytes, void **out) {
 }
 }  // namespace
 
+// Helper threads for the staging copies of az_mcts_playout_synthetic_host: the caller's boards are pageable memory, one core moves
+// ~20 GB/s into pinned staging, and at 65 536 games that copy (2.75 MB) is what delays the start of the last shard.  The
+// threads sleep on a condition variable between calls; the calling thread takes chunks from the same counter, so the call
+// makes progress on its own when they are slow to wake.  AZB200_STAGE_THREADS (default 2, 0 = none).
+// Copy into pinned staging that the CPU never reads back: streaming stores (no read-for-ownership of the destination lines).
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void stage_copy_avx2(uint8_t *dst, const uint8_t *src, size_t n) {
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = src[i]; ++i; }
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)), b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 64)), d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a); _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 64), c); _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 96), d);
+    }
+    for (; i + 32 <= n; i += 32) _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)));
+    _mm_sfence();
+    for (; i < n; ++i) dst[i] = src[i];
+}
+#endif
+static void stage_copy(void *dst, const void *src, size_t n) {
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("AZB200_PLAIN_STAGE_COPY");
+    if (avx2) { stage_copy_avx2((uint8_t *)dst, (const uint8_t *)src, n); return; }
+#endif
+    memcpy(dst, src, n);
+}
+struct StagePool {
+    struct Chunk { void *dst[2]; const void *src[2]; size_t n[2]; };
+    Chunk chunks[16];
+    int total = 0;
+    std::atomic<int> next{0};
+    std::atomic<int> done[16];
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv, cv_idle;
+    uint64_t gen = 0; int active = 0; bool quit = false;
+    void copy_chunk(int i) {
+        for (int q = 0; q < 2; ++q) if (chunks[i].n[q]) stage_copy(chunks[i].dst[q], chunks[i].src[q], chunks[i].n[q]);
+        done[i].store(1, std::memory_order_release);
+    }
+    bool take_one() {
+        const int i = next.fetch_add(1, std::memory_order_relaxed);
+        if (i >= total) return false;
+        copy_chunk(i);
+        return true;
+    }
+    void worker() {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return quit || gen != seen; });
+            if (quit) return;
+            seen = gen; ++active;
+            lk.unlock();
+            while (take_one()) {}
+            lk.lock();
+            if (--active == 0) cv_idle.notify_all();
+        }
+    }
+    void start(int n) { for (int i = 0; i < n; ++i) threads.emplace_back([this] { worker(); }); }
+    // the job in chunks[0..count) has been filled in by the caller (only while no worker is active: begin() waits for that)
+    void begin() { std::unique_lock<std::mutex> lk(mu); cv_idle.wait(lk, [&] { return active == 0; }); }
+    void submit(int count) {
+        { std::lock_guard<std::mutex> lk(mu); total = count; for (int i = 0; i < count; ++i) done[i].store(0, std::memory_order_relaxed); next.store(0); ++gen; }
+        if (!threads.empty()) cv.notify_all();
+    }
+    void wait_chunk(int j) {          // the calling thread copies what is left while it waits
+        while (!done[j].load(std::memory_order_acquire)) if (!take_one()) std::this_thread::yield();
+    }
+    ~StagePool() {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv.notify_all();
+        for (auto &t : threads) t.join();
+    }
+};
+
 struct az_mcts {
     int game = 0, n = 0, device = 0;
     int A = 0, S = 0, W = 0, max_depth = 0, max_edges = 0;
@@ -1301,9 +1402,10 @@ struct az_mcts {
     // CUDA graphs of whole playout loops (az_mcts_playout_synthetic_dev): the native loop issues ~600 launches per move at
     // ~6.5 us of host time each; a captured graph replays them with one call.  Keyed by everything a launch bakes in.
     struct GraphKey {
-        int mode, n_playout, K, ns, W, variant, wave_max, hints, kcap; uint32_t cap; const void *ptrs[10]; az_search_config cfg; uint64_t seed, env_base;
+        int mode, n_playout, K, ns, W, variant, wave_max, hints, kcap, split; uint32_t cap; const void *ptrs[10]; az_search_config cfg; uint64_t seed, env_base;
     };
-    struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t epoch0; int launches; uint64_t last_use; };
+    // (split != 0: one graph per shard - `shard_exec` - launched on the shard's own stream, az_mcts_playout_synthetic_host)
+    struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t epoch0; int launches; uint64_t last_use; std::vector<cudaGraphExec_t> shard_exec; };
     std::vector<GraphEntry> graphs;
     unsigned long long *d_epoch_add = nullptr;
     int use_graphs = 1;               // AZB200_GRAPHS=0 disables
@@ -1347,6 +1449,13 @@ struct az_mcts {
     bool err_check_pending = false;              // a back-prop was queued without reading the device error flag back
     std::vector<int8_t> last_boards; std::vector<int32_t> last_turns; bool roots_valid = false;   // host searches: roots already packed on the device
     int32_t *h_counts = nullptr;                 // pinned staging of the visit counts
+    // pipelined host playout (az_mcts_playout_synthetic_host): pinned staging of the caller's boards / turns, per-shard events
+    // (the copy that last read a shard's staging has completed), int64 visit counts on the device, per-shard device error flags
+    uint8_t *h_stage = nullptr, *io_stage = nullptr; StagePool *stage_pool = nullptr;
+    int64_t *io_counts64 = nullptr; int *h_err16 = nullptr;
+    // visit counts already on the host (pinned pool block) and the tree generation they belong to: handed to the next
+    // az_mcts_get_counts64_pinned if no kernel changed the trees in between
+    uint64_t tree_gen = 1, counts_gen = 0; int counts_block = -1; int64_t *counts_ptr = nullptr;
     unsigned long long *d_stats = nullptr; int *d_err = nullptr;
     uint64_t launches = 0;
     bool stats_on = false;
@@ -1696,6 +1805,7 @@ static int launch_backprop(az_mcts *h, bool vl, int K, int removeK, int use_sym,
                             const float *p2, const float *ml, const uint8_t *it, const int32_t *sym, cudaStream_t s) {
     const int cnt = h->d.env_cnt;
     const int g = grid_groups(cnt, h->W);
+    h->tree_gen++;                          // visit counts change: counts already fetched to the host are stale
     {   // which select produced the leaves of this range?  (read-only selects leave work to the back-prop, the others do not)
         const int lo = h->d.env_lo, hi = lo + cnt;
         bool found = false, ro = false, mixed = false;
@@ -1988,10 +2098,16 @@ void az_mcts_destroy(az_mcts *h) {
     if (h->h_in2) cudaFreeHost(h->h_in2);
     for (int j = 0; j < 2; ++j) if (h->h_in_ev[j]) cudaEventDestroy(h->h_in_ev[j]);
     if (h->h_counts) cudaFreeHost(h->h_counts);
+    delete h->stage_pool;
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->io_stage) cudaFree(h->io_stage);
+    if (h->h_err16) cudaFreeHost(h->h_err16);
+    if (h->io_counts64) cudaFree(h->io_counts64);
+    if (h->counts_block >= 0) az_pinned_release(h->counts_block);
     if (h->ev) cudaEventDestroy(h->ev);
     for (auto &pr : h->sel_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto &pr : h->bp_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
+    for (auto &g : h->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); for (auto e : g.shard_exec) if (e) cudaGraphExecDestroy(e); }
     if (h->d_epoch_add) cudaFree(h->d_epoch_add);
     for (int j = 0; j < 16; ++j) { if (h->side_ev[j]) cudaEventDestroy(h->side_ev[j]); if (h->side[j]) cudaStreamDestroy(h->side[j]); }
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -2057,6 +2173,7 @@ int az_mcts_set_seed(az_mcts *h, int64_t seed) {
 int az_mcts_reset_env(az_mcts *h, int i) {
     if (i < 0 || i >= h->n) return AZ_OK;   // silently ignored (BatchedMCTS.h:93-99)
     { int rc = enter_host(h); if (rc) return rc; }
+    h->tree_gen++;
     k_reset<<<1, 32, 0, h->stream>>>(h->d, i);
     h->internal_pending = true;
     h->launches++;
@@ -2067,6 +2184,7 @@ int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream) 
     int rc = check_cfg(h, 1); if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     rc = enter_dev(h, s); if (rc) return rc;
+    h->tree_gen++;
     if (h->game == GAME_C4) k_prune<C4><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, h->cfg, d_actions);
     else k_prune<Oth><<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, h->cfg, d_actions);
     h->launches++;
@@ -2088,6 +2206,7 @@ int az_mcts_prune_roots_dev(az_mcts *h, const int32_t *d_actions, void *stream) 
 int az_mcts_reset_all_dev(az_mcts *h, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int rc = enter_dev(h, s); if (rc) return rc;
+    h->tree_gen++;
     k_reset<<<grid_threads((size_t)h->n), 128, 0, s>>>(h->d, -1);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -2121,7 +2240,9 @@ int az_mcts_prune_roots(az_mcts *h, const int32_t *actions) {
     h->compaction = saved;
     if (rc) return rc;
     if (all_reset) { h->bump_bound = 0; h->bounds.clear(); h->base_after_prune = 0; h->bound_stale = false; }
-    CU(h, cudaStreamSynchronize(h->stream));
+    // no synchronisation: `actions` (pageable) has been staged when cudaMemcpyAsync returns, io_actions is only touched on this
+    // stream, and every later entry point is ordered after this one (the re-root overlaps the caller's next host work)
+    h->internal_pending = true;
     return AZ_OK;
 }
 
@@ -2385,7 +2506,8 @@ int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, in
             if (h->graphs.size() >= 6) {                      // drop the least recently used
                 size_t v = 0;
                 for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].last_use < h->graphs[v].last_use) v = i;
-                cudaGraphExecDestroy(h->graphs[v].exec);
+                if (h->graphs[v].exec) cudaGraphExecDestroy(h->graphs[v].exec);
+                for (auto se : h->graphs[v].shard_exec) if (se) cudaGraphExecDestroy(se);
                 h->graphs.erase(h->graphs.begin() + (long)v);
             }
             const uint64_t epoch0 = h->d.epoch;
@@ -2413,7 +2535,7 @@ int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, in
                 if (launches_out) *launches_out = launches;
                 return AZ_OK;
             }
-            h->graphs.push_back({key, exec, epoch0, launches, 0});
+            h->graphs.push_back({key, exec, epoch0, launches, 0, {}});
             ge = &h->graphs.back();
         }
         const unsigned long long delta = (unsigned long long)(h->d.epoch - ge->epoch0);
@@ -2421,6 +2543,7 @@ int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, in
         CU(h, cudaGraphLaunch(ge->exec, run));
         if (!main) { CU(h, cudaEventRecord(h->ev, run)); CU(h, cudaStreamWaitEvent(main, h->ev, 0)); }
         ge->last_use = ++h->graph_clock; h->graph_replays++;
+        h->tree_gen++;
         launches = ge->launches;
         // host-side state the issued loop would have left behind
         h->d.epoch += (uint64_t)iters.size();
@@ -2434,6 +2557,233 @@ int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, in
         h->launches += (uint64_t)launches;
     }
     h->user_stream = main; h->user_pending = true;
+    if (launches_out) *launches_out = launches;
+    return AZ_OK;
+}
+
+// ---- the same loop from HOST arrays, pipelined shard by shard --------------------------------------------------------------
+// What a host caller pays around the device loop - staging the boards, the host-to-device copy, the pack kernel, enqueueing the
+// loop, the visit-count kernel, the device-to-host copy - is done per tree shard on the shard's own stream: the GPU starts on
+// shard 0 while the host still stages shard 1, and the counts of a finished shard travel while the others search.  One CUDA
+// graph per shard (the single graph of az_mcts_playout_synthetic_dev cannot start before everything is staged).  The counts
+// land as int64 in a pinned pool block that the next az_mcts_get_counts64_pinned hands to the caller (no second pass).
+static int issue_shard_loop(az_mcts *h, int mode, const std::vector<int> &iters, int kmax, int lo, int cnt, cudaStream_t s, int *launches) {
+    float *pol = (float *)(h->io_in), *d, *p1, *p2, *ml;
+    {   const InLayout L = in_layout((size_t)h->io_rows, h->A);
+        uint8_t *q = h->io_in;
+        pol = (float *)(q + L.policy); d = (float *)(q + L.d); p1 = (float *)(q + L.p1); p2 = (float *)(q + L.p2); ml = (float *)(q + L.ml); }
+    const size_t r0 = (size_t)lo * kmax;
+    for (size_t it = 0; it < iters.size(); ++it) {
+        const int k = iters[it], kk = std::max(k, 1);
+        int rc = do_search(h, k, h->io_roots, h->io_leaves, s, lo, cnt, true, (int64_t)r0); if (rc) return rc;
+        rc = az_eval_synthetic_dev(h->game, mode, cnt * kk, h->io_leaves + r0, pol + r0 * h->A, d + r0, p1 + r0, p2 + r0, ml + r0, s);
+        if (rc) AZ_FAIL(h, rc, "synthetic evaluator launch failed");
+        rc = do_backprop(h, k, pol, d, p1, p2, ml, nullptr, nullptr, s, lo, cnt, (int64_t)r0); if (rc) return rc;
+        *launches += 3;
+    }
+    return AZ_OK;
+}
+
+static void drop_cached_counts(az_mcts *h) {
+    if (h->counts_block >= 0) { az_pinned_release(h->counts_block); h->counts_block = -1; h->counts_ptr = nullptr; }
+}
+
+int az_mcts_playout_synthetic_host(az_mcts *h, int mode, int n_playout, int K, int shards, const int8_t *boards, const int32_t *turns,
+                                   int want_counts, int *launches_out) {
+    if (n_playout < 0 || K < 0) AZ_FAIL(h, AZ_ERR_INVALID, "playout: n_playout and K must be >= 0");
+    int rc = enter_host(h); if (rc) return rc;
+    drop_cached_counts(h);
+    shards = std::min(std::max(shards, 1), 16);
+    const int per = (((h->n + shards - 1) / shards) + 31) / 32 * 32;
+    const int ns = std::max(1, (h->n + per - 1) / per);
+    std::vector<int> iters;
+    if (K <= 1) iters.assign((size_t)n_playout, 0);
+    else if (n_playout > 0) {
+        iters.push_back(0);
+        for (int rem = n_playout - 1; rem > 0; rem -= std::min(K, rem)) iters.push_back(std::min(K, rem));
+    }
+    int kmax = 1;
+    for (int k : iters) kmax = std::max(kmax, k);
+    rc = ensure_io(h, h->n * kmax); if (rc) return rc;
+    rc = check_cfg(h, K); if (rc) return rc;
+    const size_t cnt_all = (size_t)h->n * h->A;
+    // staging (pinned) and its device twin: shard j = [boards of its trees | turns of its trees] in one piece, so one copy moves it
+    const size_t stage_bytes = (size_t)h->n * (h->S + 4) + 32 * 17;
+    auto off_b = [&](int j, int lo) { return (size_t)lo * (h->S + 4) + 32 * (size_t)j; };
+    auto off_t = [&](int j, int lo, int cnt) { return off_b(j, lo) + (((size_t)cnt * h->S + 15) & ~(size_t)15); };
+    if (!h->h_stage) {
+        CU(h, cudaMallocHost((void **)&h->h_stage, stage_bytes));
+        CU(h, cudaMalloc((void **)&h->io_stage, stage_bytes));
+        CU(h, cudaMallocHost((void **)&h->h_err16, sizeof(int) * 16));
+        CU(h, cudaMalloc((void **)&h->io_counts64, sizeof(int64_t) * cnt_all));
+    }
+    for (int j = 0; j < ns; ++j) {
+        if (!h->side[j]) { CU(h, cudaStreamCreateWithFlags(&h->side[j], cudaStreamNonBlocking)); CU(h, cudaEventCreateWithFlags(&h->side_ev[j], cudaEventDisableTiming)); }
+    }
+    h->roots_valid = false;                 // io_roots no longer holds what host_search packed last
+    int64_t *cdst = nullptr; int block = -1;
+    if (want_counts) {
+        void *bp = nullptr;
+        block = pinned_acquire(sizeof(int64_t) * cnt_all, &bp);
+        if (block < 0) AZ_FAIL(h, AZ_ERR_NOMEM, "cannot allocate %zu bytes of pinned host memory for the visit counts", sizeof(int64_t) * cnt_all);
+        cdst = (int64_t *)bp;
+    }
+    auto fail = [&](int code) { if (block >= 0) az_pinned_release(block); return code; };
+    int launches = 0;
+    cudaStream_t s0 = h->stream;
+    const InLayout IL = in_layout((size_t)h->io_rows, h->A);
+    float *pol = (float *)(h->io_in + IL.policy), *dv = (float *)(h->io_in + IL.d), *p1 = (float *)(h->io_in + IL.p1),
+          *p2 = (float *)(h->io_in + IL.p2), *ml = (float *)(h->io_in + IL.ml);
+    const bool pipelined = ns > 1 && h->use_graphs && !h->time_select && !h->stats_on && iters.size() >= 4 && !h->lazy_live;
+    if (!pipelined) {
+        // small batches / measurement modes: everything on the internal stream, the loop through the whole-batch entry point
+        const size_t ot = off_t(0, 0, h->n), total = ot + sizeof(int32_t) * (size_t)h->n;
+        memcpy(h->h_stage, boards, (size_t)h->n * h->S); memcpy(h->h_stage + ot, turns, sizeof(int32_t) * (size_t)h->n);
+        CU(h, cudaMemcpyAsync(h->io_stage, h->h_stage, total, cudaMemcpyHostToDevice, s0));
+        rc = az_pack_roots_dev(h->game, h->n, (const int8_t *)h->io_stage, (const int32_t *)(h->io_stage + ot), h->io_roots, s0);
+        if (rc) { h->err = "pack_roots launch failed"; return fail(rc); }
+        rc = az_mcts_playout_synthetic_dev(h, mode, n_playout, K, ns, h->io_roots, h->io_leaves, pol, dv, p1, p2, ml, s0, &launches); if (rc) return fail(rc);
+        launches += 1;
+        if (want_counts) {
+            if (h->game == GAME_C4) k_counts64_range<C4><<<grid_threads((size_t)h->n), 128, 0, s0>>>(h->d, 0, h->n, h->io_counts64);
+            else k_counts64_range<Oth><<<grid_threads((size_t)h->n), 128, 0, s0>>>(h->d, 0, h->n, h->io_counts64);
+            CU(h, cudaMemcpyAsync(cdst, h->io_counts64, sizeof(int64_t) * cnt_all, cudaMemcpyDeviceToHost, s0));
+            launches += 1;
+        }
+        h->launches += (uint64_t)(want_counts ? 2 : 1);
+        rc = check_device_error(h); if (rc) return fail(rc);     // (synchronises the internal stream)
+    } else {
+        if (K > 0) { rc = ensure_kcap(h, K); if (rc) return fail(rc); }
+        for (int k : iters) bp_prepare(h, k > 0, k);
+        if (!h->d_epoch_add) { CU(h, cudaMalloc((void **)&h->d_epoch_add, sizeof(unsigned long long))); }
+        h->d.env_lo = 0; h->d.env_cnt = h->n;
+        rc = ensure_arena(h, n_playout, s0); if (rc) return fail(rc);          // the whole loop's growth, before any capture
+        az_mcts::GraphKey key;
+        memset(&key, 0, sizeof(key));
+        key.mode = mode; key.n_playout = n_playout; key.K = K; key.ns = ns; key.W = h->W; key.variant = h->variant; key.wave_max = h->wave_max; key.hints = h->d.hints;
+        key.kcap = h->kcap; key.split = 1; key.cap = h->cap; key.cfg = h->cfg; key.seed = h->d.seed; key.env_base = h->d.env_base;
+        const void *pp[10] = {h->io_roots, h->io_leaves, pol, dv, p1, p2, ml, h->d.pool, h->d.leaf_vl, h->h_stage};
+        memcpy(key.ptrs, pp, sizeof(pp));
+        az_mcts::GraphEntry *ge = nullptr;
+        for (auto &g : h->graphs) if (memcmp(&g.key, &key, sizeof(key)) == 0) { ge = &g; break; }
+        if (!ge) {
+            if (h->graphs.size() >= 6) {
+                size_t v = 0;
+                for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].last_use < h->graphs[v].last_use) v = i;
+                if (h->graphs[v].exec) cudaGraphExecDestroy(h->graphs[v].exec);
+                for (auto se : h->graphs[v].shard_exec) if (se) cudaGraphExecDestroy(se);
+                h->graphs.erase(h->graphs.begin() + (long)v);
+            }
+            const uint64_t epoch0 = h->d.epoch;
+            std::vector<cudaGraphExec_t> execs;
+            int per_shard_launches = 0;
+            bool ok = true;
+            h->d.epoch_add = h->d_epoch_add;
+            for (int j = 0; j < ns && ok; ++j) {
+                const int lo = j * per, cnt = std::min(per, h->n - lo);
+                h->d.epoch = epoch0;                                  // every shard walks the same epochs
+                h->capturing = true;
+                cudaGraph_t graph = nullptr;
+                int l = 0;
+                cudaError_t e = cudaStreamBeginCapture(h->side[j], cudaStreamCaptureModeThreadLocal);
+                if (e == cudaSuccess) {
+                    // the shard's staging -> device copy and its pack kernel are nodes of the graph too (fixed addresses): one call starts a shard
+                    const size_t ob = off_b(j, lo), ot = off_t(j, lo, cnt);
+                    e = cudaMemcpyAsync(h->io_stage + ob, h->h_stage + ob, ot - ob + sizeof(int32_t) * (size_t)cnt, cudaMemcpyHostToDevice, h->side[j]);
+                    if (e == cudaSuccess) {
+                        rc = az_pack_roots_dev(h->game, cnt, (const int8_t *)(h->io_stage + ob), (const int32_t *)(h->io_stage + ot), h->io_roots + lo, h->side[j]);
+                        if (rc) h->err = "pack_roots launch failed";
+                    }
+                    if (e == cudaSuccess && rc == AZ_OK) rc = issue_shard_loop(h, mode, iters, kmax, lo, cnt, h->side[j], &l);
+                    l += 1;
+                    const cudaError_t e2 = cudaStreamEndCapture(h->side[j], &graph);
+                    if (e == cudaSuccess) e = e2;
+                }
+                h->capturing = false;
+                cudaGraphExec_t exec = nullptr;
+                if (rc == AZ_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+                if (rc != AZ_OK || e != cudaSuccess || !exec) { ok = false; cudaGetLastError(); break; }
+                execs.push_back(exec);
+                per_shard_launches += l;
+            }
+            h->d.epoch_add = nullptr;
+            h->d.epoch = epoch0;
+            if (!ok) {
+                for (auto e : execs) cudaGraphExecDestroy(e);
+                h->bounds.clear(); h->bound_stale = true;
+                AZ_FAIL(h, fail(AZ_ERR_CUDA), "playout_synthetic_host: the shard loops could not be captured into CUDA graphs");
+            }
+            h->graphs.push_back({key, nullptr, epoch0, per_shard_launches, 0, execs});
+            ge = &h->graphs.back();
+        }
+        const unsigned long long delta = (unsigned long long)(h->d.epoch - ge->epoch0);
+        CU(h, cudaMemcpyAsync(h->d_epoch_add, &delta, sizeof(delta), cudaMemcpyHostToDevice, s0));
+        CU(h, cudaEventRecord(h->ev, s0));
+        for (int j = 0; j < ns; ++j) h->h_err16[j] = 0;
+        static const bool TRACE = getenv("AZB200_TRACE") != nullptr;
+        double tr_t[64]; int tr_n = 0;
+        auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        if (TRACE) tr_t[tr_n++] = now();
+        // (the staging is free: every call returns only after all its shards - and with them their copies - have completed)
+        if (!h->stage_pool) {
+            h->stage_pool = new StagePool();
+            const char *e = getenv("AZB200_STAGE_THREADS");
+            h->stage_pool->start(std::min(std::max(e ? atoi(e) : 2, 0), 8));
+        }
+        StagePool &sp = *h->stage_pool;
+        sp.begin();
+        for (int j = 0; j < ns; ++j) {
+            const int lo = j * per, cnt = std::min(per, h->n - lo);
+            sp.chunks[j] = {{h->h_stage + off_b(j, lo), h->h_stage + off_t(j, lo, cnt)}, {boards + (size_t)lo * h->S, turns + lo},
+                            {(size_t)cnt * h->S, sizeof(int32_t) * (size_t)cnt}};
+        }
+        sp.submit(ns);
+        for (int j = 0; j < ns; ++j) {                                     // fronts: a shard starts as soon as ITS boards are staged
+            cudaStream_t sj = h->side[j];
+            cudaError_t e = cudaStreamWaitEvent(sj, h->ev, 0);             // after the re-root / whatever the internal stream holds
+            sp.wait_chunk(j);
+            if (e != cudaSuccess) { for (int q = j + 1; q < ns; ++q) sp.wait_chunk(q); fail(0); AZ_FAIL(h, AZ_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e)); }
+            e = cudaGraphLaunch(ge->shard_exec[(size_t)j], sj);
+            if (e != cudaSuccess) { for (int q = j + 1; q < ns; ++q) sp.wait_chunk(q); fail(0); AZ_FAIL(h, AZ_ERR_CUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(e)); }
+            if (TRACE) tr_t[tr_n++] = now();
+        }
+        for (int j = 0; j < ns; ++j) {                                     // tails: queued while the GPU is already searching
+            const int lo = j * per, cnt = std::min(per, h->n - lo);
+            cudaStream_t sj = h->side[j];
+            if (want_counts) {
+                if (h->game == GAME_C4) k_counts64_range<C4><<<grid_threads((size_t)cnt), 128, 0, sj>>>(h->d, lo, cnt, h->io_counts64);
+                else k_counts64_range<Oth><<<grid_threads((size_t)cnt), 128, 0, sj>>>(h->d, lo, cnt, h->io_counts64);
+                CU(h, cudaMemcpyAsync(cdst + (size_t)lo * h->A, h->io_counts64 + (size_t)lo * h->A, sizeof(int64_t) * (size_t)cnt * h->A, cudaMemcpyDeviceToHost, sj));
+            }
+            CU(h, cudaMemcpyAsync(h->h_err16 + j, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, sj));
+            CU(h, cudaEventRecord(h->side_ev[j], sj));
+        }
+        if (TRACE) tr_t[tr_n++] = now();
+        ge->last_use = ++h->graph_clock; h->graph_replays++;
+        launches = ge->launches + (want_counts ? ns : 0);
+        // host-side state the issued loop would have left behind
+        h->d.epoch += (uint64_t)iters.size();
+        h->tree_gen++;
+        if (K > 0) h->prepared_K = iters.back() > 0 ? iters.back() : h->prepared_K;
+        h->last_select_ro = select_is_ro(h, iters.back() > 0, std::max(iters.back(), 1));
+        for (int j = 0; j < ns; ++j) {
+            h->d.env_lo = j * per; h->d.env_cnt = std::min(per, h->n - j * per);
+            note_select(h, iters.back() > 0, iters.back());
+        }
+        h->d.env_lo = 0; h->d.env_cnt = h->n;
+        h->launches += (uint64_t)launches;
+        bool dev_err = false;
+        for (int j = 0; j < ns; ++j) {
+            cudaError_t se = cudaEventSynchronize(h->side_ev[j]);
+            if (se != cudaSuccess) { fail(0); AZ_FAIL(h, AZ_ERR_CUDA, "playout_synthetic_host: shard %d failed: %s", j, cudaGetErrorString(se)); }
+            dev_err = dev_err || h->h_err16[j] != 0;
+            if (TRACE) tr_t[tr_n++] = now();
+        }
+        if (TRACE) { fprintf(stderr, "[trace]"); for (int i = 1; i < tr_n; ++i) fprintf(stderr, " %.0f", tr_t[i] - tr_t[0]); fprintf(stderr, "\n"); }
+        if (dev_err) { fail(0); AZ_FAIL(h, AZ_ERR_NOMEM, "device tree arena overflow (internal sizing error)"); }
+    }
+    if (want_counts) { h->counts_block = block; h->counts_ptr = cdst; h->counts_gen = h->tree_gen; }
     if (launches_out) *launches_out = launches;
     return AZ_OK;
 }
@@ -2520,6 +2870,30 @@ int az_mcts_get_counts64(az_mcts *h, int64_t *out) {
     CU(h, cudaMemcpyAsync(h->h_counts, h->io_counts, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     widen_counts(h->h_counts, out, cnt);
+    return AZ_OK;
+}
+// The int64 counts in a pinned pool block that the CALLER owns until az_pinned_release(*block_out): either the block the last
+// az_mcts_playout_synthetic_host already filled (nothing touched the trees since), or a fresh one (counts widened on the device, one copy).
+int az_mcts_get_counts64_pinned(az_mcts *h, int64_t **out, int *block_out) {
+    int rc = enter_host(h); if (rc) return rc;
+    if (h->counts_block >= 0 && h->counts_gen == h->tree_gen && !h->user_pending) {
+        *out = h->counts_ptr; *block_out = h->counts_block;
+        h->counts_block = -1; h->counts_ptr = nullptr;
+        return AZ_OK;
+    }
+    drop_cached_counts(h);
+    const size_t cnt = (size_t)h->n * h->A;
+    if (!h->io_counts64) CU(h, cudaMalloc((void **)&h->io_counts64, sizeof(int64_t) * cnt));
+    void *bp = nullptr;
+    const int block = pinned_acquire(sizeof(int64_t) * cnt, &bp);
+    if (block < 0) AZ_FAIL(h, AZ_ERR_NOMEM, "cannot allocate %zu bytes of pinned host memory for the visit counts", sizeof(int64_t) * cnt);
+    if (h->game == GAME_C4) k_counts64_range<C4><<<grid_threads((size_t)h->n), 128, 0, h->stream>>>(h->d, 0, h->n, h->io_counts64);
+    else k_counts64_range<Oth><<<grid_threads((size_t)h->n), 128, 0, h->stream>>>(h->d, 0, h->n, h->io_counts64);
+    h->launches++;
+    cudaError_t e = cudaMemcpyAsync(bp, h->io_counts64, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { az_pinned_release(block); AZ_FAIL(h, AZ_ERR_CUDA, "get_counts64_pinned: %s", cudaGetErrorString(e)); }
+    *out = (int64_t *)bp; *block_out = block;
     return AZ_OK;
 }
 int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream) {

@@ -271,10 +271,14 @@ class _BatchedMCTS:
         return out
 
     def get_all_counts_array64(self):
-        """The counts as int64 [n_envs, A] - the dtype np.array(get_all_counts()) has in the reference wrapper."""
-        out = np.empty((self._n, self._A), np.int64)
-        self._ck(self._L.az_mcts_get_counts64(self._h, _ptr(out)))
-        return out
+        """The counts as int64 [n_envs, A] - the dtype np.array(get_all_counts()) has in the reference wrapper.  The array is a view
+        of a pinned block (the destination of the one device-to-host copy, or the block playout_synthetic_host already filled) that
+        goes back to the library's pool when the array is garbage collected."""
+        ptr, block = C.c_void_p(), C.c_int(-1)
+        self._ck(self._L.az_mcts_get_counts64_pinned(self._h, C.byref(ptr), C.byref(block)))
+        buf = (C.c_int64 * (self._n * self._A)).from_address(ptr.value)
+        weakref.finalize(buf, self._L.az_pinned_release, block.value)
+        return np.frombuffer(buf, dtype=np.int64).reshape(self._n, self._A)
 
     def get_all_root_stats(self):
         out = np.empty((self._n, 6 + 8 * self._A), np.float32)
@@ -309,6 +313,19 @@ class _BatchedMCTS:
         out = C.c_int(0)
         self._ck(self._L.az_mcts_playout_synthetic_dev(self._h, int(mode), int(n_playout), int(K), int(shards), roots_ptr, leaves_ptr,
                                                        policy, d, p1w, p2w, ml, stream or None, C.byref(out)))
+        return out.value
+
+    def playout_synthetic_host(self, mode, n_playout, K, shards, input_boards, turns, want_counts=True):
+        """The same loop from host arrays, pipelined shard by shard (staging, copies, pack, loop and visit counts on the shard's own
+        stream; include/azb200.h).  Synchronous.  With want_counts the next get_all_counts_array64() is free.  Returns kernel launches."""
+        b = _carr(input_boards, np.int8)
+        t = _carr(turns, np.int32)
+        if b.size != self._n * self._S or t.size != self._n:
+            raise RuntimeError(f"playout: boards / turns must hold n_envs ({self._n}) games")
+        self._push_cfg()
+        out = C.c_int(0)
+        self._ck(self._L.az_mcts_playout_synthetic_host(self._h, int(mode), int(n_playout), int(K), int(shards), _ptr(b), _ptr(t),
+                                                        1 if want_counts else 0, C.byref(out)))
         return out.value
 
     def set_compaction(self, mode):

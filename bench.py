@@ -459,10 +459,11 @@ def main():
             tt = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        e2e = {"value": world * G * n_playout * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": G * (S + 4 + 4), "d2h_bytes_per_step": G * A * 4,
+        e2e = {"value": world * G * n_playout * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": G * (S + 4 + 4), "d2h_bytes_per_step": G * A * 8,
                "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
                "api": "BatchedMCTS.prune_roots + batch_playout(numpy boards, numpy turns) + get_visits_count() (wrapper mirror of "
-                      "src/MCTS_cpp.py; evaluator runs on the device)"}
+                      "src/MCTS_cpp.py; evaluator runs on the device; az_mcts_playout_synthetic_host: boards staged / copied / searched / "
+                      "counted shard by shard on 8 streams, int64 counts copied straight into the returned array's pinned memory)"}
         del wrap
         # secondary: the split host-buffer plugin API (search_batch[_vl] / backprop_batch[_vl] with numpy leaves every iteration)
         if world == 1 and not args.no_split:

@@ -187,6 +187,18 @@ int az_mcts_stream_handover_dev(az_mcts *h, void *stream);
 int az_mcts_playout_synthetic_dev(az_mcts *h, int mode, int n_playout, int K, int shards, const az_root *d_roots,
                                   az_leaf *d_leaves, float *d_policy, float *d_d, float *d_p1w, float *d_p2w,
                                   float *d_moves_left, void *stream, int *launches_out);
+/* The same loop from HOST arrays (boards i8[n, R, C], turns i32[n], as search_batch takes them: mcts_bindings.cpp:89-134), pipelined
+ * shard by shard: staging, host-to-device copy, pack kernel, the shard's loop (its own CUDA graph), visit-count kernel and
+ * device-to-host copy run on the shard's own stream, so the GPU searches shard 0 while the host still stages shard 1 and finished
+ * shards' counts travel while the others search.  Synchronous (returns when every shard is done, like the reference's calls).
+ * want_counts != 0: the int64 visit counts are left in a pinned block that the next az_mcts_get_counts64_pinned hands out
+ * (src/player.py:333-343 calls get_visits_count right after batch_playout).  Uses the engine's own device buffers. */
+int az_mcts_playout_synthetic_host(az_mcts *h, int mode, int n_playout, int K, int shards, const int8_t *boards,
+                                   const int32_t *turns, int want_counts, int *launches_out);
+/* get_all_counts as int64[n*A] (np.array(get_all_counts()), src/MCTS_cpp.py:81,442-443) in a pinned pool block the CALLER owns until
+ * az_pinned_release(*block_out): the counts are widened on the device and copied once, straight into the memory the caller's
+ * array lives in. */
+int az_mcts_get_counts64_pinned(az_mcts *h, int64_t **out, int *block_out);
 int az_mcts_search_eval_dev(az_mcts *h, int evaluator, const az_root *d_roots, int n_playout, void *stream);
 int az_mcts_get_counts_dev(az_mcts *h, int32_t *d_out, void *stream);
 int az_mcts_get_root_stats_dev(az_mcts *h, float *d_out, void *stream);

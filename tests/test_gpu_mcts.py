@@ -716,3 +716,54 @@ def test_time_budgeted_search_runs_on_the_device_path():
     full.batch_playout(ev, boards, turns, vl_batch=4)
     if (sims - 1) % 4 == 0:                                   # the timed run stopped on a full K = 4 batch: same schedule, same trees
         assert np.array_equal(full.get_visits_count(), c)
+
+
+@pytest.mark.parametrize("game,n,npl,K", [("Connect4", 16384 + 96, 60, 4), ("Connect4", 300, 30, 4), ("Connect4", 16384, 21, 1),
+                                          ("Othello", 16384, 24, 4)])
+def test_host_pipelined_playout_matches_the_device_loop(game, n, npl, K):
+    """az_mcts_playout_synthetic_host (host boards in, every shard staged / copied / searched / counted on its own stream, one CUDA graph
+    per shard, int64 counts left in pinned memory) against the device-resident loop it pipelines, with everything RNG-dependent on
+    (Dirichlet noise, leaf symmetry): same visit counts and root statistics over three moves with tree reuse, and the counts a
+    get_visits_count() hands out are the ones of the trees at that moment (a re-root or a reset in between is seen)."""
+    bm = importlib.import_module("alphazero-al_b200.batched_mcts")
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    import torch
+    boards, turns = random_positions(game, n, 8, 23)
+    cfg = dict(SERVER_DEFAULTS, dirichlet_alpha=0.3) if game == "Connect4" else dict(OTH_CFG, dirichlet_alpha=0.3, noise_epsilon=0.25)
+    ev = ds.SyntheticEvaluator(game, "hash")
+    wrap = bm.BatchedMCTS(n, cfg["c_init"], cfg["c_base"], cfg["dirichlet_alpha"], npl, game_name=game, noise_epsilon=cfg.get("noise_epsilon", 0.25),
+                          fpu_reduction=cfg["fpu_reduction"], use_symmetry=True, mlh_slope=cfg.get("mlh_slope", 0.0), mlh_cap=cfg.get("mlh_cap", 0.2),
+                          score_utility_factor=cfg.get("score_utility_factor", 0.0), score_scale=cfg.get("score_scale", 8.0))
+    wrap.seed(5)
+    eng = _cuda(game, n)
+    for f in ("c_init", "c_base", "dirichlet_alpha", "noise_epsilon", "fpu_reduction", "mlh_slope", "mlh_cap", "score_utility_factor", "score_scale",
+              "use_symmetry", "value_decay", "vl_count"):
+        setattr(eng.config, f, getattr(wrap.mcts.config, f))
+    eng.set_seed(5)
+    A = eng.action_size
+    buf = ds.LeafBuffers(n, n * max(K, 1), A, eng.board_shape, torch.device("cuda"))
+    stream = torch.cuda.current_stream().cuda_stream
+    db, dt = torch.from_numpy(boards).cuda(), torch.from_numpy(turns).cuda()
+    rng = np.random.default_rng(3)
+    for mv in range(3):
+        wrap.batch_playout(ev, boards, turns, vl_batch=K)
+        c = wrap.get_visits_count()
+        assert c.dtype == np.int64 and c.shape == (n, A)
+        buf.pack_roots(db, dt, stream)
+        ds.playout_device(eng, buf, npl, K, ev, stream)
+        ref = eng.get_all_counts_array()
+        assert np.array_equal(c, ref), f"move {mv}"
+        assert np.array_equal(wrap.mcts.get_all_root_stats().view(np.uint32), eng.get_all_root_stats().view(np.uint32))
+        assert np.array_equal(wrap.get_visits_count(), ref)          # a second fetch: computed again, same numbers
+        # re-root on a visited move (tree reuse), a few trees reset; the host boards are NOT advanced (both engines search the same
+        # root boards again: what matters here is that both do the same thing)
+        act = np.where(ref.max(1) > 0, ref.argmax(1), -1).astype(np.int32)
+        act[rng.integers(0, n, 5)] = -1
+        wrap.prune_roots(act)
+        eng.prune_roots(act)
+        after = wrap.get_visits_count()                               # not the counts fetched before the re-root
+        assert np.array_equal(after, eng.get_all_counts_array())
+        assert not np.array_equal(after, c)
+    held = c.copy()
+    del wrap
+    assert np.array_equal(c, held)                                    # the pinned block outlives the engine
