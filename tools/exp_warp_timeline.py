@@ -42,3 +42,6 @@ for n_done in (41, 121):                         # look at the select of iterati
     cnt = np.array([(smid == i).sum() for i in range(148)])
     print(f"   mean warp duration by SM: min {by_sm.min():.1f} p50 {np.median(by_sm):.1f} max {by_sm.max():.1f} us; warps per SM min {cnt.min()} max {cnt.max()}")
     print("   us per level iteration: mean %.2f p10 %.2f p90 %.2f" % ((dur / levels).mean(), np.percentile(dur / levels, 10), np.percentile(dur / levels, 90)))
+    stt = e.get_stats() if hasattr(e, "get_stats") else None
+    if stt:
+        print("   stats:", {k: stt[k] for k in ("sims", "depth", "edges_scanned")}, "mean depth per simulation %.2f -> %.1f level steps per tree and launch" % (stt["depth"] / max(stt["sims"], 1), K * stt["depth"] / max(stt["sims"], 1)))
