@@ -2333,9 +2333,9 @@ static int host_backprop(az_mcts *h, int K, const float *pol, const float *d, co
         const int sel = h->h_in_sel; h->h_in_sel ^= 1;
         uint8_t *p = sel ? h->h_in2 : h->h_in;
         CU(h, cudaEventSynchronize(h->h_in_ev[sel]));          // the copy that last read this buffer has completed
-        // streaming stores: the pinned buffer is only read by the copy engine (0.118 -> 0.093 ms per 8192-game K = 4 call; handing
-        // pieces to the staging threads as well made the call faster still, 0.089, but the caller's numpy evaluator and the next
-        // search slower by more than that - the arrays end up in other cores' caches)
+        // streaming stores: the pinned buffer is only read by the copy engine (0.115-0.118 ms per 8192-game K = 4 call; handing
+        // pieces to the staging threads as well made the call itself faster, 0.085-0.103, but the caller's numpy evaluator and
+        // the next search slower by more than that in three A/B runs - not used here)
         stage_copy(p + L.policy, pol, rows * h->A * 4); stage_copy(p + L.d, d, rows * 4); stage_copy(p + L.p1, p1, rows * 4);
         stage_copy(p + L.p2, p2, rows * 4); stage_copy(p + L.ml, ml, rows * 4); stage_copy(p + L.term, it, rows);
         if (sym) stage_copy(p + L.sym, sym, rows * 4);
