@@ -2237,17 +2237,19 @@ int az_mcts_set_compaction(az_mcts *h, int mode) {
 uint64_t az_mcts_compactions(const az_mcts *h) { return h->compactions; }
 int az_mcts_prune_roots(az_mcts *h, const int32_t *actions) {
     { int rc = enter_host(h); if (rc) return rc; }
-    CU(h, cudaMemcpyAsync(h->io_actions, actions, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
     // no action can match an edge (all negative): every tree is reset (MCTS.h:107), the arenas are empty afterwards - nothing to
-    // compact and the host's arena bound is exactly 0
-    bool all_reset = true;
-    for (int i = 0; i < h->n && all_reset; ++i) all_reset = actions[i] < 0;
-    const int saved = h->compaction;
-    if (all_reset) h->compaction = 0;
+    // compact, the host's arena bound is exactly 0, and the actions need not travel at all
+    int32_t signs = -1;
+    for (int i = 0; i < h->n; ++i) signs &= actions[i];           // (no early exit: vectorised)
+    if (signs < 0) {
+        int rc = check_cfg(h, 1); if (rc) return rc;
+        rc = az_mcts_reset_all_dev(h, h->stream); if (rc) return rc;
+        h->internal_pending = true;
+        return AZ_OK;
+    }
+    CU(h, cudaMemcpyAsync(h->io_actions, actions, sizeof(int32_t) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
     int rc = az_mcts_prune_roots_dev(h, h->io_actions, h->stream);
-    h->compaction = saved;
     if (rc) return rc;
-    if (all_reset) { h->bump_bound = 0; h->bounds.clear(); h->base_after_prune = 0; h->bound_stale = false; }
     // no synchronisation: `actions` (pageable) has been staged when cudaMemcpyAsync returns, io_actions is only touched on this
     // stream, and every later entry point is ordered after this one (the re-root overlaps the caller's next host work)
     h->internal_pending = true;
