@@ -344,6 +344,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL prints its version banner to STDOUT: keep stdout to the one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     mcts_cpp = importlib.import_module("alphazero-al_b200.mcts_cpp")
     ds = importlib.import_module("alphazero-al_b200.device_search")
