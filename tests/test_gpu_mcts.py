@@ -767,3 +767,33 @@ def test_host_pipelined_playout_matches_the_device_loop(game, n, npl, K):
     held = c.copy()
     del wrap
     assert np.array_equal(c, held)                                    # the pinned block outlives the engine
+
+
+def test_host_pipelined_playout_edge_cases():
+    """az_mcts_playout_synthetic_host: without counts (the next get_visits_count computes them), float boards (cast like the pybind
+    layer's forcecast), a batch too small for shards (whole-batch path), a ragged last shard, an engine destroyed with cached counts, and
+    the counts against the C restatement driven call by call with the host twin of the evaluator."""
+    mc = importlib.import_module("alphazero-al_b200.mcts_cpp")
+    ds = importlib.import_module("alphazero-al_b200.device_search")
+    ev_mod = importlib.import_module("alphazero-al_b200.evaluators")
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True)
+    for n, shards, npl, K in ((96, 2, 21, 4), (80, 1, 9, 4), (4096 + 40, 3, 13, 2)):
+        boards, turns = random_positions("Connect4", n, 10, 5)
+        e, o = _cuda("Connect4", n), _orc("Connect4", n)
+        set_config(e, **cfg); set_config(o, **cfg)
+        e.set_seed(9); o.set_seed(9)
+        e.set_wave_max(0)
+        launches = e.playout_synthetic_host(ds.SYN_MODES["hash"], npl, K, shards, boards.astype(np.float32), turns.astype(np.int64), want_counts=False)
+        assert launches > 0
+        playout(o, ev_mod.HashEvaluator("Connect4", "hash"), boards, turns, npl, K)
+        want = counts(o, n, 7)
+        assert np.array_equal(e.get_all_counts_array64(), want)
+        assert np.array_equal(np.asarray(e.get_all_counts()).reshape(n, 7), want)
+        assert e.get_all_root_stats().tobytes() == o.get_all_root_stats().tobytes()
+        e.reset_env(3)
+        after = e.get_all_counts_array64()
+        assert after[3].sum() == 0 and np.array_equal(np.delete(after, 3, 0), np.delete(want, 3, 0))
+        e.playout_synthetic_host(ds.SYN_MODES["hash"], 5, 4, shards, boards, turns)      # counts cached in the engine ...
+        del e                                                                             # ... and released with it
+    with pytest.raises(RuntimeError):
+        _cuda("Connect4", 64).playout_synthetic_host(0, 8, 4, 1, np.zeros((63, 6, 7), np.int8), np.ones(63, np.int32))
