@@ -1368,7 +1368,12 @@ struct StagePool {
             if (--active == 0) cv_idle.notify_all();
         }
     }
-    void start(int n) { for (int i = 0; i < n; ++i) threads.emplace_back([this] { worker(); }); }
+    void start(int n) {
+        for (int i = 0; i < n; ++i) {
+            try { threads.emplace_back([this] { worker(); }); }
+            catch (...) { break; }             // no thread to be had: the calling thread copies everything itself (wait_chunk)
+        }
+    }
     // the job in chunks[0..count) has been filled in by the caller (only while no worker is active: begin() waits for that)
     void begin() { std::unique_lock<std::mutex> lk(mu); cv_idle.wait(lk, [&] { return active == 0; }); }
     void submit(int count) {
@@ -1959,7 +1964,7 @@ static int do_backprop(az_mcts *h, int K, const float *pol, const float *d, cons
 }
 static StagePool &stage_pool_of(az_mcts *h) {
     if (!h->stage_pool) {
-        h->stage_pool = new StagePool();
+        h->stage_pool = new StagePool();       // (threads are created here, on the first host-pipelined playout of this engine)
         const char *e = getenv("AZB200_STAGE_THREADS");
         h->stage_pool->start(std::min(std::max(e ? atoi(e) : 2, 0), 8));
     }
@@ -2887,7 +2892,7 @@ int az_mcts_get_counts64(az_mcts *h, int64_t *out) {
 // az_mcts_playout_synthetic_host already filled (nothing touched the trees since), or a fresh one (counts widened on the device, one copy).
 int az_mcts_get_counts64_pinned(az_mcts *h, int64_t **out, int *block_out) {
     int rc = enter_host(h); if (rc) return rc;
-    if (h->counts_block >= 0 && h->counts_gen == h->tree_gen && !h->user_pending) {
+    if (h->counts_block >= 0 && h->counts_gen == h->tree_gen) {
         *out = h->counts_ptr; *block_out = h->counts_block;
         h->counts_block = -1; h->counts_ptr = nullptr;
         return AZ_OK;
