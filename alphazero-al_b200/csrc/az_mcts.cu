@@ -1678,10 +1678,12 @@ static int auto_lanes(int game, int n) {
 // ms per move, thread-per-tree / staggered): n=800 K=8: 2048 trees 10.5 / 6.4, 8192 trees 11.0 / 7.9, 16384 trees 12.5 / 11.7,
 // 32768 trees 15.0 / 17.6; n=200 K=4: 100 trees 1.96 / 1.48, 8192 trees 2.33 / 2.01, 16384 trees 2.71 / 2.50, 32768 trees 3.33 / 3.36.
 static bool use_wave(const az_mcts *h, bool vl, int K) {
-    // trees x 8 <= wave_max lanes (default 131 072: up to 16 384 trees).  Measured with the root-once thread-per-tree select (ms per move,
-    // staggered / thread per tree): K = 4: 8192 trees 1.96 / 2.31, 16 384 2.43 / 2.63, 32 768 3.35 / 3.12; K = 8, n = 800: 8192 7.77 / 10.5,
-    // 16 384 11.3 / 11.8, 32 768 17.7 / 14.5 (tools/exp_wave.py)
-    return vl && K >= 1 && K <= 8 && K <= h->kcap && h->wave_max > 0 && (int64_t)h->n * 8 <= (int64_t)h->wave_max;
+    // K <= 4: trees x 4 <= wave_max (default 131 072: up to 32 768 trees), K <= 8: trees x 8.  Measured with the root-once thread-per-tree
+    // select (ms per move, staggered / thread per tree): fresh roots, K = 4: 8192 trees 1.96 / 2.31, 16 384 2.43 / 2.63, 32 768 3.35 / 3.12;
+    // K = 8, n = 800: 8192 7.77 / 10.5, 16 384 11.3 / 11.8, 32 768 17.7 / 14.5 (tools/exp_wave.py).  Self-play with tree reuse (deeper
+    // trees: 3.3 levels per descent instead of 2.3), K = 4, ms per ply: 32 768 slots 4.15 / 4.60, 65 536 slots 6.66 / 5.89
+    // (tools/exp_selfplay_breakdown.py) - the 32 768-tree case goes to the staggered kernel because self-play is what runs at that size.
+    return vl && K >= 1 && K <= 8 && K <= h->kcap && h->wave_max > 0 && (int64_t)h->n * (K <= 4 ? 4 : 8) <= (int64_t)h->wave_max;
 }
 // Does the select launch for K simulations leave the tree untouched (read-only: back-prop applies the leaf flags)?
 static bool select_is_ro(const az_mcts *h, bool vl, int K) {

@@ -214,8 +214,8 @@ int az_mcts_set_variant(az_mcts *h, int variant);
 int az_mcts_get_variant(const az_mcts *h);
 /* Staggered-descent select (Connect4, lanes == 1, lean kernels, 1 <= K <= 8): small batches give every virtual-loss descent
  * its own lane, descent k starting one tree level after descent k-1 (K + depth - 1 dependent level steps instead of K x depth;
- * simulate_vl, MCTS.h:443-545, same results bit for bit).  Used when n_envs x 8 <= max_lanes; default 131072 = up to 16 384 trees
- * (measured crossover against the thread-per-tree select that scores the root once per launch), 0 = off.  Env: AZB200_WAVE_MAX.
+ * simulate_vl, MCTS.h:443-545, same results bit for bit).  Used when n_envs x group width (4 lanes per tree for K <= 4, 8 for
+ * K <= 8) <= max_lanes; default 131072 (measured crossover: self-play with tree reuse at 32 768 trees), 0 = off.  Env: AZB200_WAVE_MAX.
  * Othello (2 <= K <= 4) has the same scheme on its lane-group kernels - a warp per tree, the K descents in 8-lane groups one
  * level apart - when n_envs x 16 <= max_lanes (8192 trees by default). */
 int az_mcts_set_wave_max(az_mcts *h, int max_lanes);
