@@ -797,3 +797,23 @@ def test_host_pipelined_playout_edge_cases():
         del e                                                                             # ... and released with it
     with pytest.raises(RuntimeError):
         _cuda("Connect4", 64).playout_synthetic_host(0, 8, 4, 1, np.zeros((63, 6, 7), np.int8), np.ones(63, np.int32))
+
+
+@pytest.mark.parametrize("K", [4, 2])
+def test_c4_root_scored_once_with_dirichlet_noise_equals_other_kernel_families(K):
+    """Root noise is drawn on the device (not comparable with the host restatement's libm), so the read-only thread-per-tree select - which
+    mixes the noise into the root priors ONCE per launch and makes the K root choices from that - is compared with the kernel families
+    that score the root per descent: the first-generation thread-per-tree kernels and the 8-lane kernels, same seed, noise and leaf
+    symmetry on, tree reuse over several moves (re-roots redraw the noise), near-full boards (fewer than 7 root edges)."""
+    n = 160
+    cfg = dict(SERVER_DEFAULTS, use_symmetry=True, dirichlet_alpha=0.3, noise_epsilon=0.25)
+    for plies in (6, 30):
+        boards, turns = random_positions("Connect4", n, plies, 400 + plies + K)
+        lean = _cuda("Connect4", n); lean.set_lanes(1); lean.set_wave_max(0)
+        first = _cuda("Connect4", n); first.set_lanes(1); first.set_wave_max(0); first.set_variant(0)
+        wide = _cuda("Connect4", n); wide.set_lanes(8)
+        compare_engines(lean, first, "Connect4", n, 70, K, cfg, boards=boards, turns=turns, moves=4, seed=11)
+        lean2 = _cuda("Connect4", n); lean2.set_lanes(1); lean2.set_wave_max(0)
+        compare_engines(lean2, wide, "Connect4", n, 70, K, cfg, boards=boards, turns=turns, moves=4, seed=11)
+        stats = lean2.get_all_root_stats()
+        assert (stats[:, 6:].reshape(n, 7, 8)[:, :, 3] > 0).any()          # the noise column is populated
