@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
                                                   const float *__restrict__ mlv, const uint8_t *__restrict__ is_term,
                                                   const int32_t *__restrict__ sym_ids) {
     constexpr int NJ = (G::A + W - 1) / W;
+    __shared__ float psum_s[(G::GAME == GAME_OTH) ? CTA / W : 1][(G::GAME == GAME_OTH) ? G::MAX_EDGES + 2 : 1];   // Othello: legal policy values in order
     const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
     if (gid >= d.env_cnt) return;
     const int lane = threadIdx.x & (W - 1);
@@ -576,13 +577,19 @@ __global__ void __launch_bounds__(CTA) k_backprop(Dev d, az_search_config cfg, i
             } else if (pass_only) {
                 psum += gshfl<W>(gm, pmine[NJ - 1], 0);   // action 64 lives in lane 0, last register
             } else {
-                // ascending legal actions = register j (actions j * W ...), then lane: no 64-bit bit scan, no dynamic register select
+                // ascending legal actions: their policy values are compacted into shared memory in that order (rank = number of legal
+                // actions below), then every lane adds them up sequentially - a load and a dependent add per legal move (a shuffle per
+                // move from a bit-scan loop was 35 % of this kernel's stall samples, profiles/r2_ncu_full_oth.csv before this change)
+                float *ps = psum_s[threadIdx.x / W];
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
-                    uint32_t m = (uint32_t)(legal >> ((j * W) & 63)) & ((W >= 32) ? 0xFFFFFFFFu : ((1u << W) - 1u));
-                    if (j * W >= 64) m = 0u;
-                    while (m) { const int l = __ffs((int)m) - 1; m &= m - 1; psum += gshfl<W>(gm, pmine[j], l); }
+                    const int a = j * W + lane;
+                    if (a < 64 && ((legal >> a) & 1ULL)) ps[popc64(legal & ((1ULL << a) - 1ULL))] = pmine[j];
                 }
+                gsync<W>(gm);
+#pragma unroll 4
+                for (int i = 0; i < ne; ++i) psum += ps[i];
+                gsync<W>(gm);                                // (the next simulation of this tree overwrites the row)
             }
             const float denom = psum + 1e-8f;
             const uint32_t alloc = (uint32_t)ne;

@@ -248,6 +248,7 @@ template <class G, int W>
 __global__ void __launch_bounds__(CTA, 8) k_select_ws(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
                                                    az_leaf *__restrict__ leaves) {
     constexpr int NCH = (G::MAX_EDGES + W - 1) / W;
+    __shared__ float seen_s[CTA / W][G::MAX_EDGES + 2];              // per lane group: the visited children's priors in edge order
     const unsigned FULL = 0xFFFFFFFFu;
     const int tree = (blockIdx.x * CTA + threadIdx.x) >> 5;          // one warp per tree
     if (tree >= d.env_cnt) return;
@@ -290,13 +291,17 @@ __global__ void __launch_bounds__(CTA, 8) k_select_ws(Dev d, az_search_config cf
                 const int cur_infl = (int)(cur.meta & INFL_MASK);
                 const float parent_q = mean_q(cur.n, cur.wp1, cur.wp2, (cur.meta & F_TURN_P1) != 0);
                 float seen_policy = 0.0f;
+                {   // the priors of the visited children (0 for the others: + 0.0f is exact) go to the group's row in shared memory, then every
+                    // lane adds them in edge order: a load and a dependent add per edge instead of a ballot / bit-scan / shuffle loop
+                    float *sp_ = seen_s[threadIdx.x / W];
 #pragma unroll 1
-                for (int c0 = 0; c0 < ne; c0 += W) {
-                    const int e = c0 + lane;
-                    float pv = 0.0f;                                              // + 0.0f is exact: only visited children matter
-                    if (e < ne) { const uint2 pn = *reinterpret_cast<const uint2 *>(arena + off + e); if ((int)pn.y > 0) pv = __uint_as_float(pn.x); }
-                    unsigned vmask = (__ballot_sync(gm, pv != 0.0f) >> ((threadIdx.x & 31) & ~(W - 1))) & ((1u << W) - 1u);
-                    while (vmask) { const int l = __ffs((int)vmask) - 1; vmask &= vmask - 1; seen_policy += gshfl<W>(gm, pv, l); }
+                    for (int c0 = 0; c0 < ne; c0 += W) {
+                        const int e = c0 + lane;
+                        if (e < ne) { const uint2 pn = *reinterpret_cast<const uint2 *>(arena + off + e); sp_[e] = (int)pn.y > 0 ? __uint_as_float(pn.x) : 0.0f; }
+                    }
+                    __syncwarp(gm);
+#pragma unroll 4
+                    for (int e = 0; e < ne; ++e) seen_policy += sp_[e];
                 }
                 const float fscale = (1.0f + parent_q) / 2.0f;
                 const float eff_fpu = cfg.fpu_reduction * fscale;
