@@ -295,6 +295,7 @@ template <class G, int W, bool VL>
 __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
                                                 az_leaf *__restrict__ leaves) {
     constexpr int NCH = (G::MAX_EDGES + W - 1) / W;
+    __shared__ float seen_s[(G::GAME == GAME_OTH) ? CTA / W : 1][(G::GAME == GAME_OTH) ? G::MAX_EDGES + 2 : 1];   // Othello: visited children's priors in edge order
     const int gid = (blockIdx.x * CTA + threadIdx.x) / W;
     if (gid >= d.env_cnt) return;
     const int lane = threadIdx.x & (W - 1);
@@ -333,6 +334,20 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
             const int cur_infl = (int)(cur.meta & INFL_MASK);
             const float parent_q = mean_q(cur.n, cur.wp1, cur.wp2, (cur.meta & F_TURN_P1) != 0);
             float seen_policy = 0.0f;
+            if (G::GAME == GAME_OTH) {
+                // the priors of the visited children (0 for the others: + 0.0f is exact) go to the group's row in shared memory, then
+                // every lane adds them in edge order (as k_select_ws does)
+                float *sp_ = seen_s[threadIdx.x / W];
+#pragma unroll 1
+                for (int c0 = 0; c0 < ne; c0 += W) {
+                    const int e = c0 + lane;
+                    if (e < ne) { const uint2 pn = *reinterpret_cast<const uint2 *>(arena + off + e); sp_[e] = (int)pn.y > 0 ? __uint_as_float(pn.x) : 0.0f; }
+                }
+                gsync<W>(gm);
+#pragma unroll 4
+                for (int e = 0; e < ne; ++e) seen_policy += sp_[e];
+                gsync<W>(gm);                                                 // (the next level of this descent overwrites the row)
+            } else {
 #pragma unroll 1
             for (int c0 = 0; c0 < ne; c0 += W) {
                 const int e = c0 + lane;
@@ -340,6 +355,7 @@ __global__ void __launch_bounds__(CTA) k_select(Dev d, az_search_config cfg, int
                 if (e < ne) { const uint2 pn = *reinterpret_cast<const uint2 *>(arena + off + e); if ((int)pn.y > 0) pv = __uint_as_float(pn.x); }
                 unsigned vmask = (__ballot_sync(gm, pv != 0.0f) >> ((threadIdx.x & 31) & ~(W - 1))) & ((W == 32) ? 0xFFFFFFFFu : ((1u << W) - 1u));
                 while (vmask) { const int l = __ffs((int)vmask) - 1; vmask &= vmask - 1; seen_policy += gshfl<W>(gm, pv, l); }
+            }
             }
             const float fscale = (1.0f + parent_q) / 2.0f;
             const float eff_fpu = cfg.fpu_reduction * fscale;
