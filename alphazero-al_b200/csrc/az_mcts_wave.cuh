@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(CTA_W) k_select_w(Dev d, az_search_config cfg,
 // reach a given level in k order, so every load sees exactly what the sequential loop would have seen.  The level body is
 // k_select's.
 template <class G, int W>
-__global__ void __launch_bounds__(CTA, 8) k_select_ws(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
+__global__ void __launch_bounds__(CTA, 7) k_select_ws(Dev d, az_search_config cfg, int K, const az_root *__restrict__ roots,
                                                    az_leaf *__restrict__ leaves) {
     constexpr int NCH = (G::MAX_EDGES + W - 1) / W;
     __shared__ float seen_s[CTA / W][G::MAX_EDGES + 2];              // per lane group: the visited children's priors in edge order
